@@ -1,0 +1,42 @@
+"""Case list and helpers shared by oracle/make_goldens.py and tests (TEST INFRASTRUCTURE ONLY)."""
+import numpy as np
+import torch
+
+DEFORM_CASES = [
+    dict(name="deform1d_n193_b2", b=2, n=193, seed=11),
+    dict(name="deform1d_n128_b1_even", b=1, n=128, seed=12),
+    dict(name="deform1d_n517_b1", b=1, n=517, seed=13),
+]
+NYSTROM_CASES = [
+    dict(name="nystrom_d64_m16_n100_b2", b=2, n=100, dim=64, dim_head=8, m=16, seed=21),
+    dict(name="nystrom_d512_m256_n300_b1", b=1, n=300, dim=512, dim_head=64, m=256, seed=22),
+    dict(name="nystrom_d128_m64_n256_b1_nopad", b=1, n=256, dim=128, dim_head=16, m=64, seed=23),
+]
+TOWER_CASES = [dict(name="dctmil_n301_b1", B=1, N=300, seed=31)]
+TRANSMIL_CASES = [dict(name="transmil_n150_b1", B=1, N=150, seed=41)]
+PATHOMIC_CASES = [
+    dict(name="pathomic_diag_n260_b2", B=2, N=260, seed=51, task="diag2021"),
+    dict(name="pathomic_surv_n132_b1", B=1, N=132, seed=52, task="survival"),
+]
+
+MAX_KEEP = 8192
+
+
+def thin(v):
+    """Deterministic sub-sample of a big tensor so fixtures stay small: tensors with more
+    than MAX_KEEP elements are viewed as [rows, -1] and strided (odd strides) on both axes."""
+    if isinstance(v, torch.Tensor):
+        v = v.detach().cpu()
+    numel = int(np.prod(v.shape)) if v.ndim else 1
+    if numel <= MAX_KEEP:
+        return v
+    v2 = v.reshape(v.shape[0], -1) if v.ndim > 1 else v.reshape(1, -1)
+    r, c = v2.shape
+    cdiv = lambda a, b: (a + b - 1) // b
+    sc = 1
+    while r * cdiv(c, sc) > MAX_KEEP and sc < c:
+        sc += 2
+    sr = 1
+    while cdiv(r, sr) * cdiv(c, sc) > MAX_KEEP:
+        sr += 2
+    return v2[::sr, ::sc]

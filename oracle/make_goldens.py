@@ -1,0 +1,206 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (build container only).
+
+    python -m oracle.make_goldens            # needs /root/reference (read-only, never copied)
+
+The reference ships no tests or golden vectors, so the oracle is
+pinned against outputs of the reference's own modules, imported from /root/reference
+with the shims SURVEY.md section 8(c) lists: stub matplotlib / lifelines / sksurv /
+imblearn, alias the absent pip package ``nystrom_attention`` to the vendored
+models/NystromAttention.py, and patch ``.cuda()`` to identity (the reference hard-codes
+it at mil.py:239, DeformCrossTransMIL.py:116).  Inputs and weights come from
+``dml_b200.synth`` (numpy PCG64), so the fixtures only hold OUTPUTS and gradients;
+tests regenerate the inputs from the same seeds.  /root/reference does not exist on
+the GPU box - nothing but this script reads it.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def install_reference_shims():
+    if not os.path.isdir(REF):
+        raise SystemExit("make_goldens needs the reference checkout at /root/reference")
+    sys.path.insert(0, REF)
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    stub("matplotlib")
+    stub("matplotlib.pyplot")
+    stub("lifelines")
+    stub("lifelines.utils", concordance_index=None)
+    stub("lifelines.statistics", logrank_test=None)
+    stub("sksurv")
+    stub("sksurv.metrics", concordance_index_censored=None)
+    stub("imblearn")
+    stub("imblearn.over_sampling", RandomOverSampler=None)
+    stub("imblearn.metrics", sensitivity_score=None, specificity_score=None)
+    from models.NystromAttention import NystromAttention  # vendored copy == pip package algorithm
+    stub("nystrom_attention", NystromAttention=NystromAttention)
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
+def shapes_of(module):
+    return {k: tuple(v.shape) for k, v in module.state_dict().items()}
+
+
+def load_synth(module, seed, gain=1.0):
+    from dml_b200 import synth
+    sd = synth.fill_like(shapes_of(module), seed, gain)
+    module.load_state_dict(sd, strict=True)
+    return sd
+
+
+def grads_of(module, loss):
+    names = [k for k, p in module.named_parameters() if p.requires_grad]
+    params = [p for _, p in module.named_parameters() if p.requires_grad]
+    gs = torch.autograd.grad(loss, params, allow_unused=True)
+    return {k: g for k, g in zip(names, gs) if g is not None}
+
+
+def pack(d):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    return out
+
+
+from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, thin)
+
+
+def gen_deform():
+    from dml_b200 import synth
+    from models.DeformableAttention1D import DeformCrossAttention1D
+    for c in DEFORM_CASES:
+        mod = DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6)
+        load_synth(mod, c["seed"], gain=2.0)
+        x1 = synth.normal((c["b"], 128, c["n"]), c["seed"], "x1").requires_grad_()
+        x2 = synth.normal((c["b"], 128, c["n"]), c["seed"], "x2").requires_grad_()
+        r = synth.normal((c["b"], 128, c["n"]), c["seed"], "r")
+        out, vgrid = mod(x1, x2, return_vgrid=True)
+        loss = (out * r).sum()
+        gx1, gx2 = torch.autograd.grad(loss, (x1, x2), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(out=thin(out), vgrid=vgrid, gx1=thin(gx1), gx2=thin(gx2))
+        d.update({"grad." + k: thin(v) for k, v in g.items()})
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], float(out.abs().mean()), float(gx1.abs().mean()))
+
+
+def gen_nystrom():
+    from dml_b200 import synth
+    from models.NystromAttention import NystromAttention
+    from models.cmta_utils import NystromAttention as NystromCMTA
+    for c in NYSTROM_CASES:
+        kw = dict(dim=c["dim"], dim_head=c["dim_head"], heads=8, num_landmarks=c["m"], pinv_iterations=6,
+                  residual=True, dropout=0.1)
+        mod = NystromAttention(**kw).eval()
+        load_synth(mod, c["seed"], gain=2.0)
+        x = synth.normal((c["b"], c["n"], c["dim"]), c["seed"], "x").requires_grad_()
+        r = synth.normal((c["b"], c["n"], c["dim"]), c["seed"], "r")
+        out = mod(x)
+        loss = (out * r).sum()
+        (gx,) = torch.autograd.grad(loss, (x,), retain_graph=True)
+        g = grads_of(mod, loss)
+        # the second vendored copy must agree bit for bit
+        mod2 = NystromCMTA(**kw).eval()
+        mod2.load_state_dict(mod.state_dict())
+        assert torch.equal(mod2(x), out)
+        d = dict(out=thin(out), gx=thin(gx))
+        for k, v in g.items():
+            d["grad." + k] = thin(v)
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], float(out.abs().mean()), float(gx.abs().mean()))
+
+
+class _Args:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def pathomic_args(task):
+    return _Args(path_dim=128, omic_dim=128, mmhid=128, attn_dim=1, return_vgrid=False, label_dim=4,
+                 input_size_omic_tumor=59, input_size_omic_immune=361, return_grad="False", dropout_rate=0.1,
+                 init_type="max", fusion_type="concat", task_type=task)
+
+
+def gen_towers():
+    from dml_b200 import synth
+    from models.DeformCrossTransMIL import DeformCrossTransMIL
+    from models.mil import TransMIL
+    from models.model import DeformPathomicNet
+    for c in TOWER_CASES:
+        mod = DeformCrossTransMIL(pathomic_args("diag2021"), n_classes=4).eval()
+        load_synth(mod, c["seed"])
+        path = synth.synthetic_bag(c["N"], c["seed"], c["B"])["x_path"].requires_grad_()
+        omic = synth.normal((c["B"], 128), c["seed"], "omic").requires_grad_()
+        enc, logits, _ = mod(path, omic)
+        loss = (enc * synth.normal(enc.shape, c["seed"], "r_enc")).sum() + (logits * synth.normal(logits.shape, c["seed"], "r_log")).sum()
+        gpath, gomic = torch.autograd.grad(loss, (path, omic), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(encoded=enc, logits=logits, gpath=thin(gpath[0]), gomic=gomic)
+        for k, v in g.items():
+            d["grad." + k] = thin(v)
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], logits.detach().numpy().round(4))
+    for c in TRANSMIL_CASES:
+        mod = TransMIL(_Args(label_dim=3, path_dim=128)).eval()
+        load_synth(mod, c["seed"])
+        x = synth.synthetic_bag(c["N"], c["seed"], c["B"])["x_path"].requires_grad_()
+        enc, logits, _ = mod(x)
+        loss = (enc * synth.normal(enc.shape, c["seed"], "r_enc")).sum() + (logits * synth.normal(logits.shape, c["seed"], "r_log")).sum()
+        (gx,) = torch.autograd.grad(loss, (x,), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(encoded=enc, logits=logits, gx=thin(gx[0]))
+        for k, v in g.items():
+            d["grad." + k] = thin(v)
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], logits.detach().numpy().round(4))
+    for c in PATHOMIC_CASES:
+        mod = DeformPathomicNet(pathomic_args(c["task"])).eval()
+        load_synth(mod, c["seed"])
+        bag = synth.synthetic_bag(c["N"], c["seed"], c["B"])
+        out = mod(x_path=bag["x_path"], x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
+        feats, vt, vi, logits = out[0], out[1], out[2], out[3]
+        if c["task"] == "diag2021":
+            w = torch.tensor([1.0, 4.15, 2.93, 2.43])
+            loss = torch.nn.CrossEntropyLoss(weight=w)(logits[2], bag["label_diag"])       # train_test.py:790,834
+        else:
+            from utils.utils import NLLSurvLoss
+            S = torch.cumprod(1 - logits[2], dim=1)                                         # train_test.py:826
+            loss = NLLSurvLoss(alpha=0.15)(hazards=logits[2], S=S, Y=bag["label_surv"], c=bag["censor"], alpha=0)
+        g = grads_of(mod, loss)
+        d = dict(features=feats, hazard_tumor=logits[0], hazard_immune=logits[1], hazard=logits[2], loss=loss)
+        for k, v in g.items():
+            d["grad." + k] = thin(v)
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], float(loss), logits[2].detach().numpy().round(4))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
+    install_reference_shims()
+    torch.manual_seed(0)
+    torch.set_grad_enabled(True)
+    gen_deform()
+    gen_nystrom()
+    gen_towers()
+
+
+if __name__ == "__main__":
+    main()
