@@ -1,0 +1,96 @@
+"""Drop-in mirror of the reference ``models/DeformCrossTransMIL.py`` (FusionNet, DeformCrossTransLayer,
+DeformCrossTransMIL, Pooler) with the same constructor/forward signatures and state_dict keys
+(SURVEY.md section 8b / appendix A).  attn_dim == 1 is the supported (and the only working) branch.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .DeformableAttention1D import DeformCrossAttention1D
+from .DeformableAttention2D import DeformCrossAttention2D
+
+
+class FusionNet(nn.Module):
+    """Linear(2*feature_dim -> feature_dim) on cat(gene_features, image_features)
+    (reference :28-38).  Evaluated as two half-GEMMs so that the [B, N, 2*dim] concat (and the
+    [B, N, dim] repeat of the per-bag omic vector, :105) are never materialised."""
+
+    def __init__(self, feature_dim=128):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.fusion_layer = nn.Linear(feature_dim * 2, feature_dim)
+
+    def forward(self, gene_features, image_features):
+        W, b = self.fusion_layer.weight, self.fusion_layer.bias
+        fd = self.feature_dim
+        if image_features.dim() == gene_features.dim() - 1:      # per-bag vector [B, dim], broadcast over tokens
+            second = (F.linear(image_features, W[:, fd:]) + b)[:, None, :]
+        else:
+            second = F.linear(image_features, W[:, fd:]) + b
+        return ops.mm_tf32(gene_features, W[:, :fd].t()) + second
+
+
+class DeformCrossTransLayer(nn.Module):
+    def __init__(self, norm_layer=nn.LayerNorm, dim=128):
+        super().__init__()
+        self.norm = norm_layer(dim)
+        self.attn2d = DeformCrossAttention2D(dim=128, dim_head=64, heads=8, dropout=0.1, downsample_factor=4,
+                                             offset_scale=4, offset_groups=8, offset_kernel_size=6)
+        self.attn1d = DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6)
+
+    def forward(self, x1, x2, attn_dim, return_vgrid):
+        if attn_dim == 1:
+            # one LayerNorm shared by both streams (reference :44,66)
+            x = self.attn1d(self.norm(x1).transpose(1, 2), self.norm(x2).transpose(1, 2))
+            return x1 + x.transpose(1, 2)
+        raise NotImplementedError("attn_dim == 2 is broken in the reference as shipped (SURVEY.md Q6) and "
+                                  "DeformCrossAttention2D is not built yet (row N1)")
+
+
+class Pooler(nn.Module):
+    def __init__(self, hidden_size):
+        super().__init__()
+        self.dense = nn.Linear(hidden_size, hidden_size)
+        self.activation = nn.Tanh()
+
+    def forward(self, hidden_states):
+        return self.activation(self.dense(torch.mean(hidden_states, dim=1)))
+
+
+class DeformCrossTransMIL(nn.Module):
+    def __init__(self, args, n_classes=4):
+        super().__init__()
+        self.fusion_layer = FusionNet(feature_dim=128)
+        self._fc1 = nn.Sequential(nn.Linear(1024, args.path_dim), nn.ReLU())
+        self.cls_token = nn.Parameter(torch.randn(1, 1, args.path_dim))
+        self.args = args
+        self.n_classes = n_classes
+        self.layer3 = DeformCrossTransLayer(dim=args.path_dim)
+        self.norm = nn.LayerNorm(args.path_dim)
+        self._fc2 = nn.Linear(args.path_dim, self.n_classes)
+        self.pooler = Pooler(args.path_dim)
+        self.multimodal_projection = nn.Linear(args.path_dim, self.args.path_dim)
+
+    def forward(self, path, omic):
+        if getattr(self.args, "attn_dim", 1) != 1:
+            raise NotImplementedError("only attn_dim == 1 is supported (SURVEY.md Q6)")
+        if getattr(self.args, "return_vgrid", False):
+            raise NotImplementedError("return_vgrid with attn_dim == 1 raises in the reference (SURVEY.md Q6)")
+        fc1 = self._fc1[0]
+        if path.dtype == torch.bfloat16:      # bf16 bags: fc1 on the bf16 tensor-core path, fp32 afterwards
+            path = F.relu(F.linear(path, fc1.weight.to(torch.bfloat16), fc1.bias.to(torch.bfloat16))).float()
+        else:
+            path = F.relu(ops.mm_tf32(path.float(), fc1.weight.t()) + fc1.bias)
+        h = self.fusion_layer(path, omic.float())
+        B = h.shape[0]
+        cls_tokens = self.cls_token.expand(B, -1, -1).to(h.device)
+        h = torch.cat((cls_tokens, h), dim=1)
+        path = torch.cat((cls_tokens, path), dim=1)
+        h = self.layer3(h, path, 1, False)
+        h = self.norm(h[:, 0])                 # LayerNorm is per token: norm(h)[:, 0] == norm(h[:, 0])
+        logits = self._fc2(h)
+        encoded = self.multimodal_projection(h)
+        return encoded, logits, None

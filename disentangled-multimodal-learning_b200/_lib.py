@@ -1,0 +1,98 @@
+"""ctypes binding of libdml_b200.so (the C ABI declared in include/dml_b200.h).
+
+There is no fallback: if the library is missing or the device is not a B200 (sm_100a) every
+call raises.  The library is built in-tree by ``build.py`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdml_b200.so")
+
+_vp, _i, _f, _ll, _fp = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_void_p
+
+# name -> (restype, argtypes).  Every symbol of include/dml_b200.h is listed; tests/test_abi.py checks
+# that the header and this table agree and that the shared object exports all of them.
+SIGNATURES = {
+    "dml_runtime_check": (_i, []),
+    "dml_version": (C.c_char_p, []),
+    "dml_cpb_table_bytes": (C.c_size_t, []),
+    "dml_cpb_seg_max": (_i, []),
+    "dml_cpb_table_build": (_i, [_fp] * 6 + [_i, _i, _f, _vp, _vp]),
+    "dml_cpb_eval": (_i, [_vp, _fp, _i, _fp, _vp, _vp]),
+    "dml_cpb_param_grad": (_i, [_fp] * 6 + [_i, _i, _vp, _fp, _fp, _vp]),
+    "dml_offsets_kv_len": (_i, [_i, _i, _i]),
+    "dml_offsets_fwd": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp]),
+    "dml_offsets_bwd": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp, _vp]),
+    "dml_kv_gather_fwd": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
+    "dml_kv_gather_bwd": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _vp]),
+    "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
+    "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 6 + [_vp]),
+    "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
+    "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
+    "dml_softmax_rows_fwd": (_i, [_fp, _fp, _ll, _i, _vp]),
+    "dml_softmax_rows_bwd": (_i, [_fp, _fp, _fp, _ll, _i, _vp]),
+    "dml_res_conv_merge_fwd": (_i, [_fp, _fp, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _vp]),
+    "dml_res_conv_merge_bwd": (_i, [_fp, _fp, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _vp]),
+}
+
+_lock = threading.Lock()
+_lib = None
+_checked_devices = set()
+
+
+class DmlError(RuntimeError):
+    pass
+
+
+def load(check_device: bool = False):
+    """dlopen the shared object (once) and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise DmlError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a).  dml_b200 has no CPU / eager fallback.")
+                lib = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = lib
+    if check_device:
+        dev = torch.cuda.current_device()
+        if dev not in _checked_devices:
+            rc = _lib.dml_runtime_check()
+            if rc != 0:
+                raise DmlError(f"dml_b200 needs an sm_100a (B200) device; dml_runtime_check() = {rc}")
+            _checked_devices.add(dev)
+    return _lib
+
+
+_ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace too small"}
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point on the current CUDA device/stream; raise on failure."""
+    lib = load(check_device=True)
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        what = _ERR.get(rc) or (f"CUDA error {rc}" if rc > 0 else f"error {rc}")
+        raise DmlError(f"{name} failed: {what}")
+
+
+def ptr(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise DmlError("dml_b200 ops need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,143 @@
+"""Mirror of the callers in the reference ``models/model.py`` that sit directly on the hot path:
+MaxNet (:173-218), DeformPathomicNet (:471-568) and the part of ``define_net`` (:51-104) that selects
+them.  The reference file itself keeps working unmodified against these operators;
+this copy exists so that bench.py / tests can build the network on the GPU box, where /root/reference
+is absent.  Same names, forward signatures and state_dict keys."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import Parameter
+
+from .DeformCrossTransMIL import DeformCrossTransMIL
+from .mil import TransMIL
+
+
+def init_max_weights(module):
+    """utils/utils.py:214-219 - normal(0, 1/sqrt(fan_in)) weights, zero biases for every nn.Linear."""
+    for m in module.modules():
+        if type(m) == nn.Linear:
+            stdv = 1. / math.sqrt(m.weight.size(1))
+            m.weight.data.normal_(0, stdv)
+            m.bias.data.zero_()
+
+
+class MaxNet(nn.Module):
+    def __init__(self, input_dim=59, omic_dim=32, return_grad='False', dropout_rate=0.25, label_dim=1, init_max=True):
+        super().__init__()
+        hidden = [64, 48, 32, 32]
+        self.return_grad = return_grad
+        dims = [input_dim, hidden[0], hidden[1], hidden[2], omic_dim]
+        self.encoder = nn.Sequential(*[
+            nn.Sequential(nn.Linear(dims[i], dims[i + 1]), nn.ELU(), nn.AlphaDropout(p=dropout_rate, inplace=False))
+            for i in range(4)])
+        self.relu = nn.ReLU(inplace=False)
+        self.classifier = nn.Sequential(nn.Linear(omic_dim, label_dim))
+        if init_max:
+            init_max_weights(self)
+        self.output_range = Parameter(torch.FloatTensor([6]), requires_grad=False)
+        self.output_shift = Parameter(torch.FloatTensor([-3]), requires_grad=False)
+
+    def forward(self, **kwargs):
+        x = kwargs['x_omic']
+        features = self.relu(self.encoder(x))
+        logits = self.classifier(features)
+        return features, logits, None
+
+
+class DeformPathomicNet(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        init_max = True if args.init_type == "max" else False
+        self.args = args
+        self.omic_net_tumor = MaxNet(input_dim=args.input_size_omic_tumor, omic_dim=args.omic_dim,
+                                     return_grad=args.return_grad, dropout_rate=args.dropout_rate,
+                                     label_dim=args.label_dim, init_max=init_max)
+        self.omic_net_immune = MaxNet(input_dim=args.input_size_omic_immune, omic_dim=args.omic_dim,
+                                      return_grad=args.return_grad, dropout_rate=args.dropout_rate,
+                                      label_dim=args.label_dim, init_max=init_max)
+        self.pathomic_net_tumor = DeformCrossTransMIL(args)
+        self.pathomic_net_immune = DeformCrossTransMIL(args)
+        if args.fusion_type != "concat":
+            raise NotImplementedError("fusion_type != 'concat' (BilinearFusion) is outside the hot path "
+                                      "(SURVEY.md #11); every shipped YAML uses 'concat'")
+        self.classifier = nn.Linear(args.mmhid * 2, args.label_dim)
+        self.classifier_tumor = nn.Sequential(nn.Linear(args.mmhid, args.label_dim))
+        self.classifier_immune = nn.Sequential(nn.Linear(args.mmhid, args.label_dim))
+        self.return_grad = args.return_grad
+        self.fusion_type = args.fusion_type
+        self.output_range = Parameter(torch.FloatTensor([6]), requires_grad=False)
+        self.output_shift = Parameter(torch.FloatTensor([-3]), requires_grad=False)
+
+    def forward(self, **kwargs):
+        if getattr(self.args, "return_vgrid", False):
+            raise NotImplementedError("return_vgrid is broken in the reference for attn_dim == 1 (SURVEY.md Q6)")
+        omic_vec_tumor, _, _ = self.omic_net_tumor(x_omic=kwargs['x_omic_tumor'])
+        vec_tumor, _, grads_tumor = self.pathomic_net_tumor(path=kwargs['x_path'], omic=omic_vec_tumor)
+        omic_vec_immune, _, _ = self.omic_net_immune(x_omic=kwargs['x_omic_immune'])
+        vec_immune, _, grads_immune = self.pathomic_net_immune(path=kwargs['x_path'], omic=omic_vec_immune)
+        features = torch.cat((vec_tumor, vec_immune), 1)
+        hazard = self.classifier(features)
+        hazard_tumor = self.classifier_tumor(vec_tumor)
+        hazard_immune = self.classifier_immune(vec_immune)
+        if self.args.task_type == "survival":
+            hazard = torch.sigmoid(hazard)
+            hazard_tumor = torch.sigmoid(hazard_tumor)
+            hazard_immune = torch.sigmoid(hazard_immune)
+        logits = [hazard_tumor, hazard_immune, hazard]
+        return features, vec_tumor, vec_immune, logits, None, grads_tumor, grads_immune
+
+
+DIAG2021_CE_WEIGHTS = (1.0, 4.15, 2.93, 2.43)   # train_test.py:790
+GRADE_CE_WEIGHTS = (1.47, 1.51, 1.0)            # train_test.py:791
+
+
+def nll_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
+    """utils/utils.py:245-261."""
+    batch_size = len(Y)
+    Y = Y.view(batch_size, 1)
+    c = c.view(batch_size, 1).float()
+    if S is None:
+        S = torch.cumprod(1 - hazards, dim=1)
+    S_padded = torch.cat([torch.ones_like(c), S], 1)
+    uncensored = -(1 - c) * (torch.log(torch.gather(S_padded, 1, Y).clamp(min=eps))
+                             + torch.log(torch.gather(hazards, 1, Y).clamp(min=eps)))
+    censored = -c * torch.log(torch.gather(S_padded, 1, Y + 1).clamp(min=eps))
+    neg_l = censored + uncensored
+    return ((1 - alpha) * neg_l + alpha * uncensored).mean()
+
+
+def bag_loss(logits, label, task_type, censor=None):
+    """The loss trainDeformPathomicModel back-propagates (train_test.py:826-853): fused head only."""
+    hz = logits[2]
+    if task_type == "diag2021":
+        return F.cross_entropy(hz, label, weight=torch.tensor(DIAG2021_CE_WEIGHTS, device=hz.device))
+    if task_type == "grade":
+        return F.cross_entropy(hz, label, weight=torch.tensor(GRADE_CE_WEIGHTS, device=hz.device))
+    if task_type == "survival":
+        S = torch.cumprod(1 - hz, dim=1)
+        return nll_loss(hz, S, label, censor, alpha=0)
+    raise ValueError(task_type)
+
+
+class Args:
+    """Namespace with the YAML keys the hot-path models read (config/config_mine_*.yaml)."""
+
+    def __init__(self, **kw):
+        d = dict(path_dim=128, omic_dim=128, mmhid=128, attn_dim=1, return_vgrid=False, label_dim=4,
+                 input_size_omic_tumor=59, input_size_omic_immune=361, return_grad="False", dropout_rate=0.1,
+                 init_type="max", fusion_type="concat", task_type="diag2021", mode="deformpathomic")
+        d.update(kw)
+        self.__dict__.update(d)
+
+
+def define_net(args):
+    """The two branches of the reference define_net (model.py:51-104) that reach the hot path."""
+    if args.mode == "deformpathomic":
+        return DeformPathomicNet(args=args)
+    if args.mode in ("path", "transmil"):       # model.py:58-59: TransMIL is the commented-out alternative
+        return TransMIL(args)
+    raise NotImplementedError(f"mode {args.mode!r} is outside the hot path (SURVEY.md section 2)")

@@ -1,0 +1,269 @@
+"""torch.autograd.Function wrappers around the C ABI (include/dml_b200.h).
+
+Host code here only allocates buffers, orders the launches on torch's current stream and
+calls plain library GEMMs (torch.matmul -> cuBLAS) for the unfused projections; every
+fused / hot operator is a hand-written sm_100a kernel reached through ``_lib.call``.
+"""
+from __future__ import annotations
+
+import math
+from contextlib import contextmanager
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+CPB_GRAD_FLOATS = 1192  # DML_CPB_GRAD_FLOATS in include/dml_b200.h
+
+
+@contextmanager
+def tf32_matmul():
+    """fp32 GEMMs of this path run on the tensor cores in TF32 (fp32 accumulate)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def mm_f32out(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 -> fp32 2-D GEMM (weight gradients: no bf16 rounding of the long-K sums)."""
+    return torch.mm(a, b, out_dtype=F32)
+
+
+def centre_taps(n: int):
+    """Sequence taps of the degenerate grid sample (y = 0, align_corners=False), reference
+    DeformableAttention1D.py:36-43: iy = ((0 + 1) * n - 1) / 2."""
+    iy = ((0.0 + 1.0) * n - 1.0) / 2.0
+    i0 = int(math.floor(iy))
+    w1 = iy - i0
+    return i0, min(i0 + 1, n - 1), 1.0 - w1, w1
+
+
+def kv_length(n: int, ksize: int, stride: int) -> int:
+    pad = (ksize - stride) // 2
+    return (n + 2 * pad - ksize) // stride + 1
+
+
+class DeformCrossAttn1DFn(torch.autograd.Function):
+    """Forward + backward of DeformCrossAttention1D (DeformableAttention1D.py:156-240) on
+    token-major inputs x1t, x2t [B, n, dim] (fp32).  Returns (out [B, n, dim] fp32, vgrid [(B G), n_kv])."""
+
+    @staticmethod
+    def forward(ctx, x1t, x2t, Wq, Wk, Wv, Wo, bo, w0, b0, w2, m_w1, m_b1, m_W2, m_b2, m_W3, m_b3, cfg):
+        H, d, G, stride, ks, offset_scale = cfg
+        B, n, dim = x1t.shape
+        C = H * d
+        Cg = C // G
+        nout = H // G
+        hid = m_w1.shape[0]
+        scale = d ** -0.5
+        dev = x1t.device
+        n_kv = kv_length(n, ks, stride)
+        if n_kv < 1:
+            raise _lib.DmlError(f"sequence of {n} tokens is too short for offset kernel {ks}/stride {stride}")
+        st = stream()
+
+        x1b = x1t.to(BF16).contiguous()
+        x2f = x2t.to(F32).contiguous()
+        Wq_b = Wq.reshape(C, dim).to(BF16)
+        Wk_b = Wk.reshape(C, dim).to(BF16)
+        Wv_b = Wv.reshape(C, dim).to(BF16)
+        Wo_b = Wo.reshape(dim, C).to(BF16)
+        w0f, b0f, w2f = w0.reshape(Cg, ks).contiguous().float(), b0.contiguous().float(), w2.reshape(Cg).contiguous().float()
+        mlp = [t.contiguous().float() for t in (m_w1.reshape(-1), m_b1, m_W2, m_b2, m_W3, m_b3)]
+
+        q = torch.matmul(x1b, Wq_b.t())                                   # [B,n,C] bf16 (to_q, :175)
+        vgrid = torch.empty(B * G, n_kv, device=dev, dtype=F32)
+        g = torch.empty_like(vgrid)
+        call("dml_offsets_fwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), B, n, C, G, ks, stride, float(offset_scale),
+             ptr(vgrid), ptr(g), st)
+        i0, i1, wy0, wy1 = centre_taps(n)
+        kv = torch.empty(B, n_kv, dim, device=dev, dtype=BF16)
+        call("dml_kv_gather_fwd", ptr(x2f), ptr(g), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(kv), st)
+        k = torch.matmul(kv, Wk_b.t())                                    # [B,n_kv,C] bf16 (:199)
+        v = torch.matmul(kv, Wv_b.t())
+        table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
+        t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
+        call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), st)
+        o = torch.empty(B, n, C, device=dev, dtype=BF16)
+        lse = torch.empty(B, H, n, device=dev, dtype=F32)
+        call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n, n_kv, C, C, C, C, nout,
+             scale, ptr(o), ptr(lse), st)
+        out = torch.matmul(o, Wo_b.t()).float() + bo                       # to_out (:233)
+
+        ctx.cfg = cfg
+        ctx.taps = (i0, i1, wy0, wy1)
+        ctx.save_for_backward(x1b, x2f, q, kv, k, v, g, table, o, lse, Wq_b, Wk, Wv, Wo_b, w0f, b0f, w2f, *mlp)
+        return out, vgrid
+
+    @staticmethod
+    def backward(ctx, dout, dvgrid):
+        (x1b, x2f, q, kv, k, v, g, table, o, lse, Wq_b, Wk, Wv, Wo_b, w0f, b0f, w2f, *mlp) = ctx.saved_tensors
+        H, d, G, stride, ks, offset_scale = ctx.cfg
+        i0, i1, wy0, wy1 = ctx.taps
+        B, n, dim = x1b.shape
+        C, Cg, nout, hid = H * d, (H * d) // G, H // G, mlp[0].shape[0]
+        n_kv = kv.shape[1]
+        scale = d ** -0.5
+        dev = x1b.device
+        st = stream()
+
+        dout = dout.contiguous()
+        dout_b = dout.to(BF16)
+        dWo = mm_f32out(dout_b.reshape(-1, dim).t(), o.reshape(-1, C))      # [dim, C]
+        dbo = dout.sum(dim=(0, 1))
+        d_o = torch.matmul(dout_b, Wo_b)                                   # [B,n,C] bf16
+
+        dq_attn = torch.empty(B, n, C, device=dev, dtype=F32)
+        dk = torch.empty(B, n_kv, C, device=dev, dtype=F32)
+        dv = torch.empty_like(dk)
+        dg = torch.empty(B * G, n_kv, device=dev, dtype=F32)
+        segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=dev, dtype=F32)
+        dsum = torch.empty(B, H, n, device=dev, dtype=F32)
+        call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o), ptr(lse), B, H, d, n,
+             n_kv, C, C, C, C, nout, scale, ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), st)
+        mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
+        call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), st)
+
+        # key / value projections (small: n_kv x dim x C), fp32 on the TF32 tensor-core path
+        Wk2, Wv2 = Wk.reshape(C, dim).float(), Wv.reshape(C, dim).float()
+        with tf32_matmul():
+            kvf = kv.reshape(-1, dim).float()
+            dWk = dk.reshape(-1, C).t() @ kvf
+            dWv = dv.reshape(-1, C).t() @ kvf
+            dkv = (dk @ Wk2 + dv @ Wv2).contiguous()                       # [B,n_kv,dim]
+        dcentre = torch.empty(B, dim, device=dev, dtype=F32)
+        call("dml_kv_gather_bwd", ptr(x2f), ptr(g), ptr(dkv), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(dcentre),
+             ptr(dg), st)
+        dx2t = torch.zeros_like(x2f)
+        dx2t[:, i0] += wy0 * dcentre
+        if wy1 != 0.0:
+            dx2t[:, i1] += wy1 * dcentre
+
+        d_off = dg * (2.0 / max(n_kv - 1, 1))                              # g = 2 vgrid / max(n_kv-1,1) - 1
+        if dvgrid is not None:
+            d_off = d_off + dvgrid
+        d_off = d_off.contiguous()
+        dy_ws = torch.empty(B * G, n_kv, Cg, device=dev, dtype=F32)
+        wgrad = torch.empty(Cg * ks + 2 * Cg, device=dev, dtype=F32)
+        dq = torch.empty(B, n, C, device=dev, dtype=BF16)
+        call("dml_offsets_bwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), ptr(dq_attn), scale, B, n, C, G, ks,
+             stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), ptr(dq), st)
+        dWq = mm_f32out(dq.reshape(-1, C).t(), x1b.reshape(-1, dim))       # [C, dim]
+        dx1t = torch.matmul(dq, Wq_b).float()
+
+        dw0 = wgrad[: Cg * ks].reshape(Cg, 1, ks)
+        db0 = wgrad[Cg * ks: Cg * ks + Cg]
+        dw2 = wgrad[Cg * ks + Cg:].reshape(1, Cg, 1)
+        g_w1 = mlp_g[0:hid].reshape(hid, 1)
+        g_b1 = mlp_g[32:32 + hid]
+        g_W2 = mlp_g[64:64 + 1024].reshape(32, 32)[:hid, :hid]
+        g_b2 = mlp_g[1088:1088 + hid]
+        g_W3 = mlp_g[1120:1184].reshape(2, 32)[:nout, :hid]
+        g_b3 = mlp_g[1184:1184 + nout]
+        return (dx1t, dx2t, dWq.reshape(C, dim, 1), dWk.reshape(C, dim, 1), dWv.reshape(C, dim, 1),
+                dWo.reshape(dim, C, 1), dbo, dw0, db0, dw2, g_w1, g_b1, g_W2.contiguous(), g_b2, g_W3.contiguous(),
+                g_b3, None)
+
+
+class LandmarkPoolFn(torch.autograd.Function):
+    """mean over l consecutive (front-padded) tokens: x [B, n_pad, H*d] (may be a column slice of the
+    fused qkv buffer) -> [B, H, n_pad/l, d] * mult  (NystromAttention.py:102-118)."""
+
+    @staticmethod
+    def forward(ctx, x, l, H, d, mult):
+        B, n_pad, W = x.shape
+        assert W == H * d and x.stride(2) == 1 and x.stride(0) == n_pad * x.stride(1)
+        out = torch.empty(B, H, n_pad // l, d, device=x.device, dtype=F32)
+        call("dml_landmark_pool_fwd", ptr(x), x.stride(1), 0, B, n_pad, l, H, d, float(mult), ptr(out), stream())
+        ctx.meta = (B, n_pad, l, H, d, float(mult))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, n_pad, l, H, d, mult = ctx.meta
+        dout = dout.contiguous()
+        dx = torch.empty(B, n_pad, H * d, device=dout.device, dtype=F32)
+        call("dml_landmark_pool_bwd", ptr(dout), B, n_pad, l, H, d, mult, ptr(dx), stream())
+        return dx, None, None, None, None
+
+
+class SoftmaxRowsFn(torch.autograd.Function):
+    """softmax over the last dim of a contiguous fp32 tensor (NystromAttention.py:137)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        cols = x.shape[-1]
+        call("dml_softmax_rows_fwd", ptr(x), ptr(y), x.numel() // cols, cols, stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(y)
+        cols = y.shape[-1]
+        call("dml_softmax_rows_bwd", ptr(y), ptr(dy), ptr(dx), y.numel() // cols, cols, stream())
+        return dx
+
+
+class ResConvMergeFn(torch.autograd.Function):
+    """y[b,i,(h d)] = a[b,h,i,d] + depthwise conv_K(v)[b,i,(h d)]  (NystromAttention.py:144-149).
+    v [B, n_pad, H*d] may be a column slice of the fused qkv buffer; w [H,1,K,1]."""
+
+    @staticmethod
+    def forward(ctx, a, v, w):
+        B, H, n_pad, d = a.shape
+        assert v.stride(2) == 1 and v.stride(0) == n_pad * v.stride(1)
+        a = a.contiguous()
+        wf = w.reshape(H, -1).contiguous().float()
+        K = wf.shape[1]
+        y = torch.empty(B, n_pad, H * d, device=a.device, dtype=F32)
+        call("dml_res_conv_merge_fwd", ptr(a), ptr(v), v.stride(1), 0, ptr(wf), K, B, n_pad, H, d, ptr(y), stream())
+        ctx.save_for_backward(v, wf)
+        ctx.meta = (B, H, n_pad, d, K, tuple(w.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, wf = ctx.saved_tensors
+        B, H, n_pad, d, K, wshape = ctx.meta
+        dy = dy.contiguous()
+        da = torch.empty(B, H, n_pad, d, device=dy.device, dtype=F32)
+        dv = torch.empty(B, n_pad, H * d, device=dy.device, dtype=F32)
+        dw = torch.empty(H, K, device=dy.device, dtype=F32)
+        call("dml_res_conv_merge_bwd", ptr(dy), ptr(v), v.stride(1), 0, ptr(wf), K, B, n_pad, H, d, ptr(da), ptr(dv),
+             ptr(dw), stream())
+        return da, dv, dw.reshape(wshape)
+
+
+class MatmulTF32Fn(torch.autograd.Function):
+    """a @ b for fp32 operands on the TF32 tensor-core path, forward and backward (same batch dims)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        with tf32_matmul():
+            return torch.matmul(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        with tf32_matmul():
+            da = torch.matmul(g, b.transpose(-1, -2)) if ctx.needs_input_grad[0] else None
+            db = torch.matmul(a.transpose(-1, -2), g) if ctx.needs_input_grad[1] else None
+        if db is not None and db.dim() > b.dim():
+            db = db.reshape(-1, *b.shape).sum(0)
+        return da, db
+
+
+def mm_tf32(a, b):
+    return MatmulTF32Fn.apply(a, b)

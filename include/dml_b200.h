@@ -1,0 +1,113 @@
+/* dml_b200.h - C ABI of libdml_b200.so: the B200 (sm_100a) kernels behind the WSI multimodal-MIL
+ * attention hot path of helenypzhang/Disentangled-Multimodal-Learning.
+ *
+ * The reference has no FFI of its own (pure PyTorch); the boundary it exposes
+ * for this path is the nn.Module API.  Each entry point below replaces the
+ * ATen call sequence of the cited reference lines; the Python mirror modules in
+ * disentangled-multimodal-learning_b200/ bind them with ctypes and expose the
+ * reference's class names, constructor/forward signatures and state_dict keys.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated; tensors are dense
+ *     row-major with the explicit leading dimensions given; "bf16" buffers are passed as void*;
+ *   - no allocation inside: outputs, saved-for-backward tensors and workspaces are caller-owned;
+ *   - `stream` is a cudaStream_t; calls are asynchronous and never synchronise the host;
+ *   - return value: 0 = ok, < 0 = argument error (DML_E*), > 0 = the cudaError_t of the failed launch;
+ *   - sm_100a only: dml_runtime_check() refuses any other device.
+ */
+#ifndef DML_B200_H_
+#define DML_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DML_E_INVAL (-1)       /* bad pointer / shape */
+#define DML_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define DML_E_WORKSPACE (-3)
+
+#define DML_CPB_GRAD_FLOATS 1192 /* dw1[32] db1[32] dW2[32*32] db2[32] dW3[2*32] db3[2] (+pad) */
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+/* 0 if the current device is compute capability 10.x (B200); DML_E_UNSUPPORTED otherwise.      */
+int dml_runtime_check(void);
+const char* dml_version(void);
+
+/* ---- continuous position bias (CPB.forward, models/DeformableAttention1D.py:84-102) ---------- */
+/* Exact piecewise-linear table of the scalar-input ReLU MLP 1->hid->hid->nout (hid<=32, nout<=2),
+ * valid for |t| <= t_max.  table: dml_cpb_table_bytes() bytes.  Weight layouts = nn.Linear.       */
+size_t dml_cpb_table_bytes(void);
+int dml_cpb_seg_max(void);
+int dml_cpb_table_build(const float* w1, const float* b1, const float* W2, const float* b2, const float* W3,
+                        const float* b3, int hid, int nout, float t_max, void* table, void* stream);
+/* Diagnostics: evaluate the table at count values of t: out float[count][2] = (bias0, bias1), seg int[count]
+ * (may be NULL) = segment index.  Used by the tests to pin the table against the dense MLP.                 */
+int dml_cpb_eval(const void* table, const float* t, int count, float* out, int* seg, void* stream);
+/* Gradients of the six MLP parameters from the per-segment sums written by dml_deform_attn_bwd.
+ * segsum: float[dml_cpb_seg_max()][4] = (sum d0, sum d0*t, sum d1, sum d1*t); grads: float[DML_CPB_GRAD_FLOATS]
+ * laid out dw1[32] db1[32] dW2[32][32] db2[32] dW3[2][32] db3[2] (rows/cols beyond hid/nout are zero). */
+int dml_cpb_param_grad(const float* w1, const float* b1, const float* W2, const float* b2, const float* W3,
+                       const float* b3, int hid, int nout, const void* table, const float* segsum, float* grads,
+                       void* stream);
+
+/* ---- offsets (to_offsets Sequential :139-146; vgrid + normalize_grid :186-188, :45-48) -------- */
+/* n_kv = floor((n + 2*pad - ksize)/stride) + 1, pad = (ksize - stride)/2.                          */
+int dml_offsets_kv_len(int n, int ksize, int stride);
+/* q: bf16 [B, n, C] token-major UNSCALED queries, C = G*128.  w0 [128, ksize], b0 [128], w2 [128].
+ * vgrid, gnorm: float [(B*G), n_kv];  vgrid = j + tanh(.)*offset_scale, gnorm = 2 vgrid/max(n_kv-1,1) - 1. */
+int dml_offsets_fwd(const void* q, const float* w0, const float* b0, const float* w2, int B, int n, int C, int G,
+                    int ksize, int stride, float offset_scale, float* vgrid, float* gnorm, void* stream);
+/* d_off: float [(B*G), n_kv] gradient w.r.t. the offsets (= w.r.t. vgrid).  dq_attn: float [B,n,C] gradient of
+ * the attention w.r.t. the SCALED queries (multiplied by attn_scale here).  dy_ws: float [(B*G), n_kv, 128]
+ * workspace.  wgrad: float [128*ksize + 128 + 128] = dw0 | db0 | dw2.  dq_out: bf16 [B,n,C] total dq.        */
+int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float* w2, const float* d_off,
+                    const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
+                    float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* stream);
+
+/* ---- key/value gather (grid_sample_1d :36-43, :190-195; shipped degenerate semantics) */
+/* x2: float [B, n, dim] token-major; (i0,wy0),(i1,wy1): the sequence taps of y = 0 (centre of the sequence);
+ * kv: bf16 [B, n_kv, dim] = (x2[i0]*wy0 + x2[i1]*wy1) * tent(gnorm).                                 */
+int dml_kv_gather_fwd(const float* x2, const float* gnorm, int B, int n, int dim, int G, int n_kv, int i0, int i1,
+                      float wy0, float wy1, void* kv, void* stream);
+/* dkv: float [B, n_kv, dim].  dcentre: float [B, dim] (overwritten) = sum_j dkv*tent;  dg: float [(B*G), n_kv],
+ * ACCUMULATED into (call after dml_deform_attn_bwd, which initialises it).                           */
+int dml_kv_gather_bwd(const float* x2, const float* gnorm, const float* dkv, int B, int n, int dim, int G, int n_kv,
+                      int i0, int i1, float wy0, float wy1, float* dcentre, float* dg, void* stream);
+
+/* ---- fused deformable attention (:203-231): softmax(scale*q.k^T + CPB bias) v ---------------- */
+/* q bf16 [B,n,ldq], k/v bf16 [B,n_kv,ldk/ldv], head h in columns h*dim_head..; gnorm float [(B*G), n_kv],
+ * G = H/heads_per_group; out bf16 [B,n,ldo]; lse float [B,H,n] (log2 domain, saved for backward).     */
+int dml_deform_attn_fwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
+                        int H, int dim_head, int n, int n_kv, int ldq, int ldk, int ldv, int ldo,
+                        int heads_per_group, float scale, void* out, float* lse, void* stream);
+/* d_out bf16 [B,n,ldo] (ldo == H*dim_head).  dsum_ws float [B,H,n] workspace.  Outputs (fp32, dense
+ * [.., H*dim_head]): dq = dS.K (NOT yet multiplied by scale), dk, dv; dg float [(B*G), n_kv] and
+ * segsum float [dml_cpb_seg_max()][4] are zeroed here and then accumulated.                          */
+int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
+                        const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
+                        int n_kv, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
+                        float* dsum_ws, float* dq, float* dk, float* dv, float* dg, float* segsum, void* stream);
+
+/* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
+/* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]
+ * = mult * sum over l consecutive (padded) rows.                                                      */
+int dml_landmark_pool_fwd(const float* x, int ld, int col0, int B, int n_pad, int l, int H, int d, float mult,
+                          float* out, void* stream);
+int dml_landmark_pool_bwd(const float* dout, int B, int n_pad, int l, int H, int d, float mult, float* dx,
+                          void* stream); /* dx float [B,n_pad,H*d] (overwritten) */
+/* row softmax of the similarity matrices (:137) and its backward; rows are independent segments.     */
+int dml_softmax_rows_fwd(const float* x, float* y, long long rows, int cols, void* stream);
+int dml_softmax_rows_bwd(const float* y, const float* dy, float* dx, long long rows, int cols, void* stream);
+/* y[b,i,h*d+c] = a[b,h,i,c] + depthwise K-tap conv along i of v (:144-149), v float [B,n_pad,ldv] at col0. */
+int dml_res_conv_merge_fwd(const float* a, const float* v, int ldv, int col0, const float* w, int K, int B, int n_pad,
+                           int H, int d, float* y, void* stream);
+/* da float [B,H,n_pad,d], dv float [B,n_pad,H*d], dw float [H,K] (all overwritten).                   */
+int dml_res_conv_merge_bwd(const float* dy, const float* v, int ldv, int col0, const float* w, int K, int B, int n_pad,
+                           int H, int d, float* da, float* dv, float* dw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DML_B200_H_ */

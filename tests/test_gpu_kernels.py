@@ -1,0 +1,230 @@
+"""Kernel-level parity on the GPU, through the C ABI, against plain torch fp32 maths on the same
+(bf16-rounded where the kernel stores bf16) inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dml_b200 import _lib, ops, synth
+from dml_b200._lib import call, ptr, stream
+from oracle import deform1d as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def mlp_params(seed, hid=32, nout=2, gain=2.0):
+    shp = {"w1": (hid, 1), "b1": (hid,), "W2": (hid, hid), "b2": (hid,), "W3": (nout, hid), "b3": (nout,)}
+    P = synth.fill_like(shp, seed, gain)
+    P["w1"] = synth.uniform((hid, 1), seed, "w1x", 2.0)        # wide slopes -> many breakpoints inside [-T, T]
+    P["b1"] = synth.uniform((hid,), seed, "b1x", 1.0)
+    return {k: v.to(DEV) for k, v in P.items()}
+
+
+def dense_mlp(t, P):
+    h = F.relu(t[:, None] * P["w1"][:, 0] + P["b1"])
+    h = F.relu(h @ P["W2"].t() + P["b2"])
+    return h @ P["W3"].t() + P["b3"]
+
+
+def build_table(P, t_max, hid=32, nout=2):
+    table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=DEV, dtype=torch.uint8)
+    args = [P[k].reshape(-1).contiguous() if k == "w1" else P[k].contiguous() for k in ("w1", "b1", "W2", "b2", "W3", "b3")]
+    call("dml_cpb_table_build", *[ptr(a) for a in args], hid, nout, t_max, ptr(table), stream())
+    return table, args
+
+
+@pytest.mark.parametrize("seed,hid,nout", [(1, 32, 2), (2, 32, 2), (3, 16, 1), (4, 32, 1)])
+def test_cpb_table_matches_dense_mlp(seed, hid, nout):
+    P = mlp_params(seed, hid, nout)
+    T = 1.2
+    table, _ = build_table(P, T, hid, nout)
+    hdr = table[:16].view(torch.int32)
+    nseg, kmax = int(hdr[0]), int(hdr[1])
+    assert 1 <= nseg <= 1089 and 0 <= kmax <= 64
+    t = torch.linspace(-T * 0.999, T * 0.999, 200001, device=DEV)
+    out = torch.empty(t.numel(), 2, device=DEV)
+    seg = torch.empty(t.numel(), device=DEV, dtype=torch.int32)
+    call("dml_cpb_eval", ptr(table), ptr(t), t.numel(), ptr(out), ptr(seg), stream())
+    ref = dense_mlp(t.double(), {k: v.double() for k, v in P.items()})
+    err = (out[:, :nout].double() - ref).abs().max().item()
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()), (err, nseg, kmax)
+    assert int(seg.min()) == 0 and int(seg.max()) == nseg - 1
+    assert bool((seg[1:] >= seg[:-1]).all())          # segments are ordered in t
+
+
+def attn_reference(q, k, v, g, P, H_, nout, scale, n):
+    """fp32 torch maths of DeformableAttention1D.py:203-231 on [B,n,H*64] / [B,n_kv,H*64] inputs."""
+    B, n_kv = k.shape[0], k.shape[1]
+    d = 64
+    qh = q.float().reshape(B, n, H_, d).transpose(1, 2)
+    kh = k.float().reshape(B, n_kv, H_, d).transpose(1, 2)
+    vh = v.float().reshape(B, n_kv, H_, d).transpose(1, 2)
+    sim = torch.einsum("bhid,bhjd->bhij", qh, kh) * scale
+    seq = O.normalize_grid(torch.arange(n, device=q.device)).float()
+    Pd = {"rel_pos_bias.mlp.0.0.weight": P["w1"], "rel_pos_bias.mlp.0.0.bias": P["b1"],
+          "rel_pos_bias.mlp.1.0.weight": P["W2"], "rel_pos_bias.mlp.1.0.bias": P["b2"],
+          "rel_pos_bias.mlp.2.weight": P["W3"], "rel_pos_bias.mlp.2.bias": P["b3"]}
+    sim = sim + O.cpb_bias(seq, g, Pd, H_ // nout)
+    attn = sim.softmax(-1)
+    out = torch.einsum("bhij,bhjd->bhid", attn, vh)
+    return out.transpose(1, 2).reshape(B, n, H_ * d)
+
+
+@pytest.mark.parametrize("B,n,n_kv", [(1, 193, 48), (2, 130, 64), (1, 517, 129), (1, 64, 1)])
+def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv):
+    Hh, d, nout = 8, 64, 2
+    G, C = Hh // nout, Hh * d
+    seed = 100 + n
+    q = (synth.normal((B, n, C), seed, "q") * 0.7).to(DEV).to(torch.bfloat16)
+    k = (synth.normal((B, n_kv, C), seed, "k") * 0.7).to(DEV).to(torch.bfloat16)
+    v = synth.normal((B, n_kv, C), seed, "v").to(DEV).to(torch.bfloat16)
+    vgrid = torch.arange(n_kv, device=DEV)[None] + synth.uniform((B * G, n_kv), seed, "off", 2.0).to(DEV)
+    g = O.normalize_grid(vgrid).contiguous()
+    P = mlp_params(seed)
+    t_max = math.log1p(2.0 + 4.0 / max(n_kv - 1, 1)) * 1.001 + 1e-3
+    table, margs = build_table(P, t_max)
+    scale = d ** -0.5
+    o = torch.empty(B, n, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, Hh, n, device=DEV)
+    call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, C, C, C, C, nout, scale,
+         ptr(o), ptr(lse), stream())
+    qf, kf, vf = (t.float().requires_grad_() for t in (q, k, v))
+    gf = g.clone().requires_grad_()
+    Pf = {kk: vv.clone().requires_grad_() for kk, vv in P.items()}
+    ref = attn_reference(qf, kf, vf, gf, Pf, Hh, nout, scale, n)
+    H.assert_close(o.float(), ref, 6e-3, "attention output (bf16 store)")
+
+    r = synth.normal((B, n, C), seed, "r").to(DEV).to(torch.bfloat16)
+    loss = (ref * r.float()).sum()
+    grads = torch.autograd.grad(loss, [qf, kf, vf, gf] + [Pf[x] for x in ("w1", "b1", "W2", "b2", "W3", "b3")])
+    dq = torch.empty(B, n, C, device=DEV)
+    dk = torch.empty(B, n_kv, C, device=DEV)
+    dv = torch.empty_like(dk)
+    dg = torch.empty(B * G, n_kv, device=DEV)
+    segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=DEV)
+    dsum = torch.empty(B, Hh, n, device=DEV)
+    call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r), ptr(lse), B, Hh, d, n, n_kv,
+         C, C, C, C, nout, scale, ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), stream())
+    mg = torch.empty(ops.CPB_GRAD_FLOATS, device=DEV)
+    call("dml_cpb_param_grad", *[ptr(a) for a in margs], 32, nout, ptr(table), ptr(segsum), ptr(mg), stream())
+    tol = 1.5e-2   # bf16 P / dS operands in the MMAs; compared against exact fp32 maths
+    H.assert_close(dq * scale, grads[0], tol, "dq")
+    H.assert_close(dk, grads[1], tol, "dk")
+    H.assert_close(dv, grads[2], tol, "dv")
+    if n_kv > 1:
+        H.assert_close(dg, grads[3], tol, "dg")
+    H.assert_close(mg[0:32], grads[4][:, 0], tol, "d mlp.w1")
+    H.assert_close(mg[32:64], grads[5], tol, "d mlp.b1")
+    H.assert_close(mg[64:1088].reshape(32, 32), grads[6], tol, "d mlp.W2")
+    H.assert_close(mg[1088:1120], grads[7], tol, "d mlp.b2")
+    H.assert_close(mg[1120:1184].reshape(2, 32), grads[8], tol, "d mlp.W3")
+    assert float(mg[1184:1186].abs().max()) < 1e-2 * max(1.0, float(grads[8].abs().max()))   # softmax shift invariance
+
+
+@pytest.mark.parametrize("B,n", [(2, 193), (1, 128), (1, 1030)])
+def test_offsets_and_gather_match_oracle(B, n):
+    G, C, dim, ks, stride, osc = 4, 512, 128, 6, 4, 2.0
+    seed = 200 + n
+    P = {k: v.to(DEV) for k, v in synth.fill_like(H.deform_shapes(), seed, gain=2.0).items()}
+    q = synth.normal((B, n, C), seed, "q").to(DEV).to(torch.bfloat16)
+    n_kv = O.kv_length(n, ks, stride)
+    vgrid = torch.empty(B * G, n_kv, device=DEV)
+    g = torch.empty_like(vgrid)
+    w0 = P["to_offsets.0.weight"].reshape(128, ks).contiguous()
+    b0 = P["to_offsets.0.bias"].contiguous()
+    w2 = P["to_offsets.2.weight"].reshape(128).contiguous()
+    call("dml_offsets_fwd", ptr(q), ptr(w0), ptr(b0), ptr(w2), B, n, C, G, ks, stride, osc, ptr(vgrid), ptr(g), stream())
+    qf = q.float().requires_grad_()
+    Pf = {k: v.clone().requires_grad_() for k, v in P.items()}
+    gq = qf.transpose(1, 2).reshape(B * G, C // G, n)
+    off = O.offsets_net(gq, Pf, stride, osc)
+    vg_ref = torch.arange(n_kv, device=DEV) + off
+    assert n_kv == _lib.load().dml_offsets_kv_len(n, ks, stride)
+    H.assert_close(vgrid, vg_ref, 1e-5, "vgrid")
+    assert float((g - O.normalize_grid(vg_ref)).abs().max()) < 2e-6
+
+    # gather forward / backward against the closed form AND the literal grid_sample
+    x2 = synth.normal((B, n, dim), seed, "x2").to(DEV)
+    kv = torch.empty(B, n_kv, dim, device=DEV, dtype=torch.bfloat16)
+    i0, i1, wy0, wy1 = ops.centre_taps(n)
+    assert (i0, wy0, wy1) == (O.centre_taps(n)[0], O.centre_taps(n)[2], O.centre_taps(n)[3])
+    call("dml_kv_gather_fwd", ptr(x2), ptr(g), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(kv), stream())
+    x2f = x2.clone().requires_grad_()
+    gf = g.clone().requires_grad_()
+    lit = O.grid_sample_1d_literal(x2f.transpose(1, 2).reshape(B * G, dim // G, n), gf).reshape(B, dim, n_kv).transpose(1, 2)
+    H.assert_close(kv.float(), lit, 5e-3, "kv_feats (bf16 store)")
+    assert torch.equal(kv, lit.to(torch.bfloat16)) or n % 2 == 0     # bit-exact before the bf16 store for odd n
+    dkv = synth.normal((B, n_kv, dim), seed, "dkv").to(DEV)
+    gx2, gg = torch.autograd.grad((lit * dkv).sum(), (x2f, gf))
+    dcentre = torch.empty(B, dim, device=DEV)
+    dg = torch.zeros(B * G, n_kv, device=DEV)
+    call("dml_kv_gather_bwd", ptr(x2), ptr(g), ptr(dkv), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(dcentre), ptr(dg), stream())
+    dx2 = torch.zeros_like(x2)
+    dx2[:, i0] += wy0 * dcentre
+    if wy1:
+        dx2[:, i1] += wy1 * dcentre
+    H.assert_close(dx2, gx2, 1e-5, "d x2")
+    H.assert_close(dg, gg, 1e-5, "d g (gather)")
+
+    # offsets backward
+    d_off = synth.normal((B * G, n_kv), seed, "d_off").to(DEV)
+    dq_attn = synth.normal((B, n, C), seed, "dq_attn").to(DEV)
+    grads = torch.autograd.grad((off * d_off).sum(), [qf, Pf["to_offsets.0.weight"], Pf["to_offsets.0.bias"], Pf["to_offsets.2.weight"]])
+    dy_ws = torch.empty(B * G, n_kv, 128, device=DEV)
+    wgrad = torch.empty(128 * ks + 256, device=DEV)
+    dq = torch.empty(B, n, C, device=DEV, dtype=torch.bfloat16)
+    call("dml_offsets_bwd", ptr(q), ptr(w0), ptr(b0), ptr(w2), ptr(d_off), ptr(dq_attn), 0.125, B, n, C, G, ks, stride, osc,
+         ptr(dy_ws), ptr(wgrad), ptr(dq), stream())
+    H.assert_close(dq.float(), grads[0] + 0.125 * dq_attn, 5e-3, "dq total (bf16 store)")
+    H.assert_close(wgrad[:128 * ks].reshape(128, 1, ks), grads[1], 1e-4, "d to_offsets.0.weight")
+    H.assert_close(wgrad[128 * ks:128 * ks + 128], grads[2], 1e-4, "d to_offsets.0.bias")
+    H.assert_close(wgrad[128 * ks + 128:].reshape(1, 128, 1), grads[3], 1e-4, "d to_offsets.2.weight")
+
+
+@pytest.mark.parametrize("B,n_pad,l,Hh,d", [(2, 96, 6, 8, 16), (1, 512, 2, 8, 64), (1, 16640, 65, 8, 64)])
+def test_landmark_pool(B, n_pad, l, Hh, d):
+    W = Hh * d
+    qkv = synth.normal((B, n_pad, 3 * W), 7, "qkv").to(DEV)
+    for col0, mult in ((0, 0.125 / l), (W, 1.0 / l)):
+        x = qkv[..., col0:col0 + W].detach().requires_grad_()
+        y = ops.LandmarkPoolFn.apply(x, l, Hh, d, mult)
+        ref = x.reshape(B, n_pad // l, l, Hh, d).sum(2).permute(0, 2, 1, 3) * mult
+        H.assert_close(y, ref, 2e-6, "landmarks")
+        r = synth.normal(tuple(y.shape), 8, "r").to(DEV)
+        (gx,) = torch.autograd.grad((y * r).sum(), x)
+        (gr,) = torch.autograd.grad((ref * r).sum(), x)
+        H.assert_close(gx, gr, 1e-6, "d landmarks")
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 16), (2, 8, 300, 256), (8, 256, 16640), (4, 7, 1023), (2, 3, 640)])
+def test_softmax_rows(shape):
+    x = (synth.normal(shape, 9, "x") * 3).to(DEV).requires_grad_()
+    y = ops.SoftmaxRowsFn.apply(x)
+    ref = x.softmax(-1)
+    H.assert_close(y, ref, 2e-6, "softmax")
+    r = synth.normal(shape, 10, "r").to(DEV)
+    (gx,) = torch.autograd.grad((y * r).sum(), x)
+    (gr,) = torch.autograd.grad((ref * r).sum(), x)
+    H.assert_close(gx, gr, 1e-5, "d softmax")
+
+
+@pytest.mark.parametrize("B,n_pad,Hh,d,K", [(2, 100, 8, 16, 33), (1, 300, 8, 64, 33), (1, 1000, 8, 32, 33), (1, 64, 8, 64, 5)])
+def test_res_conv_merge(B, n_pad, Hh, d, K):
+    W = Hh * d
+    qkv = synth.normal((B, n_pad, 3 * W), 11, "qkv").to(DEV)
+    a = synth.normal((B, Hh, n_pad, d), 11, "a").to(DEV).requires_grad_()
+    w = synth.uniform((Hh, 1, K, 1), 11, "w", 0.3).to(DEV).requires_grad_()
+    v = qkv[..., 2 * W:].detach().requires_grad_()
+    y = ops.ResConvMergeFn.apply(a, v, w)
+    vh = v.reshape(B, n_pad, Hh, d).transpose(1, 2)
+    ref = (a + F.conv2d(vh, w, padding=(K // 2, 0), groups=Hh)).transpose(1, 2).reshape(B, n_pad, W)
+    H.assert_close(y, ref, 2e-6, "res_conv merge")
+    r = synth.normal((B, n_pad, W), 12, "r").to(DEV)
+    ga, gv, gw = torch.autograd.grad((y * r).sum(), (a, v, w))
+    ra, rv, rw = torch.autograd.grad((ref * r).sum(), (a, v, w))
+    H.assert_close(ga, ra, 1e-6, "d a")
+    H.assert_close(gv, rv, 2e-6, "d v")
+    H.assert_close(gw, rw, 2e-5, "d w")

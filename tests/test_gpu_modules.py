@@ -1,0 +1,189 @@
+"""Module-level parity on the GPU: the drop-in mirrors (called exactly like the reference's
+nn.Modules, weights loaded through load_state_dict(strict=True)) against
+ (a) the golden vectors produced by the reference itself (tests/golden, oracle/make_goldens.py) and
+ (b) the oracle restatement run in fp32 on the same seeded inputs, including 16k-token bags.
+Tolerances (BASELINE.json north_star): 5e-3 relative for the bf16 deformable path, 1e-3 for the
+fp32/TF32 Nystrom path; integer artefacts bit-exact."""
+import pytest
+import torch
+
+from dml_b200 import synth
+from dml_b200.DeformableAttention1D import DeformCrossAttention1D
+from dml_b200.DeformCrossTransMIL import DeformCrossTransMIL
+from dml_b200.NystromAttention import NystromAttention
+from dml_b200.model import Args, bag_loss, define_net
+from oracle import deform1d, nystrom, towers
+from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, PATHOMIC_CASES, TOWER_CASES, TRANSMIL_CASES, thin)
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_BF16 = 5e-3
+TOL_TF32 = 1e-3
+
+
+def load(module, shapes, seed, gain=1.0):
+    sd = synth.fill_like(shapes, seed, gain)
+    module.load_state_dict(sd, strict=True)
+    return module.to(DEV)
+
+
+def check_param_grads(module, loss, G, tol, atol_zero=1e-4, extra_atol=None):
+    names = [k for k, p in module.named_parameters() if p.requires_grad]
+    params = [p for _, p in module.named_parameters() if p.requires_grad]
+    gs = torch.autograd.grad(loss, params, allow_unused=True)
+    seen = 0
+    worst = {}
+    for k, g in zip(names, gs):
+        key = "grad." + k
+        if key not in G:
+            assert g is None or float(g.abs().max()) == 0.0, f"unexpected gradient for {k}"
+            continue
+        assert g is not None, f"missing gradient for {k}"
+        ref = G[key].to(DEV)
+        scale = float(ref.abs().max())
+        atol = atol_zero if k.endswith("rel_pos_bias.mlp.2.bias") else (extra_atol or 0.0) * 0
+        H.assert_close(thin(g.cpu()), G[key], tol, key, atol=atol)
+        seen += 1
+    assert seen > 0
+
+
+@pytest.mark.parametrize("c", DEFORM_CASES, ids=lambda c: c["name"])
+def test_deform1d_module_matches_reference_golden(c):
+    G = H.golden(c["name"])
+    mod = load(DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6),
+               H.deform_shapes(), c["seed"], gain=2.0)
+    x1 = synth.normal((c["b"], 128, c["n"]), c["seed"], "x1").to(DEV).requires_grad_()
+    x2 = synth.normal((c["b"], 128, c["n"]), c["seed"], "x2").to(DEV).requires_grad_()
+    r = synth.normal((c["b"], 128, c["n"]), c["seed"], "r").to(DEV)
+    out, vgrid = mod(x1, x2, return_vgrid=True)
+    assert out.shape == x1.shape and vgrid.shape == G["vgrid"].shape        # n_kv is an integer artefact
+    H.assert_close(vgrid.cpu(), G["vgrid"], 1e-4, "vgrid")
+    H.assert_close(thin(out.cpu()), G["out"], TOL_BF16, "out")
+    loss = (out * r).sum()
+    gx1, gx2 = torch.autograd.grad(loss, (x1, x2), retain_graph=True)
+    H.assert_close(thin(gx1.cpu()), G["gx1"], TOL_BF16, "gx1")
+    H.assert_close(thin(gx2.cpu()), G["gx2"], TOL_BF16, "gx2")
+    check_param_grads(mod, loss, G, TOL_BF16, atol_zero=2e-2)
+
+
+@pytest.mark.parametrize("c", [c for c in NYSTROM_CASES if c["dim_head"] * 8 >= 128], ids=lambda c: c["name"])
+def test_nystrom_module_matches_reference_golden(c):
+    G = H.golden(c["name"])
+    mod = load(NystromAttention(dim=c["dim"], dim_head=c["dim_head"], heads=8, num_landmarks=c["m"], pinv_iterations=6,
+                                residual=True, dropout=0.1), H.nystrom_shapes(c["dim"], c["dim_head"]), c["seed"], 2.0).eval()
+    x = synth.normal((c["b"], c["n"], c["dim"]), c["seed"], "x").to(DEV).requires_grad_()
+    r = synth.normal((c["b"], c["n"], c["dim"]), c["seed"], "r").to(DEV)
+    out = mod(x)
+    H.assert_close(thin(out.cpu()), G["out"], TOL_TF32, "out")
+    loss = (out * r).sum()
+    (gx,) = torch.autograd.grad(loss, (x,), retain_graph=True)
+    H.assert_close(thin(gx.cpu()), G["gx"], TOL_TF32, "gx")
+    check_param_grads(mod, loss, G, TOL_TF32)
+
+
+@pytest.mark.parametrize("c", TOWER_CASES, ids=lambda c: c["name"])
+def test_deform_cross_trans_mil_matches_reference_golden(c):
+    G = H.golden(c["name"])
+    mod = load(DeformCrossTransMIL(Args(), n_classes=4), H.dctmil_shapes(), c["seed"]).eval()
+    path = synth.synthetic_bag(c["N"], c["seed"], c["B"])["x_path"].to(DEV).requires_grad_()
+    omic = synth.normal((c["B"], 128), c["seed"], "omic").to(DEV).requires_grad_()
+    enc, logits, _ = mod(path, omic)
+    H.assert_close(enc.cpu(), G["encoded"], TOL_BF16, "encoded")
+    H.assert_close(logits.cpu(), G["logits"], TOL_BF16, "logits")
+    loss = (enc * synth.normal(enc.shape, c["seed"], "r_enc").to(DEV)).sum() + \
+           (logits * synth.normal(logits.shape, c["seed"], "r_log").to(DEV)).sum()
+    gpath, gomic = torch.autograd.grad(loss, (path, omic), retain_graph=True)
+    H.assert_close(thin(gpath[0].cpu()), G["gpath"], TOL_BF16, "gpath")
+    H.assert_close(gomic.cpu(), G["gomic"], TOL_BF16, "gomic")
+    check_param_grads(mod, loss, G, TOL_BF16, atol_zero=2e-2)
+
+
+@pytest.mark.parametrize("c", TRANSMIL_CASES, ids=lambda c: c["name"])
+def test_transmil_matches_reference_golden(c):
+    G = H.golden(c["name"])
+    mod = load(define_net(Args(mode="path", label_dim=3)), H.transmil_shapes(), c["seed"]).eval()
+    x = synth.synthetic_bag(c["N"], c["seed"], c["B"])["x_path"].to(DEV).requires_grad_()
+    enc, logits, _ = mod(x)
+    H.assert_close(enc.cpu(), G["encoded"], TOL_TF32, "encoded")
+    H.assert_close(logits.cpu(), G["logits"], TOL_TF32, "logits")
+    loss = (enc * synth.normal(enc.shape, c["seed"], "r_enc").to(DEV)).sum() + \
+           (logits * synth.normal(logits.shape, c["seed"], "r_log").to(DEV)).sum()
+    (gx,) = torch.autograd.grad(loss, (x,), retain_graph=True)
+    H.assert_close(thin(gx[0].cpu()), G["gx"], TOL_TF32, "gx")
+    check_param_grads(mod, loss, G, TOL_TF32)
+
+
+@pytest.mark.parametrize("c", PATHOMIC_CASES, ids=lambda c: c["name"])
+def test_deform_pathomic_net_matches_reference_golden(c):
+    G = H.golden(c["name"])
+    mod = load(define_net(Args(task_type=c["task"])), H.pathomic_shapes(), c["seed"]).eval()
+    bag = {k: v.to(DEV) for k, v in synth.synthetic_bag(c["N"], c["seed"], c["B"]).items()}
+    feats, vt, vi, logits, *_ = mod(x_path=bag["x_path"], x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
+    H.assert_close(feats.cpu(), G["features"], TOL_BF16, "features")
+    H.assert_close(logits[2].cpu(), G["hazard"], TOL_BF16, "hazard / logits")
+    H.assert_close(logits[0].cpu(), G["hazard_tumor"], TOL_BF16, "hazard_tumor")
+    label = bag["label_diag"] if c["task"] == "diag2021" else bag["label_surv"]
+    loss = bag_loss(logits, label, c["task"], bag["censor"])
+    H.assert_close(loss.cpu(), G["loss"], TOL_BF16, "loss")
+    check_param_grads(mod, loss, G, TOL_BF16, atol_zero=2e-2)
+
+
+def _oracle_params(module):
+    return {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in module.state_dict().items()}
+
+
+@pytest.mark.parametrize("n", [2049, 16385])
+def test_deform1d_large_bag_against_chunked_oracle(n):
+    """North-star size (n = 16 385 tokens -> n_kv = 4 096): the reference module cannot run it
+    (~190 GB); the row-chunked oracle (same maths, pinned against the reference at small n) can."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    seed = 77
+    mod = load(DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6),
+               H.deform_shapes(), seed, gain=2.0)
+    x1 = synth.normal((1, 128, n), seed, "x1").to(DEV).requires_grad_()
+    x2 = synth.normal((1, 128, n), seed, "x2").to(DEV).requires_grad_()
+    r = synth.normal((1, 128, n), seed, "r").to(DEV)
+    out, vgrid = mod(x1, x2, return_vgrid=True)
+    assert vgrid.shape == (4, deform1d.kv_length(n))
+    loss = (out * r).sum()
+    params = [p for _, p in mod.named_parameters()]
+    grads = torch.autograd.grad(loss, [x1, x2] + params)
+    P = _oracle_params(mod)
+    x1o, x2o = x1.detach().clone().requires_grad_(), x2.detach().clone().requires_grad_()
+    ref, aux = deform1d.deform_cross_attention_1d(x1o, x2o, P, offset_scale=2, row_block=1024, return_aux=True)
+    H.assert_close(vgrid, aux["vgrid"], 1e-4, "vgrid")
+    H.assert_close(out, ref, TOL_BF16, "out")
+    names = [k for k, _ in mod.named_parameters()]
+    rgrads = torch.autograd.grad((ref * r).sum(), [x1o, x2o] + [P[k] for k in names])
+    for nm, a, b in zip(["x1", "x2"] + names, grads, rgrads):
+        H.assert_close(a, b, TOL_BF16, "grad " + nm, atol=2e-2 if nm.endswith("mlp.2.bias") else 0.0)
+
+
+def test_attention_rows_are_a_convex_combination_of_values_at_16k():
+    """Size-independent property at the full bag size: with to_out = identity-like weights the output
+    of every query row lies inside the per-channel [min, max] of the projected values (softmax rows
+    sum to one)."""
+    from dml_b200 import ops
+    from dml_b200._lib import call, ptr, stream
+    import math
+    B, n, n_kv, Hh, d = 1, 16385, 4096, 8, 64
+    C = Hh * d
+    q = synth.normal((B, n, C), 5, "q").to(DEV).to(torch.bfloat16)
+    k = synth.normal((B, n_kv, C), 5, "k").to(DEV).to(torch.bfloat16)
+    v = synth.normal((B, n_kv, C), 5, "v").to(DEV).to(torch.bfloat16)
+    g = deform1d.normalize_grid(torch.arange(n_kv, device=DEV)[None] + synth.uniform((4, n_kv), 5, "o", 2.0).to(DEV)).contiguous()
+    P = synth.fill_like({"w1": (32, 1), "b1": (32,), "W2": (32, 32), "b2": (32,), "W3": (2, 32), "b3": (2,)}, 5, 2.0)
+    P = {kk: vv.to(DEV).contiguous() for kk, vv in P.items()}
+    from dml_b200 import _lib
+    table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=DEV, dtype=torch.uint8)
+    call("dml_cpb_table_build", ptr(P["w1"]), ptr(P["b1"]), ptr(P["W2"]), ptr(P["b2"]), ptr(P["W3"]), ptr(P["b3"]), 32, 2,
+         math.log1p(2.0 + 4.0 / (n_kv - 1)) * 1.001 + 1e-3, ptr(table), stream())
+    o = torch.empty(B, n, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B, Hh, n, device=DEV)
+    call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, C, C, C, C, 2, d ** -0.5,
+         ptr(o), ptr(lse), stream())
+    vmin, vmax = v.float().amin(1, keepdim=True), v.float().amax(1, keepdim=True)
+    assert bool(torch.isfinite(o.float()).all()) and bool(torch.isfinite(lse).all())
+    assert bool((o.float() >= vmin - 2e-2).all()) and bool((o.float() <= vmax + 2e-2).all())
