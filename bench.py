@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py - WSI bags/sec, forward+backward, N = 16k patches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at N=1 = BASELINE.json configs[1]: DeformPathomicNet (two DeformCrossTransMIL towers,
+attn_dim=1) on one 16 384-patch bf16 bag, diag2021 weighted-CE loss; a step = fwd + loss + bwd
+(+ gradient all-reduce for N>1) + AdamW.  Bags are sharded one per rank per step (weak scaling).
+`value`: inputs resident in HBM (a rotating set of distinct bags larger than L2).  `e2e`: same step
+through the public nn.Module API with HOST (pinned) bags, H2D copy and D2H loss read inside the
+timed region.  `--impl reference`: the CPU oracle port of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_PATCHES = 16384
+TASK = "diag2021"
+METRIC = "WSI bags/sec fwd+bwd (N=16k patches)"
+UNIT = "bags/s"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work; n = N + 1 tokens, n_kv keys, H = 8, d = 64, G = 4, hid = 32
+# ---------------------------------------------------------------------------------------------
+def attn_flops(n, n_kv, H=8, d=64, G=4, hid=32, nout=2):
+    qk = 2.0 * H * n * n_kv * d
+    pv = qk
+    cpb_dense = 2.0 * G * n * n_kv * (hid + hid * hid + hid * nout)
+    return dict(qk=qk, pv=pv, cpb_dense=cpb_dense)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi's numbers through NVML) - runs during the timed region
+# ---------------------------------------------------------------------------------------------
+class Clocks:
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_bags_per_s(n_sample, repeats=1, seed=42):
+    """fwd + loss + bwd of DeformPathomicNet (oracle restatement of the reference, fp32, all host threads)
+    on one N=n_sample bag; the pair-count-dominated cost is extrapolated to N_PATCHES by (N/n_sample)^2."""
+    from dml_b200 import synth
+    from dml_b200.model import Args, define_net
+    from oracle import towers
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = define_net(Args(task_type=TASK))
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    P = {k: v.requires_grad_(v.is_floating_point()) for k, v in synth.fill_like(shapes, seed).items()}
+    def one_pass(n_bag, row_block=512):
+        bag = synth.synthetic_bag(n_bag, seed)
+        t0 = time.perf_counter()
+        _, _, _, logits = towers.deform_pathomic_net(bag["x_path"], bag["x_omic_tumor"], bag["x_omic_immune"], P,
+                                                     task_type=TASK, row_block=row_block)
+        loss = towers.bag_loss(logits, bag["label_diag"], TASK)
+        torch.autograd.grad(loss, [p for p in P.values() if p.requires_grad], allow_unused=True)
+        return time.perf_counter() - t0
+
+    one_pass(128, row_block=64)                    # warm-up (thread pool, autograd/checkpoint import)
+    if n_sample <= 0:                              # auto: the largest of 1024/2048/4096 predicted to stay under ~30 s
+        t1k = one_pass(1024)
+        n_sample = 4096 if t1k * 16 < 30 else (2048 if t1k * 4 < 30 else 1024)
+    best = min(one_pass(n_sample) for _ in range(max(1, repeats)))
+    scale = (N_PATCHES / n_sample) ** 2
+    return 1.0 / (best * scale), best, scale, n_sample
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(max(1, args.steps)):
+        v, sec, scale, n_sample = cpu_reference_bags_per_s(args.cpu_sample, repeats=1)
+        vals.append(v)
+        if time.perf_counter() - t0 > 150:
+            break
+    v = max(vals)
+    cores = os.cpu_count()
+    sample = (f"oracle port of the reference (torch fp32, row-chunked CPB attention), one N={n_sample}-patch bag fwd+loss+bwd "
+              f"= {sec:.2f} s on {cores} host threads, scaled x{scale:.0f} (pair count) to N={N_PATCHES}")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": 1, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"DeformPathomicNet(attn_dim=1) {TASK}, 1 bag x {N_PATCHES} patches x 1024 feats, CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-patches", type=int, default=N_PATCHES)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="bag size of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bags-resident", type=int, default=6, help="distinct bags rotated through (input set > L2)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert args.warmup >= 3 or args.steps <= 2, "timing rules: at least 3 warm-up steps"
+
+    import torch.distributed as dist
+    from dml_b200 import _lib, synth
+    from dml_b200.model import Args, bag_loss, define_net
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    N = args.n_patches
+    net = define_net(Args(task_type=TASK))
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(synth.fill_like(shapes, 42), strict=True)
+    net.to(dev).train()
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.01, fused=True)
+    flat_sizes = [p.numel() for p in params]
+
+    # a rotating set of distinct bags per rank (bf16, [1, N, 1024] = 33.5 MB each): > L2 in total
+    nb = max(2, args.bags_resident)
+    host_bags, dev_bags = [], []
+    for i in range(nb):
+        b = synth.synthetic_bag(N, seed=1000 + rank * 64 + i)
+        hb = {"x_path": b["x_path"].to(torch.bfloat16).pin_memory(), "x_omic_tumor": b["x_omic_tumor"].pin_memory(),
+              "x_omic_immune": b["x_omic_immune"].pin_memory(), "label": b["label_diag"].pin_memory()}
+        host_bags.append(hb)
+        dev_bags.append({k: v.to(dev) for k, v in hb.items()})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_bags[0].values())
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)           # one flat NCCL all-reduce (C2/C3)
+        for p, g in zip(params, flat.split(flat_sizes)):
+            p.grad = g.view_as(p)
+
+    def step(bag):
+        out = net(x_path=bag["x_path"], x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
+        loss = bag_loss(out[3], bag["label"], TASK)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident arm ----
+    def resident(steps):
+        for s in range(steps):
+            step(dev_bags[s % nb])
+
+    resident(args.warmup)
+    launches0 = _lib.launch_count
+    with Clocks(local_rank) as clk:
+        ms = timed(resident, args.steps)
+    launches = _lib.launch_count - launches0
+    value = world * args.steps / (ms / 1000.0)
+
+    # ---- end-to-end arm: host (pinned) bags -> H2D on a copy stream (double-buffered) -> step -> D2H loss ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    losses_host = torch.zeros(max(args.steps, args.warmup), dtype=torch.float32).pin_memory()
+
+    def e2e(steps):
+        cur = torch.cuda.current_stream()
+        staged = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def stage(slot, s):
+            with torch.cuda.stream(copy_stream):
+                staged[slot] = {k: v.to(dev, non_blocking=True) for k, v in host_bags[s % nb].items()}
+                ready[slot].record(copy_stream)
+
+        stage(0, 0)
+        for s in range(steps):
+            slot = s & 1
+            if s + 1 < steps:
+                copy_stream.wait_stream(cur) if s > 0 else None
+                stage(slot ^ 1, s + 1)
+            cur.wait_event(ready[slot])
+            loss = step(staged[slot])
+            for v in staged[slot].values():
+                v.record_stream(cur)
+            losses_host[s].copy_(loss.detach(), non_blocking=True)
+        cur.synchronize()
+
+    e2e(args.warmup)
+    ms_e2e = timed(e2e, args.steps)
+    e2e_value = world * args.steps / (ms_e2e / 1000.0)
+
+    # ---- per-kernel device times (CUDA events on the launching stream, separate untimed-for-headline pass) ----
+    events = []
+
+    def hook(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        events.append((name, phase, ev))
+
+    _lib._timing_hook = hook
+    prof_steps = 3
+    resident(prof_steps)
+    torch.cuda.synchronize()
+    _lib._timing_hook = None
+    ktime = {}
+    for i in range(0, len(events), 2):
+        (nm, _, a), (_, _, b) = events[i], events[i + 1]
+        ktime.setdefault(nm, []).append(a.elapsed_time(b))
+    kavg = {k: sum(v) / len(v) for k, v in ktime.items()}         # ms per call
+    kcalls = {k: len(v) / prof_steps for k, v in ktime.items()}
+
+    pk, pk_kind = peaks()
+    n, n_kv = N + 1, (N + 1 + 2 - 6) // 4 + 1
+    fl = attn_flops(n, n_kv)
+    # dominant entry point: the attention backward (3 kernels: prep + dK/dV/dg/segsums + dQ), then the forward
+    top = max(kavg, key=lambda k: kavg[k] * kcalls[k])
+    exec_fwd = fl["qk"] + fl["pv"]                                   # tensor-core FLOPs the fused kernels execute
+    exec_bwd = 7.0 * fl["qk"]                                        # S^T,dP^T,dV,dK (4) + S,dP,dQ (3) GEMMs of n x n_kv x 64
+    exec_fl = {"dml_deform_attn_fwd": exec_fwd, "dml_deform_attn_bwd": exec_bwd}.get(top)
+    roof = None
+    if exec_fl:
+        ach = exec_fl / (kavg[top] * 1e-3) / 1e12
+        dense = (fl["qk"] + fl["pv"] + fl["cpb_dense"]) * (1.0 if top.endswith("fwd") else 2.0)
+        roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_kind + " (sustained)",
+                "ms_per_launch": kavg[top],
+                "note": "achieved = tensor-core FLOPs actually required once the CPB MLP is evaluated through its exact "
+                        "piecewise-linear table (QK^T/PV-class GEMMs only); dense_math_* = the reference's dense maths "
+                        "(CPB 32x32 layer included) for the same launch",
+                "dense_math_tflop": dense / 1e12,
+                "dense_math_roofline_ms": dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3,
+                "time_vs_dense_math_roofline": kavg[top] / (dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, scale, n_used = cpu_reference_bags_per_s(args.cpu_sample, repeats=1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle port, one N={n_used}-patch bag fwd+loss+bwd = {sec:.2f} s on {os.cpu_count()} host "
+                         f"threads, scaled x{scale:.0f} (pair count) to N={N}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"DeformPathomicNet(attn_dim=1) {TASK}: 2 DeformCrossTransMIL towers, 1 bag x {N} patches x "
+                                       f"1024 bf16 feats per GPU per step (n={n} tokens, n_kv={n_kv})",
+                           "step": "fwd + weighted-CE + bwd" + (" + flat NCCL grad all-reduce" if world > 1 else "") + " + fused AdamW",
+                           "parallelism": f"bag-sharded dp{world}", "l2": f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"},
+                "clocks": clk.summary(),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches,
+                "kernel_ms_per_step": {k: round(kavg[k] * kcalls[k], 4) for k in sorted(kavg, key=lambda k: -kavg[k] * kcalls[k])},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,7 +32,7 @@ SIGNATURES = {
     "dml_kv_gather_fwd": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dml_kv_gather_bwd": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _vp]),
     "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
-    "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 6 + [_vp]),
+    "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
     "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_softmax_rows_fwd": (_i, [_fp, _fp, _ll, _i, _vp]),
@@ -78,11 +78,27 @@ def load(check_device: bool = False):
 
 _ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace too small"}
 
+# kernels launched per entry point (memsets not counted) - bench.py reports the total as gpu_launches
+KERNELS_PER_CALL = {
+    "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2,
+    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_bwd": 3,
+    "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
+    "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1,
+}
+launch_count = 0        # kernels of libdml_b200.so launched by this process
+_timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events
+
 
 def call(name: str, *args):
     """Invoke an int-returning entry point on the current CUDA device/stream; raise on failure."""
+    global launch_count
     lib = load(check_device=True)
+    if _timing_hook is not None:
+        _timing_hook(name, 0)
     rc = getattr(lib, name)(*args)
+    if _timing_hook is not None:
+        _timing_hook(name, 1)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         what = _ERR.get(rc) or (f"CUDA error {rc}" if rc > 0 else f"error {rc}")
         raise DmlError(f"{name} failed: {what}")

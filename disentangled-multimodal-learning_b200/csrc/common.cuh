@@ -1,6 +1,7 @@
 // Shared device helpers for the dml_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,6 +32,7 @@ namespace dml {
 
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
+typedef __half h16;      // 16-bit operand type of the attention core (fp16: 11-bit significand, fp32 accumulate)
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -55,6 +57,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   bf162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// (x0, x1) -> packed fp16 pair `hi` and the packed fp16 residual pair `lo` (x ~= hi + lo to 22 bits)
+__device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ---- cp.async (LDGSTS) 16-byte copies with zero-fill predicate ----
@@ -91,7 +107,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Tile of [rows][64] bf16 (128 B per row = 8 chunks of 16 B), XOR-swizzled on the chunk index so
+// D(16x8,f32) += A(16x16,f16,row) * B(16x8,f16,col)
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Tile of [rows][64] 16-bit elements (128 B per row = 8 chunks of 16 B), XOR-swizzled on the chunk index so
 // that ldmatrix (8 rows x 16 B) and 16-B row-wise stores are bank-conflict free.
 __device__ __forceinline__ int swz64(int row, int chunk) { return row * 64 + ((chunk ^ (row & 7)) << 3); }
 

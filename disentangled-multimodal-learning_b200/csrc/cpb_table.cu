@@ -122,13 +122,17 @@ cpb_table_build_kernel(const float* __restrict__ w1, const float* __restrict__ b
   const int nseg = nbp + 1;
   if (tid == 0) s_nbp = nbp;
 
-  float4* coef = reinterpret_cast<float4*>(table + kTabCoef);
-  float* bpf = reinterpret_cast<float*>(table + kTabBp);
-  uint16_t* cellseg = reinterpret_cast<uint16_t*>(table + kTabCell);
+  float4* cellcoef = reinterpret_cast<float4*>(table + kTabCellCoef);
+  float* cellbp = reinterpret_cast<float*>(table + kTabCellBp);
+  uint16_t* cellseg = reinterpret_cast<uint16_t*>(table + kTabCellSeg);
+  float4* segcoef = reinterpret_cast<float4*>(table + kTabSegCoef);
+  float* segbp = reinterpret_cast<float*>(table + kTabSegBp);
   uint32_t* mask1 = table + kTabMask1;
   uint32_t* mask2 = table + kTabMask2;
+  const double LN2 = 0.693147180559945309417, LOG2E = 1.44269504088896340736;
 
   // ---- per-segment affine coefficients, evaluated from the active sets at the segment midpoint ----
+  // stored as (a0, c0*log2e, a1, c1*log2e): in x = t/ln2 and in the softmax's log2 domain the slope is unchanged.
   for (int s = tid; s < kCpbSegMax + kCpbBpPad; s += blockDim.x) {
     if (s < nseg) {
       double lo = (s == 0) ? -dT : cand[s - 1];
@@ -151,46 +155,55 @@ cpb_table_build_kernel(const float* __restrict__ w1, const float* __restrict__ b
           a[1] += (double)m.W3[32 + k] * P; c[1] += (double)m.W3[32 + k] * Q;
         }
       }
-      coef[s] = make_float4((float)a[0], (float)c[0], (float)a[1], (float)c[1]);
+      segcoef[s] = make_float4((float)a[0], (float)(c[0] * LOG2E), (float)a[1], (float)(c[1] * LOG2E));
       mask1[s] = m1;
       mask2[s] = m2;
     } else if (s < kCpbSegMax) {
-      coef[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      segcoef[s] = make_float4(0.f, 0.f, 0.f, 0.f);
       mask1[s] = 0;
       mask2[s] = 0;
     }
-    bpf[s] = (s < nbp) ? (float)cand[s] : __int_as_float(0x7f800000);
+    segbp[s] = (s < nbp) ? (float)(cand[s] / LN2) : __int_as_float(0x7f800000);
   }
+  __syncthreads();
 
-  // ---- cell -> first candidate segment; kmax = most breakpoints any lookup has to step over ----
-  const double cw = 2.0 * dT / (double)kCpbCells;
-  const double eps = 1e-6 * dT + 1e-9;
-  int my_kmax = 0;
+  // ---- uniform cells over x in [-X, X]: affine pieces on both sides of the first breakpoint of the cell ----
+  const double X = dT / LN2;
+  const double cw = 2.0 * X / (double)kCpbCells;
+  int my_dirty = 0;
   for (int c = tid; c < kCpbCells; c += blockDim.x) {
-    double t0 = -dT + c * cw - eps, t1 = -dT + (c + 1) * cw + eps;
-    int lo = 0, hi = nbp;  // first index with cand[idx] > t0  ==  #{bp <= t0}
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (cand[mid] <= t0) lo = mid + 1; else hi = mid; }
-    int s0 = lo;
-    lo = s0; hi = nbp;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (cand[mid] <= t1) lo = mid + 1; else hi = mid; }
+    const double x0 = (-X + c * cw) * LN2, x1 = (-X + (c + 1) * cw) * LN2;   // cell bounds in t units
+    int lo = 0, hi = nbp;  // #{bp <= x0}
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cand[mid] <= x0) lo = mid + 1; else hi = mid; }
+    const int s0 = lo;
+    lo = s0; hi = nbp;     // #{bp < x1}
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cand[mid] < x1) lo = mid + 1; else hi = mid; }
+    const int inside = lo - s0;
+    const int s1 = inside >= 1 ? s0 + 1 : s0;
+    float bpv = __int_as_float(0x7f800000);
+    if (inside == 1) bpv = (float)(cand[s0] / LN2);
+    else if (inside >= 2) { bpv = __int_as_float(0x7fc00000); ++my_dirty; }
+    const float4 e0 = segcoef[s0], e1 = segcoef[s1];
+    cellcoef[c] = make_float4(e0.x, e0.y, e1.x, e1.y);
+    cellcoef[kCpbCells + c] = make_float4(e0.z, e0.w, e1.z, e1.w);
+    cellbp[c] = bpv;
     cellseg[c] = (uint16_t)s0;
-    my_kmax = max(my_kmax, lo - s0);
   }
-  atomicMax(&s_kmax, my_kmax);
+  atomicAdd(&s_kmax, my_dirty);
   __syncthreads();
   if (tid == 0) {
     table[0] = (uint32_t)nseg;
-    table[1] = (uint32_t)s_kmax;
-    table[2] = __float_as_uint(T);
-    table[3] = __float_as_uint((float)((double)kCpbCells / (2.0 * dT)));
+    table[1] = (uint32_t)s_kmax;   // number of flagged (>= 2 breakpoints) cells
+    table[2] = __float_as_uint((float)X);
+    table[3] = __float_as_uint((float)((double)kCpbCells / (2.0 * X)));
     table[4] = (uint32_t)hid;
     table[5] = (uint32_t)nout;
     for (int i = 6; i < 16; ++i) table[i] = 0;
   }
 }
 
-// Parameter gradients from the per-segment sums  segsum[s] = (A0, B0, A1, B1),
-// A_o = sum delta_o, B_o = sum delta_o * t over all (i, j) pairs whose t fell in segment s.
+// Parameter gradients from the per-segment sums  segsum[s] = (A0, Bx0, A1, Bx1),
+// A_o = sum delta_o, Bx_o = sum delta_o * x (x = t / ln2) over all (i, j) pairs whose t fell in segment s.
 // Inside segment s the MLP is  z2_k = P_k t + Q_k  (layer-1 active set m1), out_o = sum_k W3[o,k] act2_k z2_k + b3[o].
 // grads layout (floats, must be zeroed by the caller): dw1[32] db1[32] dW2[32*32] db2[32] dW3[2*32] db3[2]
 __global__ void __launch_bounds__(1024, 1)
@@ -211,7 +224,7 @@ cpb_param_grad_kernel(const float* __restrict__ w1, const float* __restrict__ b1
 
   for (int s = blockIdx.x; s < nseg; s += gridDim.x) {
     const float4 ss = reinterpret_cast<const float4*>(segsum)[s];
-    const float A[2] = {ss.x, ss.z}, B[2] = {ss.y, ss.w};
+    const float A[2] = {ss.x, ss.z}, B[2] = {ss.y * kLn2, ss.w * kLn2};   // sums of delta*x arrive in x = t/ln2 units
     if (A[0] == 0.f && A[1] == 0.f && B[0] == 0.f && B[1] == 0.f) continue;  // uniform across the CTA
     const uint32_t m1 = mask1[s], m2 = mask2[s];
     if (tid < 32) {
@@ -255,20 +268,22 @@ cpb_param_grad_kernel(const float* __restrict__ w1, const float* __restrict__ b1
   }
 }
 
-// Evaluate the table at arbitrary t (diagnostics / tests): out[i] = (bias0, bias1), seg[i] = segment index.
+// Evaluate the table at arbitrary t (diagnostics / tests): out[i] = (bias0, bias1) in natural units, seg[i] = segment.
 __global__ void cpb_eval_kernel(const uint32_t* __restrict__ table, const float* __restrict__ t, int count,
                                 float* __restrict__ out, int* __restrict__ seg) {
-  extern __shared__ uint32_t tab[];
-  cpb_stage(tab, table, threadIdx.x, blockDim.x);
-  __syncthreads();
-  const CpbView tb = cpb_view(tab);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const float tt = t[i];
-    const int s = cpb_segment(tb, tt);
-    const float4 c = tb.coef[s];
-    out[2 * i] = fmaf(c.x, tt, c.y);
-    out[2 * i + 1] = fmaf(c.z, tt, c.w);
-    if (seg) seg[i] = s;
+  extern __shared__ __align__(16) uint8_t sm[];
+  for (int o = 0; o < 2; ++o) {
+    __syncthreads();
+    const CpbView tb = cpb_stage(sm, table, o, true, threadIdx.x, blockDim.x);
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+      const float x = t[i] * kLog2e;
+      float a, c;
+      int s = 0;
+      cpb_lookup<true>(tb, x, a, c, s);
+      out[2 * i + o] = fmaf(a, x, c) * kLn2;
+      if (seg && o == 0) seg[i] = s;
+    }
   }
 }
 
@@ -278,7 +293,13 @@ extern "C" {
 
 int dml_cpb_eval(const void* table, const float* t, int count, float* out, int* seg, void* stream) {
   DML_CHECK_ARG(table && t && out && count > 0);
-  dml::cpb_eval_kernel<<<dml::cdiv(count, 256) < 296 ? dml::cdiv(count, 256) : 296, 256, dml::kTabSmemWords * 4,
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dml::cpb_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dml::kCpbSmemBwdBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  dml::cpb_eval_kernel<<<dml::cdiv(count, 256) < 296 ? dml::cdiv(count, 256) : 296, 256, dml::kCpbSmemBwdBytes,
                          (cudaStream_t)stream>>>((const uint32_t*)table, t, count, out, seg);
   DML_RETURN_LAUNCH();
 }

@@ -19,21 +19,21 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-__device__ __forceinline__ void load4(const bf16* p, float (&v)[4]) {
+__device__ __forceinline__ void load4(const h16* p, float (&v)[4]) {
   uint2 u = *reinterpret_cast<const uint2*>(p);
-  bf162 a = *reinterpret_cast<bf162*>(&u.x), b = *reinterpret_cast<bf162*>(&u.y);
+  __half2 a = *reinterpret_cast<__half2*>(&u.x), b = *reinterpret_cast<__half2*>(&u.y);
   v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
 }
 
 // ------------------------------------------------------------------------------------------------
-// offsets forward: q [B, n, C] bf16 (token-major, UNSCALED queries), groups G, Cg = C/G = 128 channels/group.
+// offsets forward: q [B, n, C] fp16 (token-major, UNSCALED queries), groups G, Cg = C/G = 128 channels/group.
 //   conv[c] = b0[c] + sum_t w0[c,t] q[b, stride*j - pad + t, g*Cg + c]     (zero padding)
 //   u = sum_c w2[c] gelu(conv[c]);  off = tanh(u) * offset_scale;  vgrid = j + off;
 //   g = 2 vgrid / max(n_kv - 1, 1) - 1
 // One warp per (b, g, j); lane owns 4 consecutive channels (Cg == 128).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-offsets_fwd_kernel(const bf16* __restrict__ q, const float* __restrict__ w0, const float* __restrict__ b0,
+offsets_fwd_kernel(const h16* __restrict__ q, const float* __restrict__ w0, const float* __restrict__ b0,
                    const float* __restrict__ w2, int B, int n, int C, int G, int ks, int stride, int pad, int n_kv,
                    float offset_scale, float* __restrict__ vgrid, float* __restrict__ gnorm) {
   const int lane = threadIdx.x & 31;
@@ -54,7 +54,7 @@ offsets_fwd_kernel(const bf16* __restrict__ q, const float* __restrict__ w0, con
   for (int item = warp; item < total; item += nwarps) {
     const int j = item % n_kv, bg = item / n_kv, b = bg / G, g = bg % G;
     float acc[4] = {bb[0], bb[1], bb[2], bb[3]};
-    const bf16* base = q + (size_t)b * n * C + g * Cg + c0;
+    const h16* base = q + (size_t)b * n * C + g * Cg + c0;
 #pragma unroll
     for (int t = 0; t < kMaxTaps; ++t) {
       const int p = stride * j - pad + t;
@@ -85,7 +85,7 @@ offsets_fwd_kernel(const bf16* __restrict__ q, const float* __restrict__ w0, con
 // warps in shared memory and added to global with one atomic per (CTA, element).
 // wgrad layout: dw0[Cg*ks] | db0[Cg] | dw2[Cg]   (zeroed by the host wrapper)
 __global__ void __launch_bounds__(256)
-offsets_bwd_kernel(const bf16* __restrict__ q, const float* __restrict__ w0, const float* __restrict__ b0,
+offsets_bwd_kernel(const h16* __restrict__ q, const float* __restrict__ w0, const float* __restrict__ b0,
                    const float* __restrict__ w2, const float* __restrict__ d_off, int B, int n, int C, int G, int ks,
                    int stride, int pad, int n_kv, float offset_scale, float* __restrict__ dy,
                    float* __restrict__ wgrad) {
@@ -114,7 +114,7 @@ offsets_bwd_kernel(const bf16* __restrict__ q, const float* __restrict__ w0, con
     const int j = item % n_kv, bg = item / n_kv, b = bg / G, g = bg % G;
     float acc[4] = {bb[0], bb[1], bb[2], bb[3]};
     float xv[kMaxTaps][4];
-    const bf16* base = q + (size_t)b * n * C + g * Cg + c0;
+    const h16* base = q + (size_t)b * n * C + g * Cg + c0;
 #pragma unroll
     for (int t = 0; t < kMaxTaps; ++t) {
       const int p = stride * j - pad + t;
@@ -172,11 +172,11 @@ offsets_bwd_kernel(const bf16* __restrict__ q, const float* __restrict__ w0, con
 
 // offsets backward, pass B (elementwise over [B, n, C]):
 //   dq[b,p,c] = dq_attn[b,p,c] * scale + sum_{j : 0 <= p + pad - stride*j < ks} dy[(b,g), j, c'] * w0[c', p + pad - stride*j]
-// writes the total query gradient as bf16 (A operand of the dWq / dx1 GEMMs).
+// writes the total query gradient in fp32 (operand of the TF32 dWq / dx1 GEMMs).
 __global__ void __launch_bounds__(256)
 offsets_dq_combine_kernel(const float* __restrict__ dq_attn, const float* __restrict__ dy,
                           const float* __restrict__ w0, int B, int n, int C, int G, int ks, int stride, int pad,
-                          int n_kv, float scale, bf16* __restrict__ dq) {
+                          int n_kv, float scale, float* __restrict__ dq) {
   const int Cg = C / G;
   const size_t total4 = (size_t)B * n * C / 4;
   for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (size_t)gridDim.x * blockDim.x) {
@@ -197,10 +197,7 @@ offsets_dq_combine_kernel(const float* __restrict__ dq_attn, const float* __rest
       r[2] = fmaf(d.z, w0[(cc + 2) * ks + t], r[2]);
       r[3] = fmaf(d.w, w0[(cc + 3) * ks + t], r[3]);
     }
-    uint2 o;
-    o.x = pack_bf16(r[0], r[1]);
-    o.y = pack_bf16(r[2], r[3]);
-    *reinterpret_cast<uint2*>(dq + i) = o;
+    *reinterpret_cast<float4*>(dq + i) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -208,7 +205,7 @@ offsets_dq_combine_kernel(const float* __restrict__ dq_attn, const float* __rest
 // key/value gather.  Shipped semantics (quirk T1): the sampling grid's learned coordinate lands on the
 // size-1 W axis, y is always 0 => every key j samples the CENTRE of the sequence (taps i0, i1 with
 // weights wy0, wy1 given by the host from iy = (n-1)/2) times the x tent weight 1-|g/2|.
-//   kv[b, j, c] = (x2[b,i0,c] wy0 + x2[b,i1,c] wy1) * tent(g[(b,grp(c)), j])       (bf16 out, token-major)
+//   kv[b, j, c] = (x2[b,i0,c] wy0 + x2[b,i1,c] wy1) * tent(g[(b,grp(c)), j])       (fp32 out, token-major)
 // x2 [B, n, dim] fp32 token-major; dim/G channels per group; one warp per (b, j), lane owns dim/32 channels.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tent_weight(float g, float* dtent) {
@@ -225,7 +222,7 @@ __device__ __forceinline__ float tent_weight(float g, float* dtent) {
 template <int VPL>  // channels per lane (dim = 32 * VPL)
 __global__ void __launch_bounds__(256)
 kv_gather_fwd_kernel(const float* __restrict__ x2, const float* __restrict__ gnorm, int B, int n, int dim, int G,
-                     int n_kv, int i0, int i1, float wy0, float wy1, bf16* __restrict__ kv) {
+                     int n_kv, int i0, int i1, float wy0, float wy1, float* __restrict__ kv) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -246,9 +243,9 @@ kv_gather_fwd_kernel(const float* __restrict__ x2, const float* __restrict__ gno
       }
     }
     const float tw = tent_weight(gnorm[(size_t)(b * G + grp) * n_kv + j], nullptr);
-    bf16* o = kv + ((size_t)b * n_kv + j) * dim + c0;
-#pragma unroll
-    for (int e = 0; e < VPL; e += 2) *reinterpret_cast<uint32_t*>(o + e) = pack_bf16(cen[e] * tw, cen[e + 1] * tw);
+    float* o = kv + ((size_t)b * n_kv + j) * dim + c0;
+    static_assert(VPL == 4, "one float4 per lane");
+    *reinterpret_cast<float4*>(o) = make_float4(cen[0] * tw, cen[1] * tw, cen[2] * tw, cen[3] * tw);
   }
 }
 
@@ -318,7 +315,7 @@ int dml_offsets_fwd(const void* q, const float* w0, const float* b0, const float
   DML_CHECK_ARG(n_kv >= 1);
   const int warps = B * G * n_kv;
   const int blocks = min(dml::cdiv(warps, 8), 148 * 8);
-  dml::offsets_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const dml::bf16*)q, w0, b0, w2, B, n, C, G, ksize,
+  dml::offsets_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const dml::h16*)q, w0, b0, w2, B, n, C, G, ksize,
                                                                     stride, pad, n_kv, offset_scale, vgrid, gnorm);
   DML_RETURN_LAUNCH();
 }
@@ -335,12 +332,12 @@ int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float
   if (e != cudaSuccess) return (int)e;
   const int warps = B * G * n_kv;
   const int blocks = min(dml::cdiv(warps, 8), 148 * 2);
-  dml::offsets_bwd_kernel<<<blocks, 256, 0, st>>>((const dml::bf16*)q, w0, b0, w2, d_off, B, n, C, G, ksize, stride, pad,
+  dml::offsets_bwd_kernel<<<blocks, 256, 0, st>>>((const dml::h16*)q, w0, b0, w2, d_off, B, n, C, G, ksize, stride, pad,
                                                  n_kv, offset_scale, dy_ws, wgrad);
   const size_t total4 = (size_t)B * n * C / 4;
   const int blocks2 = (int)min((total4 + 255) / 256, (size_t)148 * 16);
   dml::offsets_dq_combine_kernel<<<blocks2, 256, 0, st>>>(dq_attn, dy_ws, w0, B, n, C, G, ksize, stride, pad, n_kv,
-                                                         attn_scale, (dml::bf16*)dq_out);
+                                                         attn_scale, (float*)dq_out);
   DML_RETURN_LAUNCH();
 }
 
@@ -352,7 +349,7 @@ int dml_kv_gather_fwd(const float* x2, const float* gnorm, int B, int n, int dim
   const int warps = B * n_kv;
   const int blocks = min(dml::cdiv(warps, 8), 148 * 8);
   dml::kv_gather_fwd_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(x2, gnorm, B, n, dim, G, n_kv, i0, i1, wy0, wy1,
-                                                                        (dml::bf16*)kv);
+                                                                        (float*)kv);
   DML_RETURN_LAUNCH();
 }
 

@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 BF16 = torch.bfloat16
+F16 = torch.float16
 F32 = torch.float32
 CPB_GRAD_FLOATS = 1192  # DML_CPB_GRAD_FLOATS in include/dml_b200.h
 
@@ -24,6 +25,17 @@ def tf32_matmul():
     """fp32 GEMMs of this path run on the tensor cores in TF32 (fp32 accumulate)."""
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@contextmanager
+def fp32_matmul():
+    """Exact fp32 GEMMs (no TF32) for the few small products whose rounding is amplified downstream."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
         yield
     finally:
@@ -49,9 +61,22 @@ def kv_length(n: int, ksize: int, stride: int) -> int:
     return (n + 2 * pad - ksize) // stride + 1
 
 
+def grad_scale(t: torch.Tensor) -> torch.Tensor:
+    """Device-side power-of-two loss scale for an fp16 operand: float[2] = (s, 1/s) with
+    8 <= s * max|t| < 16 (no host sync; s = 1 for an all-zero tensor)."""
+    amax = t.detach().abs().amax().float()
+    s = torch.exp2(torch.floor(torch.log2(8.0 / amax.clamp_min(1e-30))).clamp(-60.0, 60.0))
+    s = torch.where(amax > 0, s, torch.ones_like(s))
+    return torch.stack([s, 1.0 / s]).contiguous()
+
+
 class DeformCrossAttn1DFn(torch.autograd.Function):
     """Forward + backward of DeformCrossAttention1D (DeformableAttention1D.py:156-240) on
-    token-major inputs x1t, x2t [B, n, dim] (fp32).  Returns (out [B, n, dim] fp32, vgrid [(B G), n_kv])."""
+    token-major inputs x1t, x2t [B, n, dim] (fp32).  Returns (out [B, n, dim] fp32, vgrid [(B G), n_kv]).
+
+    Precision policy: activations and every projection stay fp32 (TF32 tensor-core GEMMs, fp32
+    accumulate); the attention core takes fp16 q/k/v (11-bit significand like TF32) and keeps the softmax
+    statistics, the position bias, the output and all accumulators in fp32."""
 
     @staticmethod
     def forward(ctx, x1t, x2t, Wq, Wk, Wv, Wo, bo, w0, b0, w2, m_w1, m_b1, m_W2, m_b2, m_W3, m_b3, cfg):
@@ -68,56 +93,60 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
             raise _lib.DmlError(f"sequence of {n} tokens is too short for offset kernel {ks}/stride {stride}")
         st = stream()
 
-        x1b = x1t.to(BF16).contiguous()
+        x1f = x1t.to(F32).contiguous()
         x2f = x2t.to(F32).contiguous()
-        Wq_b = Wq.reshape(C, dim).to(BF16)
-        Wk_b = Wk.reshape(C, dim).to(BF16)
-        Wv_b = Wv.reshape(C, dim).to(BF16)
-        Wo_b = Wo.reshape(dim, C).to(BF16)
+        Wq2, Wk2, Wv2 = (W.reshape(C, dim).float() for W in (Wq, Wk, Wv))
+        Wo2 = Wo.reshape(dim, C).float()
         w0f, b0f, w2f = w0.reshape(Cg, ks).contiguous().float(), b0.contiguous().float(), w2.reshape(Cg).contiguous().float()
         mlp = [t.contiguous().float() for t in (m_w1.reshape(-1), m_b1, m_W2, m_b2, m_W3, m_b3)]
 
-        q = torch.matmul(x1b, Wq_b.t())                                   # [B,n,C] bf16 (to_q, :175)
+        with fp32_matmul():   # q/k/v feed the softmax exponent: exact fp32 projections, one fp16 rounding at the end
+            q = torch.matmul(x1f, Wq2.t()).to(F16)                        # [B,n,C] (to_q, :175)
         vgrid = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         g = torch.empty_like(vgrid)
         call("dml_offsets_fwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), B, n, C, G, ks, stride, float(offset_scale),
              ptr(vgrid), ptr(g), st)
         i0, i1, wy0, wy1 = centre_taps(n)
-        kv = torch.empty(B, n_kv, dim, device=dev, dtype=BF16)
+        kv = torch.empty(B, n_kv, dim, device=dev, dtype=F32)
         call("dml_kv_gather_fwd", ptr(x2f), ptr(g), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(kv), st)
-        k = torch.matmul(kv, Wk_b.t())                                    # [B,n_kv,C] bf16 (:199)
-        v = torch.matmul(kv, Wv_b.t())
+        with fp32_matmul():
+            k = torch.matmul(kv, Wk2.t()).to(F16)                         # [B,n_kv,C] (:199)
+            v = torch.matmul(kv, Wv2.t()).to(F16)
         table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
         t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
         call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), st)
-        o = torch.empty(B, n, C, device=dev, dtype=BF16)
+        o = torch.empty(B, n, C, device=dev, dtype=F32)
         lse = torch.empty(B, H, n, device=dev, dtype=F32)
         call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n, n_kv, C, C, C, C, nout,
              scale, ptr(o), ptr(lse), st)
-        out = torch.matmul(o, Wo_b.t()).float() + bo                       # to_out (:233)
+        with tf32_matmul():
+            out = torch.matmul(o, Wo2.t()) + bo                           # to_out (:233)
 
         ctx.cfg = cfg
         ctx.taps = (i0, i1, wy0, wy1)
-        ctx.save_for_backward(x1b, x2f, q, kv, k, v, g, table, o, lse, Wq_b, Wk, Wv, Wo_b, w0f, b0f, w2f, *mlp)
+        ctx.save_for_backward(x1f, x2f, q, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp)
         return out, vgrid
 
     @staticmethod
     def backward(ctx, dout, dvgrid):
-        (x1b, x2f, q, kv, k, v, g, table, o, lse, Wq_b, Wk, Wv, Wo_b, w0f, b0f, w2f, *mlp) = ctx.saved_tensors
+        (x1f, x2f, q, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp) = ctx.saved_tensors
         H, d, G, stride, ks, offset_scale = ctx.cfg
         i0, i1, wy0, wy1 = ctx.taps
-        B, n, dim = x1b.shape
+        B, n, dim = x1f.shape
         C, Cg, nout, hid = H * d, (H * d) // G, H // G, mlp[0].shape[0]
         n_kv = kv.shape[1]
         scale = d ** -0.5
-        dev = x1b.device
+        dev = x1f.device
         st = stream()
 
-        dout = dout.contiguous()
-        dout_b = dout.to(BF16)
-        dWo = mm_f32out(dout_b.reshape(-1, dim).t(), o.reshape(-1, C))      # [dim, C]
+        dout = dout.contiguous().float()
+        with fp32_matmul():   # dO feeds dS = P (dP - D) directly: exact fp32, one fp16 rounding below
+            d_o = torch.matmul(dout, Wo2)                                  # [B,n,C] fp32
+        with tf32_matmul():
+            dWo = dout.reshape(-1, dim).t() @ o.reshape(-1, C)             # [dim, C]
         dbo = dout.sum(dim=(0, 1))
-        d_o = torch.matmul(dout_b, Wo_b)                                   # [B,n,C] bf16
+        dscale = grad_scale(d_o)
+        d_o16 = (d_o * dscale[0]).to(F16)
 
         dq_attn = torch.empty(B, n, C, device=dev, dtype=F32)
         dk = torch.empty(B, n_kv, C, device=dev, dtype=F32)
@@ -125,15 +154,14 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dg = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=dev, dtype=F32)
         dsum = torch.empty(B, H, n, device=dev, dtype=F32)
-        call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o), ptr(lse), B, H, d, n,
-             n_kv, C, C, C, C, nout, scale, ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), st)
+        call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
+             n, n_kv, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
+             ptr(segsum), st)
         mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
         call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), st)
 
-        # key / value projections (small: n_kv x dim x C), fp32 on the TF32 tensor-core path
-        Wk2, Wv2 = Wk.reshape(C, dim).float(), Wv.reshape(C, dim).float()
         with tf32_matmul():
-            kvf = kv.reshape(-1, dim).float()
+            kvf = kv.reshape(-1, dim)
             dWk = dk.reshape(-1, C).t() @ kvf
             dWv = dv.reshape(-1, C).t() @ kvf
             dkv = (dk @ Wk2 + dv @ Wv2).contiguous()                       # [B,n_kv,dim]
@@ -151,11 +179,12 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         d_off = d_off.contiguous()
         dy_ws = torch.empty(B * G, n_kv, Cg, device=dev, dtype=F32)
         wgrad = torch.empty(Cg * ks + 2 * Cg, device=dev, dtype=F32)
-        dq = torch.empty(B, n, C, device=dev, dtype=BF16)
+        dq = torch.empty(B, n, C, device=dev, dtype=F32)
         call("dml_offsets_bwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), ptr(dq_attn), scale, B, n, C, G, ks,
              stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), ptr(dq), st)
-        dWq = mm_f32out(dq.reshape(-1, C).t(), x1b.reshape(-1, dim))       # [C, dim]
-        dx1t = torch.matmul(dq, Wq_b).float()
+        with tf32_matmul():
+            dWq = dq.reshape(-1, C).t() @ x1f.reshape(-1, dim)             # [C, dim]
+            dx1t = torch.matmul(dq, Wq2)
 
         dw0 = wgrad[: Cg * ks].reshape(Cg, 1, ks)
         db0 = wgrad[Cg * ks: Cg * ks + Cg]
@@ -245,25 +274,31 @@ class ResConvMergeFn(torch.autograd.Function):
         return da, dv, dw.reshape(wshape)
 
 
-class MatmulTF32Fn(torch.autograd.Function):
-    """a @ b for fp32 operands on the TF32 tensor-core path, forward and backward (same batch dims)."""
+class MatmulFn(torch.autograd.Function):
+    """a @ b for fp32 operands, forward and backward (same batch dims); tf32=True takes the TF32
+    tensor-core path (fp32 accumulate), tf32=False exact fp32."""
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, tf32):
         ctx.save_for_backward(a, b)
-        with tf32_matmul():
+        ctx.tf32 = tf32
+        with (tf32_matmul() if tf32 else fp32_matmul()):
             return torch.matmul(a, b)
 
     @staticmethod
     def backward(ctx, g):
         a, b = ctx.saved_tensors
-        with tf32_matmul():
+        with (tf32_matmul() if ctx.tf32 else fp32_matmul()):
             da = torch.matmul(g, b.transpose(-1, -2)) if ctx.needs_input_grad[0] else None
             db = torch.matmul(a.transpose(-1, -2), g) if ctx.needs_input_grad[1] else None
         if db is not None and db.dim() > b.dim():
             db = db.reshape(-1, *b.shape).sum(0)
-        return da, db
+        return da, db, None
 
 
 def mm_tf32(a, b):
-    return MatmulTF32Fn.apply(a, b)
+    return MatmulFn.apply(a, b, True)
+
+
+def mm_fp32(a, b):
+    return MatmulFn.apply(a, b, False)

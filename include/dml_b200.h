@@ -55,20 +55,20 @@ int dml_cpb_param_grad(const float* w1, const float* b1, const float* W2, const 
 /* ---- offsets (to_offsets Sequential :139-146; vgrid + normalize_grid :186-188, :45-48) -------- */
 /* n_kv = floor((n + 2*pad - ksize)/stride) + 1, pad = (ksize - stride)/2.                          */
 int dml_offsets_kv_len(int n, int ksize, int stride);
-/* q: bf16 [B, n, C] token-major UNSCALED queries, C = G*128.  w0 [128, ksize], b0 [128], w2 [128].
+/* q: fp16 [B, n, C] token-major UNSCALED queries, C = G*128.  w0 [128, ksize], b0 [128], w2 [128].
  * vgrid, gnorm: float [(B*G), n_kv];  vgrid = j + tanh(.)*offset_scale, gnorm = 2 vgrid/max(n_kv-1,1) - 1. */
 int dml_offsets_fwd(const void* q, const float* w0, const float* b0, const float* w2, int B, int n, int C, int G,
                     int ksize, int stride, float offset_scale, float* vgrid, float* gnorm, void* stream);
 /* d_off: float [(B*G), n_kv] gradient w.r.t. the offsets (= w.r.t. vgrid).  dq_attn: float [B,n,C] gradient of
  * the attention w.r.t. the SCALED queries (multiplied by attn_scale here).  dy_ws: float [(B*G), n_kv, 128]
- * workspace.  wgrad: float [128*ksize + 128 + 128] = dw0 | db0 | dw2.  dq_out: bf16 [B,n,C] total dq.        */
+ * workspace.  wgrad: float [128*ksize + 128 + 128] = dw0 | db0 | dw2.  dq_out: float [B,n,C] total dq.       */
 int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float* w2, const float* d_off,
                     const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
                     float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* stream);
 
 /* ---- key/value gather (grid_sample_1d :36-43, :190-195; shipped degenerate semantics) */
 /* x2: float [B, n, dim] token-major; (i0,wy0),(i1,wy1): the sequence taps of y = 0 (centre of the sequence);
- * kv: bf16 [B, n_kv, dim] = (x2[i0]*wy0 + x2[i1]*wy1) * tent(gnorm).                                 */
+ * kv: float [B, n_kv, dim] = (x2[i0]*wy0 + x2[i1]*wy1) * tent(gnorm).                                 */
 int dml_kv_gather_fwd(const float* x2, const float* gnorm, int B, int n, int dim, int G, int n_kv, int i0, int i1,
                       float wy0, float wy1, void* kv, void* stream);
 /* dkv: float [B, n_kv, dim].  dcentre: float [B, dim] (overwritten) = sum_j dkv*tent;  dg: float [(B*G), n_kv],
@@ -77,18 +77,22 @@ int dml_kv_gather_bwd(const float* x2, const float* gnorm, const float* dkv, int
                       int i0, int i1, float wy0, float wy1, float* dcentre, float* dg, void* stream);
 
 /* ---- fused deformable attention (:203-231): softmax(scale*q.k^T + CPB bias) v ---------------- */
-/* q bf16 [B,n,ldq], k/v bf16 [B,n_kv,ldk/ldv], head h in columns h*dim_head..; gnorm float [(B*G), n_kv],
- * G = H/heads_per_group; out bf16 [B,n,ldo]; lse float [B,H,n] (log2 domain, saved for backward).     */
+/* q fp16 [B,n,ldq], k/v fp16 [B,n_kv,ldk/ldv] (the 16-bit operand type of the attention MMAs is IEEE half:
+ * 11-bit significand, fp32 accumulate), head h in columns h*dim_head..; gnorm float [(B*G), n_kv],
+ * G = H/heads_per_group; out FLOAT [B,n,ldo]; lse float [B,H,n] (log2 domain, saved for backward).     */
 int dml_deform_attn_fwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
                         int H, int dim_head, int n, int n_kv, int ldq, int ldk, int ldv, int ldo,
                         int heads_per_group, float scale, void* out, float* lse, void* stream);
-/* d_out bf16 [B,n,ldo] (ldo == H*dim_head).  dsum_ws float [B,H,n] workspace.  Outputs (fp32, dense
+/* out float [B,n,ldo] as written by the forward; d_out fp16 [B,n,ldo] (ldo == H*dim_head) = s * dL/dout with the
+ * power-of-two loss scale s the caller chose so that s*max|dL/dout| is O(10) (fp16 range); dscale: device float[2]
+ * = (s, 1/s), read by the kernels (no host sync) to un-scale every output.  dsum_ws float [B,H,n] workspace.  Outputs (fp32, dense
  * [.., H*dim_head]): dq = dS.K (NOT yet multiplied by scale), dk, dv; dg float [(B*G), n_kv] and
  * segsum float [dml_cpb_seg_max()][4] are zeroed here and then accumulated.                          */
 int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
                         const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
                         int n_kv, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
-                        float* dsum_ws, float* dq, float* dk, float* dv, float* dg, float* segsum, void* stream);
+                        const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
+                        float* segsum, void* stream);
 
 /* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
 /* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]

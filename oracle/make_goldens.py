@@ -197,9 +197,13 @@ def main():
     install_reference_shims()
     torch.manual_seed(0)
     torch.set_grad_enabled(True)
-    gen_deform()
-    gen_nystrom()
-    gen_towers()
+    # oneDNN is switched OFF while the reference runs: its fp32 depthwise-conv weight gradient is wrong by
+    # 5-8 % (max-abs) for the [1, 8, 256, d] res_conv shape (torch 2.11 CPU; fp64 and the native ATen kernel
+    # agree to 1e-6) - a CPU-backend artefact, not reference semantics.  tests/test_oracle_golden.py does the same.
+    with torch.backends.mkldnn.flags(enabled=False):
+        gen_deform()
+        gen_nystrom()
+        gen_towers()
 
 
 if __name__ == "__main__":

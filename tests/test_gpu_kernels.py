@@ -43,7 +43,7 @@ def test_cpb_table_matches_dense_mlp(seed, hid, nout):
     table, _ = build_table(P, T, hid, nout)
     hdr = table[:16].view(torch.int32)
     nseg, kmax = int(hdr[0]), int(hdr[1])
-    assert 1 <= nseg <= 1089 and 0 <= kmax <= 64
+    assert 1 <= nseg <= 1089 and 0 <= kmax <= 2048   # hdr[1] = cells holding >= 2 breakpoints (slow-path cells)
     t = torch.linspace(-T * 0.999, T * 0.999, 200001, device=DEV)
     out = torch.empty(t.numel(), 2, device=DEV)
     seg = torch.empty(t.numel(), device=DEV, dtype=torch.int32)
@@ -78,16 +78,16 @@ def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv):
     Hh, d, nout = 8, 64, 2
     G, C = Hh // nout, Hh * d
     seed = 100 + n
-    q = (synth.normal((B, n, C), seed, "q") * 0.7).to(DEV).to(torch.bfloat16)
-    k = (synth.normal((B, n_kv, C), seed, "k") * 0.7).to(DEV).to(torch.bfloat16)
-    v = synth.normal((B, n_kv, C), seed, "v").to(DEV).to(torch.bfloat16)
+    q = (synth.normal((B, n, C), seed, "q") * 0.7).to(DEV).to(torch.float16)
+    k = (synth.normal((B, n_kv, C), seed, "k") * 0.7).to(DEV).to(torch.float16)
+    v = synth.normal((B, n_kv, C), seed, "v").to(DEV).to(torch.float16)
     vgrid = torch.arange(n_kv, device=DEV)[None] + synth.uniform((B * G, n_kv), seed, "off", 2.0).to(DEV)
     g = O.normalize_grid(vgrid).contiguous()
     P = mlp_params(seed)
     t_max = math.log1p(2.0 + 4.0 / max(n_kv - 1, 1)) * 1.001 + 1e-3
     table, margs = build_table(P, t_max)
     scale = d ** -0.5
-    o = torch.empty(B, n, C, device=DEV, dtype=torch.bfloat16)
+    o = torch.empty(B, n, C, device=DEV, dtype=torch.float32)
     lse = torch.empty(B, Hh, n, device=DEV)
     call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, C, C, C, C, nout, scale,
          ptr(o), ptr(lse), stream())
@@ -95,10 +95,13 @@ def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv):
     gf = g.clone().requires_grad_()
     Pf = {kk: vv.clone().requires_grad_() for kk, vv in P.items()}
     ref = attn_reference(qf, kf, vf, gf, Pf, Hh, nout, scale, n)
-    H.assert_close(o.float(), ref, 6e-3, "attention output (bf16 store)")
+    H.assert_close(o, ref, 2e-3, "attention output (fp16 P in the PV MMA)")
 
-    r = synth.normal((B, n, C), seed, "r").to(DEV).to(torch.bfloat16)
-    loss = (ref * r.float()).sum()
+    r = (synth.normal((B, n, C), seed, "r") * 1e-3).to(DEV)            # small upstream gradient: exercises the fp16 loss scale
+    dscale = ops.grad_scale(r)
+    r16 = (r * dscale[0]).to(torch.float16)
+    r = r16.float() * dscale[1]
+    loss = (ref * r).sum()
     grads = torch.autograd.grad(loss, [qf, kf, vf, gf] + [Pf[x] for x in ("w1", "b1", "W2", "b2", "W3", "b3")])
     dq = torch.empty(B, n, C, device=DEV)
     dk = torch.empty(B, n_kv, C, device=DEV)
@@ -106,22 +109,23 @@ def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv):
     dg = torch.empty(B * G, n_kv, device=DEV)
     segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=DEV)
     dsum = torch.empty(B, Hh, n, device=DEV)
-    call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r), ptr(lse), B, Hh, d, n, n_kv,
-         C, C, C, C, nout, scale, ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), stream())
+    call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r16), ptr(lse), B, Hh, d, n, n_kv,
+         C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), stream())
     mg = torch.empty(ops.CPB_GRAD_FLOATS, device=DEV)
     call("dml_cpb_param_grad", *[ptr(a) for a in margs], 32, nout, ptr(table), ptr(segsum), ptr(mg), stream())
-    tol = 1.5e-2   # bf16 P / dS operands in the MMAs; compared against exact fp32 maths
-    H.assert_close(dq * scale, grads[0], tol, "dq")
-    H.assert_close(dk, grads[1], tol, "dk")
+    tol = 3e-3     # fp16 P / dS operands in the MMAs; compared against exact fp32 maths
+    zero = 1e-6 if n_kv == 1 else 0.0   # one key: softmax == 1, dS == 0 -> dq, dk are exactly zero in the reference
+    H.assert_close(dq * scale, grads[0], tol, "dq", atol=zero)
+    H.assert_close(dk, grads[1], tol, "dk", atol=zero)
     H.assert_close(dv, grads[2], tol, "dv")
     if n_kv > 1:
         H.assert_close(dg, grads[3], tol, "dg")
-    H.assert_close(mg[0:32], grads[4][:, 0], tol, "d mlp.w1")
-    H.assert_close(mg[32:64], grads[5], tol, "d mlp.b1")
-    H.assert_close(mg[64:1088].reshape(32, 32), grads[6], tol, "d mlp.W2")
-    H.assert_close(mg[1088:1120], grads[7], tol, "d mlp.b2")
-    H.assert_close(mg[1120:1184].reshape(2, 32), grads[8], tol, "d mlp.W3")
-    assert float(mg[1184:1186].abs().max()) < 1e-2 * max(1.0, float(grads[8].abs().max()))   # softmax shift invariance
+    H.assert_close(mg[0:32], grads[4][:, 0], tol, "d mlp.w1", atol=zero)
+    H.assert_close(mg[32:64], grads[5], tol, "d mlp.b1", atol=zero)
+    H.assert_close(mg[64:1088].reshape(32, 32), grads[6], tol, "d mlp.W2", atol=zero)
+    H.assert_close(mg[1088:1120], grads[7], tol, "d mlp.b2", atol=zero)
+    H.assert_close(mg[1120:1184].reshape(2, 32), grads[8], tol, "d mlp.W3", atol=zero)
+    assert float(mg[1184:1186].abs().max()) < 1e-2 * max(1e-3, float(grads[8].abs().max()))   # softmax shift invariance
 
 
 @pytest.mark.parametrize("B,n", [(2, 193), (1, 128), (1, 1030)])
@@ -129,7 +133,7 @@ def test_offsets_and_gather_match_oracle(B, n):
     G, C, dim, ks, stride, osc = 4, 512, 128, 6, 4, 2.0
     seed = 200 + n
     P = {k: v.to(DEV) for k, v in synth.fill_like(H.deform_shapes(), seed, gain=2.0).items()}
-    q = synth.normal((B, n, C), seed, "q").to(DEV).to(torch.bfloat16)
+    q = synth.normal((B, n, C), seed, "q").to(DEV).to(torch.float16)
     n_kv = O.kv_length(n, ks, stride)
     vgrid = torch.empty(B * G, n_kv, device=DEV)
     g = torch.empty_like(vgrid)
@@ -148,15 +152,15 @@ def test_offsets_and_gather_match_oracle(B, n):
 
     # gather forward / backward against the closed form AND the literal grid_sample
     x2 = synth.normal((B, n, dim), seed, "x2").to(DEV)
-    kv = torch.empty(B, n_kv, dim, device=DEV, dtype=torch.bfloat16)
+    kv = torch.empty(B, n_kv, dim, device=DEV, dtype=torch.float32)
     i0, i1, wy0, wy1 = ops.centre_taps(n)
     assert (i0, wy0, wy1) == (O.centre_taps(n)[0], O.centre_taps(n)[2], O.centre_taps(n)[3])
     call("dml_kv_gather_fwd", ptr(x2), ptr(g), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(kv), stream())
     x2f = x2.clone().requires_grad_()
     gf = g.clone().requires_grad_()
     lit = O.grid_sample_1d_literal(x2f.transpose(1, 2).reshape(B * G, dim // G, n), gf).reshape(B, dim, n_kv).transpose(1, 2)
-    H.assert_close(kv.float(), lit, 5e-3, "kv_feats (bf16 store)")
-    assert torch.equal(kv, lit.to(torch.bfloat16)) or n % 2 == 0     # bit-exact before the bf16 store for odd n
+    H.assert_close(kv, lit, 1e-6, "kv_feats")
+    assert torch.equal(kv, lit) or n % 2 == 0     # the closed form of the degenerate sample is bit-exact for odd n
     dkv = synth.normal((B, n_kv, dim), seed, "dkv").to(DEV)
     gx2, gg = torch.autograd.grad((lit * dkv).sum(), (x2f, gf))
     dcentre = torch.empty(B, dim, device=DEV)
@@ -175,10 +179,10 @@ def test_offsets_and_gather_match_oracle(B, n):
     grads = torch.autograd.grad((off * d_off).sum(), [qf, Pf["to_offsets.0.weight"], Pf["to_offsets.0.bias"], Pf["to_offsets.2.weight"]])
     dy_ws = torch.empty(B * G, n_kv, 128, device=DEV)
     wgrad = torch.empty(128 * ks + 256, device=DEV)
-    dq = torch.empty(B, n, C, device=DEV, dtype=torch.bfloat16)
+    dq = torch.empty(B, n, C, device=DEV, dtype=torch.float32)
     call("dml_offsets_bwd", ptr(q), ptr(w0), ptr(b0), ptr(w2), ptr(d_off), ptr(dq_attn), 0.125, B, n, C, G, ks, stride, osc,
          ptr(dy_ws), ptr(wgrad), ptr(dq), stream())
-    H.assert_close(dq.float(), grads[0] + 0.125 * dq_attn, 5e-3, "dq total (bf16 store)")
+    H.assert_close(dq, grads[0] + 0.125 * dq_attn, 1e-5, "dq total")
     H.assert_close(wgrad[:128 * ks].reshape(128, 1, ks), grads[1], 1e-4, "d to_offsets.0.weight")
     H.assert_close(wgrad[128 * ks:128 * ks + 128], grads[2], 1e-4, "d to_offsets.0.bias")
     H.assert_close(wgrad[128 * ks + 128:].reshape(1, 128, 1), grads[3], 1e-4, "d to_offsets.2.weight")
