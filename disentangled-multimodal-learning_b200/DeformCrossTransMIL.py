@@ -80,8 +80,9 @@ class DeformCrossTransMIL(nn.Module):
         if getattr(self.args, "return_vgrid", False):
             raise NotImplementedError("return_vgrid with attn_dim == 1 raises in the reference (SURVEY.md Q6)")
         fc1 = self._fc1[0]
-        if path.dtype == torch.bfloat16:      # bf16 bags: fc1 on the bf16 tensor-core path, fp32 afterwards
-            path = F.relu(F.linear(path, fc1.weight.to(torch.bfloat16), fc1.bias.to(torch.bfloat16))).float()
+        if path.dtype == torch.bfloat16:      # bf16 bags: fc1 on the bf16 tensor-core path (fp32 accumulate/output)
+            B_, N_, K_ = path.shape
+            path = F.relu(ops.LinearBf16BagFn.apply(path.reshape(B_ * N_, K_), fc1.weight, fc1.bias).reshape(B_, N_, -1))
         else:
             path = F.relu(ops.mm_tf32(path.float(), fc1.weight.t()) + fc1.bias)
         h = self.fusion_layer(path, omic.float())

@@ -302,3 +302,35 @@ def mm_tf32(a, b):
 
 def mm_fp32(a, b):
     return MatmulFn.apply(a, b, False)
+
+
+def split_bf16(t: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 pair with hi + lo == t to 16 significant bits."""
+    hi = t.to(BF16)
+    return hi, (t - hi.float()).to(BF16)
+
+
+class LinearBf16BagFn(torch.autograd.Function):
+    """y = x @ W^T + b for a bf16 bag x [M, K] (the bag is GIVEN in bf16: no rounding is added to it) and fp32
+    W [N, K]: the weight enters as a (hi, lo) bf16 pair and the incoming gradient likewise, so the product and
+    the weight gradient carry fp32-class accuracy on the bf16 tensor-core path (fp32 accumulate / output)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        Wh, Wl = split_bf16(W)
+        y = torch.mm(x, Wh.t(), out_dtype=F32)
+        y += torch.mm(x, Wl.t(), out_dtype=F32)
+        ctx.save_for_backward(x, W)
+        return y + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dyh, dyl = split_bf16(dy)
+        dW = torch.mm(dyh.t(), x, out_dtype=F32)
+        dW += torch.mm(dyl.t(), x, out_dtype=F32)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            with tf32_matmul():
+                dx = (dy @ W).to(x.dtype)
+        return dx, dW, dy.sum(0)
