@@ -39,13 +39,14 @@ cpb_table_build_kernel(const float* __restrict__ w1, const float* __restrict__ b
   __shared__ double l1[34];
   __shared__ MlpSmem m;
   __shared__ int s_n1, s_nbp, s_kmax;
+  __shared__ unsigned s_amax[2];
   const int tid = threadIdx.x;
   const double dT = (double)T;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
   load_mlp(m, w1, b1, W2, b2, W3, b3, hid, nout, tid, blockDim.x);
   for (int i = tid; i < kSortN; i += blockDim.x) cand[i] = INF;
-  if (tid == 0) s_kmax = 0;
+  if (tid == 0) { s_kmax = 0; s_amax[0] = 0u; s_amax[1] = 0u; }
   __syncthreads();
 
   // ---- layer-1 breakpoints: w1[k] t + b1[k] = 0 ----
@@ -156,6 +157,8 @@ cpb_table_build_kernel(const float* __restrict__ w1, const float* __restrict__ b
         }
       }
       segcoef[s] = make_float4((float)a[0], (float)(c[0] * LOG2E), (float)a[1], (float)(c[1] * LOG2E));
+      atomicMax(&s_amax[0], __float_as_uint(fabsf((float)a[0]) * 1.0000002f));   // non-negative floats order like uints
+      atomicMax(&s_amax[1], __float_as_uint(fabsf((float)a[1]) * 1.0000002f));
       mask1[s] = m1;
       mask2[s] = m2;
     } else if (s < kCpbSegMax) {
@@ -198,7 +201,9 @@ cpb_table_build_kernel(const float* __restrict__ w1, const float* __restrict__ b
     table[3] = __float_as_uint((float)((double)kCpbCells / (2.0 * X)));
     table[4] = (uint32_t)hid;
     table[5] = (uint32_t)nout;
-    for (int i = 6; i < 16; ++i) table[i] = 0;
+    table[6] = s_amax[0];
+    table[7] = s_amax[1];
+    for (int i = 8; i < 16; ++i) table[i] = 0;
   }
 }
 

@@ -22,12 +22,12 @@ namespace dml {
 
 constexpr int kCpbHidMax = 32;
 constexpr int kCpbOutMax = 2;
-constexpr int kCpbCells = 2048;
+constexpr int kCpbCells = 1024;
 constexpr int kCpbSegMax = kCpbHidMax + kCpbHidMax * (kCpbHidMax + 1) + 1 + 15;  // 1104 (padded)
 constexpr int kCpbBpPad = 16;
 
 // Table layout in 32-bit words (one device buffer, produced by cpb_table_build):
-constexpr int kTabHdr = 0;                                   // int nseg, int ndirty, float X, float inv_cell, int hid, int nout
+constexpr int kTabHdr = 0;                                   // int nseg, int ndirty, float X, float inv_cell, int hid, int nout, float amax0, float amax1 (max |slope| per output)
 constexpr int kTabCellCoef = 16;                             // float4[2][kCpbCells]
 constexpr int kTabCellBp = kTabCellCoef + 2 * 4 * kCpbCells; // float[kCpbCells]
 constexpr int kTabCellSeg = kTabCellBp + kCpbCells;          // uint16[kCpbCells]   segment index at the start of the cell

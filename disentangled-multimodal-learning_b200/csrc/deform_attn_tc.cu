@@ -1,0 +1,519 @@
+// Fused deformable cross-attention forward on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Reference maths (DeformableAttention1D.py:203-231 + CPB :84-102), per head h of offset group grp = h / 2:
+//     S[i,j] = scale * q_h[i,:].k_h[j,:] + bias_{h % 2}(x_ij),   x_ij = sign(p) log2(|p| + 1),  p = seq_i - g[grp, j]
+//     P = softmax_j(S);  out_h[i,:] = sum_j P[i,j] v_h[j,:]
+//
+// One CTA = one (batch, offset group, 256 consecutive queries): the TWO heads of the group are processed together,
+// so the position x_ij, its log and its table cell are evaluated once per (i, j) and shared by both heads.
+//
+//   warp 8    TMA producer: Q tiles once, then a 3-stage ring of {K_h0, K_h1, V_h0, V_h1} 64-key tiles
+//             (cp.async.bulk.tensor, 128-byte swizzle) + the 64 sampling positions g of the tile
+//   warp 9    MMA issuer (one elected thread): S = Q K^T (SS form, operands in shared memory) and O += P V
+//             (TS form: P is read from TMEM, V from shared memory as an MN-major operand); owns the TMEM allocation
+//   warps 0-3 softmax group 0 = queries [i0, i0+128);  warps 4-7 softmax group 1 = queries [i0+128, i0+256).
+//             Thread t of a group owns query row t: TMEM lane t holds its S row and its O row, so the row maximum,
+//             the row sum and the position s_i are thread-private (no shuffles), and the 32 lanes of a warp look up
+//             nearly the same table cell (consecutive queries) -> broadcast shared-memory reads.
+//
+// TMEM (512 columns x 128 lanes, fp32): group g at column 256 g:  S_h0 [0,64)  S_h1 [64,128)  O_h0 [128,192)  O_h1 [192,256).
+// P (fp16) overwrites S in place: the 16 fp32 columns of key chunk c become 8 columns of P_hi and 8 columns of P_lo
+// (P = P_hi + P_lo, 22 significant bits), consumed by two K=16 MMAs per chunk.  The two groups alternate on the tensor
+// pipe: while one group's softmax runs on the CUDA cores the other group's MMAs execute.
+//
+// Online softmax without a correction pass in the common case: before the main sweep a cheap sweep over the raw S
+// tile gives an upper bound of the row maximum (max S + an upper bound of the piecewise-linear bias over the tile's
+// position window); the running reference m is only raised when that bound exceeds it by more than 2^8, and only then
+// are the O rows rescaled in TMEM (safe: all earlier MMAs of the group have completed when S arrives).
+#include <cuda.h>
+#include <math.h>
+
+#include "../../include/dml_b200.h"
+#include "common.cuh"
+#include "cpb_table.cuh"
+
+namespace dml {
+namespace tc {
+
+constexpr int kD = 64;            // head dim
+constexpr int kBM = 128;          // query rows per softmax group (= TMEM lanes)
+constexpr int kGroups = 2;        // softmax groups per CTA
+constexpr int kBN = 64;           // keys per tile
+constexpr int kStages = 3;
+constexpr int kThreads = 32 * 10;
+constexpr uint32_t kTileQ = kBM * kD * 2;   // 16384 B
+constexpr uint32_t kTileKV = kBN * kD * 2;  // 8192 B
+constexpr uint32_t kStageBytes = 4 * kTileKV;
+constexpr float kRaise = 8.0f;    // raise the softmax reference only when the bound exceeds it by 2^8
+
+// shared-memory map (dynamic, base aligned to 1024 B)
+constexpr uint32_t kOffQ = 0;                                        // [group][head] 128x64 fp16
+constexpr uint32_t kOffKV = kOffQ + kGroups * 2 * kTileQ;            // [stage]{K0,K1,V0,V1} 64x64 fp16
+constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;           // [stage][64 g + gmin + gmax + pad] floats
+constexpr uint32_t kGStride = 72 * 4;
+constexpr uint32_t kOffCoef = kOffG + kStages * kGStride + 160;      // float4[2][kCpbCells]   (16-B aligned)
+constexpr uint32_t kOffBp = kOffCoef + 2 * kCpbCells * 16;           // float[kCpbCells]
+constexpr uint32_t kOffBar = kOffBp + kCpbCells * 4;                 // mbarriers (8 B each)
+constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,
+              kBarPFull = kBarSFull + kGroups, kNumBars = kBarPFull + kGroups;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;             // + slack for the 1024-B alignment
+static_assert(kOffCoef % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct Params {
+  const float* g;        // [(B G), n_kv] normalised sampling positions
+  const uint32_t* table; // cpb table (device)
+  float* o;              // fp32 [B, n, ldo]
+  float* lse;            // [B, H, n] (log2 domain)
+  int B, H, n, n_kv, ldo, n_seq;
+  float scale;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {   // no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// wait for the TMEM loads; the registers are listed so that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  tmem_ld_wait(a);
+  asm volatile("" : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+               "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle, 8-row groups 1024 B apart (K-major and MN-major alike here)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = 64
+constexpr uint32_t kIdescS = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);                 // A, B K-major
+constexpr uint32_t kIdescPV = kIdescS | (1u << 16);                                                // B (= V) MN-major
+
+__device__ __forceinline__ float seq_pos(int i, int n) { return (2.0f * (float)i) / (float)max(n - 1, 1) - 1.0f; }
+
+struct Lookup {   // shared-memory image of the table, both head outputs
+  const float4* coef0; const float4* coef1; const float* bp; const uint32_t* gtab; float c1, c2;
+};
+static __device__ __noinline__ void lookup_slow(const uint32_t* gtab, int cell, float x, float& a0, float& c0, float& a1,
+                                                float& c1) {
+  const uint16_t* cs = reinterpret_cast<const uint16_t*>(gtab + kTabCellSeg);
+  const float* sbp = reinterpret_cast<const float*>(gtab + kTabSegBp);
+  const float4* sc = reinterpret_cast<const float4*>(gtab + kTabSegCoef);
+  int s = cs[cell];
+  while (s < kCpbSegMax - 1 && x >= __ldg(sbp + s)) ++s;
+  const float4 e = __ldg(sc + s);
+  a0 = e.x; c0 = e.y; a1 = e.z; c1 = e.w;
+}
+// bias_o (log2 domain) = a_o x + c_o for both outputs
+__device__ __forceinline__ void lookup2(const Lookup& L, float x, float& a0, float& c0, float& a1, float& c1) {
+  const int cell = min(max(__float2int_rd(fmaf(x, L.c1, L.c2)), 0), kCpbCells - 1);
+  const float b = L.bp[cell];
+  const float4 e0 = L.coef0[cell], e1 = L.coef1[cell];
+  const bool hi = x >= b;
+  a0 = hi ? e0.z : e0.x; c0 = hi ? e0.w : e0.y;
+  a1 = hi ? e1.z : e1.x; c1 = hi ? e1.w : e1.y;
+  if (__builtin_expect(b != b, 0)) lookup_slow(L.gtab, cell, x, a0, c0, a1, c1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
+                          const __grid_constant__ CUtensorMap mv, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * (kGroups * kBM), grp = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / 2;
+  const int ntiles = cdiv(p.n_kv, kBN);
+  auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    mbar_init(bar(kBarQ), 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), 1); }
+    for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  {  // stage the cell table (both outputs) into shared memory
+    float4* coef = reinterpret_cast<float4*>(sgen + kOffCoef);
+    const float4* gcoef = reinterpret_cast<const float4*>(p.table + kTabCellCoef);
+    for (int i = tid; i < 2 * kCpbCells; i += kThreads) coef[i] = __ldg(gcoef + i);
+    float4* bp4 = reinterpret_cast<float4*>(sgen + kOffBp);
+    const float4* gbp = reinterpret_cast<const float4*>(p.table + kTabCellBp);
+    for (int i = tid; i < kCpbCells / 4; i += kThreads) bp4[i] = __ldg(gbp + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_expect_tx(bar(kBarQ), kGroups * 2 * kTileQ);
+      for (int g = 0; g < kGroups; ++g)
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(sbase + kOffQ + (g * 2 + h) * kTileQ, &mq, bar(kBarQ), (grp * 2 + h) * kD, i0 + g * kBM, b);
+    }
+    const float* gb = p.g + (size_t)(b * G + grp) * p.n_kv;
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kStages;
+      mbar_wait(bar(kBarKvEmpty + st), ((j / kStages) & 1) ^ 1);
+      const uint32_t dst = sbase + kOffKV + st * kStageBytes;
+      if (lane == 0) {
+        mbar_expect_tx_only(bar(kBarKvFull + st), kStageBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_3d(dst + h * kTileKV, &mk, bar(kBarKvFull + st), (grp * 2 + h) * kD, j * kBN, b);
+          tma_load_3d(dst + (2 + h) * kTileKV, &mv, bar(kBarKvFull + st), (grp * 2 + h) * kD, j * kBN, b);
+        }
+      }
+      float* gs = reinterpret_cast<float*>(sgen + kOffG + st * kGStride);
+      const float g0 = __ldg(gb + min(j * kBN + lane, p.n_kv - 1)), g1 = __ldg(gb + min(j * kBN + 32 + lane, p.n_kv - 1));
+      gs[lane] = g0;
+      gs[lane + 32] = g1;
+      const float gmn = -warp_max(-fminf(g0, g1)), gmx = warp_max(fmaxf(g0, g1));
+      if (lane == 0) { gs[64] = gmn; gs[65] = gmx; }
+      mbar_arrive(bar(kBarKvFull + st));                     // 32 arrivals (release) + the TMA bytes complete the phase
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      mbar_wait(bar(kBarQ), 0);
+      auto issue_s = [&](int j, int g) {
+        const int st = j % kStages;
+        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t da = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), db = smem_desc(kv + h * kTileKV);
+          const uint32_t d = tmem + g * 256 + h * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(d, da + 2 * k, db + 2 * k, kIdescS, k > 0);
+        }
+        tc_commit(bar(kBarSFull + g));
+      };
+      mbar_wait(bar(kBarKvFull + 0), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(0, 1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kStages;
+        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
+        for (int g = 0; g < kGroups; ++g) {
+          mbar_wait(bar(kBarPFull + g), j & 1);
+          tc_fence_after();
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t db = smem_desc(kv + (2 + h) * kTileKV);
+            const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_ts(d, a + 16 * k, db + 128 * k, kIdescPV, (j > 0) || (k > 0));       // P_hi chunk k
+              mma_ts(d, a + 16 * k + 8, db + 128 * k, kIdescPV, 1);                    // P_lo chunk k
+            }
+          }
+          if (g == kGroups - 1) tc_commit(bar(kBarKvEmpty + st));    // stage free once every MMA reading it is done
+          if (j + 1 < ntiles) {
+            if (g == 0) {
+              mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
+              tc_fence_after();
+            }
+            issue_s(j + 1, g);
+          } else {
+            tc_commit(bar(kBarSFull + g));   // final: O complete
+          }
+        }
+      }
+    }
+  } else {
+    // =========================== softmax groups ===========================
+    const int g = warp >> 2;                        // group
+    const int row = (warp & 3) * 32 + lane;         // TMEM lane = query row inside the group's tile
+    const int gi = i0 + g * kBM + row;
+    const uint32_t tbase = tmem + g * 256 + (((uint32_t)(warp & 3) * 32u) << 16);
+    Lookup L;
+    L.coef0 = reinterpret_cast<const float4*>(sgen + kOffCoef);
+    L.coef1 = L.coef0 + kCpbCells;
+    L.bp = reinterpret_cast<const float*>(sgen + kOffBp);
+    L.gtab = p.table;
+    {
+      const float X = __uint_as_float(__ldg(p.table + 2)), inv = __uint_as_float(__ldg(p.table + 3));
+      L.c1 = inv;
+      L.c2 = X * inv;
+    }
+    const float amax0 = __uint_as_float(__ldg(p.table + 6)), amax1 = __uint_as_float(__ldg(p.table + 7));
+    const float s_i = seq_pos(gi, p.n_seq);
+    const float sc2 = p.scale * kLog2e;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kStages;
+      const float* gs = reinterpret_cast<const float*>(sgen + kOffG + st * kGStride);
+      mbar_wait(bar(kBarKvFull + st), (j / kStages) & 1);       // g tile visible to this thread
+      mbar_wait(bar(kBarSFull + g), j & 1);                     // S(j) landed; every earlier MMA of the group is complete
+      tc_fence_after();
+      const int jrem = p.n_kv - j * kBN;                        // valid keys in this tile (>= 1)
+
+      // ---- sweep 1: upper bound of the row maximum ----
+      float r0 = -INFINITY, r1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t a[16], bq[16];
+        tmem_ld16(tbase + c * 16, a);
+        tmem_ld16(tbase + 64 + c * 16, bq);
+        tmem_ld_wait2(a, bq);
+        if (jrem >= kBN) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            r0 = fmaxf(r0, __uint_as_float(a[e]));
+            r1 = fmaxf(r1, __uint_as_float(bq[e]));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c * 16 + e < jrem) {
+              r0 = fmaxf(r0, __uint_as_float(a[e]));
+              r1 = fmaxf(r1, __uint_as_float(bq[e]));
+            }
+        }
+      }
+      float bh0, bh1;
+      {
+        const float xlo = cpb_x(s_i - gs[65]), xhi = cpb_x(s_i - gs[64]);
+        float a0, c0, a1, c1, e0, f0, e1, f1;
+        lookup2(L, xlo, a0, c0, a1, c1);
+        lookup2(L, xhi, e0, f0, e1, f1);
+        const float half = 0.5f * (xhi - xlo) + 1e-6f;
+        bh0 = fmaxf(fmaf(a0, xlo, c0), fmaf(e0, xhi, f0)) + amax0 * half;
+        bh1 = fmaxf(fmaf(a1, xlo, c1), fmaf(e1, xhi, f1)) + amax1 * half;
+      }
+      const float ub0 = fmaf(r0, sc2, bh0), ub1 = fmaf(r1, sc2, bh1);
+      const bool raise0 = ub0 > m0 + kRaise, raise1 = ub1 > m1 + kRaise;
+      if (__any_sync(0xffffffffu, raise0 || raise1)) {
+        const float f0 = raise0 ? ex2(m0 - ub0) : 1.0f, f1 = raise1 ? ex2(m1 - ub1) : 1.0f;   // ex2(-inf) = 0 on the first tile
+        if (raise0) { m0 = ub0; l0 *= f0; }
+        if (raise1) { m1 = ub1; l1 *= f1; }
+        if (j > 0) {                                           // rescale this warp's O rows in TMEM
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t a[16];
+            tmem_ld16(tbase + 128 + c * 16, a);
+            tmem_ld_wait(a);
+            const float f = c < 4 ? f0 : f1;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) a[e] = __float_as_uint(__uint_as_float(a[e]) * f);
+            tmem_st16(tbase + 128 + c * 16, a);
+          }
+        }
+      }
+
+      // ---- sweep 2: P = exp2(S sc2 + bias - m), in place ----
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t a[16], bq[16];
+        tmem_ld16(tbase + c * 16, a);
+        tmem_ld16(tbase + 64 + c * 16, bq);
+        tmem_ld_wait2(a, bq);
+        float p0[16], p1[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float x = cpb_x(s_i - gs[c * 16 + e]);
+          float a0, c0, a1, c1;
+          lookup2(L, x, a0, c0, a1, c1);
+          float v0 = ex2(fmaf(__uint_as_float(a[e]), sc2, fmaf(a0, x, c0)) - m0);
+          float v1 = ex2(fmaf(__uint_as_float(bq[e]), sc2, fmaf(a1, x, c1)) - m1);
+          if (c * 16 + e >= jrem) { v0 = 0.f; v1 = 0.f; }
+          p0[e] = v0;
+          p1[e] = v1;
+          l0 += v0;
+          l1 += v1;
+        }
+        uint32_t w0[16], w1[16];   // [0,8) = P_hi pairs, [8,16) = P_lo pairs
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          split_f16(p0[2 * e], p0[2 * e + 1], w0[e], w0[8 + e]);
+          split_f16(p1[2 * e], p1[2 * e + 1], w1[e], w1[8 + e]);
+        }
+        tmem_st16(tbase + c * 16, w0);
+        tmem_st16(tbase + 64 + c * 16, w1);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar(kBarPFull + g));
+    }
+
+    // ---- epilogue: O / l -> global, log-sum-exp ----
+    mbar_wait(bar(kBarSFull + g), ntiles & 1);
+    tc_fence_after();
+    const int h0 = grp * 2;
+    if (gi < p.n) {
+      float* lb = p.lse + ((size_t)b * p.H + h0) * p.n + gi;
+      lb[0] = m0 + __log2f(l0);
+      lb[p.n] = m1 + __log2f(l1);
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    float* ob = p.o + ((size_t)b * p.n + gi) * p.ldo + h0 * kD;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t a[16];
+      tmem_ld16(tbase + 128 + c * 16, a);      // warp-collective: every lane takes part, stores are predicated
+      tmem_ld_wait(a);
+      const float f = c < 4 ? inv0 : inv1;
+      if (gi < p.n) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(ob + c * 16 + e) =
+              make_float4(__uint_as_float(a[e]) * f, __uint_as_float(a[e + 1]) * f, __uint_as_float(a[e + 2]) * f,
+                          __uint_as_float(a[e + 3]) * f);
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// ---- host: tensor maps ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// fp16 [B, rows, ld] tensor, box = 64 columns x box_rows rows, 128-byte swizzle, out-of-range rows read as zero
+static int make_map(CUtensorMap* m, const void* base, int B, int rows, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return DML_EUNSUPPORTED;
+  cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * ld * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DML_OK : DML_EINVAL;
+}
+
+}  // namespace tc
+}  // namespace dml
+
+extern "C" {
+
+int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table, int B,
+                           int H, int dim_head, int n, int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo,
+                           int heads_per_group, float scale, void* out, float* lse, void* stream) {
+  using namespace dml;
+  using namespace dml::tc;
+  DML_CHECK_ARG(q && k && v && g && table && out && lse && B > 0 && H > 0 && n > 0 && n_kv > 0 && n_seq >= n);
+  if (dim_head != kD || heads_per_group != 2 || (H & 1)) return DML_EUNSUPPORTED;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 4)) return DML_EINVAL;
+  if (ldq < H * kD || ldk < H * kD || ldv < H * kD || ldo < H * kD) return DML_EINVAL;
+  if ((((uintptr_t)q) | ((uintptr_t)k) | ((uintptr_t)v) | ((uintptr_t)out)) & 15) return DML_EINVAL;
+  CUtensorMap mq, mk, mv;
+  int rc = make_map(&mq, q, B, n, ldq, kBM);
+  if (rc) return rc;
+  rc = make_map(&mk, k, B, n_kv, ldk, kBN);
+  if (rc) return rc;
+  rc = make_map(&mv, v, B, n_kv, ldv, kBN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(deform_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  Params p{};
+  p.g = g; p.table = (const uint32_t*)table; p.o = (float*)out; p.lse = lse;
+  p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.ldo = ldo; p.n_seq = n_seq; p.scale = scale;
+  dim3 grid(cdiv(n, kGroups * kBM), H / 2, B);
+  deform_attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  DML_RETURN_LAUNCH();
+}
+
+}  // extern "C"

@@ -117,7 +117,7 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), st)
         o = torch.empty(B, n, C, device=dev, dtype=F32)
         lse = torch.empty(B, H, n, device=dev, dtype=F32)
-        call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n, n_kv, C, C, C, C, nout,
+        call("dml_deform_attn_fwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n, n_kv, n, C, C, C, C, nout,
              scale, ptr(o), ptr(lse), st)
         with tf32_matmul():
             out = torch.matmul(o, Wo2.t()) + bo                           # to_out (:233)

@@ -83,6 +83,13 @@ int dml_kv_gather_bwd(const float* x2, const float* gnorm, const float* dkv, int
 int dml_deform_attn_fwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
                         int H, int dim_head, int n, int n_kv, int ldq, int ldk, int ldv, int ldo,
                         int heads_per_group, float scale, void* out, float* lse, void* stream);
+/* Same contract on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, TMA-fed 128-byte-swizzled
+ * operand tiles, both heads of an offset group per CTA (heads_per_group must be 2).  n_seq >= n is the sequence
+ * length used to normalise the query positions (rows 0..n-1 of a sequence of n_seq tokens are computed; n_seq == n
+ * for the whole module, n_seq > n for a leading slice such as the cls row only).  q/k/v/out 16-byte aligned.       */
+int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
+                           int H, int dim_head, int n, int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo,
+                           int heads_per_group, float scale, void* out, float* lse, void* stream);
 /* out float [B,n,ldo] as written by the forward; d_out fp16 [B,n,ldo] (ldo == H*dim_head) = s * dL/dout with the
  * power-of-two loss scale s the caller chose so that s*max|dL/dout| is O(10) (fp16 range); dscale: device float[2]
  * = (s, 1/s), read by the kernels (no host sync) to un-scale every output.  dsum_ws float [B,H,n] workspace.  Outputs (fp32, dense
