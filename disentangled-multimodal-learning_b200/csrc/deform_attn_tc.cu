@@ -51,14 +51,14 @@ constexpr uint32_t kOffQ = 0;                                        // [group][
 constexpr uint32_t kOffKV = kOffQ + kGroups * 2 * kTileQ;            // [stage]{K0,K1,V0,V1} 64x64 fp16
 constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;           // [stage][64 g + gmin + gmax + pad] floats
 constexpr uint32_t kGStride = 72 * 4;
-constexpr uint32_t kOffCoef = kOffG + kStages * kGStride + 160;      // float4[2][kCpbCells]   (16-B aligned)
-constexpr uint32_t kOffBp = kOffCoef + 2 * kCpbCells * 16;           // float[kCpbCells]
-constexpr uint32_t kOffBar = kOffBp + kCpbCells * 4;                 // mbarriers (8 B each)
+constexpr uint32_t kOffRec = kOffG + kStages * kGStride + 160;       // cell records, kRecBytes each (16-B aligned)
+constexpr uint32_t kRecBytes = 48;   // { bp, #dirty cells before this one (int), -, - | lo piece a0,c0,a1,c1 | hi piece a0,c0,a1,c1 }
+constexpr uint32_t kOffBar = kOffRec + (kCpbCells + 1) * kRecBytes;  // mbarriers (8 B each)
 constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,
               kBarPFull = kBarSFull + kGroups, kNumBars = kBarPFull + kGroups;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;             // + slack for the 1024-B alignment
-static_assert(kOffCoef % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kOffRec % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -160,28 +160,78 @@ constexpr uint32_t kIdescPV = kIdescS | (1u << 16);                             
 
 __device__ __forceinline__ float seq_pos(int i, int n) { return (2.0f * (float)i) / (float)max(n - 1, 1) - 1.0f; }
 
-struct Lookup {   // shared-memory image of the table, both head outputs
-  const float4* coef0; const float4* coef1; const float* bp; const uint32_t* gtab; float c1, c2;
+struct Lookup {   // shared-memory cell records (both head outputs), see kRecBytes
+  uint32_t rec;            // shared-space address of record 0
+  const uint32_t* gtab;    // table in global memory (slow path of cells holding >= 2 breakpoints)
+  float c1, c2;            // cell = floor(x c1 + c2)
 };
-static __device__ __noinline__ void lookup_slow(const uint32_t* gtab, int cell, float x, float& a0, float& c0, float& a1,
-                                                float& c1) {
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+static __device__ __noinline__ float4 lookup_slow(const uint32_t* gtab, int cell, float x) {
   const uint16_t* cs = reinterpret_cast<const uint16_t*>(gtab + kTabCellSeg);
   const float* sbp = reinterpret_cast<const float*>(gtab + kTabSegBp);
   const float4* sc = reinterpret_cast<const float4*>(gtab + kTabSegCoef);
   int s = cs[cell];
   while (s < kCpbSegMax - 1 && x >= __ldg(sbp + s)) ++s;
-  const float4 e = __ldg(sc + s);
-  a0 = e.x; c0 = e.y; a1 = e.z; c1 = e.w;
+  return __ldg(sc + s);
 }
-// bias_o (log2 domain) = a_o x + c_o for both outputs
-__device__ __forceinline__ void lookup2(const Lookup& L, float x, float& a0, float& c0, float& a1, float& c1) {
-  const int cell = min(max(__float2int_rd(fmaf(x, L.c1, L.c2)), 0), kCpbCells - 1);
-  const float b = L.bp[cell];
-  const float4 e0 = L.coef0[cell], e1 = L.coef1[cell];
-  const bool hi = x >= b;
-  a0 = hi ? e0.z : e0.x; c0 = hi ? e0.w : e0.y;
-  a1 = hi ? e1.z : e1.x; c1 = hi ? e1.w : e1.y;
-  if (__builtin_expect(b != b, 0)) lookup_slow(L.gtab, cell, x, a0, c0, a1, c1);
+// (a0, c0, a1, c1): bias_o (log2 domain) = a_o x + c_o.  x must lie inside the table domain (the producer clamps g).
+template <bool kDirty>
+__device__ __forceinline__ float4 lookup2(const Lookup& L, float x, int* cell_out = nullptr) {
+  const int cell = __float2int_rd(fmaf(x, L.c1, L.c2));
+  const uint32_t ra = L.rec + (uint32_t)cell * kRecBytes;
+  const float bpv = lds_f32(ra);
+  float4 e = lds_f32x4(ra + (x >= bpv ? 32u : 16u));
+  if (kDirty) {
+    if (bpv != bpv) e = lookup_slow(L.gtab, cell, x);
+  }
+  if (cell_out) *cell_out = cell;
+  return e;
+}
+
+// One 64-key tile of one query row, both heads: S (TMEM, fp32) -> P = exp2(S sc2 + bias - m) split into fp16 hi/lo
+// pairs written back over the same TMEM columns; l0/l1 accumulate the row sums.  kMasked: keys >= jrem are padding;
+// kDirty: the row's position window touches a table cell holding >= 2 breakpoints (slow-path lookup possible).
+template <bool kMasked, bool kDirty>
+__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tbase, uint32_t gsa, float s_i, float sc2, float m0,
+                                       float m1, int jrem, float& l0, float& l1) {
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t a[16], bq[16];
+    tmem_ld16(tbase + c * 16, a);
+    tmem_ld16(tbase + 64 + c * 16, bq);
+    float gq[16];
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      const float4 t = lds_f32x4(gsa + (uint32_t)(c * 16 + e) * 4);
+      gq[e] = t.x; gq[e + 1] = t.y; gq[e + 2] = t.z; gq[e + 3] = t.w;
+    }
+    tmem_ld_wait2(a, bq);
+    uint32_t w0[16], w1[16];   // [0,8) = P_hi pairs, [8,16) = P_lo pairs
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+      float v0[2], v1[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float x = cpb_x(s_i - gq[e + u]);
+        const float4 t = lookup2<kDirty>(L, x);
+        v0[u] = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - m0);
+        v1[u] = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - m1);
+        if (kMasked && c * 16 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
+        l0 += v0[u];
+        l1 += v1[u];
+      }
+      split_f16(v0[0], v0[1], w0[e >> 1], w0[8 + (e >> 1)]);
+      split_f16(v1[0], v1[1], w1[e >> 1], w1[8 + (e >> 1)]);
+    }
+    tmem_st16(tbase + c * 16, w0);
+    tmem_st16(tbase + 64 + c * 16, w1);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -208,13 +258,26 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  {  // stage the cell table (both outputs) into shared memory
-    float4* coef = reinterpret_cast<float4*>(sgen + kOffCoef);
+  {  // stage the cell table into shared-memory records
     const float4* gcoef = reinterpret_cast<const float4*>(p.table + kTabCellCoef);
-    for (int i = tid; i < 2 * kCpbCells; i += kThreads) coef[i] = __ldg(gcoef + i);
-    float4* bp4 = reinterpret_cast<float4*>(sgen + kOffBp);
-    const float4* gbp = reinterpret_cast<const float4*>(p.table + kTabCellBp);
-    for (int i = tid; i < kCpbCells / 4; i += kThreads) bp4[i] = __ldg(gbp + i);
+    const float* gbp = reinterpret_cast<const float*>(p.table + kTabCellBp);
+    for (int i = tid; i < kCpbCells; i += kThreads) {
+      const float4 e0 = __ldg(gcoef + i), e1 = __ldg(gcoef + kCpbCells + i);
+      float4* r = reinterpret_cast<float4*>(sgen + kOffRec + (uint32_t)i * kRecBytes);
+      r[0] = make_float4(__ldg(gbp + i), 0.f, 0.f, 0.f);
+      r[1] = make_float4(e0.x, e0.y, e1.x, e1.y);
+      r[2] = make_float4(e0.z, e0.w, e1.z, e1.w);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {   // running count of flagged (>= 2 breakpoints) cells, one-off serial scan
+    int cnt = 0;
+    for (int i = 0; i <= kCpbCells; ++i) {
+      float* r = reinterpret_cast<float*>(sgen + kOffRec + (uint32_t)i * kRecBytes);
+      reinterpret_cast<int*>(r)[1] = cnt;
+      if (i < kCpbCells && r[0] != r[0]) ++cnt;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -242,7 +305,10 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         }
       }
       float* gs = reinterpret_cast<float*>(sgen + kOffG + st * kGStride);
-      const float g0 = __ldg(gb + min(j * kBN + lane, p.n_kv - 1)), g1 = __ldg(gb + min(j * kBN + 32 + lane, p.n_kv - 1));
+      // |p| <= 1 + |g| must stay inside the table domain (log2(|p| + 1) < X): clamp, so that no cell index can leave the table
+      const float gb_max = exp2f(__uint_as_float(__ldg(p.table + 2))) * 0.9995f - 2.0f;
+      const float g0 = fminf(fmaxf(__ldg(gb + min(j * kBN + lane, p.n_kv - 1)), -gb_max), gb_max),
+                  g1 = fminf(fmaxf(__ldg(gb + min(j * kBN + 32 + lane, p.n_kv - 1)), -gb_max), gb_max);
       gs[lane] = g0;
       gs[lane + 32] = g1;
       const float gmn = -warp_max(-fminf(g0, g1)), gmx = warp_max(fmaxf(g0, g1));
@@ -303,9 +369,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const int gi = i0 + g * kBM + row;
     const uint32_t tbase = tmem + g * 256 + (((uint32_t)(warp & 3) * 32u) << 16);
     Lookup L;
-    L.coef0 = reinterpret_cast<const float4*>(sgen + kOffCoef);
-    L.coef1 = L.coef0 + kCpbCells;
-    L.bp = reinterpret_cast<const float*>(sgen + kOffBp);
+    L.rec = sbase + kOffRec;
     L.gtab = p.table;
     {
       const float X = __uint_as_float(__ldg(p.table + 2)), inv = __uint_as_float(__ldg(p.table + 3));
@@ -313,13 +377,13 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       L.c2 = X * inv;
     }
     const float amax0 = __uint_as_float(__ldg(p.table + 6)), amax1 = __uint_as_float(__ldg(p.table + 7));
-    const float s_i = seq_pos(gi, p.n_seq);
+    const float s_i = seq_pos(min(gi, p.n_seq - 1), p.n_seq);     // rows past the end: any in-domain position
     const float sc2 = p.scale * kLog2e;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
     for (int j = 0; j < ntiles; ++j) {
       const int st = j % kStages;
-      const float* gs = reinterpret_cast<const float*>(sgen + kOffG + st * kGStride);
+      const uint32_t gsa = sbase + kOffG + st * kGStride;
       mbar_wait(bar(kBarKvFull + st), (j / kStages) & 1);       // g tile visible to this thread
       mbar_wait(bar(kBarSFull + g), j & 1);                     // S(j) landed; every earlier MMA of the group is complete
       tc_fence_after();
@@ -349,14 +413,15 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         }
       }
       float bh0, bh1;
+      int ndirty;
       {
-        const float xlo = cpb_x(s_i - gs[65]), xhi = cpb_x(s_i - gs[64]);
-        float a0, c0, a1, c1, e0, f0, e1, f1;
-        lookup2(L, xlo, a0, c0, a1, c1);
-        lookup2(L, xhi, e0, f0, e1, f1);
+        const float xlo = cpb_x(s_i - lds_f32(gsa + 65 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 64 * 4));
+        int clo, chi;
+        const float4 e = lookup2<true>(L, xlo, &clo), f = lookup2<true>(L, xhi, &chi);
         const float half = 0.5f * (xhi - xlo) + 1e-6f;
-        bh0 = fmaxf(fmaf(a0, xlo, c0), fmaf(e0, xhi, f0)) + amax0 * half;
-        bh1 = fmaxf(fmaf(a1, xlo, c1), fmaf(e1, xhi, f1)) + amax1 * half;
+        bh0 = fmaxf(fmaf(e.x, xlo, e.y), fmaf(f.x, xhi, f.y)) + amax0 * half;
+        bh1 = fmaxf(fmaf(e.z, xlo, e.w), fmaf(f.z, xhi, f.w)) + amax1 * half;
+        ndirty = lds_s32(L.rec + (uint32_t)(chi + 1) * kRecBytes + 4) - lds_s32(L.rec + (uint32_t)clo * kRecBytes + 4);
       }
       const float ub0 = fmaf(r0, sc2, bh0), ub1 = fmaf(r1, sc2, bh1);
       const bool raise0 = ub0 > m0 + kRaise, raise1 = ub1 > m1 + kRaise;
@@ -379,34 +444,12 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       }
 
       // ---- sweep 2: P = exp2(S sc2 + bias - m), in place ----
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t a[16], bq[16];
-        tmem_ld16(tbase + c * 16, a);
-        tmem_ld16(tbase + 64 + c * 16, bq);
-        tmem_ld_wait2(a, bq);
-        float p0[16], p1[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float x = cpb_x(s_i - gs[c * 16 + e]);
-          float a0, c0, a1, c1;
-          lookup2(L, x, a0, c0, a1, c1);
-          float v0 = ex2(fmaf(__uint_as_float(a[e]), sc2, fmaf(a0, x, c0)) - m0);
-          float v1 = ex2(fmaf(__uint_as_float(bq[e]), sc2, fmaf(a1, x, c1)) - m1);
-          if (c * 16 + e >= jrem) { v0 = 0.f; v1 = 0.f; }
-          p0[e] = v0;
-          p1[e] = v1;
-          l0 += v0;
-          l1 += v1;
-        }
-        uint32_t w0[16], w1[16];   // [0,8) = P_hi pairs, [8,16) = P_lo pairs
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          split_f16(p0[2 * e], p0[2 * e + 1], w0[e], w0[8 + e]);
-          split_f16(p1[2 * e], p1[2 * e + 1], w1[e], w1[8 + e]);
-        }
-        tmem_st16(tbase + c * 16, w0);
-        tmem_st16(tbase + 64 + c * 16, w1);
+      const bool dirty = __any_sync(0xffffffffu, ndirty != 0);
+      if (jrem >= kBN) {
+        if (!dirty) sweep2<false, false>(L, tbase, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+        else sweep2<false, true>(L, tbase, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+      } else {
+        sweep2<true, true>(L, tbase, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
       }
       tmem_st_wait();
       tc_fence_before();
