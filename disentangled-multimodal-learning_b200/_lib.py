@@ -34,6 +34,7 @@ SIGNATURES = {
     "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
     "dml_deform_attn_fwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 11 + [_f, _vp, _fp, _vp]),
     "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
+    "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp]),
     "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_softmax_rows_fwd": (_i, [_fp, _fp, _ll, _i, _vp]),
@@ -82,7 +83,7 @@ _ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace t
 # kernels launched per entry point (memsets not counted) - bench.py reports the total as gpu_launches
 KERNELS_PER_CALL = {
     "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2,
-    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3,
+    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3,
     "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
     "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1,
 }

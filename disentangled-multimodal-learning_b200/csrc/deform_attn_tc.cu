@@ -25,12 +25,10 @@
 // tile gives an upper bound of the row maximum (max S + an upper bound of the piecewise-linear bias over the tile's
 // position window); the running reference m is only raised when that bound exceeds it by more than 2^8, and only then
 // are the O rows rescaled in TMEM (safe: all earlier MMAs of the group have completed when S arrives).
-#include <cuda.h>
 #include <math.h>
 
 #include "../../include/dml_b200.h"
-#include "common.cuh"
-#include "cpb_table.cuh"
+#include "tc_common.cuh"
 
 namespace dml {
 namespace tc {
@@ -51,9 +49,8 @@ constexpr uint32_t kOffQ = 0;                                        // [group][
 constexpr uint32_t kOffKV = kOffQ + kGroups * 2 * kTileQ;            // [stage]{K0,K1,V0,V1} 64x64 fp16
 constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;           // [stage][64 g + gmin + gmax + pad] floats
 constexpr uint32_t kGStride = 72 * 4;
-constexpr uint32_t kOffRec = kOffG + kStages * kGStride + 160;       // cell records, kRecBytes each (16-B aligned)
-constexpr uint32_t kRecBytes = 48;   // { bp, #dirty cells before this one (int), -, - | lo piece a0,c0,a1,c1 | hi piece a0,c0,a1,c1 }
-constexpr uint32_t kOffBar = kOffRec + (kCpbCells + 1) * kRecBytes;  // mbarriers (8 B each)
+constexpr uint32_t kOffRec = kOffG + kStages * kGStride + 160;       // bias table image (tc_common.cuh), 16-B aligned
+constexpr uint32_t kOffBar = kOffRec + kTabSmemBytes;                // mbarriers (8 B each)
 constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,
               kBarPFull = kBarSFull + kGroups, kNumBars = kBarPFull + kGroups;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
@@ -70,129 +67,8 @@ struct Params {
   float scale;
 };
 
-// ---- PTX wrappers -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {   // no arrival
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-      ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
-      ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-// wait for the TMEM loads; the registers are listed so that no use of them can be scheduled above the wait
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :: "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&a)[16], uint32_t (&b)[16]) {
-  tmem_ld_wait(a);
-  asm volatile("" : "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
-               "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// shared-memory matrix descriptor, 128-byte swizzle, 8-row groups 1024 B apart (K-major and MN-major alike here)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: fp16 x fp16 -> fp32, M = 128, N = 64
-constexpr uint32_t kIdescS = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);                 // A, B K-major
-constexpr uint32_t kIdescPV = kIdescS | (1u << 16);                                                // B (= V) MN-major
-
-__device__ __forceinline__ float seq_pos(int i, int n) { return (2.0f * (float)i) / (float)max(n - 1, 1) - 1.0f; }
-
-struct Lookup {   // shared-memory cell records (both head outputs), see kRecBytes
-  uint32_t rec;            // shared-space address of record 0
-  const uint32_t* gtab;    // table in global memory (slow path of cells holding >= 2 breakpoints)
-  float c1, c2;            // cell = floor(x c1 + c2)
-};
-__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-static __device__ __noinline__ float4 lookup_slow(const uint32_t* gtab, int cell, float x) {
-  const uint16_t* cs = reinterpret_cast<const uint16_t*>(gtab + kTabCellSeg);
-  const float* sbp = reinterpret_cast<const float*>(gtab + kTabSegBp);
-  const float4* sc = reinterpret_cast<const float4*>(gtab + kTabSegCoef);
-  int s = cs[cell];
-  while (s < kCpbSegMax - 1 && x >= __ldg(sbp + s)) ++s;
-  return __ldg(sc + s);
-}
-// (a0, c0, a1, c1): bias_o (log2 domain) = a_o x + c_o.  x must lie inside the table domain (the producer clamps g).
-template <bool kDirty>
-__device__ __forceinline__ float4 lookup2(const Lookup& L, float x, int* cell_out = nullptr) {
-  const int cell = __float2int_rd(fmaf(x, L.c1, L.c2));
-  const uint32_t ra = L.rec + (uint32_t)cell * kRecBytes;
-  const float bpv = lds_f32(ra);
-  float4 e = lds_f32x4(ra + (x >= bpv ? 32u : 16u));
-  if (kDirty) {
-    if (bpv != bpv) e = lookup_slow(L.gtab, cell, x);
-  }
-  if (cell_out) *cell_out = cell;
-  return e;
-}
+constexpr uint32_t kIdescS = idesc_f16(128, 64, false, false);    // S = Q K^T: A, B K-major
+constexpr uint32_t kIdescPV = idesc_f16(128, 64, false, true);    // O += P V: A in TMEM, B (= V) MN-major
 
 // One 64-key tile of one query row, both heads: S (TMEM, fp32) -> P = exp2(S sc2 + bias - m) split into fp16 hi/lo
 // pairs written back over the same TMEM columns; l0/l1 accumulate the row sums.  kMasked: keys >= jrem are padding;
@@ -219,7 +95,8 @@ __device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tbase, uint32_t
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const float x = cpb_x(s_i - gq[e + u]);
-        const float4 t = lookup2<kDirty>(L, x);
+        int cdummy, sdummy;
+        const float4 t = lookup2<kDirty, false>(L, x, cdummy, sdummy);
         v0[u] = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - m0);
         v1[u] = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - m1);
         if (kMasked && c * 16 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
@@ -258,28 +135,10 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  {  // stage the cell table into shared-memory records
-    const float4* gcoef = reinterpret_cast<const float4*>(p.table + kTabCellCoef);
-    const float* gbp = reinterpret_cast<const float*>(p.table + kTabCellBp);
-    for (int i = tid; i < kCpbCells; i += kThreads) {
-      const float4 e0 = __ldg(gcoef + i), e1 = __ldg(gcoef + kCpbCells + i);
-      float4* r = reinterpret_cast<float4*>(sgen + kOffRec + (uint32_t)i * kRecBytes);
-      r[0] = make_float4(__ldg(gbp + i), 0.f, 0.f, 0.f);
-      r[1] = make_float4(e0.x, e0.y, e1.x, e1.y);
-      r[2] = make_float4(e0.z, e0.w, e1.z, e1.w);
-    }
-  }
+  const Lookup L = tab_stage(sgen + kOffRec, sbase + kOffRec, p.table, tid, kThreads);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {   // running count of flagged (>= 2 breakpoints) cells, one-off serial scan
-    int cnt = 0;
-    for (int i = 0; i <= kCpbCells; ++i) {
-      float* r = reinterpret_cast<float*>(sgen + kOffRec + (uint32_t)i * kRecBytes);
-      reinterpret_cast<int*>(r)[1] = cnt;
-      if (i < kCpbCells && r[0] != r[0]) ++cnt;
-    }
-  }
-  tc_fence_before();
+  if (tid == 0) tab_finish(sgen + kOffRec);
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
@@ -306,7 +165,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       }
       float* gs = reinterpret_cast<float*>(sgen + kOffG + st * kGStride);
       // |p| <= 1 + |g| must stay inside the table domain (log2(|p| + 1) < X): clamp, so that no cell index can leave the table
-      const float gb_max = exp2f(__uint_as_float(__ldg(p.table + 2))) * 0.9995f - 2.0f;
+      const float gb_max = tab_gmax(p.table);
       const float g0 = fminf(fmaxf(__ldg(gb + min(j * kBN + lane, p.n_kv - 1)), -gb_max), gb_max),
                   g1 = fminf(fmaxf(__ldg(gb + min(j * kBN + 32 + lane, p.n_kv - 1)), -gb_max), gb_max);
       gs[lane] = g0;
@@ -368,14 +227,6 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const int row = (warp & 3) * 32 + lane;         // TMEM lane = query row inside the group's tile
     const int gi = i0 + g * kBM + row;
     const uint32_t tbase = tmem + g * 256 + (((uint32_t)(warp & 3) * 32u) << 16);
-    Lookup L;
-    L.rec = sbase + kOffRec;
-    L.gtab = p.table;
-    {
-      const float X = __uint_as_float(__ldg(p.table + 2)), inv = __uint_as_float(__ldg(p.table + 3));
-      L.c1 = inv;
-      L.c2 = X * inv;
-    }
     const float amax0 = __uint_as_float(__ldg(p.table + 6)), amax1 = __uint_as_float(__ldg(p.table + 7));
     const float s_i = seq_pos(min(gi, p.n_seq - 1), p.n_seq);     // rows past the end: any in-domain position
     const float sc2 = p.scale * kLog2e;
@@ -416,12 +267,12 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       int ndirty;
       {
         const float xlo = cpb_x(s_i - lds_f32(gsa + 65 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 64 * 4));
-        int clo, chi;
-        const float4 e = lookup2<true>(L, xlo, &clo), f = lookup2<true>(L, xhi, &chi);
+        int clo, chi, sdummy;
+        const float4 e = lookup2<true, false>(L, xlo, clo, sdummy), f = lookup2<true, false>(L, xhi, chi, sdummy);
         const float half = 0.5f * (xhi - xlo) + 1e-6f;
         bh0 = fmaxf(fmaf(e.x, xlo, e.y), fmaf(f.x, xhi, f.y)) + amax0 * half;
         bh1 = fmaxf(fmaf(e.z, xlo, e.w), fmaf(f.z, xhi, f.w)) + amax1 * half;
-        ndirty = lds_s32(L.rec + (uint32_t)(chi + 1) * kRecBytes + 4) - lds_s32(L.rec + (uint32_t)clo * kRecBytes + 4);
+        ndirty = tab_dirty_between(L, clo, chi);
       }
       const float ub0 = fmaf(r0, sc2, bh0), ub1 = fmaf(r1, sc2, bh1);
       const bool raise0 = ub0 > m0 + kRaise, raise1 = ub1 > m1 + kRaise;
@@ -490,37 +341,6 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
-}
-
-// ---- host: tensor maps ------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// fp16 [B, rows, ld] tensor, box = 64 columns x box_rows rows, 128-byte swizzle, out-of-range rows read as zero
-static int make_map(CUtensorMap* m, const void* base, int B, int rows, int ld, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return DML_EUNSUPPORTED;
-  cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)rows, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * ld * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? DML_OK : DML_EINVAL;
 }
 
 }  // namespace tc

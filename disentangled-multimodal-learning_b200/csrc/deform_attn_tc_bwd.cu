@@ -1,0 +1,691 @@
+// Backward of the fused deformable cross-attention on tcgen05 / TMEM / TMA (sm_100a).
+//
+// With P = softmax(S), S = scale q.k^T + bias(x) (see deform_attn_tc.cu), dO the incoming gradient (fp16, multiplied
+// by the power-of-two loss scale s), D_i = sum_d dO_id O_id:
+//     dP = dO V^T,  dS = P o (dP - D),  dQ = dS K,  dK = scale dS^T Q,  dV = P^T dO,
+//     dg_j  = - sum_{h in group} sum_i dS_ij a_h(x_ij) / (|p_ij| + 1)              (bias slope a, p = seq_i - g_j)
+//     segsum[s] = (sum dS_0, sum dS_0 x, sum dS_1, sum dS_1 x) over the pairs whose x lies in table segment s
+// Nothing of size n x n_kv is stored: both kernels recompute P from the saved log-sum-exp.
+//
+//   deform_attn_dq_tc_kernel   query-stationary (TMEM lane = query), the forward's structure: two 128-query groups per
+//                              CTA alternate on the tensor pipe; per 32-key tile S = Q K^T and dP = dO V^T (SS MMAs),
+//                              dS (fp16) overwrites S in TMEM, dQ += dS K (TS MMA, K as an MN-major operand).
+//   deform_attn_dkv_tc_kernel  key-stationary (TMEM lane = key): one 128-key tile and both heads of the group per CTA,
+//                              streaming 32-query tiles through a 4-stage TMA ring; S^T = K Q^T and dP^T = V dO^T are
+//                              double-buffered in TMEM, P^T and dS^T (fp16) overwrite them in place and feed
+//                              dV += P^T dO, dK += dS^T Q (TS MMAs, dO / Q tiles re-read as MN-major operands).  A
+//                              thread owns one key for all queries, so g_j is a register, dg_j accumulates privately
+//                              and x_ij grows monotonically along the row: the per-segment sums are run-length merged
+//                              in registers and reach shared memory only when the segment changes.
+#include <math.h>
+
+#include "../../include/dml_b200.h"
+#include "tc_common.cuh"
+
+namespace dml {
+namespace tc {
+
+constexpr int kD = 64;
+constexpr float kLseOff = 1.0e30f;   // log-sum-exp stand-in for rows past the end: P = exp2(. - 1e30) = 0
+
+struct BwdParams {
+  const float* g;        // [(B G), n_kv]
+  const uint32_t* table;
+  const float* lse;      // [B, H, n] (log2 domain)
+  const float* dsum;     // [B, H, n]  D (scaled by s like dO)
+  const float* dscale;   // device float[2] = (s, 1/s)
+  float* dq;             // fp32 [B, n, H*64]     (unscaled by `scale`, as dml_deform_attn_bwd)
+  float* dk; float* dv;  // fp32 [B, n_kv, H*64]
+  float* dg;             // [(B G), n_kv]  accumulated (zeroed by the host wrapper)
+  float* segsum;         // [kCpbSegMax][4] accumulated (zeroed by the host wrapper)
+  int B, H, n, n_kv, n_seq;
+  float scale;
+};
+
+// D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (O fp32 as written by the forward, dO the fp16 tensor the MMAs consume)
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ o, const h16* __restrict__ d_o, int B, int n,
+                                                       int H, int ld, float* __restrict__ dsum) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int per_lane = (H * kD) / 32;  // 16 for H = 8
+  const int lanes_per_head = kD / per_lane;
+  for (int row = warp; row < B * n; row += nwarps) {
+    const float* po = o + (size_t)row * ld + lane * per_lane;
+    const h16* pd = d_o + (size_t)row * ld + lane * per_lane;
+    float s = 0.f;
+    for (int e = 0; e < per_lane; e += 8) {
+      const float4 a0 = *reinterpret_cast<const float4*>(po + e), a1 = *reinterpret_cast<const float4*>(po + e + 4);
+      uint4 c = *reinterpret_cast<const uint4*>(pd + e);
+      const __half2* c2 = reinterpret_cast<const __half2*>(&c);
+      s = fmaf(a0.x, __low2float(c2[0]), s); s = fmaf(a0.y, __high2float(c2[0]), s);
+      s = fmaf(a0.z, __low2float(c2[1]), s); s = fmaf(a0.w, __high2float(c2[1]), s);
+      s = fmaf(a1.x, __low2float(c2[2]), s); s = fmaf(a1.y, __high2float(c2[2]), s);
+      s = fmaf(a1.z, __low2float(c2[3]), s); s = fmaf(a1.w, __high2float(c2[3]), s);
+    }
+    for (int off = lanes_per_head >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((lane % lanes_per_head) == 0) {
+      const int hh = lane / lanes_per_head, bb = row / n, i = row % n;
+      dsum[((size_t)bb * H + hh) * n + i] = s;
+    }
+  }
+}
+
+// =================================================================================================================
+// dQ kernel
+// =================================================================================================================
+namespace dqk {
+constexpr int kBM = 128, kGroups = 2, kBN = 32, kStages = 3, kThreads = 320;
+constexpr uint32_t kTileQ = kBM * kD * 2;       // 16 KB
+constexpr uint32_t kTileKV = kBN * kD * 2;      // 4 KB
+constexpr uint32_t kStageBytes = 4 * kTileKV;   // K0 K1 V0 V1
+constexpr uint32_t kOffQ = 0;                                           // [group][head]
+constexpr uint32_t kOffDO = kOffQ + kGroups * 2 * kTileQ;               // [group][head]
+constexpr uint32_t kOffKV = kOffDO + kGroups * 2 * kTileQ;              // [stage]{K0,K1,V0,V1}
+constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;              // [stage][32 g, gmin, gmax, pad]
+constexpr uint32_t kGStride = 40 * 4;
+constexpr uint32_t kOffTab = kOffG + kStages * kGStride + 32;           // 16-B aligned
+constexpr uint32_t kOffBar = kOffTab + kTabSmemBytes;
+constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,
+              kBarPFull = kBarSFull + kGroups, kNumBars = kBarPFull + kGroups;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;
+static_assert(kOffTab % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kIdescSD = idesc_f16(128, kBN, false, false);   // S = Q K^T, dP = dO V^T
+constexpr uint32_t kIdescDQ = idesc_f16(128, 64, false, true);     // dQ += dS K   (K MN-major)
+}  // namespace dqk
+
+// one 32-key tile of one query row, both heads: dS = P (dP - D) as fp16 pairs over the S columns
+template <bool kMasked, bool kDirty>
+__device__ __forceinline__ void dq_sweep(const Lookup& L, uint32_t tbase, uint32_t gsa, float s_i, float sc2, float lse0,
+                                         float lse1, float d0, float d1, int jrem) {
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t a[16], bq[16], pa[16], pb[16];
+    tmem_ld16(tbase + c * 16, a);
+    tmem_ld16(tbase + 32 + c * 16, bq);
+    tmem_ld16(tbase + 64 + c * 16, pa);
+    tmem_ld16(tbase + 96 + c * 16, pb);
+    float gq[16];
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+      const float4 t = lds_f32x4(gsa + (uint32_t)(c * 16 + e) * 4);
+      gq[e] = t.x; gq[e + 1] = t.y; gq[e + 2] = t.z; gq[e + 3] = t.w;
+    }
+    tmem_ld_fence();
+    reg_fence(a); reg_fence(bq); reg_fence(pa); reg_fence(pb);
+    uint32_t w0[8], w1[8];
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) {
+      float v0[2], v1[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float x = cpb_x(s_i - gq[e + u]);
+        int cdummy, sdummy;
+        const float4 t = lookup2<kDirty, false>(L, x, cdummy, sdummy);
+        const float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - lse0);
+        const float p1 = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - lse1);
+        v0[u] = p0 * (__uint_as_float(pa[e + u]) - d0);
+        v1[u] = p1 * (__uint_as_float(pb[e + u]) - d1);
+        if (kMasked && c * 16 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
+      }
+      w0[e >> 1] = pack_f16(v0[0], v0[1]);
+      w1[e >> 1] = pack_f16(v1[0], v1[1]);
+    }
+    tmem_st8(tbase + c * 8, w0);
+    tmem_st8(tbase + 32 + c * 8, w1);
+  }
+}
+
+__global__ void __launch_bounds__(dqk::kThreads, 1)
+deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mdo,
+                         const __grid_constant__ CUtensorMap mk, const __grid_constant__ CUtensorMap mv,
+                         const BwdParams p) {
+  using namespace dqk;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * (kGroups * kBM), grp = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / 2;
+  const int ntiles = cdiv(p.n_kv, kBN);
+  auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
+
+  if (tid == 0) {
+    mbar_init(bar(kBarQ), 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), 1); }
+    for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  const Lookup L = tab_stage(sgen + kOffTab, sbase + kOffTab, p.table, tid, kThreads);
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) tab_finish(sgen + kOffTab);
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      mbar_expect_tx(bar(kBarQ), 2 * kGroups * 2 * kTileQ);
+      for (int g = 0; g < kGroups; ++g)
+        for (int h = 0; h < 2; ++h) {
+          tma_load_3d(sbase + kOffQ + (g * 2 + h) * kTileQ, &mq, bar(kBarQ), (grp * 2 + h) * kD, i0 + g * kBM, b);
+          tma_load_3d(sbase + kOffDO + (g * 2 + h) * kTileQ, &mdo, bar(kBarQ), (grp * 2 + h) * kD, i0 + g * kBM, b);
+        }
+    }
+    const float* gb = p.g + (size_t)(b * G + grp) * p.n_kv;
+    const float gb_max = tab_gmax(p.table);
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kStages;
+      mbar_wait(bar(kBarKvEmpty + st), ((j / kStages) & 1) ^ 1);
+      const uint32_t dst = sbase + kOffKV + st * kStageBytes;
+      if (lane == 0) {
+        mbar_expect_tx_only(bar(kBarKvFull + st), kStageBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_3d(dst + h * kTileKV, &mk, bar(kBarKvFull + st), (grp * 2 + h) * kD, j * kBN, b);
+          tma_load_3d(dst + (2 + h) * kTileKV, &mv, bar(kBarKvFull + st), (grp * 2 + h) * kD, j * kBN, b);
+        }
+      }
+      float* gs = reinterpret_cast<float*>(sgen + kOffG + st * kGStride);
+      const float g0 = fminf(fmaxf(__ldg(gb + min(j * kBN + lane, p.n_kv - 1)), -gb_max), gb_max);
+      gs[lane] = g0;
+      const float gmn = -warp_max(-g0), gmx = warp_max(g0);
+      if (lane == 0) { gs[32] = gmn; gs[33] = gmx; }
+      mbar_arrive(bar(kBarKvFull + st));
+    }
+  } else if (warp == 9) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      mbar_wait(bar(kBarQ), 0);
+      auto issue_sd = [&](int j, int g) {
+        const int st = j % kStages;
+        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t dq_ = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), dk_ = smem_desc(kv + h * kTileKV);
+          const uint64_t dd_ = smem_desc(sbase + kOffDO + (g * 2 + h) * kTileQ), dv_ = smem_desc(kv + (2 + h) * kTileKV);
+          const uint32_t ds = tmem + g * 256 + h * 32, dp = tmem + g * 256 + 64 + h * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(ds, dq_ + 2 * k, dk_ + 2 * k, kIdescSD, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(dp, dd_ + 2 * k, dv_ + 2 * k, kIdescSD, k > 0);
+        }
+        tc_commit(bar(kBarSFull + g));
+      };
+      mbar_wait(bar(kBarKvFull + 0), 0);
+      tc_fence_after();
+      issue_sd(0, 0);
+      issue_sd(0, 1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kStages;
+        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
+        for (int g = 0; g < kGroups; ++g) {
+          mbar_wait(bar(kBarPFull + g), j & 1);
+          tc_fence_after();
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t db = smem_desc(kv + h * kTileKV);                       // K tile as [key][d]: MN-major B
+            const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 32;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) mma_ts(d, a + 8 * k, db + 128 * k, kIdescDQ, (j > 0) || (k > 0));
+          }
+          if (g == kGroups - 1) tc_commit(bar(kBarKvEmpty + st));
+          if (j + 1 < ntiles) {
+            if (g == 0) {
+              mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
+              tc_fence_after();
+            }
+            issue_sd(j + 1, g);
+          } else {
+            tc_commit(bar(kBarSFull + g));
+          }
+        }
+      }
+    }
+  } else {
+    // ---- elementwise groups ----
+    const int g = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const int gi = i0 + g * kBM + row;
+    const bool rv = gi < p.n;
+    const uint32_t tbase = tmem + g * 256 + (((uint32_t)(warp & 3) * 32u) << 16);
+    const int h0 = grp * 2;
+    const size_t ro = ((size_t)b * p.H + h0) * p.n + min(gi, p.n - 1);
+    const float lse0 = rv ? __ldg(p.lse + ro) : kLseOff, lse1 = rv ? __ldg(p.lse + ro + p.n) : kLseOff;
+    const float d0 = rv ? __ldg(p.dsum + ro) : 0.f, d1 = rv ? __ldg(p.dsum + ro + p.n) : 0.f;
+    const float s_i = seq_pos(min(gi, p.n_seq - 1), p.n_seq);
+    const float sc2 = p.scale * kLog2e;
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kStages;
+      const uint32_t gsa = sbase + kOffG + st * kGStride;
+      mbar_wait(bar(kBarKvFull + st), (j / kStages) & 1);
+      mbar_wait(bar(kBarSFull + g), j & 1);
+      tc_fence_after();
+      const int jrem = p.n_kv - j * kBN;
+      int ndirty;
+      {
+        const float xlo = cpb_x(s_i - lds_f32(gsa + 33 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 32 * 4));
+        const int clo = __float2int_rd(fmaf(xlo, L.c1, L.c2)), chi = __float2int_rd(fmaf(xhi, L.c1, L.c2));
+        ndirty = tab_dirty_between(L, clo, chi);
+      }
+      const bool dirty = __any_sync(0xffffffffu, ndirty != 0);
+      if (jrem >= kBN) {
+        if (!dirty) dq_sweep<false, false>(L, tbase, gsa, s_i, sc2, lse0, lse1, d0, d1, jrem);
+        else dq_sweep<false, true>(L, tbase, gsa, s_i, sc2, lse0, lse1, d0, d1, jrem);
+      } else {
+        dq_sweep<true, true>(L, tbase, gsa, s_i, sc2, lse0, lse1, d0, d1, jrem);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar(kBarPFull + g));
+    }
+
+    // ---- epilogue: dQ / s -> global ----
+    mbar_wait(bar(kBarSFull + g), ntiles & 1);
+    tc_fence_after();
+    const float inv_s = __ldg(p.dscale + 1);
+    float* ob = p.dq + ((size_t)b * p.n + gi) * (p.H * kD) + h0 * kD;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t a[16];
+      tmem_ld16(tbase + 128 + c * 16, a);
+      tmem_ld_wait(a);
+      if (rv) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(ob + c * 16 + e) =
+              make_float4(__uint_as_float(a[e]) * inv_s, __uint_as_float(a[e + 1]) * inv_s,
+                          __uint_as_float(a[e + 2]) * inv_s, __uint_as_float(a[e + 3]) * inv_s);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// =================================================================================================================
+// dK / dV / dg / segment-sum kernel
+// =================================================================================================================
+namespace dkvk {
+constexpr int kBK = 128, kBI = 32, kStages = 4, kThreads = 320;
+constexpr uint32_t kTileKV = kBK * kD * 2;      // 16 KB
+constexpr uint32_t kTileQ = kBI * kD * 2;       // 4 KB
+constexpr uint32_t kStageBytes = 4 * kTileQ;    // Q0 Q1 dO0 dO1
+constexpr uint32_t kOffKV = 0;                                          // K0 K1 V0 V1 (resident)
+constexpr uint32_t kOffIn = kOffKV + 4 * kTileKV;                       // [stage]{Q0,Q1,dO0,dO1}
+constexpr uint32_t kOffRow = kOffIn + kStages * kStageBytes;            // [stage]{seq[32], lse0[32], lse1[32], D0[32], D1[32]}
+constexpr uint32_t kRowStride = 5 * 32 * 4;
+constexpr uint32_t kOffTab = kOffRow + kStages * kRowStride;
+constexpr uint32_t kOffSsum = kOffTab + kTabSmemBytes;                  // float[kCpbSegMax][4]
+constexpr uint32_t kOffBar = kOffSsum + kCpbSegMax * 16;
+constexpr int kBarKv = 0, kBarInFull = 1, kBarInEmpty = kBarInFull + kStages, kBarSFull = kBarInEmpty + kStages,
+              kBarPFull = kBarSFull + 2, kBarAcc = kBarPFull + 2, kNumBars = kBarAcc + 1;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;
+static_assert(kOffTab % 16 == 0 && kOffSsum % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kIdescSD = idesc_f16(128, kBI, false, false);   // S^T = K Q^T, dP^T = V dO^T
+constexpr uint32_t kIdescAcc = idesc_f16(128, 64, false, true);    // dV += P^T dO, dK += dS^T Q  (dO / Q MN-major)
+}  // namespace dkvk
+
+struct SegRun {      // run-length state of one thread: sums of the current segment, both head outputs
+  int seg;
+  float a0, b0, a1, b1;
+};
+__device__ __forceinline__ void seg_flush(float* ssum, SegRun& r) {
+  if (r.seg >= 0) {
+    if (r.a0 != 0.f || r.b0 != 0.f) { atomicAdd(ssum + 4 * r.seg, r.a0); atomicAdd(ssum + 4 * r.seg + 1, r.b0); }
+    if (r.a1 != 0.f || r.b1 != 0.f) { atomicAdd(ssum + 4 * r.seg + 2, r.a1); atomicAdd(ssum + 4 * r.seg + 3, r.b1); }
+  }
+  r.a0 = r.b0 = r.a1 = r.b1 = 0.f;
+}
+
+// 16 queries of one key row, both heads.  S^T / dP^T (fp32, TMEM) -> P^T / dS^T (fp16 pairs, in place); accumulates
+// dg and the per-segment sums.  kExact: a thread's 16 positions span more than two table segments or touch a flagged
+// cell (rare) -> per-position segment lookup and shared-memory atomics instead of the two-bucket scheme.
+template <bool kKeyMasked, bool kExact>
+__device__ __forceinline__ void dkv_sweep(const Lookup& L, uint32_t tS, uint32_t rowa, float g_j, bool key_valid, float sc2,
+                                          int seg_first, int seg_last, float& dgacc, SegRun& run, float* ssum) {
+  uint32_t a[16], bq[16], pa[16], pb[16];
+  tmem_ld16(tS, a);
+  tmem_ld16(tS + 32, bq);
+  tmem_ld16(tS + 64, pa);
+  tmem_ld16(tS + 96, pb);
+  float sq[16], l0[16], l1[16], d0[16], d1[16];
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) {
+    float4 t = lds_f32x4(rowa + e * 4);
+    sq[e] = t.x; sq[e + 1] = t.y; sq[e + 2] = t.z; sq[e + 3] = t.w;
+    t = lds_f32x4(rowa + 128 + e * 4);
+    l0[e] = t.x; l0[e + 1] = t.y; l0[e + 2] = t.z; l0[e + 3] = t.w;
+    t = lds_f32x4(rowa + 256 + e * 4);
+    l1[e] = t.x; l1[e + 1] = t.y; l1[e + 2] = t.z; l1[e + 3] = t.w;
+    t = lds_f32x4(rowa + 384 + e * 4);
+    d0[e] = t.x; d0[e + 1] = t.y; d0[e + 2] = t.z; d0[e + 3] = t.w;
+    t = lds_f32x4(rowa + 512 + e * 4);
+    d1[e] = t.x; d1[e + 1] = t.y; d1[e + 2] = t.z; d1[e + 3] = t.w;
+  }
+  // x grows with the query index: [seg_first, seg_last] are the segments of the first / last position; the
+  // two-bucket scheme needs at most one boundary in between
+  float xb = __int_as_float(0x7f800000);      // boundary between the two buckets (+inf: a single bucket)
+  if (!kExact && seg_last != seg_first) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
+  tmem_ld_fence();
+  reg_fence(a); reg_fence(bq); reg_fence(pa); reg_fence(pb);
+  float ta0 = 0.f, tb0 = 0.f, ta1 = 0.f, tb1 = 0.f;      // whole-tile sums
+  float ha0 = 0.f, hb0 = 0.f, ha1 = 0.f, hb1 = 0.f;      // sums of the positions at or above the boundary
+  uint32_t wp0[8], wp1[8], ws0[8], ws1[8];
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float pp0[2], pp1[2], dd0[2], dd1[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float pr = sq[e + u] - g_j;
+      const float qa = fabsf(pr) + 1.0f;
+      const float x = copysignf(__log2f(qa), pr);
+      int cell, seg = 0;
+      const float4 t = lookup2<kExact, kExact>(L, x, cell, seg);
+      float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - l0[e + u]);
+      float p1 = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - l1[e + u]);
+      float s0 = p0 * (__uint_as_float(pa[e + u]) - d0[e + u]);
+      float s1 = p1 * (__uint_as_float(pb[e + u]) - d1[e + u]);
+      if (kKeyMasked && !key_valid) { p0 = 0.f; p1 = 0.f; s0 = 0.f; s1 = 0.f; }
+      pp0[u] = p0; pp1[u] = p1; dd0[u] = s0; dd1[u] = s1;
+      // d bias / d g_j = -a / (|p| + 1)
+      dgacc = fmaf(fmaf(s0, t.x, s1 * t.z), -rcp_approx(qa), dgacc);
+      if (kExact) {
+        atomicAdd(ssum + 4 * seg, s0); atomicAdd(ssum + 4 * seg + 1, s0 * x);
+        atomicAdd(ssum + 4 * seg + 2, s1); atomicAdd(ssum + 4 * seg + 3, s1 * x);
+      } else {
+        const float sx0 = s0 * x, sx1 = s1 * x;
+        ta0 += s0; tb0 += sx0; ta1 += s1; tb1 += sx1;
+        if (x >= xb) { ha0 += s0; hb0 += sx0; ha1 += s1; hb1 += sx1; }
+      }
+    }
+    wp0[e >> 1] = pack_f16(pp0[0], pp0[1]);
+    wp1[e >> 1] = pack_f16(pp1[0], pp1[1]);
+    ws0[e >> 1] = pack_f16(dd0[0], dd0[1]);
+    ws1[e >> 1] = pack_f16(dd1[0], dd1[1]);
+  }
+  tmem_st8(tS, wp0);
+  tmem_st8(tS + 32, wp1);
+  tmem_st8(tS + 64, ws0);
+  tmem_st8(tS + 96, ws1);
+  if (!kExact) {
+    if (seg_first != run.seg) { seg_flush(ssum, run); run.seg = seg_first; }
+    run.a0 += ta0 - ha0; run.b0 += tb0 - hb0; run.a1 += ta1 - ha1; run.b1 += tb1 - hb1;
+    if (seg_last != seg_first) {
+      seg_flush(ssum, run);
+      run.seg = seg_last;
+      run.a0 = ha0; run.b0 = hb0; run.a1 = ha1; run.b1 = hb1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(dkvk::kThreads, 1)
+deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mdo,
+                          const __grid_constant__ CUtensorMap mk, const __grid_constant__ CUtensorMap mv,
+                          const BwdParams p) {
+  using namespace dkvk;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j0 = blockIdx.x * kBK, grp = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / 2, h0 = grp * 2;
+  const int ntiles = cdiv(p.n, kBI);
+  auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
+  float* ssum = reinterpret_cast<float*>(sgen + kOffSsum);
+
+  if (tid == 0) {
+    mbar_init(bar(kBarKv), 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarInFull + s), 32); mbar_init(bar(kBarInEmpty + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarSFull + s), 1); mbar_init(bar(kBarPFull + s), 256); }
+    mbar_init(bar(kBarAcc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  const Lookup L = tab_stage(sgen + kOffTab, sbase + kOffTab, p.table, tid, kThreads);
+  for (int i = tid; i < kCpbSegMax * 4; i += kThreads) ssum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) tab_finish(sgen + kOffTab);
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      mbar_expect_tx(bar(kBarKv), 4 * kTileKV);
+      for (int h = 0; h < 2; ++h) {
+        tma_load_3d(sbase + kOffKV + h * kTileKV, &mk, bar(kBarKv), (h0 + h) * kD, j0, b);
+        tma_load_3d(sbase + kOffKV + (2 + h) * kTileKV, &mv, bar(kBarKv), (h0 + h) * kD, j0, b);
+      }
+    }
+    const float* lb = p.lse + ((size_t)b * p.H + h0) * p.n;
+    const float* db = p.dsum + ((size_t)b * p.H + h0) * p.n;
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % kStages;
+      mbar_wait(bar(kBarInEmpty + st), ((t / kStages) & 1) ^ 1);
+      const uint32_t dst = sbase + kOffIn + st * kStageBytes;
+      if (lane == 0) {
+        mbar_expect_tx_only(bar(kBarInFull + st), kStageBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_3d(dst + h * kTileQ, &mq, bar(kBarInFull + st), (h0 + h) * kD, t * kBI, b);
+          tma_load_3d(dst + (2 + h) * kTileQ, &mdo, bar(kBarInFull + st), (h0 + h) * kD, t * kBI, b);
+        }
+      }
+      float* rs = reinterpret_cast<float*>(sgen + kOffRow + st * kRowStride);
+      const int i = t * kBI + lane;
+      const bool iv = i < p.n;
+      const int ic = min(i, p.n - 1);
+      rs[lane] = seq_pos(min(i, p.n_seq - 1), p.n_seq);
+      rs[32 + lane] = iv ? __ldg(lb + ic) : kLseOff;
+      rs[64 + lane] = iv ? __ldg(lb + p.n + ic) : kLseOff;
+      rs[96 + lane] = iv ? __ldg(db + ic) : 0.f;
+      rs[128 + lane] = iv ? __ldg(db + p.n + ic) : 0.f;
+      mbar_arrive(bar(kBarInFull + st));
+    }
+  } else if (warp == 9) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      mbar_wait(bar(kBarKv), 0);
+      auto issue_sd = [&](int t) {
+        const int st = t % kStages, buf = t & 1;
+        const uint32_t in = sbase + kOffIn + st * kStageBytes;
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t dk_ = smem_desc(sbase + kOffKV + h * kTileKV), dq_ = smem_desc(in + h * kTileQ);
+          const uint64_t dv_ = smem_desc(sbase + kOffKV + (2 + h) * kTileKV), dd_ = smem_desc(in + (2 + h) * kTileQ);
+          const uint32_t ds = tmem + buf * 128 + h * 32, dp = tmem + buf * 128 + 64 + h * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(ds, dk_ + 2 * k, dq_ + 2 * k, kIdescSD, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_ss(dp, dv_ + 2 * k, dd_ + 2 * k, kIdescSD, k > 0);
+        }
+        tc_commit(bar(kBarSFull + buf));
+      };
+      mbar_wait(bar(kBarInFull + 0), 0);
+      tc_fence_after();
+      issue_sd(0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t % kStages, buf = t & 1;
+        if (t + 1 < ntiles) {
+          mbar_wait(bar(kBarInFull + (t + 1) % kStages), ((t + 1) / kStages) & 1);
+          tc_fence_after();
+          issue_sd(t + 1);
+        }
+        mbar_wait(bar(kBarPFull + buf), (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t in = sbase + kOffIn + st * kStageBytes;
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t dq_ = smem_desc(in + h * kTileQ), dd_ = smem_desc(in + (2 + h) * kTileQ);   // [query][d]: MN-major B
+          const uint32_t pT = tmem + buf * 128 + h * 32, sT = tmem + buf * 128 + 64 + h * 32;
+          const uint32_t dV = tmem + 256 + h * 64, dK = tmem + 384 + h * 64;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) mma_ts(dV, pT + 16 * k, dd_ + 128 * k, kIdescAcc, (t > 0) || (k > 0));
+#pragma unroll
+          for (int k = 0; k < 2; ++k) mma_ts(dK, sT + 16 * k, dq_ + 128 * k, kIdescAcc, (t > 0) || (k > 0));
+        }
+        tc_commit(bar(kBarInEmpty + st));
+      }
+      tc_commit(bar(kBarAcc));
+    }
+  } else {
+    // ---- elementwise warps: warp w -> TMEM lanes 32 (w & 3).., queries 16 (w >> 2).. of each 32-query tile ----
+    const int half = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const int gj = j0 + row;
+    const bool kvld = gj < p.n_kv;
+    const bool key_masked = (j0 + kBK) > p.n_kv;       // CTA-uniform
+    const float gmaxv = tab_gmax(p.table);
+    const float g_j = fminf(fmaxf(__ldg(p.g + (size_t)(b * G + grp) * p.n_kv + min(gj, p.n_kv - 1)), -gmaxv), gmaxv);
+    const uint32_t lane_off = ((uint32_t)(warp & 3) * 32u) << 16;
+    const float sc2 = p.scale * kLog2e;
+    float dgacc = 0.f;
+    SegRun run;
+    run.seg = -1;
+    run.a0 = run.b0 = run.a1 = run.b1 = 0.f;
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t % kStages, buf = t & 1;
+      mbar_wait(bar(kBarInFull + st), (t / kStages) & 1);
+      mbar_wait(bar(kBarSFull + buf), (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t rowa = sbase + kOffRow + st * kRowStride + half * 64;
+      const uint32_t tS = tmem + lane_off + buf * 128 + half * 16;
+      // segments of this thread's first / last position; the exact path is taken when any lane crosses more than one
+      // segment boundary inside its 16 positions or touches a flagged (>= 2 breakpoints) table cell
+      int seg_first, seg_last;
+      bool exact;
+      {
+        int c0, c1;
+        lookup2<true, true>(L, cpb_x(lds_f32(rowa) - g_j), c0, seg_first);
+        lookup2<true, true>(L, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
+        exact = __any_sync(0xffffffffu, (seg_last - seg_first > 1) || tab_dirty_between(L, c0, c1) != 0);
+      }
+      if (!key_masked) {
+        if (!exact) dkv_sweep<false, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
+        else dkv_sweep<false, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
+      } else {
+        if (!exact) dkv_sweep<true, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
+        else dkv_sweep<true, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar(kBarPFull + buf));
+    }
+    seg_flush(ssum, run);
+    const float inv_s = __ldg(p.dscale + 1);
+    if (kvld) atomicAdd(p.dg + (size_t)(b * G + grp) * p.n_kv + gj, dgacc * inv_s);
+
+    // ---- drain dV / dK ----
+    mbar_wait(bar(kBarAcc), 0);
+    tc_fence_after();
+    const float ksc = p.scale * inv_s;
+    const int ldg = p.H * kD;
+#pragma unroll
+    for (int acc = 0; acc < 4; ++acc) {     // dV h0, dV h1, dK h0, dK h1: 64 columns each, this warp takes 32 of them
+      const int h = acc & 1;
+      float* dst = (acc < 2 ? p.dv : p.dk) + ((size_t)b * p.n_kv + gj) * ldg + (h0 + h) * kD + half * 32;
+      const float f = acc < 2 ? inv_s : ksc;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t a[16];
+        tmem_ld16(tmem + lane_off + 256 + acc * 64 + half * 32 + c * 16, a);
+        tmem_ld_wait(a);
+        if (kvld) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(dst + c * 16 + e) =
+                make_float4(__uint_as_float(a[e]) * f, __uint_as_float(a[e + 1]) * f, __uint_as_float(a[e + 2]) * f,
+                            __uint_as_float(a[e + 3]) * f);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  {   // the CTA's segment sums -> global
+    const int nseg = (int)__ldg(p.table);
+    const float inv_s = __ldg(p.dscale + 1);
+    for (int i = tid; i < nseg * 4; i += kThreads) {
+      const float v = ssum[i];
+      if (v != 0.f) atomicAdd(p.segsum + i, v * inv_s);
+    }
+  }
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+}  // namespace tc
+}  // namespace dml
+
+extern "C" {
+
+int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table,
+                           const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
+                           int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
+                           const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
+                           float* segsum, void* stream) {
+  using namespace dml;
+  using namespace dml::tc;
+  DML_CHECK_ARG(q && k && v && g && table && out && d_out && lse && dscale && dsum_ws && dq && dk && dv && dg && segsum);
+  DML_CHECK_ARG(B > 0 && H > 0 && n > 0 && n_kv > 0 && n_seq >= n);
+  if (dim_head != kD || heads_per_group != 2 || (H & 1)) return DML_EUNSUPPORTED;
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return DML_EINVAL;
+  if (ldq < H * kD || ldk < H * kD || ldv < H * kD || ldo != H * kD) return DML_EINVAL;
+  if ((((uintptr_t)q) | ((uintptr_t)k) | ((uintptr_t)v) | ((uintptr_t)d_out) | ((uintptr_t)dq) | ((uintptr_t)dk) |
+       ((uintptr_t)dv)) & 15)
+    return DML_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap mq128, mdo128, mk32, mv32, mq32, mdo32, mk128, mv128;
+  int rc;
+  if ((rc = make_map(&mq128, q, B, n, ldq, 128)) || (rc = make_map(&mdo128, d_out, B, n, ldo, 128)) ||
+      (rc = make_map(&mk32, k, B, n_kv, ldk, 32)) || (rc = make_map(&mv32, v, B, n_kv, ldv, 32)) ||
+      (rc = make_map(&mq32, q, B, n, ldq, 32)) || (rc = make_map(&mdo32, d_out, B, n, ldo, 32)) ||
+      (rc = make_map(&mk128, k, B, n_kv, ldk, 128)) || (rc = make_map(&mv128, v, B, n_kv, ldv, 128)))
+    return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(deform_attn_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dqk::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(deform_attn_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkvk::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int G = H / 2;
+  cudaError_t e = cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)B * G * n_kv, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(segsum, 0, sizeof(float) * 4 * kCpbSegMax, st);
+  if (e != cudaSuccess) return (int)e;
+  BwdParams p{};
+  p.g = g; p.table = (const uint32_t*)table; p.lse = lse; p.dsum = dsum_ws; p.dscale = dscale;
+  p.dq = dq; p.dk = dk; p.dv = dv; p.dg = dg; p.segsum = segsum;
+  p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.n_seq = n_seq; p.scale = scale;
+  const int rows = B * n;
+  bwd_prep_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>((const float*)out, (const h16*)d_out, B, n, H, ldo, dsum_ws);
+  deform_attn_dkv_tc_kernel<<<dim3(cdiv(n_kv, dkvk::kBK), G, B), dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p);
+  deform_attn_dq_tc_kernel<<<dim3(cdiv(n, dqk::kGroups * dqk::kBM), G, B), dqk::kThreads, dqk::kSmemBytes, st>>>(mq128, mdo128, mk32, mv32, p);
+  DML_RETURN_LAUNCH();
+}
+
+}  // extern "C"

@@ -154,8 +154,8 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dg = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=dev, dtype=F32)
         dsum = torch.empty(B, H, n, device=dev, dtype=F32)
-        call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
-             n, n_kv, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
+        call("dml_deform_attn_bwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
+             n, n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
              ptr(segsum), st)
         mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
         call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), st)

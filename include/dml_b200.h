@@ -101,6 +101,14 @@ int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float
                         const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
                         float* segsum, void* stream);
 
+/* The same backward on tcgen05 / TMEM / TMA (two kernels: key-stationary dK/dV/dg/segment sums, query-stationary dQ;
+ * heads_per_group must be 2; n_seq as in dml_deform_attn_fwd_tc; every tensor pointer 16-byte aligned).             */
+int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
+                           const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
+                           int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
+                           const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
+                           float* segsum, void* stream);
+
 /* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
 /* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]
  * = mult * sum over l consecutive (padded) rows.                                                      */

@@ -102,8 +102,9 @@ def test_deform_attn_fwd_tcgen05_matches_torch(B, n, n_kv):
     H.assert_close(lse, lse2, 1e-5, "log-sum-exp (tcgen05 vs mma.sync)")
 
 
-@pytest.mark.parametrize("B,n,n_kv", [(1, 193, 48), (2, 130, 64), (1, 517, 129), (1, 64, 1)])
-def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv):
+@pytest.mark.parametrize("impl", ["mma", "tc"])
+@pytest.mark.parametrize("B,n,n_kv", [(1, 193, 48), (2, 130, 64), (1, 517, 129), (1, 64, 1), (1, 1100, 300)])
+def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv, impl):
     Hh, d, nout = 8, 64, 2
     G, C = Hh // nout, Hh * d
     seed = 100 + n
@@ -138,8 +139,13 @@ def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv):
     dg = torch.empty(B * G, n_kv, device=DEV)
     segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=DEV)
     dsum = torch.empty(B, Hh, n, device=DEV)
-    call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r16), ptr(lse), B, Hh, d, n, n_kv,
-         C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), stream())
+    if impl == "mma":
+        call("dml_deform_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r16), ptr(lse), B, Hh, d, n, n_kv,
+             C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), stream())
+    else:
+        call("dml_deform_attn_bwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r16), ptr(lse), B, Hh, d, n,
+             n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum),
+             stream())
     mg = torch.empty(ops.CPB_GRAD_FLOATS, device=DEV)
     call("dml_cpb_param_grad", *[ptr(a) for a in margs], 32, nout, ptr(table), ptr(segsum), ptr(mg), stream())
     tol = 3e-3     # fp16 P / dS operands in the MMAs; compared against exact fp32 maths
