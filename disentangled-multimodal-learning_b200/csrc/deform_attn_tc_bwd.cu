@@ -353,75 +353,77 @@ __device__ __forceinline__ void seg_flush(float* ssum, SegRun& r) {
 }
 
 // 16 queries of one key row, both heads.  S^T / dP^T (fp32, TMEM) -> P^T / dS^T (fp16 pairs, in place); accumulates
-// dg and the per-segment sums.  kExact: a thread's 16 positions span more than two table segments or touch a flagged
-// cell (rare) -> per-position segment lookup and shared-memory atomics instead of the two-bucket scheme.
+// dg and the per-segment sums.  Fast variant: the thread's 16 positions lie in at most two adjacent table segments
+// [seg_first, seg_last] split at xb -> two register buckets, no per-position segment lookup.  kExact (rare: some lane
+// of the warp crosses more than one boundary or touches a flagged cell): per-position segment lookup, run-length merged.
 template <bool kKeyMasked, bool kExact>
 __device__ __forceinline__ void dkv_sweep(const Lookup& L, uint32_t tS, uint32_t rowa, float g_j, bool key_valid, float sc2,
                                           int seg_first, int seg_last, float& dgacc, SegRun& run, float* ssum) {
-  uint32_t a[16], bq[16], pa[16], pb[16];
-  tmem_ld16(tS, a);
-  tmem_ld16(tS + 32, bq);
-  tmem_ld16(tS + 64, pa);
-  tmem_ld16(tS + 96, pb);
-  float sq[16], l0[16], l1[16], d0[16], d1[16];
-#pragma unroll
-  for (int e = 0; e < 16; e += 4) {
-    float4 t = lds_f32x4(rowa + e * 4);
-    sq[e] = t.x; sq[e + 1] = t.y; sq[e + 2] = t.z; sq[e + 3] = t.w;
-    t = lds_f32x4(rowa + 128 + e * 4);
-    l0[e] = t.x; l0[e + 1] = t.y; l0[e + 2] = t.z; l0[e + 3] = t.w;
-    t = lds_f32x4(rowa + 256 + e * 4);
-    l1[e] = t.x; l1[e + 1] = t.y; l1[e + 2] = t.z; l1[e + 3] = t.w;
-    t = lds_f32x4(rowa + 384 + e * 4);
-    d0[e] = t.x; d0[e + 1] = t.y; d0[e + 2] = t.z; d0[e + 3] = t.w;
-    t = lds_f32x4(rowa + 512 + e * 4);
-    d1[e] = t.x; d1[e + 1] = t.y; d1[e + 2] = t.z; d1[e + 3] = t.w;
-  }
-  // x grows with the query index: [seg_first, seg_last] are the segments of the first / last position; the
-  // two-bucket scheme needs at most one boundary in between
   float xb = __int_as_float(0x7f800000);      // boundary between the two buckets (+inf: a single bucket)
   if (!kExact && seg_last != seg_first) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
-  tmem_ld_fence();
-  reg_fence(a); reg_fence(bq); reg_fence(pa); reg_fence(pb);
   float ta0 = 0.f, tb0 = 0.f, ta1 = 0.f, tb1 = 0.f;      // whole-tile sums
   float ha0 = 0.f, hb0 = 0.f, ha1 = 0.f, hb1 = 0.f;      // sums of the positions at or above the boundary
-  uint32_t wp0[8], wp1[8], ws0[8], ws1[8];
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries (register budget)
+    uint32_t a[8], bq[8], pa[8], pb[8];
+    tmem_ld8(tS + c * 8, a);
+    tmem_ld8(tS + 32 + c * 8, bq);
+    tmem_ld8(tS + 64 + c * 8, pa);
+    tmem_ld8(tS + 96 + c * 8, pb);
+    float sq[8], l0[8], l1[8], d0[8], d1[8];
+    const uint32_t ra = rowa + c * 32;
 #pragma unroll
-  for (int e = 0; e < 16; e += 2) {
-    float pp0[2], pp1[2], dd0[2], dd1[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float pr = sq[e + u] - g_j;
-      const float qa = fabsf(pr) + 1.0f;
-      const float x = copysignf(__log2f(qa), pr);
-      int cell, seg = 0;
-      const float4 t = lookup2<kExact, kExact>(L, x, cell, seg);
-      float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - l0[e + u]);
-      float p1 = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - l1[e + u]);
-      float s0 = p0 * (__uint_as_float(pa[e + u]) - d0[e + u]);
-      float s1 = p1 * (__uint_as_float(pb[e + u]) - d1[e + u]);
-      if (kKeyMasked && !key_valid) { p0 = 0.f; p1 = 0.f; s0 = 0.f; s1 = 0.f; }
-      pp0[u] = p0; pp1[u] = p1; dd0[u] = s0; dd1[u] = s1;
-      // d bias / d g_j = -a / (|p| + 1)
-      dgacc = fmaf(fmaf(s0, t.x, s1 * t.z), -rcp_approx(qa), dgacc);
-      if (kExact) {
-        atomicAdd(ssum + 4 * seg, s0); atomicAdd(ssum + 4 * seg + 1, s0 * x);
-        atomicAdd(ssum + 4 * seg + 2, s1); atomicAdd(ssum + 4 * seg + 3, s1 * x);
-      } else {
-        const float sx0 = s0 * x, sx1 = s1 * x;
-        ta0 += s0; tb0 += sx0; ta1 += s1; tb1 += sx1;
-        if (x >= xb) { ha0 += s0; hb0 += sx0; ha1 += s1; hb1 += sx1; }
-      }
+    for (int e = 0; e < 8; e += 4) {
+      float4 t = lds_f32x4(ra + e * 4);
+      sq[e] = t.x; sq[e + 1] = t.y; sq[e + 2] = t.z; sq[e + 3] = t.w;
+      t = lds_f32x4(ra + 128 + e * 4);
+      l0[e] = t.x; l0[e + 1] = t.y; l0[e + 2] = t.z; l0[e + 3] = t.w;
+      t = lds_f32x4(ra + 256 + e * 4);
+      l1[e] = t.x; l1[e + 1] = t.y; l1[e + 2] = t.z; l1[e + 3] = t.w;
+      t = lds_f32x4(ra + 384 + e * 4);
+      d0[e] = t.x; d0[e + 1] = t.y; d0[e + 2] = t.z; d0[e + 3] = t.w;
+      t = lds_f32x4(ra + 512 + e * 4);
+      d1[e] = t.x; d1[e + 1] = t.y; d1[e + 2] = t.z; d1[e + 3] = t.w;
     }
-    wp0[e >> 1] = pack_f16(pp0[0], pp0[1]);
-    wp1[e >> 1] = pack_f16(pp1[0], pp1[1]);
-    ws0[e >> 1] = pack_f16(dd0[0], dd0[1]);
-    ws1[e >> 1] = pack_f16(dd1[0], dd1[1]);
+    tmem_ld_fence();
+    reg_fence(a); reg_fence(bq); reg_fence(pa); reg_fence(pb);
+    uint32_t wp0[4], wp1[4], ws0[4], ws1[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      float pp0[2], pp1[2], dd0[2], dd1[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float pr = sq[e + u] - g_j;
+        const float qa = fabsf(pr) + 1.0f;
+        const float x = copysignf(__log2f(qa), pr);
+        int cell, seg = 0;
+        const float4 t = lookup2<kExact, kExact>(L, x, cell, seg);
+        float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - l0[e + u]);
+        float p1 = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - l1[e + u]);
+        float s0 = p0 * (__uint_as_float(pa[e + u]) - d0[e + u]);
+        float s1 = p1 * (__uint_as_float(pb[e + u]) - d1[e + u]);
+        if (kKeyMasked && !key_valid) { p0 = 0.f; p1 = 0.f; s0 = 0.f; s1 = 0.f; }
+        pp0[u] = p0; pp1[u] = p1; dd0[u] = s0; dd1[u] = s1;
+        // d bias / d g_j = -a / (|p| + 1)
+        dgacc = fmaf(fmaf(s0, t.x, s1 * t.z), -rcp_approx(qa), dgacc);
+        if (kExact) {
+          if (seg != run.seg) { seg_flush(ssum, run); run.seg = seg; }
+          run.a0 += s0; run.b0 = fmaf(s0, x, run.b0); run.a1 += s1; run.b1 = fmaf(s1, x, run.b1);
+        } else {
+          ta0 += s0; tb0 = fmaf(s0, x, tb0); ta1 += s1; tb1 = fmaf(s1, x, tb1);
+          if (x >= xb) { ha0 += s0; hb0 = fmaf(s0, x, hb0); ha1 += s1; hb1 = fmaf(s1, x, hb1); }
+        }
+      }
+      wp0[e >> 1] = pack_f16(pp0[0], pp0[1]);
+      wp1[e >> 1] = pack_f16(pp1[0], pp1[1]);
+      ws0[e >> 1] = pack_f16(dd0[0], dd0[1]);
+      ws1[e >> 1] = pack_f16(dd1[0], dd1[1]);
+    }
+    tmem_st4(tS + c * 4, wp0);
+    tmem_st4(tS + 32 + c * 4, wp1);
+    tmem_st4(tS + 64 + c * 4, ws0);
+    tmem_st4(tS + 96 + c * 4, ws1);
   }
-  tmem_st8(tS, wp0);
-  tmem_st8(tS + 32, wp1);
-  tmem_st8(tS + 64, ws0);
-  tmem_st8(tS + 96, ws1);
   if (!kExact) {
     if (seg_first != run.seg) { seg_flush(ssum, run); run.seg = seg_first; }
     run.a0 += ta0 - ha0; run.b0 += tb0 - hb0; run.a1 += ta1 - ha1; run.b1 += tb1 - hb1;
