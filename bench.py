@@ -188,7 +188,6 @@ def main():
     net.to(dev).train()
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=0.01, fused=True)
-    flat_sizes = [p.numel() for p in params]
 
     # a rotating set of distinct bags per rank (bf16, [1, N, 1024] = 33.5 MB each): > L2 in total
     nb = max(2, args.bags_resident)
@@ -201,13 +200,12 @@ def main():
         dev_bags.append({k: v.to(dev) for k, v in hb.items()})
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_bags[0].values())
 
+    from dml_b200.parallel import FlatGradAllReducer
+    reducer = FlatGradAllReducer(params, static_presence=True) if world > 1 else None
+
     def allreduce_grads():
-        if world == 1:
-            return
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG)           # one flat NCCL all-reduce (C2/C3)
-        for p, g in zip(params, flat.split(flat_sizes)):
-            p.grad = g.view_as(p)
+        if reducer is not None:
+            reducer.allreduce()                                # one flat NCCL all-reduce (replaces C2/C3)
 
     def step(bag):
         out = net(x_path=bag["x_path"], x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
@@ -303,9 +301,10 @@ def main():
     fl = attn_flops(n, n_kv)
     # dominant entry point: the attention backward (3 kernels: prep + dK/dV/dg/segsums + dQ), then the forward
     top = max(kavg, key=lambda k: kavg[k] * kcalls[k])
-    exec_fwd = fl["qk"] + fl["pv"]                                   # tensor-core FLOPs the fused kernels execute
+    exec_fwd = fl["qk"] + 2.0 * fl["pv"]                             # S = QK^T, O += P_hi V, O += P_lo V  (tcgen05 MMAs issued)
     exec_bwd = 7.0 * fl["qk"]                                        # S^T,dP^T,dV,dK (4) + S,dP,dQ (3) GEMMs of n x n_kv x 64
-    exec_fl = {"dml_deform_attn_fwd": exec_fwd, "dml_deform_attn_bwd": exec_bwd}.get(top)
+    exec_fl = {"dml_deform_attn_fwd": fl["qk"] + fl["pv"], "dml_deform_attn_bwd": exec_bwd,
+               "dml_deform_attn_fwd_tc": exec_fwd, "dml_deform_attn_bwd_tc": exec_bwd}.get(top)
     roof = None
     if exec_fl:
         ach = exec_fl / (kavg[top] * 1e-3) / 1e12
@@ -313,9 +312,10 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_kind + " (sustained)",
                 "ms_per_launch": kavg[top],
-                "note": "achieved = tensor-core FLOPs actually required once the CPB MLP is evaluated through its exact "
-                        "piecewise-linear table (QK^T/PV-class GEMMs only); dense_math_* = the reference's dense maths "
-                        "(CPB 32x32 layer included) for the same launch",
+                "note": "achieved = tcgen05 MMA FLOPs the launch issues (QK^T/PV-class GEMMs; the CPB bias MLP is evaluated "
+                        "through its exact piecewise-linear table on the CUDA cores, which is what bounds the kernel: see "
+                        "DESIGN.md); dense_math_* = the reference's dense maths (CPB 32x32 layer included, SURVEY 8d) "
+                        "for the same launch and the time the measured bf16 peak would need for it",
                 "dense_math_tflop": dense / 1e12,
                 "dense_math_roofline_ms": dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3,
                 "time_vs_dense_math_roofline": kavg[top] / (dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3)}
@@ -330,8 +330,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"DeformPathomicNet(attn_dim=1) {TASK}: 2 DeformCrossTransMIL towers, 1 bag x {N} patches x "
+                "dtype": "fp16", "data": "synthetic",
+                "config": {"precision": "bf16 bags; attention MMAs fp16 operands (P as an fp16 hi+lo pair), fp32 accumulate and "
+                                        "fp32 softmax/bias/outputs; projections fp32/TF32 library GEMMs",
+                           "workload": f"DeformPathomicNet(attn_dim=1) {TASK}: 2 DeformCrossTransMIL towers, 1 bag x {N} patches x "
                                        f"1024 bf16 feats per GPU per step (n={n} tokens, n_kv={n_kv})",
                            "step": "fwd + weighted-CE + bwd" + (" + flat NCCL grad all-reduce" if world > 1 else "") + " + fused AdamW",
                            "parallelism": f"bag-sharded dp{world}", "l2": f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"},

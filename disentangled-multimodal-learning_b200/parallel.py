@@ -1,0 +1,94 @@
+"""Bag-sharded data parallelism of the hot path: one process per GPU, bags (patients /
+slides) are independent units, no data-path collective; one exchange step per iteration.
+
+Replaces, for this path, the reference's DistributedSampler partition (main.py:110-118, 326-341), DDP's bucketed
+gradient all-reduce (main.py:190,401) and the per-parameter all-reduce loop of the trainers
+(train_test.py:223-227 and siblings: ~100 NCCL calls per step) by ONE flat fp32 all-reduce.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bags(num_bags: int, rank: int, world: int, *, epoch: int = 0, seed: int = 0, shuffle: bool = True,
+               drop_last: bool = True) -> List[int]:
+    """Indices of the bags this rank processes in `epoch`: the same partition as
+    torch.utils.data.DistributedSampler(shuffle, seed) + DataLoader(drop_last) - a seeded permutation dealt
+    round-robin, every rank the same count."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        order = torch.randperm(num_bags, generator=g).tolist()
+    else:
+        order = list(range(num_bags))
+    if drop_last:
+        order = order[: (num_bags // world) * world]
+    else:
+        pad = (-len(order)) % world
+        order = order + order[:pad]
+    return order[rank::world]
+
+
+def balance_bags_by_cost(lengths: Sequence[int], world: int) -> List[List[int]]:
+    """Longest-processing-time assignment of variable-length bags to ranks (cost ~ N^2 for the deformable
+    attention): returns, per rank, the bag indices of one step."""
+    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
+    load = [0.0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: load[k])
+        out[r].append(i)
+        load[r] += float(lengths[i]) ** 2
+    return out
+
+
+class FlatGradAllReducer:
+    """Averages the gradients of `params` across ranks with a single collective on one flat fp32 buffer.
+    Parameters without a gradient on this rank (the never-used attn2d.* / pooler.* weights, quirk Q7) contribute
+    zeros, so every rank reduces the same layout; parameters that have no gradient on ANY rank keep grad = None
+    (checked with the same collective: a presence flag per parameter rides at the end of the buffer)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], static_presence: bool = False):
+        """static_presence: the set of parameters that receive gradients does not change from step to step (true
+        for a fixed model/mode): it is read back from the device once, later steps stay free of host syncs."""
+        self.static_presence = static_presence
+        self._present = None
+        self.params = [p for p in params if p.requires_grad]
+        self.sizes = [p.numel() for p in self.params]
+        self.total = sum(self.sizes)
+        p0 = self.params[0]
+        self.flat = torch.zeros(self.total + len(self.params), dtype=torch.float32, device=p0.device)
+
+    def allreduce(self, group=None) -> None:
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        world = dist.get_world_size(group)
+        flat = self.flat
+        flat.zero_()
+        views = flat[: self.total].split(self.sizes)
+        flags = flat[self.total:]
+        for i, (p, v) in enumerate(zip(self.params, views)):
+            if p.grad is not None:
+                v.copy_(p.grad.reshape(-1))
+                flags[i] = 1.0
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat[: self.total].div_(world)
+        if self.static_presence and self._present is not None:
+            present = self._present
+        else:
+            present = self._present = (flags > 0).tolist()
+        for p, v, has in zip(self.params, views, present):
+            if not has:
+                p.grad = None
+            elif p.grad is None:
+                p.grad = v.view_as(p).clone()
+            else:
+                p.grad.copy_(v.view_as(p))
+
+
+def allreduce_grads_flat(params: Iterable[torch.nn.Parameter], group=None) -> None:
+    """One-shot form of FlatGradAllReducer (allocates the flat buffer on each call)."""
+    FlatGradAllReducer(params).allreduce(group)
