@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
     ap.add_argument("--cpu-sample", type=int, default=0, help="bag size of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--bags-resident", type=int, default=6, help="distinct bags rotated through (input set > L2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -200,21 +201,36 @@ def main():
         dev_bags.append({k: v.to(dev) for k, v in hb.items()})
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_bags[0].values())
 
-    from dml_b200.parallel import FlatGradAllReducer
-    reducer = FlatGradAllReducer(params, static_presence=True) if world > 1 else None
+    from dml_b200.graph import GraphedTrainStep
+    model_keys = ("x_path", "x_omic_tumor", "x_omic_immune")
 
-    def allreduce_grads():
-        if reducer is not None:
-            reducer.allreduce()                                # one flat NCCL all-reduce (replaces C2/C3)
+    zero_fn = [lambda: opt.zero_grad(set_to_none=True)]
 
-    def step(bag):
-        out = net(x_path=bag["x_path"], x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
+    def eager_step(bag):                       # the same step, launched op by op (used for kernel counting / timing)
+        out = net(**{k: bag[k] for k in model_keys})
         loss = bag_loss(out[3], bag["label"], TASK)
-        opt.zero_grad(set_to_none=True)
+        zero_fn[0]()
         loss.backward()
-        allreduce_grads()
-        opt.step()
         return loss
+
+    use_graph = not args.no_graph
+    if use_graph:
+        # forward + loss + backward captured once in a CUDA graph (gradients accumulate into one flat buffer), then per
+        # step: copy the bag into the graph's static inputs, replay, flat NCCL all-reduce (N > 1), fused AdamW
+        gstep = GraphedTrainStep(net, lambda out, b: bag_loss(out[3], b["label"], TASK), dev_bags[0], optimizer=opt,
+                                 model_keys=model_keys, warmup=3)
+        step = gstep
+        zero_fn[0] = gstep.reducer.zero_grad   # gradients live in the flat buffer the graph writes: never detach them
+    else:
+        from dml_b200.parallel import FlatGradAllReducer
+        reducer = FlatGradAllReducer(params, static_presence=True) if world > 1 else None
+
+        def step(bag):
+            loss = eager_step(bag)
+            if reducer is not None:
+                reducer.allreduce()                            # one flat NCCL all-reduce (replaces C2/C3)
+            opt.step()
+            return loss
 
     def barrier():
         if world > 1:
@@ -238,37 +254,43 @@ def main():
         for s in range(steps):
             step(dev_bags[s % nb])
 
-    resident(args.warmup)
     launches0 = _lib.launch_count
+    eager_step(dev_bags[0])                                    # kernels of libdml_b200.so per step (same set the graph replays)
+    launches_per_step = _lib.launch_count - launches0
+    resident(args.warmup)
     with Clocks(local_rank) as clk:
         ms = timed(resident, args.steps)
-    launches = _lib.launch_count - launches0
+    launches = launches_per_step * args.steps
     value = world * args.steps / (ms / 1000.0)
 
     # ---- end-to-end arm: host (pinned) bags -> H2D on a copy stream (double-buffered) -> step -> D2H loss ----
     copy_stream = torch.cuda.Stream(device=dev)
     losses_host = torch.zeros(max(args.steps, args.warmup), dtype=torch.float32).pin_memory()
 
+    staged = [{k: torch.empty_like(v, device=dev) for k, v in host_bags[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e(steps):
         cur = torch.cuda.current_stream()
-        staged = [None, None]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in consumed:
+            ev.record(cur)
 
-        def stage(slot, s):
+        def stage(slot, s):                      # pinned host bag -> persistent device staging slot, on the copy stream
             with torch.cuda.stream(copy_stream):
-                staged[slot] = {k: v.to(dev, non_blocking=True) for k, v in host_bags[s % nb].items()}
+                copy_stream.wait_event(consumed[slot])
+                for k, v in host_bags[s % nb].items():
+                    staged[slot][k].copy_(v, non_blocking=True)
                 ready[slot].record(copy_stream)
 
         stage(0, 0)
         for s in range(steps):
             slot = s & 1
             if s + 1 < steps:
-                copy_stream.wait_stream(cur) if s > 0 else None
-                stage(slot ^ 1, s + 1)
+                stage(slot ^ 1, s + 1)           # overlaps the H2D copy of the next bag with this step
             cur.wait_event(ready[slot])
             loss = step(staged[slot])
-            for v in staged[slot].values():
-                v.record_stream(cur)
+            consumed[slot].record(cur)
             losses_host[s].copy_(loss.detach(), non_blocking=True)
         cur.synchronize()
 
@@ -286,7 +308,8 @@ def main():
 
     _lib._timing_hook = hook
     prof_steps = 3
-    resident(prof_steps)
+    for s_ in range(prof_steps):                               # eager launches: CUDA events around each entry point
+        eager_step(dev_bags[s_ % nb])
     torch.cuda.synchronize()
     _lib._timing_hook = None
     ktime = {}
@@ -335,7 +358,8 @@ def main():
                                         "fp32 softmax/bias/outputs; projections fp32/TF32 library GEMMs",
                            "workload": f"DeformPathomicNet(attn_dim=1) {TASK}: 2 DeformCrossTransMIL towers, 1 bag x {N} patches x "
                                        f"1024 bf16 feats per GPU per step (n={n} tokens, n_kv={n_kv})",
-                           "step": "fwd + weighted-CE + bwd" + (" + flat NCCL grad all-reduce" if world > 1 else "") + " + fused AdamW",
+                           "step": ("CUDA-graph replay of " if use_graph else "") + "fwd + weighted-CE + bwd" +
+                                   (" + flat NCCL grad all-reduce" if world > 1 else "") + " + fused AdamW",
                            "parallelism": f"bag-sharded dp{world}", "l2": f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"},
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -110,13 +110,25 @@ def nll_loss(hazards, S, Y, c, alpha=0.4, eps=1e-7):
     return ((1 - alpha) * neg_l + alpha * uncensored).mean()
 
 
+_CE_WEIGHT_CACHE = {}
+
+
+def _ce_weight(values, device):
+    """Class weights as a device tensor, created once per device (a host->device copy of a fresh tensor is not
+    allowed while a CUDA graph is being captured)."""
+    key = (values, str(device))
+    if key not in _CE_WEIGHT_CACHE:
+        _CE_WEIGHT_CACHE[key] = torch.tensor(values, device=device)
+    return _CE_WEIGHT_CACHE[key]
+
+
 def bag_loss(logits, label, task_type, censor=None):
     """The loss trainDeformPathomicModel back-propagates (train_test.py:826-853): fused head only."""
     hz = logits[2]
     if task_type == "diag2021":
-        return F.cross_entropy(hz, label, weight=torch.tensor(DIAG2021_CE_WEIGHTS, device=hz.device))
+        return F.cross_entropy(hz, label, weight=_ce_weight(DIAG2021_CE_WEIGHTS, hz.device))
     if task_type == "grade":
-        return F.cross_entropy(hz, label, weight=torch.tensor(GRADE_CE_WEIGHTS, device=hz.device))
+        return F.cross_entropy(hz, label, weight=_ce_weight(GRADE_CE_WEIGHTS, hz.device))
     if task_type == "survival":
         S = torch.cumprod(1 - hz, dim=1)
         return nll_loss(hz, S, label, censor, alpha=0)

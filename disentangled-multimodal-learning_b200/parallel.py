@@ -62,11 +62,32 @@ class FlatGradAllReducer:
         p0 = self.params[0]
         self.flat = torch.zeros(self.total + len(self.params), dtype=torch.float32, device=p0.device)
 
+    # ---- attached mode: parameters accumulate their gradients directly into views of the flat buffer ----
+    def attach(self) -> None:
+        """Call after one backward pass: parameters that received a gradient get p.grad = a view of the flat buffer
+        (autograd accumulates in place from then on), the others keep grad = None.  Afterwards use zero_grad() instead
+        of optimizer.zero_grad(); allreduce() is then a single collective with no copies."""
+        views = self.flat[: self.total].split(self.sizes)
+        self._present = [p.grad is not None for p in self.params]
+        for p, v, has in zip(self.params, views, self._present):
+            if has:
+                v.copy_(p.grad.reshape(-1))
+                p.grad = v.view_as(p)
+        self.flat[self.total:] = torch.tensor([1.0 if h else 0.0 for h in self._present], device=self.flat.device)
+        self.attached = True
+
+    def zero_grad(self) -> None:
+        self.flat[: self.total].zero_()
+
     def allreduce(self, group=None) -> None:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         world = dist.get_world_size(group)
         flat = self.flat
+        if getattr(self, "attached", False):
+            dist.all_reduce(flat[: self.total], op=dist.ReduceOp.SUM, group=group)
+            flat[: self.total].div_(world)
+            return
         flat.zero_()
         views = flat[: self.total].split(self.sizes)
         flags = flat[self.total:]
