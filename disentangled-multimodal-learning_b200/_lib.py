@@ -35,6 +35,7 @@ SIGNATURES = {
     "dml_deform_attn_fwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 11 + [_f, _vp, _fp, _vp]),
     "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
     "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp]),
+    "dml_debug_set_trace": (_i, [_vp]),
     "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_softmax_rows_fwd": (_i, [_fp, _fp, _ll, _i, _vp]),

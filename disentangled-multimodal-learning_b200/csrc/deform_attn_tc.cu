@@ -38,7 +38,7 @@ constexpr int kBM = 128;          // query rows per softmax group (= TMEM lanes)
 constexpr int kGroups = 2;        // softmax groups per CTA
 constexpr int kBN = 64;           // keys per tile
 constexpr int kStages = 3;
-constexpr int kThreads = 32 * 10;
+constexpr int kThreads = 32 * 11;   // 8 softmax warps, TMA producer, one MMA-issuing warp per group
 constexpr uint32_t kTileQ = kBM * kD * 2;   // 16384 B
 constexpr uint32_t kTileKV = kBN * kD * 2;  // 8192 B
 constexpr uint32_t kStageBytes = 4 * kTileKV;
@@ -117,7 +117,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int i0 = blockIdx.x * (kGroups * kBM), grp = blockIdx.y, b = blockIdx.z;
   const int G = p.H / 2;
   const int ntiles = cdiv(p.n_kv, kBN);
@@ -127,7 +127,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   // ---- one-time setup ----
   if (tid == 0) {
     mbar_init(bar(kBarQ), 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), kGroups); }
     for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -174,51 +174,49 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       if (lane == 0) { gs[64] = gmn; gs[65] = gmx; }
       mbar_arrive(bar(kBarKvFull + st));                     // 32 arrivals (release) + the TMA bytes complete the phase
     }
-  } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      mbar_wait(bar(kBarQ), 0);
-      auto issue_s = [&](int j, int g) {
-        const int st = j % kStages;
-        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
-        for (int h = 0; h < 2; ++h) {
-          const uint64_t da = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), db = smem_desc(kv + h * kTileKV);
-          const uint32_t d = tmem + g * 256 + h * 64;
+  } else if (warp >= 9) {
+    // =========================== MMA issuers: warp 9 -> group 0, warp 10 -> group 1 ===========================
+    // All 32 lanes run the loop (uniform operands); one elected lane executes each tcgen05 instruction.
+    const int g = warp - 9;
+    const bool leader = elect_one();
+    mbar_wait(bar(kBarQ), 0);
+    auto issue_s = [&](int j) {
+      const int st = j % kStages;
+      const uint32_t kv = sbase + kOffKV + st * kStageBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(d, da + 2 * k, db + 2 * k, kIdescS, k > 0);
-        }
-        tc_commit(bar(kBarSFull + g));
-      };
-      mbar_wait(bar(kBarKvFull + 0), 0);
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t da = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), db = smem_desc(kv + h * kTileKV);
+        const uint32_t d = tmem + g * 256 + h * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(d, da + 2 * k, db + 2 * k, kIdescS, k > 0, leader);
+      }
+      tc_commit(bar(kBarSFull + g), leader);
+    };
+    mbar_wait(bar(kBarKvFull + 0), 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kStages;
+      const uint32_t kv = sbase + kOffKV + st * kStageBytes;
+      mbar_wait(bar(kBarPFull + g), j & 1);
       tc_fence_after();
-      issue_s(0, 0);
-      issue_s(0, 1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % kStages;
-        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
-        for (int g = 0; g < kGroups; ++g) {
-          mbar_wait(bar(kBarPFull + g), j & 1);
-          tc_fence_after();
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t db = smem_desc(kv + (2 + h) * kTileKV);
-            const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 64;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              mma_ts(d, a + 16 * k, db + 128 * k, kIdescPV, (j > 0) || (k > 0));       // P_hi chunk k
-              mma_ts(d, a + 16 * k + 8, db + 128 * k, kIdescPV, 1);                    // P_lo chunk k
-            }
-          }
-          if (g == kGroups - 1) tc_commit(bar(kBarKvEmpty + st));    // stage free once every MMA reading it is done
-          if (j + 1 < ntiles) {
-            if (g == 0) {
-              mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
-              tc_fence_after();
-            }
-            issue_s(j + 1, g);
-          } else {
-            tc_commit(bar(kBarSFull + g));   // final: O complete
-          }
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t db = smem_desc(kv + (2 + h) * kTileKV);
+        const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 64;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          mma_ts(d, a + 16 * k, db + 128 * k, kIdescPV, (j > 0) || (k > 0), leader);       // P_hi chunk k
+          mma_ts(d, a + 16 * k + 8, db + 128 * k, kIdescPV, 1, leader);                    // P_lo chunk k
         }
+      }
+      tc_commit(bar(kBarKvEmpty + st), leader);        // this group's share: the stage is free once both groups' MMAs are done
+      if (j + 1 < ntiles) {
+        mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
+        tc_fence_after();
+        issue_s(j + 1);
+      } else {
+        tc_commit(bar(kBarSFull + g), leader);         // final: O complete
       }
     }
   } else {

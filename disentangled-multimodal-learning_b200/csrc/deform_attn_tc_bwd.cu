@@ -40,7 +40,9 @@ struct BwdParams {
   float* segsum;         // [kCpbSegMax][4] accumulated (zeroed by the host wrapper)
   int B, H, n, n_kv, n_seq;
   float scale;
+  long long* trace;      // debug: per-tile clock64() stamps of CTA (0,0,0) of the dQ kernel (nullptr = off)
 };
+static long long* g_trace = nullptr;
 
 // D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (O fp32 as written by the forward, dO the fp16 tensor the MMAs consume)
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ o, const h16* __restrict__ d_o, int B, int n,
@@ -75,7 +77,9 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__
 // dQ kernel
 // =================================================================================================================
 namespace dqk {
-constexpr int kBM = 128, kGroups = 2, kBN = 32, kStages = 3, kThreads = 320;
+constexpr int kBM = 128, kGroups = 2, kBN = 32, kStages = 3;
+constexpr int kEwWarps = 16;                      // 8 per group: 4 lane quarters x 2 key halves of each 32-key tile
+constexpr int kThreads = 32 * (kEwWarps + 3);    // + TMA producer + one MMA-issuing warp per group
 constexpr uint32_t kTileQ = kBM * kD * 2;       // 16 KB
 constexpr uint32_t kTileKV = kBN * kD * 2;      // 4 KB
 constexpr uint32_t kStageBytes = 4 * kTileKV;   // K0 K1 V0 V1
@@ -96,28 +100,29 @@ constexpr uint32_t kIdescSD = idesc_f16(128, kBN, false, false);   // S = Q K^T,
 constexpr uint32_t kIdescDQ = idesc_f16(128, 64, false, true);     // dQ += dS K   (K MN-major)
 }  // namespace dqk
 
-// one 32-key tile of one query row, both heads: dS = P (dP - D) as fp16 pairs over the S columns
+// 16 keys (one half of a 32-key tile) of one query row, both heads: dS = P (dP - D) as fp16 pairs written over the
+// first 8 of the 16 S columns the warp owns.  tS = TMEM address of the warp's first S column, gsa = its first g.
 template <bool kMasked, bool kDirty>
-__device__ __forceinline__ void dq_sweep(const Lookup& L, uint32_t tbase, uint32_t gsa, float s_i, float sc2, float lse0,
+__device__ __forceinline__ void dq_sweep(const Lookup& L, uint32_t tS, uint32_t gsa, float s_i, float sc2, float lse0,
                                          float lse1, float d0, float d1, int jrem) {
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
-    uint32_t a[16], bq[16], pa[16], pb[16];
-    tmem_ld16(tbase + c * 16, a);
-    tmem_ld16(tbase + 32 + c * 16, bq);
-    tmem_ld16(tbase + 64 + c * 16, pa);
-    tmem_ld16(tbase + 96 + c * 16, pb);
-    float gq[16];
+    uint32_t a[8], bq[8], pa[8], pb[8];
+    tmem_ld8(tS + c * 8, a);
+    tmem_ld8(tS + 32 + c * 8, bq);
+    tmem_ld8(tS + 64 + c * 8, pa);
+    tmem_ld8(tS + 96 + c * 8, pb);
+    float gq[8];
 #pragma unroll
-    for (int e = 0; e < 16; e += 4) {
-      const float4 t = lds_f32x4(gsa + (uint32_t)(c * 16 + e) * 4);
+    for (int e = 0; e < 8; e += 4) {
+      const float4 t = lds_f32x4(gsa + (uint32_t)(c * 8 + e) * 4);
       gq[e] = t.x; gq[e + 1] = t.y; gq[e + 2] = t.z; gq[e + 3] = t.w;
     }
     tmem_ld_fence();
     reg_fence(a); reg_fence(bq); reg_fence(pa); reg_fence(pb);
-    uint32_t w0[8], w1[8];
+    uint32_t w0[4], w1[4];
 #pragma unroll
-    for (int e = 0; e < 16; e += 2) {
+    for (int e = 0; e < 8; e += 2) {
       float v0[2], v1[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -128,13 +133,13 @@ __device__ __forceinline__ void dq_sweep(const Lookup& L, uint32_t tbase, uint32
         const float p1 = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - lse1);
         v0[u] = p0 * (__uint_as_float(pa[e + u]) - d0);
         v1[u] = p1 * (__uint_as_float(pb[e + u]) - d1);
-        if (kMasked && c * 16 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
+        if (kMasked && c * 8 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
       }
       w0[e >> 1] = pack_f16(v0[0], v0[1]);
       w1[e >> 1] = pack_f16(v1[0], v1[1]);
     }
-    tmem_st8(tbase + c * 8, w0);
-    tmem_st8(tbase + 32 + c * 8, w1);
+    tmem_st4(tS + c * 4, w0);
+    tmem_st4(tS + 32 + c * 4, w1);
   }
 }
 
@@ -146,7 +151,7 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int i0 = blockIdx.x * (kGroups * kBM), grp = blockIdx.y, b = blockIdx.z;
   const int G = p.H / 2;
   const int ntiles = cdiv(p.n_kv, kBN);
@@ -155,11 +160,11 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
 
   if (tid == 0) {
     mbar_init(bar(kBarQ), 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), 1); }
-    for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), kGroups); }
+    for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), 2 * kBM); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == kEwWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -171,7 +176,7 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kEwWarps) {
     // ---- TMA producer ----
     if (lane == 0) {
       mbar_expect_tx(bar(kBarQ), 2 * kGroups * 2 * kTileQ);
@@ -201,56 +206,57 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
       if (lane == 0) { gs[32] = gmn; gs[33] = gmx; }
       mbar_arrive(bar(kBarKvFull + st));
     }
-  } else if (warp == 9) {
-    // ---- MMA issuer ----
-    if (lane == 0) {
-      mbar_wait(bar(kBarQ), 0);
-      auto issue_sd = [&](int j, int g) {
-        const int st = j % kStages;
-        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
-        for (int h = 0; h < 2; ++h) {
-          const uint64_t dq_ = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), dk_ = smem_desc(kv + h * kTileKV);
-          const uint64_t dd_ = smem_desc(sbase + kOffDO + (g * 2 + h) * kTileQ), dv_ = smem_desc(kv + (2 + h) * kTileKV);
-          const uint32_t ds = tmem + g * 256 + h * 32, dp = tmem + g * 256 + 64 + h * 32;
+  } else if (warp > kEwWarps) {
+    // ---- MMA issuers: warp kEwWarps+1 -> group 0, kEwWarps+2 -> group 1 (all lanes run the loop, one elected lane issues) ----
+    const int g = warp - (kEwWarps + 1);
+    const bool leader = elect_one();
+    mbar_wait(bar(kBarQ), 0);
+    auto issue_sd = [&](int j) {
+      const int st = j % kStages;
+      const uint32_t kv = sbase + kOffKV + st * kStageBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(ds, dq_ + 2 * k, dk_ + 2 * k, kIdescSD, k > 0);
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t dq_ = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), dk_ = smem_desc(kv + h * kTileKV);
+        const uint64_t dd_ = smem_desc(sbase + kOffDO + (g * 2 + h) * kTileQ), dv_ = smem_desc(kv + (2 + h) * kTileKV);
+        const uint32_t ds = tmem + g * 256 + h * 32, dp = tmem + g * 256 + 64 + h * 32;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(dp, dd_ + 2 * k, dv_ + 2 * k, kIdescSD, k > 0);
-        }
-        tc_commit(bar(kBarSFull + g));
-      };
-      mbar_wait(bar(kBarKvFull + 0), 0);
-      tc_fence_after();
-      issue_sd(0, 0);
-      issue_sd(0, 1);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % kStages;
-        const uint32_t kv = sbase + kOffKV + st * kStageBytes;
-        for (int g = 0; g < kGroups; ++g) {
-          mbar_wait(bar(kBarPFull + g), j & 1);
-          tc_fence_after();
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t db = smem_desc(kv + h * kTileKV);                       // K tile as [key][d]: MN-major B
-            const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 32;
+        for (int k = 0; k < 4; ++k) mma_ss(ds, dq_ + 2 * k, dk_ + 2 * k, kIdescSD, k > 0, leader);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) mma_ts(d, a + 8 * k, db + 128 * k, kIdescDQ, (j > 0) || (k > 0));
-          }
-          if (g == kGroups - 1) tc_commit(bar(kBarKvEmpty + st));
-          if (j + 1 < ntiles) {
-            if (g == 0) {
-              mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
-              tc_fence_after();
-            }
-            issue_sd(j + 1, g);
-          } else {
-            tc_commit(bar(kBarSFull + g));
-          }
-        }
+        for (int k = 0; k < 4; ++k) mma_ss(dp, dd_ + 2 * k, dv_ + 2 * k, kIdescSD, k > 0, leader);
       }
+      tc_commit(bar(kBarSFull + g), leader);
+    };
+    mbar_wait(bar(kBarKvFull + 0), 0);
+    tc_fence_after();
+    issue_sd(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j % kStages;
+      const uint32_t kv = sbase + kOffKV + st * kStageBytes;
+      mbar_wait(bar(kBarPFull + g), j & 1);
+      tc_fence_after();
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+      if (tr) p.trace[(j * 2 + g) * 4 + 2] = clock64();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t db = smem_desc(kv + h * kTileKV);                       // K tile as [key][d]: MN-major B
+        const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 32;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) mma_ts(d, a + 16 * k, db + 128 * k, kIdescDQ, (j > 0) || (k > 0), leader);   // dS of keys 16k.. sits in columns 16k..16k+7
+      }
+      tc_commit(bar(kBarKvEmpty + st), leader);
+      if (j + 1 < ntiles) {
+        mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
+        tc_fence_after();
+        issue_sd(j + 1);
+      } else {
+        tc_commit(bar(kBarSFull + g), leader);
+      }
+      if (tr) p.trace[(j * 2 + g) * 4 + 3] = clock64();
     }
   } else {
-    // ---- elementwise groups ----
-    const int g = warp >> 2;
+    // ---- elementwise warps: group = warp / 8, TMEM lane quarter = warp & 3, key half of every tile = (warp >> 2) & 1 ----
+    const int g = warp >> 3;
+    const int half = (warp >> 2) & 1;
     const int row = (warp & 3) * 32 + lane;
     const int gi = i0 + g * kBM + row;
     const bool rv = gi < p.n;
@@ -268,7 +274,9 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
       mbar_wait(bar(kBarKvFull + st), (j / kStages) & 1);
       mbar_wait(bar(kBarSFull + g), j & 1);
       tc_fence_after();
-      const int jrem = p.n_kv - j * kBN;
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 7) == 0 && lane == 0;
+      if (tr) p.trace[(j * 2 + g) * 4 + 0] = clock64();
+      const int jrem = p.n_kv - j * kBN - half * 16;            // valid keys in this warp's half of the tile (may be <= 0)
       int ndirty;
       {
         const float xlo = cpb_x(s_i - lds_f32(gsa + 33 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 32 * 4));
@@ -276,31 +284,34 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
         ndirty = tab_dirty_between(L, clo, chi);
       }
       const bool dirty = __any_sync(0xffffffffu, ndirty != 0);
-      if (jrem >= kBN) {
-        if (!dirty) dq_sweep<false, false>(L, tbase, gsa, s_i, sc2, lse0, lse1, d0, d1, jrem);
-        else dq_sweep<false, true>(L, tbase, gsa, s_i, sc2, lse0, lse1, d0, d1, jrem);
+      const uint32_t tS = tbase + half * 16, gh = gsa + half * 64;
+      if (jrem >= 16) {
+        if (!dirty) dq_sweep<false, false>(L, tS, gh, s_i, sc2, lse0, lse1, d0, d1, jrem);
+        else dq_sweep<false, true>(L, tS, gh, s_i, sc2, lse0, lse1, d0, d1, jrem);
       } else {
-        dq_sweep<true, true>(L, tbase, gsa, s_i, sc2, lse0, lse1, d0, d1, jrem);
+        dq_sweep<true, true>(L, tS, gh, s_i, sc2, lse0, lse1, d0, d1, jrem);
       }
+      if (tr) p.trace[(j * 2 + g) * 4 + 1] = clock64();
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(kBarPFull + g));
     }
 
-    // ---- epilogue: dQ / s -> global ----
+    // ---- epilogue: dQ / s -> global (this warp: 32 of the 64 columns of each head) ----
     mbar_wait(bar(kBarSFull + g), ntiles & 1);
     tc_fence_after();
     const float inv_s = __ldg(p.dscale + 1);
     float* ob = p.dq + ((size_t)b * p.n + gi) * (p.H * kD) + h0 * kD;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
+      const int col = (c >> 1) * 64 + half * 32 + (c & 1) * 16;     // head c>>1, columns half*32 + (c&1)*16 ..
       uint32_t a[16];
-      tmem_ld16(tbase + 128 + c * 16, a);
+      tmem_ld16(tbase + 128 + col, a);
       tmem_ld_wait(a);
       if (rv) {
 #pragma unroll
         for (int e = 0; e < 16; e += 4)
-          *reinterpret_cast<float4*>(ob + c * 16 + e) =
+          *reinterpret_cast<float4*>(ob + col + e) =
               make_float4(__uint_as_float(a[e]) * inv_s, __uint_as_float(a[e + 1]) * inv_s,
                           __uint_as_float(a[e + 2]) * inv_s, __uint_as_float(a[e + 3]) * inv_s);
       }
@@ -309,7 +320,7 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kEwWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
@@ -443,7 +454,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
   const int j0 = blockIdx.x * kBK, grp = blockIdx.y, b = blockIdx.z;
   const int G = p.H / 2, h0 = grp * 2;
   const int ntiles = cdiv(p.n, kBI);
@@ -505,8 +516,9 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       mbar_arrive(bar(kBarInFull + st));
     }
   } else if (warp == 9) {
-    // ---- MMA issuer ----
-    if (lane == 0) {
+    // ---- MMA issuer (all lanes run the loop under uniform control flow, one elected lane issues) ----
+    {
+      const bool leader = elect_one();
       mbar_wait(bar(kBarKv), 0);
       auto issue_sd = [&](int t) {
         const int st = t % kStages, buf = t & 1;
@@ -516,11 +528,11 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           const uint64_t dv_ = smem_desc(sbase + kOffKV + (2 + h) * kTileKV), dd_ = smem_desc(in + (2 + h) * kTileQ);
           const uint32_t ds = tmem + buf * 128 + h * 32, dp = tmem + buf * 128 + 64 + h * 32;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(ds, dk_ + 2 * k, dq_ + 2 * k, kIdescSD, k > 0);
+          for (int k = 0; k < 4; ++k) mma_ss(ds, dk_ + 2 * k, dq_ + 2 * k, kIdescSD, k > 0, leader);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_ss(dp, dv_ + 2 * k, dd_ + 2 * k, kIdescSD, k > 0);
+          for (int k = 0; k < 4; ++k) mma_ss(dp, dv_ + 2 * k, dd_ + 2 * k, kIdescSD, k > 0, leader);
         }
-        tc_commit(bar(kBarSFull + buf));
+        tc_commit(bar(kBarSFull + buf), leader);
       };
       mbar_wait(bar(kBarInFull + 0), 0);
       tc_fence_after();
@@ -540,13 +552,13 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           const uint32_t pT = tmem + buf * 128 + h * 32, sT = tmem + buf * 128 + 64 + h * 32;
           const uint32_t dV = tmem + 256 + h * 64, dK = tmem + 384 + h * 64;
 #pragma unroll
-          for (int k = 0; k < 2; ++k) mma_ts(dV, pT + 16 * k, dd_ + 128 * k, kIdescAcc, (t > 0) || (k > 0));
+          for (int k = 0; k < 2; ++k) mma_ts(dV, pT + 16 * k, dd_ + 128 * k, kIdescAcc, (t > 0) || (k > 0), leader);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) mma_ts(dK, sT + 16 * k, dq_ + 128 * k, kIdescAcc, (t > 0) || (k > 0));
+          for (int k = 0; k < 2; ++k) mma_ts(dK, sT + 16 * k, dq_ + 128 * k, kIdescAcc, (t > 0) || (k > 0), leader);
         }
-        tc_commit(bar(kBarInEmpty + st));
+        tc_commit(bar(kBarInEmpty + st), leader);
       }
-      tc_commit(bar(kBarAcc));
+      tc_commit(bar(kBarAcc), leader);
     }
   } else {
     // ---- elementwise warps: warp w -> TMEM lanes 32 (w & 3).., queries 16 (w >> 2).. of each 32-query tile ----
@@ -643,6 +655,12 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
 
 extern "C" {
 
+/* debug: device buffer of long long[4 * 2 * ntiles] that the next dQ launches fill with clock64() stamps (NULL = off) */
+int dml_debug_set_trace(void* buf) {
+  dml::tc::g_trace = (long long*)buf;
+  return 0;
+}
+
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
                            int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
@@ -683,6 +701,7 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   p.g = g; p.table = (const uint32_t*)table; p.lse = lse; p.dsum = dsum_ws; p.dscale = dscale;
   p.dq = dq; p.dk = dk; p.dv = dv; p.dg = dg; p.segsum = segsum;
   p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.n_seq = n_seq; p.scale = scale;
+  p.trace = dml::tc::g_trace;
   const int rows = B * n;
   bwd_prep_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>((const float*)out, (const h16*)d_out, B, n, H, ldo, dsum_ws);
   deform_attn_dkv_tc_kernel<<<dim3(cdiv(n_kv, dkvk::kBK), G, B), dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p);

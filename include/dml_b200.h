@@ -109,6 +109,10 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
                            const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
                            float* segsum, void* stream);
 
+/* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
+ * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
+int dml_debug_set_trace(void* buf);
+
 /* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
 /* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]
  * = mult * sum over l consecutive (padded) rows.                                                      */
