@@ -41,10 +41,12 @@ class DeformCrossTransLayer(nn.Module):
                                              offset_scale=4, offset_groups=8, offset_kernel_size=6)
         self.attn1d = DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6)
 
-    def forward(self, x1, x2, attn_dim, return_vgrid):
+    def forward(self, x1, x2, attn_dim, return_vgrid, rows=None):
         if attn_dim == 1:
             # one LayerNorm shared by both streams (reference :44,66)
-            x = self.attn1d(self.norm(x1).transpose(1, 2), self.norm(x2).transpose(1, 2))
+            x = self.attn1d(self.norm(x1).transpose(1, 2), self.norm(x2).transpose(1, 2), rows=rows)
+            if rows:
+                return x1[:, :rows] + x.transpose(1, 2)
             return x1 + x.transpose(1, 2)
         raise NotImplementedError("attn_dim == 2 is broken in the reference as shipped (SURVEY.md Q6) and "
                                   "DeformCrossAttention2D is not built yet (row N1)")
@@ -90,7 +92,11 @@ class DeformCrossTransMIL(nn.Module):
         cls_tokens = self.cls_token.expand(B, -1, -1).to(h.device)
         h = torch.cat((cls_tokens, h), dim=1)
         path = torch.cat((cls_tokens, path), dim=1)
-        h = self.layer3(h, path, 1, False)
+        # Only the cls row of the layer output is consumed (reference :128).  args.cls_row_only = True
+        # (an extension, off by default) asks the attention for that row alone: logits and every gradient are unchanged
+        # (the offsets, keys and values still see every token), the n x n_kv attention work drops to 1 x n_kv.
+        rows = 1 if getattr(self.args, "cls_row_only", False) else None
+        h = self.layer3(h, path, 1, False, rows=rows)
         h = self.norm(h[:, 0])                 # LayerNorm is per token: norm(h)[:, 0] == norm(h[:, 0])
         logits = self._fc2(h)
         encoded = self.multimodal_projection(h)

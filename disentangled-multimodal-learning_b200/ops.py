@@ -80,7 +80,7 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x1t, x2t, Wq, Wk, Wv, Wo, bo, w0, b0, w2, m_w1, m_b1, m_W2, m_b2, m_W3, m_b3, cfg):
-        H, d, G, stride, ks, offset_scale = cfg
+        H, d, G, stride, ks, offset_scale, rows = cfg
         B, n, dim = x1t.shape
         C = H * d
         Cg = C // G
@@ -88,6 +88,7 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         hid = m_w1.shape[0]
         scale = d ** -0.5
         dev = x1t.device
+        n_out = n if not rows else min(int(rows), n)      # leading query rows whose attention output is computed
         n_kv = kv_length(n, ks, stride)
         if n_kv < 1:
             raise _lib.DmlError(f"sequence of {n} tokens is too short for offset kernel {ks}/stride {stride}")
@@ -115,22 +116,25 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
         t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
         call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), st)
-        o = torch.empty(B, n, C, device=dev, dtype=F32)
-        lse = torch.empty(B, H, n, device=dev, dtype=F32)
-        call("dml_deform_attn_fwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n, n_kv, n, C, C, C, C, nout,
-             scale, ptr(o), ptr(lse), st)
+        # offsets / keys / values always need every query position; the attention itself only the first n_out rows
+        q_att = q if n_out == n else q[:, :n_out].contiguous()
+        o = torch.empty(B, n_out, C, device=dev, dtype=F32)
+        lse = torch.empty(B, H, n_out, device=dev, dtype=F32)
+        call("dml_deform_attn_fwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n_out, n_kv, n, C, C, C, C,
+             nout, scale, ptr(o), ptr(lse), st)
         with tf32_matmul():
             out = torch.matmul(o, Wo2.t()) + bo                           # to_out (:233)
 
         ctx.cfg = cfg
         ctx.taps = (i0, i1, wy0, wy1)
-        ctx.save_for_backward(x1f, x2f, q, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp)
+        ctx.save_for_backward(x1f, x2f, q, q_att, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp)
         return out, vgrid
 
     @staticmethod
     def backward(ctx, dout, dvgrid):
-        (x1f, x2f, q, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp) = ctx.saved_tensors
-        H, d, G, stride, ks, offset_scale = ctx.cfg
+        (x1f, x2f, q, q_att, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp) = ctx.saved_tensors
+        H, d, G, stride, ks, offset_scale, _rows = ctx.cfg
+        n_out = o.shape[1]
         i0, i1, wy0, wy1 = ctx.taps
         B, n, dim = x1f.shape
         C, Cg, nout, hid = H * d, (H * d) // G, H // G, mlp[0].shape[0]
@@ -148,15 +152,19 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dscale = grad_scale(d_o)
         d_o16 = (d_o * dscale[0]).to(F16)
 
-        dq_attn = torch.empty(B, n, C, device=dev, dtype=F32)
+        dq_attn = torch.empty(B, n_out, C, device=dev, dtype=F32)
         dk = torch.empty(B, n_kv, C, device=dev, dtype=F32)
         dv = torch.empty_like(dk)
         dg = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=dev, dtype=F32)
-        dsum = torch.empty(B, H, n, device=dev, dtype=F32)
-        call("dml_deform_attn_bwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
-             n, n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
+        dsum = torch.empty(B, H, n_out, device=dev, dtype=F32)
+        call("dml_deform_attn_bwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
+             n_out, n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
              ptr(segsum), st)
+        if n_out != n:                                 # the other query rows only receive the offset-path gradient
+            full = torch.zeros(B, n, C, device=dev, dtype=F32)
+            full[:, :n_out] = dq_attn
+            dq_attn = full
         mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
         call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), st)
 

@@ -76,6 +76,12 @@ class FlatGradAllReducer:
         self.flat[self.total:] = torch.tensor([1.0 if h else 0.0 for h in self._present], device=self.flat.device)
         self.attached = True
 
+    def attach_views(self) -> None:
+        """Re-point p.grad at this reducer's flat buffer (after another reducer / optimizer call replaced them)."""
+        views = self.flat[: self.total].split(self.sizes)
+        for p, v, has in zip(self.params, views, self._present):
+            p.grad = v.view_as(p) if has else None
+
     def zero_grad(self) -> None:
         self.flat[: self.total].zero_()
 

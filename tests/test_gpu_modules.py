@@ -195,3 +195,26 @@ def test_attention_rows_are_a_convex_combination_of_values_at_16k():
     vmin, vmax = v.float().amin(1, keepdim=True), v.float().amax(1, keepdim=True)
     assert bool(torch.isfinite(o.float()).all()) and bool(torch.isfinite(lse).all())
     assert bool((o.float() >= vmin - 2e-2).all()) and bool((o.float() <= vmax + 2e-2).all())
+
+
+def test_cls_row_only_path_is_exact_at_model_level():
+    """only attention row 0 reaches the logits.  With args.cls_row_only the model must give the same
+    logits, loss and parameter gradients as the all-rows module path (same kernels, 1 query row instead of n)."""
+    seed, N = 61, 700
+    outs = []
+    for flag in (False, True):
+        mod = load(define_net(Args(task_type="diag2021", cls_row_only=flag)), H.pathomic_shapes(), seed).eval()
+        bag = {k: v.to(DEV) for k, v in synth.synthetic_bag(N, seed, 2).items()}
+        feats, vt, vi, logits, *_ = mod(x_path=bag["x_path"], x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
+        loss = bag_loss(logits, bag["label_diag"], "diag2021")
+        names = [k for k, p in mod.named_parameters() if p.requires_grad]
+        gs = torch.autograd.grad(loss, [p for _, p in mod.named_parameters() if p.requires_grad], allow_unused=True)
+        outs.append((logits[2].detach(), loss.detach(), dict(zip(names, gs))))
+    (l0, s0, g0), (l1, s1, g1) = outs
+    H.assert_close(l1, l0, 2e-5, "logits")
+    H.assert_close(s1, s0, 2e-5, "loss")
+    for k in g0:
+        assert (g0[k] is None) == (g1[k] is None), k
+        if g0[k] is not None:
+            # same maths, different GEMM shapes: the TF32 library GEMMs around the attention reassociate differently
+            H.assert_close(g1[k], g0[k], 1e-3, "grad " + k, atol=1e-7 if k.endswith("mlp.2.bias") else 0.0)
