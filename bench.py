@@ -361,7 +361,13 @@ def main():
         ach = exec_fl / (kavg[top] * 1e-3) / 1e12
         dense = (fl["qk"] + fl["pv"] + fl["cpb_dense"]) * (1.0 if top.endswith("fwd") else 2.0)
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_kind + " (sustained)",
+                "frac": ach / pk["bf16_tflops_sustained"],
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's kernels at N = 16 384 from
+                # the ncu --set full capture profiles/r1_b_ncu_full_attn_tcgen05_summary.csv (algorithmic: q,k,v,dO
+                # fp16 + O, dQ, dK, dV fp32 = 42 / 97 MB)
+                "traffic": ({"dml_deform_attn_fwd_tc": 25.4e6, "dml_deform_attn_bwd_tc": 43.8e6 + 46.5e6}.get(top)
+                            if N == N_PATCHES else None),
+                "peak_source": pk_kind + " (sustained)",
                 "ms_per_launch": kavg[top],
                 "note": "achieved = tcgen05 MMA FLOPs the launch issues (QK^T/PV-class GEMMs; the CPB bias MLP is evaluated "
                         "through its exact piecewise-linear table on the CUDA cores, which is what bounds the kernel: see "
