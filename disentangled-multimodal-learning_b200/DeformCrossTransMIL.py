@@ -44,7 +44,8 @@ class DeformCrossTransLayer(nn.Module):
     def forward(self, x1, x2, attn_dim, return_vgrid, rows=None):
         if attn_dim == 1:
             # one LayerNorm shared by both streams (reference :44,66)
-            x = self.attn1d(self.norm(x1).transpose(1, 2), self.norm(x2).transpose(1, 2), rows=rows)
+            x = self.attn1d(ops.layer_norm(x1, self.norm).transpose(1, 2), ops.layer_norm(x2, self.norm).transpose(1, 2),
+                            rows=rows)
             if rows:
                 return x1[:, :rows] + x.transpose(1, 2)
             return x1 + x.transpose(1, 2)

@@ -19,7 +19,7 @@ class TransLayer(nn.Module):
                                      residual=True, dropout=0.1)
 
     def forward(self, x):
-        return x + self.attn(self.norm(x))
+        return x + self.attn(ops.layer_norm(x, self.norm))
 
 
 class PPEG(nn.Module):

@@ -61,6 +61,18 @@ def kv_length(n: int, ksize: int, stride: int) -> int:
     return (n + 2 * pad - ksize) // stride + 1
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(dev) -> torch.cuda.Stream:
+    """One auxiliary stream per device for small kernels that only depend on the weights (the bias-table build):
+    they run next to the projections instead of in front of the attention."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
 def grad_scale(t: torch.Tensor) -> torch.Tensor:
     """Device-side power-of-two loss scale for an fp16 operand: float[2] = (s, 1/s) with
     8 <= s * max|t| < 16 (no host sync; s = 1 for an all-zero tensor)."""
@@ -101,6 +113,14 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         w0f, b0f, w2f = w0.reshape(Cg, ks).contiguous().float(), b0.contiguous().float(), w2.reshape(Cg).contiguous().float()
         mlp = [t.contiguous().float() for t in (m_w1.reshape(-1), m_b1, m_W2, m_b2, m_W3, m_b3)]
 
+        # the bias table only depends on the MLP weights: build it on the side stream, next to the projections
+        table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
+        t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
+        cur, side = torch.cuda.current_stream(), side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), stream())
+
         with fp32_matmul():   # q/k/v feed the softmax exponent: exact fp32 projections, one fp16 rounding at the end
             q = torch.matmul(x1f, Wq2.t()).to(F16)                        # [B,n,C] (to_q, :175)
         vgrid = torch.empty(B * G, n_kv, device=dev, dtype=F32)
@@ -113,9 +133,7 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         with fp32_matmul():
             k = torch.matmul(kv, Wk2.t()).to(F16)                         # [B,n_kv,C] (:199)
             v = torch.matmul(kv, Wv2.t()).to(F16)
-        table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
-        t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
-        call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), st)
+        cur.wait_stream(side)                                             # bias table ready
         # offsets / keys / values always need every query position; the attention itself only the first n_out rows
         q_att = q if n_out == n else q[:, :n_out].contiguous()
         o = torch.empty(B, n_out, C, device=dev, dtype=F32)
@@ -342,3 +360,38 @@ class LinearBf16BagFn(torch.autograd.Function):
             with tf32_matmul():
                 dx = (dy @ W).to(x.dtype)
         return dx, dW, dy.sum(0)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm over the last dim (128 / 256 / 512) of a contiguous fp32 tensor: one warp per row, statistics saved
+    for the backward, weight / bias gradients reduced per CTA (DeformCrossTransLayer.norm, TransLayer.norm)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        x = x.contiguous().float()
+        D = x.shape[-1]
+        rows = x.numel() // D
+        wf, bf = w.contiguous().float(), b.contiguous().float()
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, device=x.device, dtype=F32)
+        rstd = torch.empty_like(mean)
+        call("dml_layernorm_fwd", ptr(x), ptr(wf), ptr(bf), rows, D, float(eps), ptr(y), ptr(mean), ptr(rstd), stream())
+        ctx.save_for_backward(x, wf, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wf, mean, rstd = ctx.saved_tensors
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        dw = torch.empty(D, device=x.device, dtype=F32)
+        db = torch.empty_like(dw)
+        call("dml_layernorm_bwd", ptr(dy), ptr(x), ptr(wf), ptr(mean), ptr(rstd), rows, D, ptr(dx), ptr(dw), ptr(db), stream())
+        return dx, dw, db, None
+
+
+def layer_norm(x, norm: torch.nn.LayerNorm):
+    """norm(x) through the row-LayerNorm kernel; `norm` only holds the parameters (reference state_dict keys)."""
+    return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)

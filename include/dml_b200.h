@@ -109,6 +109,14 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
                            const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
                            float* segsum, void* stream);
 
+/* ---- row LayerNorm (DeformCrossTransLayer.norm, models/DeformCrossTransMIL.py:44,66; TransLayer.norm, mil.py:174,186) -- */
+/* x, y, dy, dx: float [rows, D] (D in {128, 256, 512}); w, b, dw, db: float [D]; mean, rstd: float [rows] saved by the
+ * forward.  Biased variance, eps inside the square root (torch.nn.LayerNorm).  dw / db are overwritten.              */
+int dml_layernorm_fwd(const float* x, const float* w, const float* b, long long rows, int D, float eps, float* y,
+                      float* mean, float* rstd, void* stream);
+int dml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                      long long rows, int D, float* dx, float* dw, float* db, void* stream);
+
 /* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
  * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
 int dml_debug_set_trace(void* buf);

@@ -267,3 +267,21 @@ def test_res_conv_merge(B, n_pad, Hh, d, K):
     H.assert_close(ga, ra, 1e-6, "d a")
     H.assert_close(gv, rv, 2e-6, "d v")
     H.assert_close(gw, rw, 2e-5, "d w")
+
+
+@pytest.mark.parametrize("rows,D", [(5, 128), (16385, 128), (1000, 256), (6085, 512)])
+def test_layernorm_rows(rows, D):
+    x = (synth.normal((rows, D), 21, "x") * 2 + 0.5).to(DEV).requires_grad_()
+    ln = torch.nn.LayerNorm(D).to(DEV)
+    with torch.no_grad():
+        ln.weight.copy_(1.0 + 0.2 * synth.uniform((D,), 21, "w").to(DEV))
+        ln.bias.copy_(synth.uniform((D,), 21, "b", 0.3).to(DEV))
+    y = ops.layer_norm(x, ln)
+    ref = ln(x)
+    H.assert_close(y, ref, 2e-6, "layernorm")
+    r = synth.normal((rows, D), 22, "r").to(DEV)
+    g = torch.autograd.grad((y * r).sum(), (x, ln.weight, ln.bias))
+    gr = torch.autograd.grad((ref * r).sum(), (x, ln.weight, ln.bias))
+    H.assert_close(g[0], gr[0], 1e-5, "d x")
+    H.assert_close(g[1], gr[1], 2e-5, "d weight")
+    H.assert_close(g[2], gr[2], 2e-5, "d bias")
