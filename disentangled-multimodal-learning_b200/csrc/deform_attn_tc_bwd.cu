@@ -280,7 +280,7 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
       int ndirty;
       {
         const float xlo = cpb_x(s_i - lds_f32(gsa + 33 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 32 * 4));
-        const int clo = __float2int_rd(fmaf(xlo, L.c1, L.c2)), chi = __float2int_rd(fmaf(xhi, L.c1, L.c2));
+        const int clo = cell_index(L, xlo), chi = cell_index(L, xhi);
         ndirty = tab_dirty_between(L, clo, chi);
       }
       const bool dirty = __any_sync(0xffffffffu, ndirty != 0);

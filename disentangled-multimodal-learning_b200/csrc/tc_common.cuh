@@ -154,7 +154,14 @@ struct Lookup {
   uint32_t bp, piece, meta;   // shared-space addresses
   const uint32_t* gtab;       // table in global memory (slow path)
   float c1, c2;               // cell = floor(x c1 + c2)
+  float c2m;                  // c2 - 0.5: cell_index() rounds on the FMA pipe instead of converting on the XU pipe
 };
+// floor(x c1 + c2) for 0 <= value < 2^22 without a float->int conversion: adding 1.5 * 2^23 leaves the integer part in the
+// low mantissa bits (round-to-nearest of value - 0.5 == floor(value) except on exact ties, where either neighbouring cell
+// describes the same continuous function).
+__device__ __forceinline__ int cell_index(const Lookup& L, float x) {
+  return __float_as_int(fmaf(x, L.c1, L.c2m) + 12582912.0f) - 0x4B400000;      // 12582912 = 1.5 * 2^23
+}
 // all threads of the CTA; the caller must __syncthreads() afterwards, then thread 0 calls tab_finish and syncs again
 __device__ __forceinline__ Lookup tab_stage(uint8_t* sgen, uint32_t saddr, const uint32_t* __restrict__ table, int tid, int nthreads) {
   float* bp = reinterpret_cast<float*>(sgen);
@@ -178,6 +185,7 @@ __device__ __forceinline__ Lookup tab_stage(uint8_t* sgen, uint32_t saddr, const
   const float X = __uint_as_float(__ldg(table + 2)), inv = __uint_as_float(__ldg(table + 3));
   L.c1 = inv;
   L.c2 = X * inv;
+  L.c2m = X * inv - 0.5f;
   return L;
 }
 __device__ __forceinline__ void tab_finish(uint8_t* sgen) {   // one thread: running count of flagged cells
@@ -207,7 +215,7 @@ static __device__ __noinline__ float4 lookup_slow(const uint32_t* gtab, int cell
 // kSeg: also return the global segment index of x.
 template <bool kDirty, bool kSeg>
 __device__ __forceinline__ float4 lookup2(const Lookup& L, float x, int& cell, int& seg) {
-  cell = __float2int_rd(fmaf(x, L.c1, L.c2));
+  cell = cell_index(L, x);
   const float bpv = lds_f32(L.bp + (uint32_t)cell * 4u);
   const bool hi = x >= bpv;
   float4 e = lds_f32x4(L.piece + (uint32_t)cell * 32u + (hi ? 16u : 0u));
