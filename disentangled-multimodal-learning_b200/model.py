@@ -48,6 +48,16 @@ class MaxNet(nn.Module):
         return features, logits, None
 
 
+_TOWER_STREAMS = {}
+
+
+def _tower_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _TOWER_STREAMS:
+        _TOWER_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _TOWER_STREAMS[key]
+
+
 class DeformPathomicNet(nn.Module):
     def __init__(self, args):
         super().__init__()
@@ -75,10 +85,26 @@ class DeformPathomicNet(nn.Module):
     def forward(self, **kwargs):
         if getattr(self.args, "return_vgrid", False):
             raise NotImplementedError("return_vgrid is broken in the reference for attn_dim == 1 (SURVEY.md Q6)")
+        # The two towers are independent until the concat: the immune tower runs on a second stream, so that its many
+        # microsecond-sized kernels (projections, norms, the small omic MLP) fill the gaps of the tumor tower and vice
+        # versa; autograd replays each backward node on the stream of its forward, so the backward overlaps the same way.
+        x_path = kwargs['x_path']
+        two_streams = x_path.is_cuda and getattr(self.args, "overlap_towers", True)
+        if two_streams:
+            cur = torch.cuda.current_stream()
+            side = _tower_stream(x_path.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                omic_vec_immune, _, _ = self.omic_net_immune(x_omic=kwargs['x_omic_immune'])
+                vec_immune, _, grads_immune = self.pathomic_net_immune(path=x_path, omic=omic_vec_immune)
         omic_vec_tumor, _, _ = self.omic_net_tumor(x_omic=kwargs['x_omic_tumor'])
-        vec_tumor, _, grads_tumor = self.pathomic_net_tumor(path=kwargs['x_path'], omic=omic_vec_tumor)
-        omic_vec_immune, _, _ = self.omic_net_immune(x_omic=kwargs['x_omic_immune'])
-        vec_immune, _, grads_immune = self.pathomic_net_immune(path=kwargs['x_path'], omic=omic_vec_immune)
+        vec_tumor, _, grads_tumor = self.pathomic_net_tumor(path=x_path, omic=omic_vec_tumor)
+        if two_streams:
+            cur.wait_stream(side)
+            vec_immune.record_stream(cur)
+        else:
+            omic_vec_immune, _, _ = self.omic_net_immune(x_omic=kwargs['x_omic_immune'])
+            vec_immune, _, grads_immune = self.pathomic_net_immune(path=x_path, omic=omic_vec_immune)
         features = torch.cat((vec_tumor, vec_immune), 1)
         hazard = self.classifier(features)
         hazard_tumor = self.classifier_tumor(vec_tumor)
