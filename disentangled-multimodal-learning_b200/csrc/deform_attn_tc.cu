@@ -7,24 +7,25 @@
 // One CTA = one (batch, offset group, 256 consecutive queries): the TWO heads of the group are processed together,
 // so the position x_ij, its log and its table cell are evaluated once per (i, j) and shared by both heads.
 //
-//   warp 8    TMA producer: Q tiles once, then a 3-stage ring of {K_h0, K_h1, V_h0, V_h1} 64-key tiles
-//             (cp.async.bulk.tensor, 128-byte swizzle) + the 64 sampling positions g of the tile
-//   warp 9    MMA issuer (one elected thread): S = Q K^T (SS form, operands in shared memory) and O += P V
-//             (TS form: P is read from TMEM, V from shared memory as an MN-major operand); owns the TMEM allocation
+//   warp 8    TMA producer: Q tiles once, then a 4-stage ring of {K_h0, K_h1, V_h0, V_h1} 32-key tiles
+//             (cp.async.bulk.tensor, 128-byte swizzle) + the 32 sampling positions g of the tile
+//   warps 9,10 MMA issuers, one per query group (uniform datapath, one elected lane): S = Q K^T (SS form, operands in
+//             shared memory) and O += P V (TS form: P is read from TMEM, V from shared memory as an MN-major operand);
+//             warp 9 owns the TMEM allocation
 //   warps 0-3 softmax group 0 = queries [i0, i0+128);  warps 4-7 softmax group 1 = queries [i0+128, i0+256).
 //             Thread t of a group owns query row t: TMEM lane t holds its S row and its O row, so the row maximum,
 //             the row sum and the position s_i are thread-private (no shuffles), and the 32 lanes of a warp look up
 //             nearly the same table cell (consecutive queries) -> broadcast shared-memory reads.
 //
-// TMEM (512 columns x 128 lanes, fp32): group g at column 256 g:  S_h0 [0,64)  S_h1 [64,128)  O_h0 [128,192)  O_h1 [192,256).
-// P (fp16) overwrites S in place: the 16 fp32 columns of key chunk c become 8 columns of P_hi and 8 columns of P_lo
-// (P = P_hi + P_lo, 22 significant bits), consumed by two K=16 MMAs per chunk.  The two groups alternate on the tensor
-// pipe: while one group's softmax runs on the CUDA cores the other group's MMAs execute.
+// TMEM (512 columns x 128 lanes, fp32): group g at column 256 g:  two S buffers of 64 columns (S_h0 32 | S_h1 32) at 0 and
+// 64, O_h0 [128,192), O_h1 [192,256).  S of key tile j+1 is computed into the other buffer while the softmax warps work
+// on tile j, so the MMA hand-off latency is hidden.  P (fp16) overwrites S in place: the 16 fp32 columns of key chunk c
+// become 8 columns of P_hi and 8 columns of P_lo (P = P_hi + P_lo, 22 significant bits), consumed by two K=16 MMAs.
 //
 // Online softmax without a correction pass in the common case: before the main sweep a cheap sweep over the raw S
 // tile gives an upper bound of the row maximum (max S + an upper bound of the piecewise-linear bias over the tile's
 // position window); the running reference m is only raised when that bound exceeds it by more than 2^8, and only then
-// are the O rows rescaled in TMEM (safe: all earlier MMAs of the group have completed when S arrives).
+// are the O rows rescaled in TMEM (after waiting for the group's previous O += P V to complete).
 #include <math.h>
 
 #include "../../include/dml_b200.h"
@@ -36,23 +37,24 @@ namespace tc {
 constexpr int kD = 64;            // head dim
 constexpr int kBM = 128;          // query rows per softmax group (= TMEM lanes)
 constexpr int kGroups = 2;        // softmax groups per CTA
-constexpr int kBN = 64;           // keys per tile
-constexpr int kStages = 3;
+constexpr int kBN = 32;           // keys per tile
+constexpr int kStages = 4;
 constexpr int kThreads = 32 * 11;   // 8 softmax warps, TMA producer, one MMA-issuing warp per group
 constexpr uint32_t kTileQ = kBM * kD * 2;   // 16384 B
-constexpr uint32_t kTileKV = kBN * kD * 2;  // 8192 B
+constexpr uint32_t kTileKV = kBN * kD * 2;  // 4096 B
 constexpr uint32_t kStageBytes = 4 * kTileKV;
 constexpr float kRaise = 8.0f;    // raise the softmax reference only when the bound exceeds it by 2^8
 
 // shared-memory map (dynamic, base aligned to 1024 B)
 constexpr uint32_t kOffQ = 0;                                        // [group][head] 128x64 fp16
 constexpr uint32_t kOffKV = kOffQ + kGroups * 2 * kTileQ;            // [stage]{K0,K1,V0,V1} 64x64 fp16
-constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;           // [stage][64 g + gmin + gmax + pad] floats
-constexpr uint32_t kGStride = 72 * 4;
-constexpr uint32_t kOffRec = kOffG + kStages * kGStride + 160;       // bias table image (tc_common.cuh), 16-B aligned
+constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;           // [stage][32 g + gmin + gmax + pad] floats
+constexpr uint32_t kGStride = 40 * 4;
+constexpr uint32_t kOffRec = kOffG + kStages * kGStride;             // bias table image (tc_common.cuh), 16-B aligned
 constexpr uint32_t kOffBar = kOffRec + kTabSmemBytes;                // mbarriers (8 B each)
-constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,
-              kBarPFull = kBarSFull + kGroups, kNumBars = kBarPFull + kGroups;
+constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,   // [group][buffer]
+              kBarPFull = kBarSFull + 2 * kGroups, kBarPvDone = kBarPFull + 2 * kGroups, kBarOFinal = kBarPvDone + kGroups,
+              kNumBars = kBarOFinal + kGroups;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;             // + slack for the 1024-B alignment
 static_assert(kOffRec % 16 == 0 && kOffBar % 8 == 0, "alignment");
@@ -67,20 +69,20 @@ struct Params {
   float scale;
 };
 
-constexpr uint32_t kIdescS = idesc_f16(128, 64, false, false);    // S = Q K^T: A, B K-major
+constexpr uint32_t kIdescS = idesc_f16(128, kBN, false, false);   // S = Q K^T: A, B K-major
 constexpr uint32_t kIdescPV = idesc_f16(128, 64, false, true);    // O += P V: A in TMEM, B (= V) MN-major
 
-// One 64-key tile of one query row, both heads: S (TMEM, fp32) -> P = exp2(S sc2 + bias - m) split into fp16 hi/lo
-// pairs written back over the same TMEM columns; l0/l1 accumulate the row sums.  kMasked: keys >= jrem are padding;
-// kDirty: the row's position window touches a table cell holding >= 2 breakpoints (slow-path lookup possible).
+// One 32-key tile of one query row, both heads: S (TMEM, fp32, S_h0 at tS, S_h1 at tS + 32) -> P = exp2(S sc2 + bias - m)
+// split into fp16 hi/lo pairs written back over the same TMEM columns; l0/l1 accumulate the row sums.  kMasked: keys
+// >= jrem are padding; kDirty: the row's position window touches a table cell holding >= 2 breakpoints.
 template <bool kMasked, bool kDirty>
-__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tbase, uint32_t gsa, float s_i, float sc2, float m0,
+__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tS, uint32_t gsa, float s_i, float sc2, float m0,
                                        float m1, int jrem, float& l0, float& l1) {
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     uint32_t a[16], bq[16];
-    tmem_ld16(tbase + c * 16, a);
-    tmem_ld16(tbase + 64 + c * 16, bq);
+    tmem_ld16(tS + c * 16, a);
+    tmem_ld16(tS + 32 + c * 16, bq);
     float gq[16];
 #pragma unroll
     for (int e = 0; e < 16; e += 4) {
@@ -106,8 +108,8 @@ __device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tbase, uint32_t
       split_f16(v0[0], v0[1], w0[e >> 1], w0[8 + (e >> 1)]);
       split_f16(v1[0], v1[1], w1[e >> 1], w1[8 + (e >> 1)]);
     }
-    tmem_st16(tbase + c * 16, w0);
-    tmem_st16(tbase + 64 + c * 16, w1);
+    tmem_st16(tS + c * 16, w0);
+    tmem_st16(tS + 32 + c * 16, w1);
   }
 }
 
@@ -128,7 +130,8 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   if (tid == 0) {
     mbar_init(bar(kBarQ), 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), kGroups); }
-    for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
+    for (int g = 0; g < 2 * kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
+    for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarPvDone + g), 1); mbar_init(bar(kBarOFinal + g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -166,12 +169,10 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       float* gs = reinterpret_cast<float*>(sgen + kOffG + st * kGStride);
       // |p| <= 1 + |g| must stay inside the table domain (log2(|p| + 1) < X): clamp, so that no cell index can leave the table
       const float gb_max = tab_gmax(p.table);
-      const float g0 = fminf(fmaxf(__ldg(gb + min(j * kBN + lane, p.n_kv - 1)), -gb_max), gb_max),
-                  g1 = fminf(fmaxf(__ldg(gb + min(j * kBN + 32 + lane, p.n_kv - 1)), -gb_max), gb_max);
+      const float g0 = fminf(fmaxf(__ldg(gb + min(j * kBN + lane, p.n_kv - 1)), -gb_max), gb_max);
       gs[lane] = g0;
-      gs[lane + 32] = g1;
-      const float gmn = -warp_max(-fminf(g0, g1)), gmx = warp_max(fmaxf(g0, g1));
-      if (lane == 0) { gs[64] = gmn; gs[65] = gmx; }
+      const float gmn = -warp_max(-g0), gmx = warp_max(g0);
+      if (lane == 0) { gs[32] = gmn; gs[33] = gmx; }
       mbar_arrive(bar(kBarKvFull + st));                     // 32 arrivals (release) + the TMA bytes complete the phase
     }
   } else if (warp >= 9) {
@@ -181,44 +182,44 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const bool leader = elect_one();
     mbar_wait(bar(kBarQ), 0);
     auto issue_s = [&](int j) {
-      const int st = j % kStages;
+      const int st = j % kStages, buf = j & 1;
       const uint32_t kv = sbase + kOffKV + st * kStageBytes;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint64_t da = smem_desc(sbase + kOffQ + (g * 2 + h) * kTileQ), db = smem_desc(kv + h * kTileKV);
-        const uint32_t d = tmem + g * 256 + h * 64;
+        const uint32_t d = tmem + g * 256 + buf * 64 + h * 32;
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_ss(d, da + 2 * k, db + 2 * k, kIdescS, k > 0, leader);
       }
-      tc_commit(bar(kBarSFull + g), leader);
+      tc_commit(bar(kBarSFull + g * 2 + buf), leader);
     };
     mbar_wait(bar(kBarKvFull + 0), 0);
     tc_fence_after();
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
-      const int st = j % kStages;
+      const int st = j % kStages, buf = j & 1;
+      if (j + 1 < ntiles) {            // S of the next tile -> the other buffer (its P(j-1) was consumed by the PV MMAs of j-1)
+        mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
+        tc_fence_after();
+        issue_s(j + 1);
+      }
       const uint32_t kv = sbase + kOffKV + st * kStageBytes;
-      mbar_wait(bar(kBarPFull + g), j & 1);
+      mbar_wait(bar(kBarPFull + g * 2 + buf), (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint64_t db = smem_desc(kv + (2 + h) * kTileKV);
-        const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + h * 64;
+        const uint32_t d = tmem + g * 256 + 128 + h * 64, a = tmem + g * 256 + buf * 64 + h * 32;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 2; ++k) {
           mma_ts(d, a + 16 * k, db + 128 * k, kIdescPV, (j > 0) || (k > 0), leader);       // P_hi chunk k
           mma_ts(d, a + 16 * k + 8, db + 128 * k, kIdescPV, 1, leader);                    // P_lo chunk k
         }
       }
       tc_commit(bar(kBarKvEmpty + st), leader);        // this group's share: the stage is free once both groups' MMAs are done
-      if (j + 1 < ntiles) {
-        mbar_wait(bar(kBarKvFull + (j + 1) % kStages), ((j + 1) / kStages) & 1);
-        tc_fence_after();
-        issue_s(j + 1);
-      } else {
-        tc_commit(bar(kBarSFull + g), leader);         // final: O complete
-      }
+      tc_commit(bar(kBarPvDone + g), leader);          // O holds the contributions of tiles 0..j
     }
+    tc_commit(bar(kBarOFinal + g), leader);            // one-shot: every MMA of the group has completed
   } else {
     // =========================== softmax groups ===========================
     const int g = warp >> 2;                        // group
@@ -233,18 +234,20 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     for (int j = 0; j < ntiles; ++j) {
       const int st = j % kStages;
       const uint32_t gsa = sbase + kOffG + st * kGStride;
+      const int buf = j & 1;
+      const uint32_t tS = tbase + buf * 64;
       mbar_wait(bar(kBarKvFull + st), (j / kStages) & 1);       // g tile visible to this thread
-      mbar_wait(bar(kBarSFull + g), j & 1);                     // S(j) landed; every earlier MMA of the group is complete
+      mbar_wait(bar(kBarSFull + g * 2 + buf), (j >> 1) & 1);    // S(j) landed
       tc_fence_after();
       const int jrem = p.n_kv - j * kBN;                        // valid keys in this tile (>= 1)
 
       // ---- sweep 1: upper bound of the row maximum ----
       float r0 = -INFINITY, r1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t a[16], bq[16];
-        tmem_ld16(tbase + c * 16, a);
-        tmem_ld16(tbase + 64 + c * 16, bq);
+        tmem_ld16(tS + c * 16, a);
+        tmem_ld16(tS + 32 + c * 16, bq);
         tmem_ld_wait2(a, bq);
         if (jrem >= kBN) {
 #pragma unroll
@@ -264,7 +267,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       float bh0, bh1;
       int ndirty;
       {
-        const float xlo = cpb_x(s_i - lds_f32(gsa + 65 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 64 * 4));
+        const float xlo = cpb_x(s_i - lds_f32(gsa + 33 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 32 * 4));
         int clo, chi, sdummy;
         const float4 e = lookup2<true, false>(L, xlo, clo, sdummy), f = lookup2<true, false>(L, xhi, chi, sdummy);
         const float half = 0.5f * (xhi - xlo) + 1e-6f;
@@ -279,6 +282,8 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         if (raise0) { m0 = ub0; l0 *= f0; }
         if (raise1) { m1 = ub1; l1 *= f1; }
         if (j > 0) {                                           // rescale this warp's O rows in TMEM
+          mbar_wait(bar(kBarPvDone + g), (j - 1) & 1);          // O += P V of tile j-1 has completed
+          tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint32_t a[16];
@@ -295,18 +300,20 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       // ---- sweep 2: P = exp2(S sc2 + bias - m), in place ----
       const bool dirty = __any_sync(0xffffffffu, ndirty != 0);
       if (jrem >= kBN) {
-        if (!dirty) sweep2<false, false>(L, tbase, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
-        else sweep2<false, true>(L, tbase, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+        if (!dirty) sweep2<false, false>(L, tS, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+        else sweep2<false, true>(L, tS, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
       } else {
-        sweep2<true, true>(L, tbase, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+        sweep2<true, true>(L, tS, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar(kBarPFull + g));
+      mbar_arrive(bar(kBarPFull + g * 2 + buf));
     }
 
     // ---- epilogue: O / l -> global, log-sum-exp ----
-    mbar_wait(bar(kBarSFull + g), ntiles & 1);
+    // (a one-shot barrier: the per-tile kBarPvDone may still be several phases behind here, and a parity wait is only
+    // meaningful when the waiter is at most one phase ahead)
+    mbar_wait(bar(kBarOFinal + g), 0);
     tc_fence_after();
     const int h0 = grp * 2;
     if (gi < p.n) {
