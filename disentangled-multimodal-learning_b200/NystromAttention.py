@@ -3,8 +3,10 @@
 
 Same constructor, forward signature and state_dict keys (to_qkv.weight, to_out.0.{weight,bias},
 res_conv.weight).  Landmark pooling, the three row softmaxes and the value-conv/merge/residual are
-hand-written kernels; the similarity / aggregation GEMMs are TF32 tensor-core library GEMMs in
-round 1 (fp32 storage: the 6-step pinv recurrence does not survive bf16).
+hand-written HBM kernels; every contraction (to_qkv, the three similarity products, the 24 products of
+the pseudo-inverse recurrence, the aggregation products, to_out, and all their gradients) runs on the
+hand-written tcgen05 / TMEM / TMA GEMM of csrc/gemm_tc.cu with fp16 hi+lo split operands (22 significant
+bits, fp32 accumulation: the 6-step pinv recurrence does not survive 11-bit operands).
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .ops import mm_fp32 as mm_tf32   # round 1: exact fp32 library GEMMs (TF32 does not survive the pinv chain at 1e-3)
+from .ops import mm_tc as mm_tf32   # every contraction on the tcgen05 split-fp16 GEMM (csrc/gemm_tc.cu): fp32-class accuracy
 
 
 def moore_penrose_iter_pinv(x, iters=6):
@@ -26,8 +28,8 @@ def moore_penrose_iter_pinv(x, iters=6):
     z = x.transpose(-1, -2) / (torch.max(col) * torch.max(row))
     eye = torch.eye(x.shape[-1], device=x.device, dtype=x.dtype)[None]
     for _ in range(iters):
-        xz = x @ z
-        z = 0.25 * z @ (13 * eye - (xz @ (15 * eye - (xz @ (7 * eye - xz)))))
+        xz = mm_tf32(x, z.contiguous())
+        z = 0.25 * mm_tf32(z.contiguous(), 13 * eye - mm_tf32(xz, 15 * eye - mm_tf32(xz, 7 * eye - xz)))
     return z
 
 
@@ -74,7 +76,7 @@ class NystromAttention(nn.Module):
         k_l = ops.LandmarkPoolFn.apply(k_s, l, h, d, 1.0 / l)
 
         attn1 = ops.SoftmaxRowsFn.apply(mm_tf32(q, k_l.transpose(-1, -2)))    # [b,h,n_pad,m]
-        attn2 = ops.SoftmaxRowsFn.apply(q_l @ k_l.transpose(-1, -2))          # [b,h,m,m]  (fp32: feeds the pinv)
+        attn2 = ops.SoftmaxRowsFn.apply(mm_tf32(q_l, k_l.transpose(-1, -2)))   # [b,h,m,m]  (feeds the pinv)
         attn3 = ops.SoftmaxRowsFn.apply(mm_tf32(q_l, k.transpose(-1, -2)))    # [b,h,m,n_pad]
         attn2_inv = moore_penrose_iter_pinv(attn2, self.pinv_iterations)      # :138
         out = mm_tf32(mm_tf32(attn1, attn2_inv), mm_tf32(attn3, v))           # :140

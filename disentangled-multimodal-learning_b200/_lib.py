@@ -37,6 +37,8 @@ SIGNATURES = {
     "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp]),
     "dml_layernorm_fwd": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _fp, _fp, _vp]),
     "dml_layernorm_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
+    "dml_split_f16": (_i, [_fp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _fp, _vp, _vp]),
+    "dml_gemm_nt_split": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _fp, _i, _ll, _vp]),
     "dml_debug_set_trace": (_i, [_vp]),
     "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
@@ -88,7 +90,7 @@ KERNELS_PER_CALL = {
     "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2,
     "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3,
     "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
-    "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1, "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1,
+    "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1, "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1, "dml_split_f16": 2, "dml_gemm_nt_split": 1,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events

@@ -54,7 +54,7 @@ class TransMIL(nn.Module):
 
     def forward(self, x):
         fc1 = self._fc1[0]
-        h = F.relu(ops.mm_fp32(x.float(), fc1.weight.t()) + fc1.bias)
+        h = F.relu(ops.mm_tc(x.float(), fc1.weight.t()) + fc1.bias)
         N = h.shape[1]
         side = int(np.ceil(np.sqrt(N)))
         add_length = side * side - N

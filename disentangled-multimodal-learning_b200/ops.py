@@ -395,3 +395,104 @@ class LayerNormFn(torch.autograd.Function):
 def layer_norm(x, norm: torch.nn.LayerNorm):
     """norm(x) through the row-LayerNorm kernel; `norm` only holds the parameters (reference state_dict keys)."""
     return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fp32-class batched GEMM on tcgen05 (csrc/gemm_tc.cu): used by NystromAttention
+# ---------------------------------------------------------------------------------------------------------------
+def _as_batched(t: torch.Tensor):
+    """[..., R, C] -> (tensor whose (R, C) block is row-major with one uniform batch stride, batch, R, C, ld, batch_stride,
+    transposed_view).  A transposed view of a row-major block is accepted as is (transposed_view = True: the memory
+    holds [C, R]); anything else is made contiguous."""
+    R, C = t.shape[-2], t.shape[-1]
+    lead = t.shape[:-2]
+    batch = 1
+    for d in lead:
+        batch *= d
+
+    def uniform(tt):
+        # the leading dims must collapse to one stride
+        st, sh = list(tt.stride()[:-2]), list(tt.shape[:-2])
+        dims = [(s_, n_) for s_, n_ in zip(st, sh) if n_ > 1]
+        if not dims:
+            return 0
+        bs = dims[-1][0]
+        expect = bs
+        for s_, n_ in reversed(dims):
+            if s_ != expect:
+                return None
+            expect = s_ * n_
+        return bs
+
+    if t.stride(-1) == 1 and t.stride(-2) >= C:
+        bs = uniform(t)
+        if bs is not None:
+            return t, batch, R, C, t.stride(-2), bs, False
+    if t.stride(-2) == 1 and t.stride(-1) >= R:
+        bs = uniform(t)
+        if bs is not None:
+            return t, batch, C, R, t.stride(-1), bs, True       # memory is [C, R] row-major
+    t = t.contiguous()
+    return t, batch, R, C, C, R * C, False
+
+
+class SplitOperand:
+    """fp32 [..., R, C] -> (hi, lo) fp16 [batch, rows, ldo] with the K axis contiguous, plus its device-side scale.
+    k_last=True: K is the last axis of `t` (rows = R); k_last=False: K is the second-to-last axis (rows = C, transposed
+    while splitting)."""
+
+    def __init__(self, t: torch.Tensor, k_last: bool):
+        t = t.float()
+        base, batch, R, C, ld, bs, tview = _as_batched(t)
+        # memory block [R, C] (after undoing a transposed view); logical K-last?  XOR with the view flag
+        transpose = (not k_last) != tview
+        rows, K = (C, R) if transpose else (R, C)
+        ldo = (K + 7) // 8 * 8
+        dev = t.device
+        self.hi = torch.empty(batch, rows, ldo, device=dev, dtype=F16)
+        self.lo = torch.empty_like(self.hi)
+        self.scale = torch.empty(2, device=dev, dtype=F32)
+        ws = torch.empty(1, device=dev, dtype=torch.int32)
+        call("dml_split_f16", ptr(base), bs, batch, R, C, ld, int(transpose), ldo, ptr(self.hi), ptr(self.lo),
+             ptr(self.scale), ptr(ws), stream())
+        self.batch, self.rows, self.K, self.ld = batch, rows, K, ldo
+
+
+def gemm_nt(A: SplitOperand, Bm: SplitOperand, out_shape, alpha: float = 1.0) -> torch.Tensor:
+    """C[b] = alpha * A[b] @ B[b]^T (fp32, contiguous `out_shape` = [..., M, N]); B may have batch 1 (shared)."""
+    assert A.K == Bm.K and (Bm.batch == A.batch)
+    c = torch.empty(out_shape, device=A.hi.device, dtype=F32)
+    M, N = A.rows, Bm.rows
+    call("dml_gemm_nt_split", ptr(A.hi), ptr(A.lo), ptr(Bm.hi), ptr(Bm.lo), ptr(A.scale), ptr(Bm.scale), float(alpha),
+         A.batch, M, N, A.K, A.ld, Bm.ld, ptr(c), N, M * N, stream())
+    return c
+
+
+class MatmulTcFn(torch.autograd.Function):
+    """a [..., M, K] @ b [..., K, N] (same leading dims, or b 2-D) on the tcgen05 split-fp16 GEMM, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        ctx.b2d = b.dim() == 2 and a.dim() > 2
+        a3 = a.reshape(-1, a.shape[-1])[None] if ctx.b2d else a
+        b3 = b[None] if ctx.b2d else b
+        out = gemm_nt(SplitOperand(a3, True), SplitOperand(b3, False), a3.shape[:-1] + (b.shape[-1],))
+        return out.reshape(a.shape[:-1] + (b.shape[-1],))
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g3 = g.reshape(-1, g.shape[-1])[None] if ctx.b2d else g
+        a3 = a.reshape(-1, a.shape[-1])[None] if ctx.b2d else a
+        b3 = b[None] if ctx.b2d else b
+        da = db = None
+        if ctx.needs_input_grad[0]:      # dA [M, K] = dC [M, N] . (B [K, N])^T
+            da = gemm_nt(SplitOperand(g3, True), SplitOperand(b3, True), a3.shape).reshape(a.shape)
+        if ctx.needs_input_grad[1]:      # dB [K, N] = A^T [K, M] . (dC^T [N, M])^T
+            db = gemm_nt(SplitOperand(a3, False), SplitOperand(g3, False), b3.shape).reshape(b.shape)
+        return da, db
+
+
+def mm_tc(a, b):
+    return MatmulTcFn.apply(a, b)

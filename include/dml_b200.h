@@ -117,6 +117,20 @@ int dml_layernorm_fwd(const float* x, const float* w, const float* b, long long 
 int dml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                       long long rows, int D, float* dx, float* dw, float* db, void* stream);
 
+/* ---- fp32-class batched GEMM on tcgen05 (NystromAttention contractions, models/NystromAttention.py:89,122-125,138-140,150) */
+/* x float [batch, R, C] (row stride ld, batch stride batch_stride elements) -> hi, lo fp16 with hi + lo = x * s, laid out
+ * [batch, R, ldo] (transpose = 0) or [batch, C, ldo] (transpose = 1), ldo a multiple of 8 >= the logical width, padding
+ * zero-filled; s = power of two with 2^9 <= s max|x| < 2^10; scale (device float[2]) receives (s, 1/s); amax_ws: 4-byte
+ * device workspace.                                                                                                  */
+int dml_split_f16(const float* x, long long batch_stride, int batch, int R, int C, int ld, int transpose, int ldo,
+                  void* hi, void* lo, float* scale, void* amax_ws, void* stream);
+/* C[b] (float [M, ldc], batch stride c_batch_stride elements) = alpha / (s_A s_B) * A[b] . B[b]^T with A = a_hi + a_lo
+ * [batch, M, lda], B = b_hi + b_lo [batch, N, ldb] as produced by dml_split_f16 (fp16, K-contiguous); accumulated as
+ * hi.hi + hi.lo + lo.hi in fp32 in TMEM.                                                                              */
+int dml_gemm_nt_split(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* scale_a,
+                      const float* scale_b, float alpha, int batch, int M, int N, int K, int lda, int ldb, float* c,
+                      int ldc, long long c_batch_stride, void* stream);
+
 /* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
  * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
 int dml_debug_set_trace(void* buf);

@@ -285,3 +285,24 @@ def test_layernorm_rows(rows, D):
     H.assert_close(g[0], gr[0], 1e-5, "d x")
     H.assert_close(g[1], gr[1], 2e-5, "d weight")
     H.assert_close(g[2], gr[2], 2e-5, "d bias")
+
+
+@pytest.mark.parametrize("batch,M,N,K", [((), 300, 200, 64), ((2, 3), 130, 64, 72), ((8,), 256, 256, 256), ((1, 8), 700, 64, 520),
+                                         ((), 1000, 1536, 512)])
+def test_gemm_tcgen05_split_matches_fp64(batch, M, N, K):
+    """dml_split_f16 + dml_gemm_nt_split (fp16 hi/lo operands, three tcgen05.mma per k-step, fp32 accumulate) against
+    an fp64 matmul, forward and both gradients; mixed magnitudes exercise the per-tensor power-of-two scales."""
+    a = (synth.normal(batch + (M, K), 31, "a") * 3.0).to(DEV).requires_grad_()
+    b = (synth.normal(batch + (K, N), 31, "b") * 1e-3).to(DEV).requires_grad_()
+    c = ops.mm_tc(a, b)
+    ref = a.double() @ b.double()
+    H.assert_close(c, ref, 5e-6, "C")      # fp32 accumulation over K plus the dropped lo.lo term (2^-22)
+    r = synth.normal(tuple(c.shape), 32, "r").to(DEV)
+    ga, gb = torch.autograd.grad((c * r).sum(), (a, b))
+    ra, rb = torch.autograd.grad((ref * r.double()).sum(), (a, b))
+    H.assert_close(ga, ra, 1e-5, "dA")
+    H.assert_close(gb, rb, 1e-5, "dB")
+    # transposed-view operand and a shared 2-D weight
+    w = synth.normal((N, K), 33, "w").to(DEV)
+    c2 = ops.mm_tc(a, w.t())
+    H.assert_close(c2, a.double() @ w.double().t(), 5e-6, "C (2-D transposed weight)")
