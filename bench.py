@@ -31,6 +31,12 @@ METRIC = "WSI bags/sec fwd+bwd (N=16k patches)"
 UNIT = "bags/s"
 
 
+def workload_name(N):
+    n, n_kv = N + 1, (N + 1 + 2 - 6) // 4 + 1
+    return (f"DeformPathomicNet(attn_dim=1) {TASK}: 2 DeformCrossTransMIL towers, 1 bag x {N} patches x 1024 bf16 feats per GPU "
+            f"per step (n={n} tokens, n_kv={n_kv})")
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -144,7 +150,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
             "warmup": 1, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"DeformPathomicNet(attn_dim=1) {TASK}, 1 bag x {N_PATCHES} patches x 1024 feats, CPU"},
+            "config": {"workload": workload_name(N_PATCHES), "step": "fwd + weighted-CE + bwd (no optimizer step)",
+                       "impl": "reference algorithm (oracle port, torch fp32) on the host cores"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -390,8 +397,7 @@ def main():
                 "dtype": "fp16", "data": "synthetic",
                 "config": {"precision": "bf16 bags; attention MMAs fp16 operands (P as an fp16 hi+lo pair), fp32 accumulate and "
                                         "fp32 softmax/bias/outputs; projections fp32/TF32 library GEMMs",
-                           "workload": f"DeformPathomicNet(attn_dim=1) {TASK}: 2 DeformCrossTransMIL towers, 1 bag x {N} patches x "
-                                       f"1024 bf16 feats per GPU per step (n={n} tokens, n_kv={n_kv})",
+                           "workload": workload_name(N),
                            "step": ("CUDA-graph replay of " if use_graph else "") + "fwd + weighted-CE + bwd" +
                                    (" + flat NCCL grad all-reduce" if world > 1 else "") + " + fused AdamW",
                            "parallelism": f"bag-sharded dp{world}", "l2": f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"},

@@ -72,24 +72,22 @@ struct Params {
 constexpr uint32_t kIdescS = idesc_f16(128, kBN, false, false);   // S = Q K^T: A, B K-major
 constexpr uint32_t kIdescPV = idesc_f16(128, 64, false, true);    // O += P V: A in TMEM, B (= V) MN-major
 
-// One 32-key tile of one query row, both heads: S (TMEM, fp32, S_h0 at tS, S_h1 at tS + 32) -> P = exp2(S sc2 + bias - m)
-// split into fp16 hi/lo pairs written back over the same TMEM columns; l0/l1 accumulate the row sums.  kMasked: keys
-// >= jrem are padding; kDirty: the row's position window touches a table cell holding >= 2 breakpoints.
+// One 32-key tile of one query row, both heads, from registers: sa / sb = the row's 32 S values of head 0 / 1 (already
+// loaded from TMEM for the bound pass) -> P = exp2(S sc2 + bias - m) split into fp16 hi/lo pairs written over the S
+// columns (S_h0 at tS, S_h1 at tS + 32); l0/l1 accumulate the row sums.  kMasked: keys >= jrem are padding; kDirty: the
+// row's position window touches a table cell holding >= 2 breakpoints.
 template <bool kMasked, bool kDirty>
-__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tS, uint32_t gsa, float s_i, float sc2, float m0,
-                                       float m1, int jrem, float& l0, float& l1) {
-#pragma unroll 1
+__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tS, uint32_t gsa, const uint32_t (&sa)[32],
+                                       const uint32_t (&sb)[32], float s_i, float sc2, float m0, float m1, int jrem,
+                                       float& l0, float& l1) {
+#pragma unroll
   for (int c = 0; c < 2; ++c) {
-    uint32_t a[16], bq[16];
-    tmem_ld16(tS + c * 16, a);
-    tmem_ld16(tS + 32 + c * 16, bq);
     float gq[16];
 #pragma unroll
     for (int e = 0; e < 16; e += 4) {
       const float4 t = lds_f32x4(gsa + (uint32_t)(c * 16 + e) * 4);
       gq[e] = t.x; gq[e + 1] = t.y; gq[e + 2] = t.z; gq[e + 3] = t.w;
     }
-    tmem_ld_wait2(a, bq);
     uint32_t w0[16], w1[16];   // [0,8) = P_hi pairs, [8,16) = P_lo pairs
 #pragma unroll
     for (int e = 0; e < 16; e += 2) {
@@ -99,8 +97,8 @@ __device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tS, uint32_t gs
         const float x = cpb_x(s_i - gq[e + u]);
         int cdummy, sdummy;
         const float4 t = lookup2<kDirty, false>(L, x, cdummy, sdummy);
-        v0[u] = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - m0);
-        v1[u] = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - m1);
+        v0[u] = ex2(fmaf(__uint_as_float(sa[c * 16 + e + u]), sc2, fmaf(t.x, x, t.y)) - m0);
+        v1[u] = ex2(fmaf(__uint_as_float(sb[c * 16 + e + u]), sc2, fmaf(t.z, x, t.w)) - m1);
         if (kMasked && c * 16 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
         l0 += v0[u];
         l1 += v1[u];
@@ -241,28 +239,33 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       tc_fence_after();
       const int jrem = p.n_kv - j * kBN;                        // valid keys in this tile (>= 1)
 
-      // ---- sweep 1: upper bound of the row maximum ----
+      // ---- the row's S tile (32 keys x 2 heads) into registers, once; bound of the row maximum ----
+      uint32_t sa[32], sb[32];
+      {
+        uint32_t t0[16], t1[16], t2[16], t3[16];
+        tmem_ld16(tS, t0);
+        tmem_ld16(tS + 16, t1);
+        tmem_ld16(tS + 32, t2);
+        tmem_ld16(tS + 48, t3);
+        tmem_ld_fence();
+        reg_fence(t0); reg_fence(t1); reg_fence(t2); reg_fence(t3);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { sa[e] = t0[e]; sa[16 + e] = t1[e]; sb[e] = t2[e]; sb[16 + e] = t3[e]; }
+      }
       float r0 = -INFINITY, r1 = -INFINITY;
+      if (jrem >= kBN) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t a[16], bq[16];
-        tmem_ld16(tS + c * 16, a);
-        tmem_ld16(tS + 32 + c * 16, bq);
-        tmem_ld_wait2(a, bq);
-        if (jrem >= kBN) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            r0 = fmaxf(r0, __uint_as_float(a[e]));
-            r1 = fmaxf(r1, __uint_as_float(bq[e]));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (c * 16 + e < jrem) {
-              r0 = fmaxf(r0, __uint_as_float(a[e]));
-              r1 = fmaxf(r1, __uint_as_float(bq[e]));
-            }
+        for (int e = 0; e < 32; ++e) {
+          r0 = fmaxf(r0, __uint_as_float(sa[e]));
+          r1 = fmaxf(r1, __uint_as_float(sb[e]));
         }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e < jrem) {
+            r0 = fmaxf(r0, __uint_as_float(sa[e]));
+            r1 = fmaxf(r1, __uint_as_float(sb[e]));
+          }
       }
       float bh0, bh1;
       int ndirty;
@@ -300,10 +303,10 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       // ---- sweep 2: P = exp2(S sc2 + bias - m), in place ----
       const bool dirty = __any_sync(0xffffffffu, ndirty != 0);
       if (jrem >= kBN) {
-        if (!dirty) sweep2<false, false>(L, tS, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
-        else sweep2<false, true>(L, tS, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+        if (!dirty) sweep2<false, false>(L, tS, gsa, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
+        else sweep2<false, true>(L, tS, gsa, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
       } else {
-        sweep2<true, true>(L, tS, gsa, s_i, sc2, m0, m1, jrem, l0, l1);
+        sweep2<true, true>(L, tS, gsa, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
       }
       tmem_st_wait();
       tc_fence_before();
