@@ -34,7 +34,8 @@ SIGNATURES = {
     "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
     "dml_deform_attn_fwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 11 + [_f, _vp, _fp, _vp]),
     "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
-    "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp]),
+    "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp, _vp]),
+    "dml_deform_attn_bwd_ws_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "dml_layernorm_fwd": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _fp, _fp, _vp]),
     "dml_layernorm_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
     "dml_split_f16": (_i, [_fp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _fp, _vp, _vp]),

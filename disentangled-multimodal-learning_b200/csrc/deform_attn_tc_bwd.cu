@@ -5,7 +5,9 @@
 //     dP = dO V^T,  dS = P o (dP - D),  dQ = dS K,  dK = scale dS^T Q,  dV = P^T dO,
 //     dg_j  = - sum_{h in group} sum_i dS_ij a_h(x_ij) / (|p_ij| + 1)              (bias slope a, p = seq_i - g_j)
 //     segsum[s] = (sum dS_0, sum dS_0 x, sum dS_1, sum dS_1 x) over the pairs whose x lies in table segment s
-// Nothing of size n x n_kv is stored: both kernels recompute P from the saved log-sum-exp.
+// Without a workspace nothing of size n x n_kv is stored: both kernels recompute P from the saved log-sum-exp.  With the
+// dS workspace (dml_deform_attn_bwd_ws_bytes) the dK/dV kernel also writes dS^T (fp16, [head][key][query]) and dQ = dS K
+// becomes a plain streaming GEMM over it (deform_attn_dq_gemm_kernel) instead of a second recomputation.
 //
 //   deform_attn_dq_tc_kernel   query-stationary (TMEM lane = query), the forward's structure: two 128-query groups per
 //                              CTA alternate on the tensor pipe; per 32-key tile S = Q K^T and dP = dO V^T (SS MMAs),
@@ -40,6 +42,8 @@ struct BwdParams {
   float* segsum;         // [kCpbSegMax][4] accumulated (zeroed by the host wrapper)
   int B, H, n, n_kv, n_seq;
   float scale;
+  h16* ds_ws;            // optional fp16 [(B H), n_kv_pad, n_pad]: dS^T (times s) written by the dK/dV kernel
+  int n_pad, n_kv_pad;
   long long* trace;      // debug: per-tile clock64() stamps of CTA (0,0,0) of the dQ kernel (nullptr = off)
 };
 static long long* g_trace = nullptr;
@@ -369,7 +373,8 @@ __device__ __forceinline__ void seg_flush(float* ssum, SegRun& r) {
 // of the warp crosses more than one boundary or touches a flagged cell): per-position segment lookup, run-length merged.
 template <bool kKeyMasked, bool kExact>
 __device__ __forceinline__ void dkv_sweep(const Lookup& L, uint32_t tS, uint32_t rowa, float g_j, bool key_valid, float sc2,
-                                          int seg_first, int seg_last, float& dgacc, SegRun& run, float* ssum) {
+                                          int seg_first, int seg_last, float& dgacc, SegRun& run, float* ssum,
+                                          h16* dsp, size_t ds_head_stride) {
   float xb = __int_as_float(0x7f800000);      // boundary between the two buckets (+inf: a single bucket)
   if (!kExact && seg_last != seg_first) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
   float ta0 = 0.f, tb0 = 0.f, ta1 = 0.f, tb1 = 0.f;      // whole-tile sums
@@ -434,6 +439,10 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, uint32_t tS, uint32_t
     tmem_st4(tS + 32 + c * 4, wp1);
     tmem_st4(tS + 64 + c * 4, ws0);
     tmem_st4(tS + 96 + c * 4, ws1);
+    if (dsp) {      // dS^T row of this key, 8 queries per head: 16-byte stores
+      *reinterpret_cast<uint4*>(dsp + c * 8) = make_uint4(ws0[0], ws0[1], ws0[2], ws0[3]);
+      *reinterpret_cast<uint4*>(dsp + ds_head_stride + c * 8) = make_uint4(ws1[0], ws1[1], ws1[2], ws1[3]);
+    }
   }
   if (!kExact) {
     if (seg_first != run.seg) { seg_flush(ssum, run); run.seg = seg_first; }
@@ -572,6 +581,8 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const uint32_t lane_off = ((uint32_t)(warp & 3) * 32u) << 16;
     const float sc2 = p.scale * kLog2e;
     float dgacc = 0.f;
+    const size_t ds_head_stride = (size_t)p.n_kv_pad * p.n_pad;
+    h16* const ds_row = p.ds_ws ? p.ds_ws + ((size_t)(b * p.H + h0) * p.n_kv_pad + gj) * p.n_pad + half * 16 : nullptr;
     SegRun run;
     run.seg = -1;
     run.a0 = run.b0 = run.a1 = run.b1 = 0.f;
@@ -593,12 +604,13 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         lookup2<true, true>(L, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
         exact = __any_sync(0xffffffffu, (seg_last - seg_first > 1) || tab_dirty_between(L, c0, c1) != 0);
       }
+      h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;
       if (!key_masked) {
-        if (!exact) dkv_sweep<false, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
-        else dkv_sweep<false, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
+        if (!exact) dkv_sweep<false, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
+        else dkv_sweep<false, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
       } else {
-        if (!exact) dkv_sweep<true, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
-        else dkv_sweep<true, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum);
+        if (!exact) dkv_sweep<true, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
+        else dkv_sweep<true, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -650,6 +662,117 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   }
 }
 
+// =================================================================================================================
+// dQ = dS K as a streaming GEMM over the dS^T workspace
+// =================================================================================================================
+namespace dqg {
+constexpr int kBM = 128, kBKey = 64, kStages = 4, kThreads = 192;   // 4 drain warps, TMA producer, MMA issuer
+constexpr uint32_t kTileA = kBKey * 64 * 2;       // 8 KB: 64 keys x 64 queries of dS^T (one 128-byte swizzle span wide)
+constexpr uint32_t kTileK = kBKey * kD * 2;       // 8 KB
+constexpr uint32_t kStageBytes = 4 * kTileA + 2 * kTileK;   // per head: two query halves of dS^T; K0 K1
+constexpr uint32_t kOffBar = kStages * kStageBytes;
+constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAcc = 2 * kStages, kNumBars = kBarAcc + 1;
+constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kIdesc = idesc_f16(128, 64, true, true);    // A = dS^T tile ([key][query]: MN-major), B = K tile ([key][d]: MN-major)
+// MN-major A of 128 queries = two 64-query spans kTileA bytes apart (leading-dimension byte offset), 8-key groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_a(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(kTileA >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+}  // namespace dqg
+
+__global__ void __launch_bounds__(dqg::kThreads, 1)
+deform_attn_dq_gemm_kernel(const __grid_constant__ CUtensorMap mds, const __grid_constant__ CUtensorMap mk, const BwdParams p) {
+  using namespace dqg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
+  const int i0 = blockIdx.x * kBM, grp = blockIdx.y, b = blockIdx.z;
+  const int h0 = grp * 2;
+  const int nsteps = p.n_kv_pad / kBKey;
+  auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarFull + s), 1); mbar_init(bar(kBarEmpty + s), 1); }
+    mbar_init(bar(kBarAcc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      for (int j = 0; j < nsteps; ++j) {
+        const int st = j % kStages;
+        mbar_wait(bar(kBarEmpty + st), ((j / kStages) & 1) ^ 1);
+        const uint32_t dst = sbase + st * kStageBytes;
+        mbar_expect_tx(bar(kBarFull + st), kStageBytes);
+        for (int h = 0; h < 2; ++h) {
+          tma_load_3d(dst + (2 * h) * kTileA, &mds, bar(kBarFull + st), i0, j * kBKey, b * p.H + h0 + h);
+          tma_load_3d(dst + (2 * h + 1) * kTileA, &mds, bar(kBarFull + st), i0 + 64, j * kBKey, b * p.H + h0 + h);
+          tma_load_3d(dst + 4 * kTileA + h * kTileK, &mk, bar(kBarFull + st), (h0 + h) * kD, j * kBKey, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer ----
+    const bool leader = elect_one();
+    for (int j = 0; j < nsteps; ++j) {
+      const int st = j % kStages;
+      mbar_wait(bar(kBarFull + st), (j / kStages) & 1);
+      tc_fence_after();
+      const uint32_t src = sbase + st * kStageBytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t da = desc_a(src + (2 * h) * kTileA), db = smem_desc(src + 4 * kTileA + h * kTileK);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tmem + h * 64, da + 128 * k, db + 128 * k, kIdesc, (j > 0) || (k > 0), leader);
+      }
+      tc_commit(bar(kBarEmpty + st), leader);
+    }
+    tc_commit(bar(kBarAcc), leader);
+  } else {
+    // ---- drain: dQ / s -> global ----
+    const int gi = i0 + warp * 32 + lane;
+    const float inv_s = __ldg(p.dscale + 1);
+    mbar_wait(bar(kBarAcc), 0);
+    tc_fence_after();
+    float* ob = p.dq + ((size_t)b * p.n + gi) * (p.H * kD) + h0 * kD;
+    const uint32_t tb = tmem + (((uint32_t)warp * 32u) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      uint32_t a[16];
+      tmem_ld16(tb + c * 16, a);
+      tmem_ld_wait(a);
+      if (gi < p.n) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(ob + c * 16 + e) =
+              make_float4(__uint_as_float(a[e]) * inv_s, __uint_as_float(a[e + 1]) * inv_s,
+                          __uint_as_float(a[e + 2]) * inv_s, __uint_as_float(a[e + 3]) * inv_s);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  }
+}
+
 }  // namespace tc
 }  // namespace dml
 
@@ -661,14 +784,21 @@ int dml_debug_set_trace(void* buf) {
   return 0;
 }
 
+/* bytes of the optional dS^T workspace of dml_deform_attn_bwd_tc: fp16 [(B H), ceil128(n_kv), ceil32(n)] */
+size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
+  if (B <= 0 || H <= 0 || n <= 0 || n_kv <= 0) return 0;
+  return (size_t)B * H * (size_t)(dml::cdiv(n_kv, 128) * 128) * (size_t)(dml::cdiv(n, 32) * 32) * 2;
+}
+
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
                            int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
                            const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
-                           float* segsum, void* stream) {
+                           float* segsum, void* ds_ws, void* stream) {
   using namespace dml;
   using namespace dml::tc;
   DML_CHECK_ARG(q && k && v && g && table && out && d_out && lse && dscale && dsum_ws && dq && dk && dv && dg && segsum);
+  if (((uintptr_t)ds_ws) & 15) return DML_EINVAL;
   DML_CHECK_ARG(B > 0 && H > 0 && n > 0 && n_kv > 0 && n_seq >= n);
   if (dim_head != kD || heads_per_group != 2 || (H & 1)) return DML_EUNSUPPORTED;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return DML_EINVAL;
@@ -690,6 +820,8 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(deform_attn_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkvk::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(deform_attn_dq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dqg::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int G = H / 2;
@@ -702,10 +834,18 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   p.dq = dq; p.dk = dk; p.dv = dv; p.dg = dg; p.segsum = segsum;
   p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.n_seq = n_seq; p.scale = scale;
   p.trace = dml::tc::g_trace;
+  p.ds_ws = (h16*)ds_ws; p.n_pad = cdiv(n, 32) * 32; p.n_kv_pad = cdiv(n_kv, 128) * 128;
+  CUtensorMap mds, mk64;
+  if (ds_ws) {
+    if ((rc = make_map(&mds, ds_ws, B * H, p.n_kv_pad, p.n_pad, 64)) || (rc = make_map(&mk64, k, B, n_kv, ldk, 64))) return rc;
+  }
   const int rows = B * n;
   bwd_prep_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>((const float*)out, (const h16*)d_out, B, n, H, ldo, dsum_ws);
   deform_attn_dkv_tc_kernel<<<dim3(cdiv(n_kv, dkvk::kBK), G, B), dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p);
-  deform_attn_dq_tc_kernel<<<dim3(cdiv(n, dqk::kGroups * dqk::kBM), G, B), dqk::kThreads, dqk::kSmemBytes, st>>>(mq128, mdo128, mk32, mv32, p);
+  if (ds_ws)
+    deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), G, B), dqg::kThreads, dqg::kSmemBytes, st>>>(mds, mk64, p);
+  else
+    deform_attn_dq_tc_kernel<<<dim3(cdiv(n, dqk::kGroups * dqk::kBM), G, B), dqk::kThreads, dqk::kSmemBytes, st>>>(mq128, mdo128, mk32, mv32, p);
   DML_RETURN_LAUNCH();
 }
 

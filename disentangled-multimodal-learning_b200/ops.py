@@ -7,6 +7,7 @@ fused / hot operator is a hand-written sm_100a kernel reached through ``_lib.cal
 from __future__ import annotations
 
 import math
+import os
 from contextlib import contextmanager
 
 import torch
@@ -80,6 +81,10 @@ def grad_scale(t: torch.Tensor) -> torch.Tensor:
     s = torch.exp2(torch.floor(torch.log2(8.0 / amax.clamp_min(1e-30))).clamp(-60.0, 60.0))
     s = torch.where(amax > 0, s, torch.ones_like(s))
     return torch.stack([s, 1.0 / s]).contiguous()
+
+
+# largest dS^T scratch the backward may allocate per call (bytes); DML_B200_DS_WS_MAX_GB overrides, 0 disables it
+DS_WS_MAX_BYTES = int(float(os.environ.get("DML_B200_DS_WS_MAX_GB", "6")) * (1 << 30))
 
 
 class DeformCrossAttn1DFn(torch.autograd.Function):
@@ -176,9 +181,14 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dg = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         segsum = torch.empty(_lib.load().dml_cpb_seg_max(), 4, device=dev, dtype=F32)
         dsum = torch.empty(B, H, n_out, device=dev, dtype=F32)
+        # dS^T scratch (fp16, n x n_kv per head): lets dQ = dS K run as a streaming GEMM instead of recomputing P a second
+        # time; bags too large for it fall back to the recomputing dQ kernel (same results)
+        ws_bytes = _lib.load().dml_deform_attn_bwd_ws_bytes(B, H, n_out, n_kv)
+        ds_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if 0 < ws_bytes <= DS_WS_MAX_BYTES else None
         call("dml_deform_attn_bwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
              n_out, n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
-             ptr(segsum), st)
+             ptr(segsum), ptr(ds_ws) if ds_ws is not None else None, st)
+        del ds_ws
         if n_out != n:                                 # the other query rows only receive the offset-path gradient
             full = torch.zeros(B, n, C, device=dev, dtype=F32)
             full[:, :n_out] = dq_attn

@@ -102,12 +102,16 @@ int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float
                         float* segsum, void* stream);
 
 /* The same backward on tcgen05 / TMEM / TMA (two kernels: key-stationary dK/dV/dg/segment sums, query-stationary dQ;
- * heads_per_group must be 2; n_seq as in dml_deform_attn_fwd_tc; every tensor pointer 16-byte aligned).             */
+ * heads_per_group must be 2; n_seq as in dml_deform_attn_fwd_tc; every tensor pointer 16-byte aligned).
+ * ds_ws: NULL, or a caller-owned scratch buffer of dml_deform_attn_bwd_ws_bytes(B, H, n, n_kv) bytes (contents
+ * undefined afterwards).  With it the dK/dV kernel also stores dS^T in fp16 and dQ = dS.K runs as a streaming GEMM
+ * over that buffer; without it dQ recomputes P and dS from q, k, lse (no n x n_kv memory).  Same results either way. */
+size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv);
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
                            int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
                            const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
-                           float* segsum, void* stream);
+                           float* segsum, void* ds_ws, void* stream);
 
 /* ---- row LayerNorm (DeformCrossTransLayer.norm, models/DeformCrossTransMIL.py:44,66; TransLayer.norm, mil.py:174,186) -- */
 /* x, y, dy, dx: float [rows, D] (D in {128, 256, 512}); w, b, dw, db: float [D]; mean, rstd: float [rows] saved by the
