@@ -334,7 +334,9 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
 // dK / dV / dg / segment-sum kernel
 // =================================================================================================================
 namespace dkvk {
-constexpr int kBK = 128, kBI = 32, kStages = 4, kThreads = 320;
+constexpr int kBK = 128, kBI = 32, kStages = 4;
+constexpr int kEwWarps = 16;                      // per head 8: 4 TMEM lane quarters x 2 query halves of each 32-query tile
+constexpr int kThreads = 32 * (kEwWarps + 2);    // + TMA producer + MMA issuer
 constexpr uint32_t kTileKV = kBK * kD * 2;      // 16 KB
 constexpr uint32_t kTileQ = kBI * kD * 2;       // 4 KB
 constexpr uint32_t kStageBytes = 4 * kTileQ;    // Q0 Q1 dO0 dO1
@@ -343,114 +345,176 @@ constexpr uint32_t kOffIn = kOffKV + 4 * kTileKV;                       // [stag
 constexpr uint32_t kOffRow = kOffIn + kStages * kStageBytes;            // [stage]{seq[32], lse0[32], lse1[32], D0[32], D1[32]}
 constexpr uint32_t kRowStride = 5 * 32 * 4;
 constexpr uint32_t kOffTab = kOffRow + kStages * kRowStride;
-constexpr uint32_t kOffSsum = kOffTab + kTabSmemBytes;                  // float[kCpbSegMax][4]
-constexpr uint32_t kOffBar = kOffSsum + kCpbSegMax * 16;
+constexpr uint32_t kOffSeg = kOffTab + kTabSmemBytes;                   // shared-memory segment arrays (seg_stage)
+constexpr uint32_t kOffBar = kOffSeg + kSegSmemBytes;
 constexpr int kBarKv = 0, kBarInFull = 1, kBarInEmpty = kBarInFull + kStages, kBarSFull = kBarInEmpty + kStages,
               kBarPFull = kBarSFull + 2, kBarAcc = kBarPFull + 2, kNumBars = kBarAcc + 1;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;
-static_assert(kOffTab % 16 == 0 && kOffSsum % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kOffTab % 16 == 0 && kOffSeg % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kIdescSD = idesc_f16(128, kBI, false, false);   // S^T = K Q^T, dP^T = V dO^T
 constexpr uint32_t kIdescAcc = idesc_f16(128, 64, false, true);    // dV += P^T dO, dK += dS^T Q  (dO / Q MN-major)
 }  // namespace dkvk
 
-struct SegRun {      // run-length state of one thread: sums of the current segment, both head outputs
+struct SegRun {      // run-length state of one thread: sums of the current segment for the thread's head
   int seg;
-  float a0, b0, a1, b1;
+  float a, b;
 };
-__device__ __forceinline__ void seg_flush(float* ssum, SegRun& r) {
-  if (r.seg >= 0) {
-    if (r.a0 != 0.f || r.b0 != 0.f) { atomicAdd(ssum + 4 * r.seg, r.a0); atomicAdd(ssum + 4 * r.seg + 1, r.b0); }
-    if (r.a1 != 0.f || r.b1 != 0.f) { atomicAdd(ssum + 4 * r.seg + 2, r.a1); atomicAdd(ssum + 4 * r.seg + 3, r.b1); }
+struct SegSink {     // where finished segment sums go: the global accumulator (fire-and-forget reductions at L2), un-scaled
+  float* sum;
+  float inv_s;
+};
+__device__ __forceinline__ void seg_flush(const SegSink& ssum, SegRun& r, int head) {
+  if (r.seg >= 0 && (r.a != 0.f || r.b != 0.f)) {
+    atomicAdd(ssum.sum + 4 * r.seg + 2 * head, r.a * ssum.inv_s);
+    atomicAdd(ssum.sum + 4 * r.seg + 2 * head + 1, r.b * ssum.inv_s);
   }
-  r.a0 = r.b0 = r.a1 = r.b1 = 0.f;
+  r.a = r.b = 0.f;
 }
 
-// 16 queries of one key row, both heads.  S^T / dP^T (fp32, TMEM) -> P^T / dS^T (fp16 pairs, in place); accumulates
-// dg and the per-segment sums.  Fast variant: the thread's 16 positions lie in at most two adjacent table segments
-// [seg_first, seg_last] split at xb -> two register buckets, no per-position segment lookup.  kExact (rare: some lane
-// of the warp crosses more than one boundary or touches a flagged cell): per-position segment lookup, run-length merged.
-template <bool kKeyMasked, bool kExact>
-__device__ __forceinline__ void dkv_sweep(const Lookup& L, uint32_t tS, uint32_t rowa, float g_j, bool key_valid, float sc2,
-                                          int seg_first, int seg_last, float& dgacc, SegRun& run, float* ssum,
-                                          h16* dsp, size_t ds_head_stride) {
-  float xb = __int_as_float(0x7f800000);      // boundary between the two buckets (+inf: a single bucket)
-  if (!kExact && seg_last != seg_first) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
-  float ta0 = 0.f, tb0 = 0.f, ta1 = 0.f, tb1 = 0.f;      // whole-tile sums
-  float ha0 = 0.f, hb0 = 0.f, ha1 = 0.f, hb1 = 0.f;      // sums of the positions at or above the boundary
+// Warp-cooperative flush (all 32 lanes call it): lanes with `need` hand (seg, a, b) over; lanes naming the same segment -
+// neighbouring keys almost always do - are summed with shuffles and one lane issues the two reductions.
+__device__ __forceinline__ void seg_flush_warp(const SegSink& ssum, bool need, int seg, float a, float b, int head, int lane) {
+  need = need && seg >= 0 && (a != 0.f || b != 0.f);
+  uint32_t pend = __ballot_sync(0xffffffffu, need);
+  while (pend) {
+    const int s = __shfl_sync(0xffffffffu, seg, __ffs(pend) - 1);
+    const bool mine = need && seg == s;
+    float va = mine ? a : 0.f, vb = mine ? b : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      va += __shfl_xor_sync(0xffffffffu, va, o);
+      vb += __shfl_xor_sync(0xffffffffu, vb, o);
+    }
+    if (lane == 0) {
+      atomicAdd(ssum.sum + 4 * s + 2 * head, va * ssum.inv_s);
+      atomicAdd(ssum.sum + 4 * s + 2 * head + 1, vb * ssum.inv_s);
+    }
+    pend &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
+// 16 queries of one key row, one head.  S^T / dP^T (fp32, TMEM) -> P^T / dS^T (fp16 pairs, in place); accumulates
+// dg and the per-segment sums.  x grows along the row, so the segment index only ever increases.
+//   kMode 0  the thread's 16 positions lie in at most two adjacent table segments [seg_first, seg_last] split at xb and
+//            touch no flagged cell: two register buckets, no per-position segment lookup (the common case);
+//   kMode 1  some lane of the warp crosses up to three boundaries or touches a flagged cell: per-position lookup in the
+//            shared-memory segment arrays, four register buckets seg_first .. seg_first + 3;
+//   kMode 2  anything else (more than kSegSmem segments, > 3 boundaries in 16 positions): per-position lookup through
+//            the global table, run-length merged with per-thread atomics.
+// tS = TMEM address of the warp's first S^T column of this head (dP^T sits 64 columns further).
+template <bool kKeyMasked, int kMode>
+__device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, uint32_t tS, uint32_t rowa, int head, float g_j,
+                                          bool key_valid, float sc2, int seg_first, int seg_last, float& dgacc, SegRun& run,
+                                          const SegSink& ssum, h16* dsp) {
+  const int lane = threadIdx.x & 31;
+  float xb = __int_as_float(0x7f800000);      // kMode 0: boundary between the two buckets (+inf: a single bucket)
+  if (kMode == 0 && seg_last != seg_first) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
+  float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};   // kMode 0: [0] whole tile, [1] at or above xb; kMode 1: per segment
 #pragma unroll 1
-  for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries (register budget)
-    uint32_t a[8], bq[8], pa[8], pb[8];
+  for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries
+    uint32_t a[8], pa[8];
     tmem_ld8(tS + c * 8, a);
-    tmem_ld8(tS + 32 + c * 8, bq);
     tmem_ld8(tS + 64 + c * 8, pa);
-    tmem_ld8(tS + 96 + c * 8, pb);
-    float sq[8], l0[8], l1[8], d0[8], d1[8];
+    float sq[8], l0[8], d0[8];
     const uint32_t ra = rowa + c * 32;
 #pragma unroll
     for (int e = 0; e < 8; e += 4) {
       float4 t = lds_f32x4(ra + e * 4);
       sq[e] = t.x; sq[e + 1] = t.y; sq[e + 2] = t.z; sq[e + 3] = t.w;
-      t = lds_f32x4(ra + 128 + e * 4);
+      t = lds_f32x4(ra + 128 + head * 128 + e * 4);
       l0[e] = t.x; l0[e + 1] = t.y; l0[e + 2] = t.z; l0[e + 3] = t.w;
-      t = lds_f32x4(ra + 256 + e * 4);
-      l1[e] = t.x; l1[e + 1] = t.y; l1[e + 2] = t.z; l1[e + 3] = t.w;
-      t = lds_f32x4(ra + 384 + e * 4);
+      t = lds_f32x4(ra + 384 + head * 128 + e * 4);
       d0[e] = t.x; d0[e + 1] = t.y; d0[e + 2] = t.z; d0[e + 3] = t.w;
-      t = lds_f32x4(ra + 512 + e * 4);
-      d1[e] = t.x; d1[e + 1] = t.y; d1[e + 2] = t.z; d1[e + 3] = t.w;
     }
     tmem_ld_fence();
-    reg_fence(a); reg_fence(bq); reg_fence(pa); reg_fence(pb);
-    uint32_t wp0[4], wp1[4], ws0[4], ws1[4];
+    reg_fence(a); reg_fence(pa);
+    uint32_t wp[4], ws[4];
+    int sg[8];                                            // kMode 1: segment of each position
+    if (kMode == 1) {
+      // all 8 positions in lock step (no per-position loop, so their loads overlap): start from the segment at the
+      // beginning of the cell, then step over boundaries until no lane of the warp moves any more
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float pr = sq[e] - g_j;
+        const float x = copysignf(__log2f(fabsf(pr) + 1.0f), pr);
+        sg[e] = lds_s32(L.meta + (uint32_t)cell_index(L, x) * 4u) & 0xffff;
+      }
+      bool more;
+      do {
+        more = false;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float pr = sq[e] - g_j;
+          const float x = copysignf(__log2f(fabsf(pr) + 1.0f), pr);
+          const bool m = x >= lds_f32(SL.bp + (uint32_t)sg[e] * 4u);
+          sg[e] += m ? 1 : 0;
+          more |= m;
+        }
+      } while (__any_sync(0xffffffffu, more));
+    }
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
-      float pp0[2], pp1[2], dd0[2], dd1[2];
+      float pp[2], dd[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const float pr = sq[e + u] - g_j;
         const float qa = fabsf(pr) + 1.0f;
         const float x = copysignf(__log2f(qa), pr);
         int cell, seg = 0;
-        const float4 t = lookup2<kExact, kExact>(L, x, cell, seg);
-        float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(t.x, x, t.y)) - l0[e + u]);
-        float p1 = ex2(fmaf(__uint_as_float(bq[e + u]), sc2, fmaf(t.z, x, t.w)) - l1[e + u]);
-        float s0 = p0 * (__uint_as_float(pa[e + u]) - d0[e + u]);
-        float s1 = p1 * (__uint_as_float(pb[e + u]) - d1[e + u]);
-        if (kKeyMasked && !key_valid) { p0 = 0.f; p1 = 0.f; s0 = 0.f; s1 = 0.f; }
-        pp0[u] = p0; pp1[u] = p1; dd0[u] = s0; dd1[u] = s1;
-        // d bias / d g_j = -a / (|p| + 1)
-        dgacc = fmaf(fmaf(s0, t.x, s1 * t.z), -rcp_approx(qa), dgacc);
-        if (kExact) {
-          if (seg != run.seg) { seg_flush(ssum, run); run.seg = seg; }
-          run.a0 += s0; run.b0 = fmaf(s0, x, run.b0); run.a1 += s1; run.b1 = fmaf(s1, x, run.b1);
+        float4 t;
+        if (kMode == 1) {
+          seg = sg[e + u];
+          t = lds_f32x4(SL.coef + (uint32_t)seg * 16u);
         } else {
-          ta0 += s0; tb0 = fmaf(s0, x, tb0); ta1 += s1; tb1 = fmaf(s1, x, tb1);
-          if (x >= xb) { ha0 += s0; hb0 = fmaf(s0, x, hb0); ha1 += s1; hb1 = fmaf(s1, x, hb1); }
+          t = lookup2<kMode == 2, kMode == 2>(L, x, cell, seg);
+        }
+        const float slope = head ? t.z : t.x, icpt = head ? t.w : t.y;
+        float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(slope, x, icpt)) - l0[e + u]);
+        float s0 = p0 * (__uint_as_float(pa[e + u]) - d0[e + u]);
+        if (kKeyMasked && !key_valid) { p0 = 0.f; s0 = 0.f; }
+        pp[u] = p0; dd[u] = s0;
+        // d bias / d g_j = -a / (|p| + 1)
+        dgacc = fmaf(s0 * slope, -rcp_approx(qa), dgacc);
+        if (kMode == 2) {
+          if (seg != run.seg) { seg_flush(ssum, run, head); run.seg = seg; }
+          run.a += s0; run.b = fmaf(s0, x, run.b);
+        } else if (kMode == 1) {
+          const int k = seg - seg_first;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float m = k == q ? s0 : 0.f;      // select, not a branch: the positions stay interleaved
+            ba[q] += m; bb[q] = fmaf(m, x, bb[q]);
+          }
+        } else {
+          ba[0] += s0; bb[0] = fmaf(s0, x, bb[0]);
+          if (x >= xb) { ba[1] += s0; bb[1] = fmaf(s0, x, bb[1]); }
         }
       }
-      wp0[e >> 1] = pack_f16(pp0[0], pp0[1]);
-      wp1[e >> 1] = pack_f16(pp1[0], pp1[1]);
-      ws0[e >> 1] = pack_f16(dd0[0], dd0[1]);
-      ws1[e >> 1] = pack_f16(dd1[0], dd1[1]);
+      wp[e >> 1] = pack_f16(pp[0], pp[1]);
+      ws[e >> 1] = pack_f16(dd[0], dd[1]);
     }
-    tmem_st4(tS + c * 4, wp0);
-    tmem_st4(tS + 32 + c * 4, wp1);
-    tmem_st4(tS + 64 + c * 4, ws0);
-    tmem_st4(tS + 96 + c * 4, ws1);
-    if (dsp) {      // dS^T row of this key, 8 queries per head: 16-byte stores
-      *reinterpret_cast<uint4*>(dsp + c * 8) = make_uint4(ws0[0], ws0[1], ws0[2], ws0[3]);
-      *reinterpret_cast<uint4*>(dsp + ds_head_stride + c * 8) = make_uint4(ws1[0], ws1[1], ws1[2], ws1[3]);
-    }
+    tmem_st4(tS + c * 4, wp);
+    tmem_st4(tS + 64 + c * 4, ws);
+    if (dsp) *reinterpret_cast<uint4*>(dsp + c * 8) = make_uint4(ws[0], ws[1], ws[2], ws[3]);   // dS^T row of this key, 8 queries
   }
-  if (!kExact) {
-    if (seg_first != run.seg) { seg_flush(ssum, run); run.seg = seg_first; }
-    run.a0 += ta0 - ha0; run.b0 += tb0 - hb0; run.a1 += ta1 - ha1; run.b1 += tb1 - hb1;
-    if (seg_last != seg_first) {
-      seg_flush(ssum, run);
-      run.seg = seg_last;
-      run.a0 = ha0; run.b0 = hb0; run.a1 = ha1; run.b1 = hb1;
+  if (kMode == 0) { ba[0] -= ba[1]; bb[0] -= bb[1]; }      // [0] below the boundary, [1] at or above it
+  if (kMode != 2) {
+    // hand the buckets to the running sums: every segment the thread has left behind is flushed (warp-cooperatively)
+    bool need = seg_first != run.seg;
+    if (__any_sync(0xffffffffu, need)) {
+      seg_flush_warp(ssum, need, run.seg, run.a, run.b, head, lane);
+      if (need) { run.seg = seg_first; run.a = run.b = 0.f; }
+    }
+    run.a += ba[0]; run.b += bb[0];
+#pragma unroll
+    for (int q = 1; q < (kMode == 1 ? 4 : 2); ++q) {
+      need = seg_last - seg_first >= q;
+      if (__any_sync(0xffffffffu, need)) {
+        seg_flush_warp(ssum, need, run.seg, run.a, run.b, head, lane);
+        if (need) { run.seg = seg_first + q; run.a = ba[q]; run.b = bb[q]; }
+      }
     }
   }
 }
@@ -469,21 +533,20 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   const int ntiles = cdiv(p.n, kBI);
   auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
-  float* ssum = reinterpret_cast<float*>(sgen + kOffSsum);
 
   if (tid == 0) {
     mbar_init(bar(kBarKv), 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarInFull + s), 32); mbar_init(bar(kBarInEmpty + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarSFull + s), 1); mbar_init(bar(kBarPFull + s), 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar(kBarSFull + s), 1); mbar_init(bar(kBarPFull + s), 32 * kEwWarps); }
     mbar_init(bar(kBarAcc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == kEwWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   const Lookup L = tab_stage(sgen + kOffTab, sbase + kOffTab, p.table, tid, kThreads);
-  for (int i = tid; i < kCpbSegMax * 4; i += kThreads) ssum[i] = 0.f;
+  const SegLookup SL = seg_stage(sgen + kOffSeg, sbase + kOffSeg, p.table, tid, kThreads);
   tc_fence_before();
   __syncthreads();
   if (tid == 0) tab_finish(sgen + kOffTab);
@@ -491,7 +554,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kEwWarps) {
     // ---- TMA producer ----
     if (lane == 0) {
       mbar_expect_tx(bar(kBarKv), 4 * kTileKV);
@@ -524,7 +587,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       rs[128 + lane] = iv ? __ldg(db + p.n + ic) : 0.f;
       mbar_arrive(bar(kBarInFull + st));
     }
-  } else if (warp == 9) {
+  } else if (warp == kEwWarps + 1) {
     // ---- MMA issuer (all lanes run the loop under uniform control flow, one elected lane issues) ----
     {
       const bool leader = elect_one();
@@ -546,6 +609,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       mbar_wait(bar(kBarInFull + 0), 0);
       tc_fence_after();
       issue_sd(0);
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
       for (int t = 0; t < ntiles; ++t) {
         const int st = t % kStages, buf = t & 1;
         if (t + 1 < ntiles) {
@@ -553,8 +617,10 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           tc_fence_after();
           issue_sd(t + 1);
         }
+        if (tr) p.trace[t * 8 + 7] = clock64();
         mbar_wait(bar(kBarPFull + buf), (t >> 1) & 1);
         tc_fence_after();
+        if (tr) p.trace[t * 8 + 5] = clock64();
         const uint32_t in = sbase + kOffIn + st * kStageBytes;
         for (int h = 0; h < 2; ++h) {
           const uint64_t dq_ = smem_desc(in + h * kTileQ), dd_ = smem_desc(in + (2 + h) * kTileQ);   // [query][d]: MN-major B
@@ -566,12 +632,15 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           for (int k = 0; k < 2; ++k) mma_ts(dK, sT + 16 * k, dq_ + 128 * k, kIdescAcc, (t > 0) || (k > 0), leader);
         }
         tc_commit(bar(kBarInEmpty + st), leader);
+        if (tr) p.trace[t * 8 + 6] = clock64();
       }
       tc_commit(bar(kBarAcc), leader);
     }
   } else {
-    // ---- elementwise warps: warp w -> TMEM lanes 32 (w & 3).., queries 16 (w >> 2).. of each 32-query tile ----
-    const int half = warp >> 2;
+    // ---- elementwise warps: warp w -> head w >> 3 of the pair, TMEM lanes 32 (w & 3).., queries 16 ((w >> 2) & 1).. of
+    //      each 32-query tile (the two heads' warps repeat the bias lookup but need no synchronisation) ----
+    const int head = warp >> 3;
+    const int half = (warp >> 2) & 1;
     const int row = (warp & 3) * 32 + lane;
     const int gj = j0 + row;
     const bool kvld = gj < p.n_kv;
@@ -581,43 +650,59 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const uint32_t lane_off = ((uint32_t)(warp & 3) * 32u) << 16;
     const float sc2 = p.scale * kLog2e;
     float dgacc = 0.f;
-    const size_t ds_head_stride = (size_t)p.n_kv_pad * p.n_pad;
-    h16* const ds_row = p.ds_ws ? p.ds_ws + ((size_t)(b * p.H + h0) * p.n_kv_pad + gj) * p.n_pad + half * 16 : nullptr;
+    h16* const ds_row = p.ds_ws ? p.ds_ws + ((size_t)(b * p.H + h0 + head) * p.n_kv_pad + gj) * p.n_pad + half * 16 : nullptr;
     SegRun run;
     run.seg = -1;
-    run.a0 = run.b0 = run.a1 = run.b1 = 0.f;
+    run.a = run.b = 0.f;
+    const float inv_s = __ldg(p.dscale + 1);
+    const SegSink ssum{p.segsum, inv_s};
 
+    const bool tr0 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 0;
+    const bool tr3 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 3;
     for (int t = 0; t < ntiles; ++t) {
       const int st = t % kStages, buf = t & 1;
       mbar_wait(bar(kBarInFull + st), (t / kStages) & 1);
+      if (tr0) p.trace[t * 8 + 0] = clock64();
       mbar_wait(bar(kBarSFull + buf), (t >> 1) & 1);
       tc_fence_after();
+      if (tr0) p.trace[t * 8 + 1] = clock64();
+      if (tr3) p.trace[t * 8 + 3] = clock64();
       const uint32_t rowa = sbase + kOffRow + st * kRowStride + half * 64;
-      const uint32_t tS = tmem + lane_off + buf * 128 + half * 16;
-      // segments of this thread's first / last position; the exact path is taken when any lane crosses more than one
-      // segment boundary inside its 16 positions or touches a flagged (>= 2 breakpoints) table cell
-      int seg_first, seg_last;
-      bool exact;
+      const uint32_t tS = tmem + lane_off + buf * 128 + head * 32 + half * 16;
+      // segments of this thread's first / last position -> which variant the whole warp takes (see dkv_sweep)
+      int seg_first, seg_last, mode;
       {
         int c0, c1;
-        lookup2<true, true>(L, cpb_x(lds_f32(rowa) - g_j), c0, seg_first);
-        lookup2<true, true>(L, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
-        exact = __any_sync(0xffffffffu, (seg_last - seg_first > 1) || tab_dirty_between(L, c0, c1) != 0);
+        if (SL.staged) {
+          lookup_seg(L, SL, cpb_x(lds_f32(rowa) - g_j), c0, seg_first);
+          lookup_seg(L, SL, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
+        } else {
+          lookup2<true, true>(L, cpb_x(lds_f32(rowa) - g_j), c0, seg_first);
+          lookup2<true, true>(L, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
+        }
+        const int span = seg_last - seg_first;
+        const bool general = __any_sync(0xffffffffu, span > 1 || tab_dirty_between(L, c0, c1) != 0);
+        mode = !general ? 0 : (SL.staged && !__any_sync(0xffffffffu, span > 3)) ? 1 : 2;
       }
       h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;
+#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp)
       if (!key_masked) {
-        if (!exact) dkv_sweep<false, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
-        else dkv_sweep<false, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
+        if (mode == 0) DML_DKV_SWEEP(false, 0);
+        else if (mode == 1) DML_DKV_SWEEP(false, 1);
+        else DML_DKV_SWEEP(false, 2);
       } else {
-        if (!exact) dkv_sweep<true, false>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
-        else dkv_sweep<true, true>(L, tS, rowa, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, ds_head_stride);
+        if (mode == 0) DML_DKV_SWEEP(true, 0);
+        else if (mode == 1) DML_DKV_SWEEP(true, 1);
+        else DML_DKV_SWEEP(true, 2);
       }
+#undef DML_DKV_SWEEP
+      if (tr0) p.trace[t * 8 + 2] = clock64();
+      if (tr3) p.trace[t * 8 + 4] = clock64();
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(kBarPFull + buf));
     }
-    seg_flush(ssum, run);
-    const float inv_s = __ldg(p.dscale + 1);
+    seg_flush_warp(ssum, true, run.seg, run.a, run.b, head, lane);
     if (kvld) atomicAdd(p.dg + (size_t)(b * G + grp) * p.n_kv + gj, dgacc * inv_s);
 
     // ---- drain dV / dK ----
@@ -626,8 +711,9 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const float ksc = p.scale * inv_s;
     const int ldg = p.H * kD;
 #pragma unroll
-    for (int acc = 0; acc < 4; ++acc) {     // dV h0, dV h1, dK h0, dK h1: 64 columns each, this warp takes 32 of them
-      const int h = acc & 1;
+    for (int a2 = 0; a2 < 2; ++a2) {        // dV h0, dV h1, dK h0, dK h1: 64 columns each; this warp: its head's two, 32 columns of each
+      const int acc = a2 * 2 + head;
+      const int h = head;
       float* dst = (acc < 2 ? p.dv : p.dk) + ((size_t)b * p.n_kv + gj) * ldg + (h0 + h) * kD + half * 32;
       const float f = acc < 2 ? inv_s : ksc;
 #pragma unroll
@@ -648,15 +734,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  {   // the CTA's segment sums -> global
-    const int nseg = (int)__ldg(p.table);
-    const float inv_s = __ldg(p.dscale + 1);
-    for (int i = tid; i < nseg * 4; i += kThreads) {
-      const float v = ssum[i];
-      if (v != 0.f) atomicAdd(p.segsum + i, v * inv_s);
-    }
-  }
-  if (warp == 9) {
+  if (warp == kEwWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }

@@ -225,6 +225,39 @@ __device__ __forceinline__ float4 lookup2(const Lookup& L, float x, int& cell, i
   }
   return e;
 }
+// ---- optional shared-memory copy of the first kSegSmem table segments (upper boundary, coefficients): the general
+// lookup for x ranges that touch flagged cells or several segment boundaries, without going to global memory ----
+constexpr int kSegSmem = 256;
+constexpr uint32_t kSegSmemBytes = kSegSmem * 4 + kSegSmem * 16;
+struct SegLookup {
+  uint32_t bp, coef;     // shared-space addresses: float[kSegSmem], float4[kSegSmem]
+  bool staged;           // false: the table has more segments than fit (callers fall back to lookup2<true, .>)
+};
+__device__ __forceinline__ SegLookup seg_stage(uint8_t* sgen, uint32_t saddr, const uint32_t* __restrict__ table, int tid, int nthreads) {
+  SegLookup S;
+  S.bp = saddr;
+  S.coef = saddr + kSegSmem * 4;
+  const int nseg = (int)__ldg(table);
+  S.staged = nseg <= kSegSmem;
+  if (S.staged) {
+    float* bp = reinterpret_cast<float*>(sgen);
+    float4* coef = reinterpret_cast<float4*>(sgen + kSegSmem * 4);
+    const float* gbp = reinterpret_cast<const float*>(table + kTabSegBp);
+    const float4* gc = reinterpret_cast<const float4*>(table + kTabSegCoef);
+    for (int i = tid; i < kSegSmem; i += nthreads) {
+      bp[i] = i < nseg - 1 ? __ldg(gbp + i) : __int_as_float(0x7f800000);
+      coef[i] = __ldg(gc + min(i, nseg - 1));
+    }
+  }
+  return S;
+}
+__device__ __forceinline__ float4 lookup_seg(const Lookup& L, const SegLookup& S, float x, int& cell, int& seg) {
+  cell = cell_index(L, x);
+  int s = lds_s32(L.meta + (uint32_t)cell * 4u) & 0xffff;
+  while (x >= lds_f32(S.bp + (uint32_t)s * 4u)) ++s;
+  seg = s;
+  return lds_f32x4(S.coef + (uint32_t)s * 16u);
+}
 __device__ __forceinline__ int tab_dirty_between(const Lookup& L, int cell_lo, int cell_hi) {   // flagged cells in [lo, hi]
   return (lds_s32(L.meta + (uint32_t)(cell_hi + 1) * 4u) >> 16) - (lds_s32(L.meta + (uint32_t)cell_lo * 4u) >> 16);
 }
