@@ -407,10 +407,11 @@ __device__ __forceinline__ void seg_flush_warp(const SegSink& ssum, bool need, i
 template <bool kKeyMasked, int kMode>
 __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, uint32_t tS, uint32_t rowa, int head, float g_j,
                                           bool key_valid, float sc2, int seg_first, int seg_last, float& dgacc, SegRun& run,
-                                          const SegSink& ssum, h16* dsp) {
+                                          const SegSink& ssum, h16* dsp, long long* trc = nullptr) {
   const int lane = threadIdx.x & 31;
   float xb = __int_as_float(0x7f800000);      // kMode 0: boundary between the two buckets (+inf: a single bucket)
-  if (kMode == 0 && seg_last != seg_first) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
+  if (kMode == 0 && seg_last != seg_first)
+    xb = SL.staged ? lds_f32(SL.bp + (uint32_t)seg_first * 4u) : __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
   float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};   // kMode 0: [0] whole tile, [1] at or above xb; kMode 1: per segment
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries
@@ -431,24 +432,23 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
     tmem_ld_fence();
     reg_fence(a); reg_fence(pa);
     uint32_t wp[4], ws[4];
-    int sg[8];                                            // kMode 1: segment of each position
+    int sg[8];                                            // kMode 1: segment and x of each position
+    float xs[8];
     if (kMode == 1) {
       // all 8 positions in lock step (no per-position loop, so their loads overlap): start from the segment at the
       // beginning of the cell, then step over boundaries until no lane of the warp moves any more
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float pr = sq[e] - g_j;
-        const float x = copysignf(__log2f(fabsf(pr) + 1.0f), pr);
-        sg[e] = lds_s32(L.meta + (uint32_t)cell_index(L, x) * 4u) & 0xffff;
+        xs[e] = copysignf(__log2f(fabsf(pr) + 1.0f), pr);
+        sg[e] = lds_s32(L.meta + (uint32_t)cell_index(L, xs[e]) * 4u) & 0xffff;
       }
       bool more;
       do {
         more = false;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float pr = sq[e] - g_j;
-          const float x = copysignf(__log2f(fabsf(pr) + 1.0f), pr);
-          const bool m = x >= lds_f32(SL.bp + (uint32_t)sg[e] * 4u);
+          const bool m = xs[e] >= lds_f32(SL.bp + (uint32_t)sg[e] * 4u);
           sg[e] += m ? 1 : 0;
           more |= m;
         }
@@ -461,7 +461,7 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
       for (int u = 0; u < 2; ++u) {
         const float pr = sq[e + u] - g_j;
         const float qa = fabsf(pr) + 1.0f;
-        const float x = copysignf(__log2f(qa), pr);
+        const float x = kMode == 1 ? xs[e + u] : copysignf(__log2f(qa), pr);
         int cell, seg = 0;
         float4 t;
         if (kMode == 1) {
@@ -500,22 +500,33 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
     if (dsp) *reinterpret_cast<uint4*>(dsp + c * 8) = make_uint4(ws[0], ws[1], ws[2], ws[3]);   // dS^T row of this key, 8 queries
   }
   if (kMode == 0) { ba[0] -= ba[1]; bb[0] -= bb[1]; }      // [0] below the boundary, [1] at or above it
+  if (trc) *trc = clock64();
   if (kMode != 2) {
-    // hand the buckets to the running sums: every segment the thread has left behind is flushed (warp-cooperatively)
-    bool need = seg_first != run.seg;
-    if (__any_sync(0xffffffffu, need)) {
-      seg_flush_warp(ssum, need, run.seg, run.a, run.b, head, lane);
-      if (need) { run.seg = seg_first; run.a = run.b = 0.f; }
-    }
-    run.a += ba[0]; run.b += bb[0];
+    // hand the buckets to the running sums.  Completed segments of this lane, in order: the old run when it is not
+    // seg_first (else it merges into bucket 0), then buckets 0 .. span-1; bucket `span` becomes the new run.  Round j
+    // flushes every lane's j-th completed segment warp-cooperatively, so a tile costs as many rounds as the worst lane
+    // has completed segments (one in the usual boundary-crossing tile).
+    constexpr int kB = kMode == 1 ? 4 : 2;
+    const int span = seg_last - seg_first;
+    const bool old = seg_first != run.seg;
+    if (!old) { ba[0] += run.a; bb[0] += run.b; }
+    const int mine = (old ? 1 : 0) + span;
+    if (__any_sync(0xffffffffu, mine > 0)) {
+      const int rounds = __reduce_max_sync(0xffffffffu, mine);
+      for (int j = 0; j < rounds; ++j) {
+        const int idx = j - (old ? 1 : 0);               // -1: the old run, else bucket idx
+        float fa = run.a, fb = run.b;
 #pragma unroll
-    for (int q = 1; q < (kMode == 1 ? 4 : 2); ++q) {
-      need = seg_last - seg_first >= q;
-      if (__any_sync(0xffffffffu, need)) {
-        seg_flush_warp(ssum, need, run.seg, run.a, run.b, head, lane);
-        if (need) { run.seg = seg_first + q; run.a = ba[q]; run.b = bb[q]; }
+        for (int q = 0; q < kB - 1; ++q)
+          if (idx == q) { fa = ba[q]; fb = bb[q]; }
+        seg_flush_warp(ssum, j < mine, idx < 0 ? run.seg : seg_first + idx, fa, fb, head, lane);
       }
     }
+    run.seg = seg_last;
+    run.a = ba[0]; run.b = bb[0];
+#pragma unroll
+    for (int q = 1; q < kB; ++q)
+      if (span == q) { run.a = ba[q]; run.b = bb[q]; }
   }
 }
 
@@ -662,7 +673,6 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     for (int t = 0; t < ntiles; ++t) {
       const int st = t % kStages, buf = t & 1;
       mbar_wait(bar(kBarInFull + st), (t / kStages) & 1);
-      if (tr0) p.trace[t * 8 + 0] = clock64();
       mbar_wait(bar(kBarSFull + buf), (t >> 1) & 1);
       tc_fence_after();
       if (tr0) p.trace[t * 8 + 1] = clock64();
@@ -685,7 +695,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         mode = !general ? 0 : (SL.staged && !__any_sync(0xffffffffu, span > 3)) ? 1 : 2;
       }
       h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;
-#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp)
+#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
       if (!key_masked) {
         if (mode == 0) DML_DKV_SWEEP(false, 0);
         else if (mode == 1) DML_DKV_SWEEP(false, 1);

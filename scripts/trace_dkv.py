@@ -21,7 +21,7 @@ np.save("gpurun_out/trace_dkv.npy", t)
 for lo, hi in ((8, 100), (200, 300), (400, 500)):
     w = t[lo:hi]
     print(f"tiles {lo}-{hi}: period {np.diff(w[:, 1]).mean():.0f}"
-          f" | warp0: wait S {(w[:, 1] - w[:, 0]).mean():.0f} sweep {(w[:, 2] - w[:, 1]).mean():.0f}"
+          f" | warp0: sweep {(w[:, 2] - w[:, 1]).mean():.0f} of which segment hand-over {(w[:, 2] - w[:, 0]).mean():.0f}"
           f" | warp3: sweep {(w[:, 4] - w[:, 3]).mean():.0f} start skew vs warp0 {(w[:, 3] - w[:, 1]).mean():.0f}"
           f" | MMA: warp0 sweep done -> P seen {(w[:, 5] - w[:, 2]).mean():.0f}, issue dV/dK {(w[:, 6] - w[:, 5]).mean():.0f},"
           f" S(t+1) issued - S(t) seen by warp0 {(w[:, 7] - w[:, 1]).mean():.0f}")
