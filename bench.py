@@ -360,7 +360,7 @@ def main():
     # dominant entry point: the attention backward (3 kernels: prep + dK/dV/dg/segsums + dQ), then the forward
     top = max(kavg, key=lambda k: kavg[k] * kcalls[k])
     exec_fwd = fl["qk"] + 2.0 * fl["pv"]                             # S = QK^T, O += P_hi V, O += P_lo V  (tcgen05 MMAs issued)
-    exec_bwd = 7.0 * fl["qk"]                                        # S^T,dP^T,dV,dK (4) + S,dP,dQ (3) GEMMs of n x n_kv x 64
+    exec_bwd = 5.0 * fl["qk"]                                        # S^T,dP^T,dV,dK (4) + dQ = dS K over the dS^T workspace (1): GEMMs of n x n_kv x 64
     exec_fl = {"dml_deform_attn_fwd": fl["qk"] + fl["pv"], "dml_deform_attn_bwd": exec_bwd,
                "dml_deform_attn_fwd_tc": exec_fwd, "dml_deform_attn_bwd_tc": exec_bwd}.get(top)
     roof = None
@@ -370,9 +370,10 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's kernels at N = 16 384 from
-                # the ncu --set full capture profiles/r1_b_ncu_full_attn_tcgen05_summary.csv (algorithmic: q,k,v,dO
-                # fp16 + O, dQ, dK, dV fp32 = 42 / 97 MB)
-                "traffic": ({"dml_deform_attn_fwd_tc": 25.4e6, "dml_deform_attn_bwd_tc": 43.8e6 + 46.5e6}.get(top)
+                # ncu (profiles/r1_c_ncu_attn_dram_bytes.csv).  Backward: 70 MB + 1043 MB (dK/dV kernel, writes the fp16
+                # dS^T workspace: 8 heads x 4096 x 16416 x 2 B = 1.08 GB) + 1086 MB + 29 MB (dQ GEMM, reads it back);
+                # algorithmic without the workspace: q,k,v,dO fp16 + O, dQ, dK, dV fp32 = 97 MB
+                "traffic": ({"dml_deform_attn_fwd_tc": 25.4e6, "dml_deform_attn_bwd_tc": 2229e6}.get(top)
                             if N == N_PATCHES else None),
                 "peak_source": pk_kind + " (sustained)",
                 "ms_per_launch": kavg[top],

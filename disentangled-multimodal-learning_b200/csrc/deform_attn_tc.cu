@@ -139,7 +139,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   const Lookup L = tab_stage(sgen + kOffRec, sbase + kOffRec, p.table, tid, kThreads);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) tab_finish(sgen + kOffRec);
+  if (warp == 0) tab_finish(sgen + kOffRec, lane);
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;

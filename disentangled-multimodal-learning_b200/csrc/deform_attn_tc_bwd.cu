@@ -44,6 +44,7 @@ struct BwdParams {
   float scale;
   h16* ds_ws;            // optional fp16 [(B H), n_kv_pad, n_pad]: dS^T (times s) written by the dK/dV kernel
   int n_pad, n_kv_pad;
+  int qsplit;            // dK/dV kernel: the query tiles of one key block are shared by this many CTAs (blockIdx.x % qsplit)
   long long* trace;      // debug: per-tile clock64() stamps of CTA (0,0,0) of the dQ kernel (nullptr = off)
 };
 static long long* g_trace = nullptr;
@@ -175,7 +176,7 @@ deform_attn_dq_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_co
   const Lookup L = tab_stage(sgen + kOffTab, sbase + kOffTab, p.table, tid, kThreads);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) tab_finish(sgen + kOffTab);
+  if (warp == 0) tab_finish(sgen + kOffTab, lane);
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
@@ -539,9 +540,13 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
-  const int j0 = blockIdx.x * kBK, grp = blockIdx.y, b = blockIdx.z;
+  // blockIdx.x = key block * qsplit + part: `part` takes the query tiles [t_begin, t_end) of the key block.  With 128 key
+  // blocks x head pairs on 148 SMs a whole-item decomposition leaves 20 SMs idle; qsplit CTAs per item fill the waves
+  // (the host picks qsplit) and add their dK / dV into the zeroed outputs with float4 reductions.
+  const int j0 = (blockIdx.x / p.qsplit) * kBK, grp = blockIdx.y, b = blockIdx.z;
   const int G = p.H / 2, h0 = grp * 2;
-  const int ntiles = cdiv(p.n, kBI);
+  const int t_begin = (int)((long long)cdiv(p.n, kBI) * (blockIdx.x % p.qsplit) / p.qsplit);
+  const int ntiles = (int)((long long)cdiv(p.n, kBI) * (blockIdx.x % p.qsplit + 1) / p.qsplit);      // end of this CTA's tile range
   auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
 
@@ -560,7 +565,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   const SegLookup SL = seg_stage(sgen + kOffSeg, sbase + kOffSeg, p.table, tid, kThreads);
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) tab_finish(sgen + kOffTab);
+  if (warp == 0) tab_finish(sgen + kOffTab, lane);
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
@@ -576,9 +581,9 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     }
     const float* lb = p.lse + ((size_t)b * p.H + h0) * p.n;
     const float* db = p.dsum + ((size_t)b * p.H + h0) * p.n;
-    for (int t = 0; t < ntiles; ++t) {
-      const int st = t % kStages;
-      mbar_wait(bar(kBarInEmpty + st), ((t / kStages) & 1) ^ 1);
+    for (int t = t_begin; t < ntiles; ++t) {
+      const int it = t - t_begin, st = it % kStages;
+      mbar_wait(bar(kBarInEmpty + st), ((it / kStages) & 1) ^ 1);
       const uint32_t dst = sbase + kOffIn + st * kStageBytes;
       if (lane == 0) {
         mbar_expect_tx_only(bar(kBarInFull + st), kStageBytes);
@@ -603,8 +608,8 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     {
       const bool leader = elect_one();
       mbar_wait(bar(kBarKv), 0);
-      auto issue_sd = [&](int t) {
-        const int st = t % kStages, buf = t & 1;
+      auto issue_sd = [&](int it) {
+        const int st = it % kStages, buf = it & 1;
         const uint32_t in = sbase + kOffIn + st * kStageBytes;
         for (int h = 0; h < 2; ++h) {
           const uint64_t dk_ = smem_desc(sbase + kOffKV + h * kTileKV), dq_ = smem_desc(in + h * kTileQ);
@@ -621,9 +626,10 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       tc_fence_after();
       issue_sd(0);
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
-      for (int t = 0; t < ntiles; ++t) {
+      const int nit = ntiles - t_begin;
+      for (int t = 0; t < nit; ++t) {                    // t counts this CTA's tiles from here on
         const int st = t % kStages, buf = t & 1;
-        if (t + 1 < ntiles) {
+        if (t + 1 < nit) {
           mbar_wait(bar(kBarInFull + (t + 1) % kStages), ((t + 1) / kStages) & 1);
           tc_fence_after();
           issue_sd(t + 1);
@@ -661,7 +667,8 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const uint32_t lane_off = ((uint32_t)(warp & 3) * 32u) << 16;
     const float sc2 = p.scale * kLog2e;
     float dgacc = 0.f;
-    h16* const ds_row = p.ds_ws ? p.ds_ws + ((size_t)(b * p.H + h0 + head) * p.n_kv_pad + gj) * p.n_pad + half * 16 : nullptr;
+    h16* const ds_row =
+        p.ds_ws ? p.ds_ws + ((size_t)(b * p.H + h0 + head) * p.n_kv_pad + gj) * p.n_pad + t_begin * kBI + half * 16 : nullptr;
     SegRun run;
     run.seg = -1;
     run.a = run.b = 0.f;
@@ -670,7 +677,8 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
 
     const bool tr0 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 0;
     const bool tr3 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 3;
-    for (int t = 0; t < ntiles; ++t) {
+    const int nit = ntiles - t_begin;
+    for (int t = 0; t < nit; ++t) {                      // t counts this CTA's tiles
       const int st = t % kStages, buf = t & 1;
       mbar_wait(bar(kBarInFull + st), (t / kStages) & 1);
       mbar_wait(bar(kBarSFull + buf), (t >> 1) & 1);
@@ -694,7 +702,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         const bool general = __any_sync(0xffffffffu, span > 1 || tab_dirty_between(L, c0, c1) != 0);
         mode = !general ? 0 : (SL.staged && !__any_sync(0xffffffffu, span > 3)) ? 1 : 2;
       }
-      h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;
+      h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;      // ds_row already points at this CTA's first tile
 #define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
       if (!key_masked) {
         if (mode == 0) DML_DKV_SWEEP(false, 0);
@@ -733,10 +741,13 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         tmem_ld_wait(a);
         if (kvld) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(dst + c * 16 + e) =
-                make_float4(__uint_as_float(a[e]) * f, __uint_as_float(a[e + 1]) * f, __uint_as_float(a[e + 2]) * f,
-                            __uint_as_float(a[e + 3]) * f);
+          for (int e = 0; e < 16; e += 4) {
+            const float4 v = make_float4(__uint_as_float(a[e]) * f, __uint_as_float(a[e + 1]) * f, __uint_as_float(a[e + 2]) * f,
+                                         __uint_as_float(a[e + 3]) * f);
+            float4* o = reinterpret_cast<float4*>(dst + c * 16 + e);
+            if (p.qsplit == 1) *o = v;
+            else atomicAdd(o, v);
+          }
         }
       }
     }
@@ -929,7 +940,30 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   }
   const int rows = B * n;
   bwd_prep_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>((const float*)out, (const h16*)d_out, B, n, H, ldo, dsum_ws);
-  deform_attn_dkv_tc_kernel<<<dim3(cdiv(n_kv, dkvk::kBK), G, B), dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p);
+  {
+    // query split of the dK/dV kernel: the qsplit in 1..16 with the shortest estimated makespan
+    // ceil(items * qsplit / SMs) / qsplit, each extra part charged 8 % for its prologue (table staging, K/V load, pipeline
+    // fill) and reduction traffic - measured at n = 16385: 128 items on 148 SMs are faster unsplit (1.53 ms) than as
+    // 1024 parts in 7 waves (1.61 ms), so the split only pays when the items leave most of the SMs idle
+    static int nsm = 0;
+    if (!nsm) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
+    }
+    const int items = cdiv(n_kv, dkvk::kBK) * G * B, ntiles = cdiv(n, dkvk::kBI);
+    int best = 1;
+    double best_t = (double)cdiv(items, nsm);
+    for (int sp = 2; sp <= 16 && ntiles / sp >= 48; ++sp) {
+      const double t = (double)cdiv(items * sp, nsm) / sp * (1.0 + 0.08 * (sp - 1));
+      if (t < best_t) { best_t = t; best = sp; }
+    }
+    p.qsplit = best;
+    if (best > 1) {
+      if ((e = cudaMemsetAsync(dk, 0, sizeof(float) * (size_t)B * n_kv * H * kD, st)) != cudaSuccess) return (int)e;
+      if ((e = cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)B * n_kv * H * kD, st)) != cudaSuccess) return (int)e;
+    }
+    deform_attn_dkv_tc_kernel<<<dim3(cdiv(n_kv, dkvk::kBK) * best, G, B), dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p);
+  }
   if (ds_ws)
     deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), G, B), dqg::kThreads, dqg::kSmemBytes, st>>>(mds, mk64, p);
   else

@@ -162,7 +162,7 @@ struct Lookup {
 __device__ __forceinline__ int cell_index(const Lookup& L, float x) {
   return __float_as_int(fmaf(x, L.c1, L.c2m) + 12582912.0f) - 0x4B400000;      // 12582912 = 1.5 * 2^23
 }
-// all threads of the CTA; the caller must __syncthreads() afterwards, then thread 0 calls tab_finish and syncs again
+// all threads of the CTA; the caller must __syncthreads() afterwards, then warp 0 calls tab_finish and syncs again
 __device__ __forceinline__ Lookup tab_stage(uint8_t* sgen, uint32_t saddr, const uint32_t* __restrict__ table, int tid, int nthreads) {
   float* bp = reinterpret_cast<float*>(sgen);
   float4* piece = reinterpret_cast<float4*>(sgen + kCpbCells * 4);
@@ -188,15 +188,30 @@ __device__ __forceinline__ Lookup tab_stage(uint8_t* sgen, uint32_t saddr, const
   L.c2m = X * inv - 0.5f;
   return L;
 }
-__device__ __forceinline__ void tab_finish(uint8_t* sgen) {   // one thread: running count of flagged cells
+__device__ __forceinline__ void tab_finish(uint8_t* sgen, int lane) {   // one warp: running count of flagged cells
+  static_assert(kCpbCells % 32 == 0, "cells per lane");
+  constexpr int kPer = kCpbCells / 32;                 // contiguous cells per lane
   const float* bp = reinterpret_cast<const float*>(sgen);
   uint32_t* meta = reinterpret_cast<uint32_t*>(sgen + kCpbCells * 36);
-  uint32_t cnt = 0;
-  for (int i = 0; i <= kCpbCells; ++i) {
-    const uint32_t lo = i < kCpbCells ? (meta[i] & 0xffffu) : 0u;
-    meta[i] = lo | (cnt << 16);
-    if (i < kCpbCells && bp[i] != bp[i]) ++cnt;
+  uint32_t own = 0;
+  for (int i = 0; i < kPer; ++i) {
+    const float v = bp[lane * kPer + i];
+    own += v != v ? 1u : 0u;
   }
+  uint32_t incl = own;                                 // inclusive scan over the lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  uint32_t cnt = incl - own;                           // flagged cells before this lane's first cell
+  for (int i = 0; i < kPer; ++i) {
+    const int c = lane * kPer + i;
+    const float v = bp[c];
+    meta[c] = (meta[c] & 0xffffu) | (cnt << 16);
+    cnt += v != v ? 1u : 0u;
+  }
+  if (lane == 31) meta[kCpbCells] = cnt << 16;
 }
 // largest |g| for which every |p| <= 1 + |g| stays inside the table domain
 __device__ __forceinline__ float tab_gmax(const uint32_t* __restrict__ table) {

@@ -18,10 +18,9 @@ torch.cuda.synchronize()
 _lib.load().dml_debug_set_trace(None)
 t = buf.cpu().numpy().reshape(nt, 8).astype(np.int64)
 np.save("gpurun_out/trace_dkv.npy", t)
-for lo, hi in ((8, 100), (200, 300), (400, 500)):
+for lo, hi in ((8, 100), (200, 300), (330, 430)):
     w = t[lo:hi]
     print(f"tiles {lo}-{hi}: period {np.diff(w[:, 1]).mean():.0f}"
           f" | warp0: sweep {(w[:, 2] - w[:, 1]).mean():.0f} of which segment hand-over {(w[:, 2] - w[:, 0]).mean():.0f}"
-          f" | warp3: sweep {(w[:, 4] - w[:, 3]).mean():.0f} start skew vs warp0 {(w[:, 3] - w[:, 1]).mean():.0f}"
           f" | MMA: warp0 sweep done -> P seen {(w[:, 5] - w[:, 2]).mean():.0f}, issue dV/dK {(w[:, 6] - w[:, 5]).mean():.0f},"
           f" S(t+1) issued - S(t) seen by warp0 {(w[:, 7] - w[:, 1]).mean():.0f}")
