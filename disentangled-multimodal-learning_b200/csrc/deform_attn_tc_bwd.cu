@@ -407,12 +407,11 @@ __device__ __forceinline__ void seg_flush_warp(const SegSink& ssum, bool need, i
 // tS = TMEM address of the warp's first S^T column of this head (dP^T sits 64 columns further).
 template <bool kKeyMasked, int kMode>
 __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, uint32_t tS, uint32_t rowa, int head, float g_j,
-                                          bool key_valid, float sc2, int seg_first, int seg_last, float& dgacc, SegRun& run,
+                                          bool key_valid, float sc2, int seg_first, int seg_last, float xb, float& dgacc, SegRun& run,
                                           const SegSink& ssum, h16* dsp, long long* trc = nullptr) {
   const int lane = threadIdx.x & 31;
-  float xb = __int_as_float(0x7f800000);      // kMode 0: boundary between the two buckets (+inf: a single bucket)
-  if (kMode == 0 && seg_last != seg_first)
-    xb = SL.staged ? lds_f32(SL.bp + (uint32_t)seg_first * 4u) : __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
+  const uint32_t hoff = head ? 8u : 0u;
+  // xb (kMode 0): upper boundary of segment seg_first = the split between the two buckets
   float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};   // kMode 0: [0] whole tile, [1] at or above xb; kMode 1: per segment
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries
@@ -464,14 +463,14 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
         const float qa = fabsf(pr) + 1.0f;
         const float x = kMode == 1 ? xs[e + u] : copysignf(__log2f(qa), pr);
         int cell, seg = 0;
-        float4 t;
+        float2 t;                                          // this head's (slope, intercept)
         if (kMode == 1) {
           seg = sg[e + u];
-          t = lds_f32x4(SL.coef + (uint32_t)seg * 16u);
+          t = lds_f32x2(SL.coef + (uint32_t)seg * 16u + hoff);
         } else {
-          t = lookup2<kMode == 2, kMode == 2>(L, x, cell, seg);
+          t = lookup2h<kMode == 2, kMode == 2>(L, x, hoff, cell, seg);
         }
-        const float slope = head ? t.z : t.x, icpt = head ? t.w : t.y;
+        const float slope = t.x, icpt = t.y;
         float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(slope, x, icpt)) - l0[e + u]);
         float s0 = p0 * (__uint_as_float(pa[e + u]) - d0[e + u]);
         if (kKeyMasked && !key_valid) { p0 = 0.f; s0 = 0.f; }
@@ -689,21 +688,37 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       const uint32_t tS = tmem + lane_off + buf * 128 + head * 32 + half * 16;
       // segments of this thread's first / last position -> which variant the whole warp takes (see dkv_sweep)
       int seg_first, seg_last, mode;
-      {
-        int c0, c1;
-        if (SL.staged) {
-          lookup_seg(L, SL, cpb_x(lds_f32(rowa) - g_j), c0, seg_first);
-          lookup_seg(L, SL, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
+      float xb = __int_as_float(0x7f800000);
+      const float x_first = cpb_x(lds_f32(rowa) - g_j), x_last = cpb_x(lds_f32(rowa + 15 * 4) - g_j);
+      if (SL.staged) {
+        // x only grows from tile to tile, so the first segment is found by stepping on from where the last tile ended
+        // (run.seg), and two boundaries decide the variant: xb = end of seg_first, and the one after it
+        int sf = run.seg;
+        if (sf < 0) { int c; lookup_seg(L, SL, x_first, c, sf); }
+        else { while (x_first >= lds_f32(SL.bp + (uint32_t)sf * 4u)) ++sf; }
+        seg_first = sf;
+        xb = lds_f32(SL.bp + (uint32_t)sf * 4u);
+        const float xb2 = lds_f32(SL.bp + (uint32_t)sf * 4u + 4u);
+        const bool dirty = tab_dirty_between(L, cell_index(L, x_first), cell_index(L, x_last)) != 0;
+        if (!__any_sync(0xffffffffu, x_last >= xb2 || dirty)) {
+          seg_last = sf + (x_last >= xb ? 1 : 0);
+          mode = 0;
         } else {
-          lookup2<true, true>(L, cpb_x(lds_f32(rowa) - g_j), c0, seg_first);
-          lookup2<true, true>(L, cpb_x(lds_f32(rowa + 15 * 4) - g_j), c1, seg_last);
+          int sl = sf;
+          while (x_last >= lds_f32(SL.bp + (uint32_t)sl * 4u)) ++sl;
+          seg_last = sl;
+          mode = __any_sync(0xffffffffu, sl - sf > 3) ? 2 : 1;
         }
+      } else {
+        int c0, c1;
+        lookup2<true, true>(L, x_first, c0, seg_first);
+        lookup2<true, true>(L, x_last, c1, seg_last);
         const int span = seg_last - seg_first;
-        const bool general = __any_sync(0xffffffffu, span > 1 || tab_dirty_between(L, c0, c1) != 0);
-        mode = !general ? 0 : (SL.staged && !__any_sync(0xffffffffu, span > 3)) ? 1 : 2;
+        mode = __any_sync(0xffffffffu, span > 1 || tab_dirty_between(L, c0, c1) != 0) ? 2 : 0;
+        if (span == 1) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
       }
       h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;      // ds_row already points at this CTA's first tile
-#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
+#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, xb, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
       if (!key_masked) {
         if (mode == 0) DML_DKV_SWEEP(false, 0);
         else if (mode == 1) DML_DKV_SWEEP(false, 1);

@@ -27,11 +27,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"      // %2: suspend-time hint, so a waiting warp
+      "@P1 bra DONE;\n"                                                     // sleeps in the barrier unit instead of
+      "bra LAB_WAIT;\n"                                                     // re-polling through the issue slots
       "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
@@ -118,6 +118,11 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn, bool b
 __device__ __forceinline__ float seq_pos(int i, int n) { return (2.0f * (float)i) / (float)max(n - 1, 1) - 1.0f; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -253,7 +258,7 @@ __device__ __forceinline__ SegLookup seg_stage(uint8_t* sgen, uint32_t saddr, co
   S.bp = saddr;
   S.coef = saddr + kSegSmem * 4;
   const int nseg = (int)__ldg(table);
-  S.staged = nseg <= kSegSmem;
+  S.staged = nseg < kSegSmem;      // strict: callers may read one boundary past the last segment
   if (S.staged) {
     float* bp = reinterpret_cast<float*>(sgen);
     float4* coef = reinterpret_cast<float4*>(sgen + kSegSmem * 4);
@@ -272,6 +277,22 @@ __device__ __forceinline__ float4 lookup_seg(const Lookup& L, const SegLookup& S
   while (x >= lds_f32(S.bp + (uint32_t)s * 4u)) ++s;
   seg = s;
   return lds_f32x4(S.coef + (uint32_t)s * 16u);
+}
+// one head's (a, c) only: `hoff` = 8 * head selects the pair inside the 16-byte piece
+template <bool kDirty, bool kSeg>
+__device__ __forceinline__ float2 lookup2h(const Lookup& L, float x, uint32_t hoff, int& cell, int& seg) {
+  cell = cell_index(L, x);
+  const float bpv = lds_f32(L.bp + (uint32_t)cell * 4u);
+  const bool hi = x >= bpv;
+  float2 e = lds_f32x2(L.piece + (uint32_t)cell * 32u + (hi ? 16u : 0u) + hoff);
+  if (kSeg) seg = (lds_s32(L.meta + (uint32_t)cell * 4u) & 0xffff) + (hi ? 1 : 0);
+  if (kDirty) {
+    if (bpv != bpv) {
+      const float4 f = lookup_slow(L.gtab, cell, x, kSeg ? &seg : nullptr);
+      e = hoff ? make_float2(f.z, f.w) : make_float2(f.x, f.y);
+    }
+  }
+  return e;
 }
 __device__ __forceinline__ int tab_dirty_between(const Lookup& L, int cell_lo, int cell_hi) {   // flagged cells in [lo, hi]
   return (lds_s32(L.meta + (uint32_t)(cell_hi + 1) * 4u) >> 16) - (lds_s32(L.meta + (uint32_t)cell_lo * 4u) >> 16);
