@@ -624,7 +624,11 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       mbar_wait(bar(kBarInFull + 0), 0);
       tc_fence_after();
       issue_sd(0);
+#ifdef DML_TRACE
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#else
+      constexpr bool tr = false;
+#endif
       const int nit = ntiles - t_begin;
       for (int t = 0; t < nit; ++t) {                    // t counts this CTA's tiles from here on
         const int st = t % kStages, buf = t & 1;
@@ -674,13 +678,17 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const float inv_s = __ldg(p.dscale + 1);
     const SegSink ssum{p.segsum, inv_s};
 
+#ifdef DML_TRACE      // clock64() stamps of CTA 0 for scripts/trace_dkv.py (build with -DDML_TRACE)
     const bool tr0 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 0;
     const bool tr3 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 3;
+#else
+    constexpr bool tr0 = false, tr3 = false;
+#endif
     const int nit = ntiles - t_begin;
     for (int t = 0; t < nit; ++t) {                      // t counts this CTA's tiles
       const int st = t % kStages, buf = t & 1;
-      mbar_wait(bar(kBarInFull + st), (t / kStages) & 1);
-      mbar_wait(bar(kBarSFull + buf), (t >> 1) & 1);
+      mbar_wait_relaxed(bar(kBarInFull + st), (t / kStages) & 1);
+      mbar_wait_relaxed(bar(kBarSFull + buf), (t >> 1) & 1);
       tc_fence_after();
       if (tr0) p.trace[t * 8 + 1] = clock64();
       if (tr3) p.trace[t * 8 + 3] = clock64();
