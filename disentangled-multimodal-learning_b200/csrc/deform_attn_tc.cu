@@ -155,7 +155,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const float* gb = p.g + (size_t)(b * G + grp) * p.n_kv;
     for (int j = 0; j < ntiles; ++j) {
       const int st = j % kStages;
-      mbar_wait(bar(kBarKvEmpty + st), ((j / kStages) & 1) ^ 1);
+      mbar_wait_relaxed(bar(kBarKvEmpty + st), ((j / kStages) & 1) ^ 1);
       const uint32_t dst = sbase + kOffKV + st * kStageBytes;
       if (lane == 0) {
         mbar_expect_tx_only(bar(kBarKvFull + st), kStageBytes);
@@ -202,7 +202,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         issue_s(j + 1);
       }
       const uint32_t kv = sbase + kOffKV + st * kStageBytes;
-      mbar_wait(bar(kBarPFull + g * 2 + buf), (j >> 1) & 1);
+      mbar_wait_relaxed(bar(kBarPFull + g * 2 + buf), (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

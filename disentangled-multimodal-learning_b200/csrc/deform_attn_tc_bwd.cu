@@ -582,7 +582,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const float* db = p.dsum + ((size_t)b * p.H + h0) * p.n;
     for (int t = t_begin; t < ntiles; ++t) {
       const int it = t - t_begin, st = it % kStages;
-      mbar_wait(bar(kBarInEmpty + st), ((it / kStages) & 1) ^ 1);
+      mbar_wait_relaxed(bar(kBarInEmpty + st), ((it / kStages) & 1) ^ 1);
       const uint32_t dst = sbase + kOffIn + st * kStageBytes;
       if (lane == 0) {
         mbar_expect_tx_only(bar(kBarInFull + st), kStageBytes);
@@ -638,7 +638,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           issue_sd(t + 1);
         }
         if (tr) p.trace[t * 8 + 7] = clock64();
-        mbar_wait(bar(kBarPFull + buf), (t >> 1) & 1);
+        mbar_wait_relaxed(bar(kBarPFull + buf), (t >> 1) & 1);
         tc_fence_after();
         if (tr) p.trace[t * 8 + 5] = clock64();
         const uint32_t in = sbase + kOffIn + st * kStageBytes;
