@@ -246,3 +246,30 @@ def test_too_short_sequence_is_rejected():
     x = synth.normal((1, 128, 2), 92, "x").to(DEV)
     with pytest.raises(Exception):
         mod(x, x)
+
+
+def test_backward_workspace_and_recompute_paths_agree(monkeypatch):
+    """dQ through the stored dS^T (workspace) and dQ recomputed from q, k, lse are two kernels for the same maths."""
+    from dml_b200 import ops
+    from dml_b200.DeformableAttention1D import DeformCrossAttention1D
+    n = 2100
+    mod = DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6)
+    mod.load_state_dict(synth.fill_like(H.deform_shapes(), 77, gain=1.5), strict=True)
+    mod.to(DEV)
+    x1 = synth.normal((1, 128, n), 5, "x1").to(DEV).requires_grad_()
+    x2 = synth.normal((1, 128, n), 5, "x2").to(DEV).requires_grad_()
+    r = synth.normal((1, 128, n), 5, "r").to(DEV)
+    grads = []
+    for limit in (ops.DS_WS_MAX_BYTES, 0):
+        monkeypatch.setattr(ops, "DS_WS_MAX_BYTES", limit)
+        g = torch.autograd.grad((mod(x1, x2) * r).sum(), [x1, x2] + list(mod.parameters()), allow_unused=True)
+        grads.append(g)
+    names = ["x1", "x2"] + [k for k, _ in mod.named_parameters()]
+    for nm, a, b in zip(names, *grads):
+        if a is None:
+            assert b is None
+            continue
+        if nm.endswith("mlp.2.bias"):      # analytically zero (softmax shift invariance): only rounding noise is left
+            assert float((a - b).abs().max()) <= 1e-3 * max(1e-6, float(grads[0][names.index("rel_pos_bias.mlp.2.weight")].abs().max()))
+            continue
+        H.assert_close(a, b, 2e-4, f"grad {nm}: workspace vs recompute")
