@@ -87,6 +87,15 @@ def grad_scale(t: torch.Tensor) -> torch.Tensor:
 DS_WS_MAX_BYTES = int(float(os.environ.get("DML_B200_DS_WS_MAX_GB", "6")) * (1 << 30))
 
 
+def _proj_nt(x, W, out_shape=None):
+    """x [B, rows, K] (tensor or an already split [1, B*rows, K] operand) times W[N, K]^T on the tcgen05 split GEMM."""
+    if not isinstance(x, SplitOperand):
+        out_shape = x.shape[:-1] + (W.shape[0],)
+        x = SplitOperand(x.reshape(1, -1, x.shape[-1]), True)
+    c = gemm_nt(x, SplitOperand(W[None], True), (1, x.rows, W.shape[0]))
+    return c.reshape(out_shape)
+
+
 class DeformCrossAttn1DFn(torch.autograd.Function):
     """Forward + backward of DeformCrossAttention1D (DeformableAttention1D.py:156-240) on
     token-major inputs x1t, x2t [B, n, dim] (fp32).  Returns (out [B, n, dim] fp32, vgrid [(B G), n_kv]).
@@ -126,8 +135,9 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         with torch.cuda.stream(side):
             call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), stream())
 
-        with fp32_matmul():   # q/k/v feed the softmax exponent: exact fp32 projections, one fp16 rounding at the end
-            q = torch.matmul(x1f, Wq2.t()).to(F16)                        # [B,n,C] (to_q, :175)
+        # q/k/v feed the softmax exponent: fp32-class projections (fp16 hi/lo pairs on tcgen05, 22-bit operands - the
+        # SIMT sgemm they replace was 94 us per call), one fp16 rounding at the end
+        q = _proj_nt(x1f, Wq2).to(F16)                                    # [B,n,C] (to_q, :175)
         vgrid = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         g = torch.empty_like(vgrid)
         call("dml_offsets_fwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), B, n, C, G, ks, stride, float(offset_scale),
@@ -135,9 +145,9 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         i0, i1, wy0, wy1 = centre_taps(n)
         kv = torch.empty(B, n_kv, dim, device=dev, dtype=F32)
         call("dml_kv_gather_fwd", ptr(x2f), ptr(g), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(kv), st)
-        with fp32_matmul():
-            k = torch.matmul(kv, Wk2.t()).to(F16)                         # [B,n_kv,C] (:199)
-            v = torch.matmul(kv, Wv2.t()).to(F16)
+        kv_split = SplitOperand(kv.reshape(1, B * n_kv, dim), True)
+        k = _proj_nt(kv_split, Wk2, (B, n_kv, C)).to(F16)                 # [B,n_kv,C] (:199)
+        v = _proj_nt(kv_split, Wv2, (B, n_kv, C)).to(F16)
         cur.wait_stream(side)                                             # bias table ready
         # offsets / keys / values always need every query position; the attention itself only the first n_out rows
         q_att = q if n_out == n else q[:, :n_out].contiguous()
@@ -167,8 +177,9 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         st = stream()
 
         dout = dout.contiguous().float()
-        with fp32_matmul():   # dO feeds dS = P (dP - D) directly: exact fp32, one fp16 rounding below
-            d_o = torch.matmul(dout, Wo2)                                  # [B,n,C] fp32
+        # dO feeds dS = P (dP - D) directly: fp32-class product, one fp16 rounding below
+        d_o = gemm_nt(SplitOperand(dout.reshape(1, -1, dim), True), SplitOperand(Wo2[None], False),
+                      (1, dout.shape[0] * dout.shape[1], C)).reshape(dout.shape[0], dout.shape[1], C)   # [B,n,C] fp32
         with tf32_matmul():
             dWo = dout.reshape(-1, dim).t() @ o.reshape(-1, C)             # [dim, C]
         dbo = dout.sum(dim=(0, 1))
