@@ -398,20 +398,22 @@ __device__ __forceinline__ void seg_flush_warp(const SegSink& ssum, bool need, i
 
 // 16 queries of one key row, one head.  S^T / dP^T (fp32, TMEM) -> P^T / dS^T (fp16 pairs, in place); accumulates
 // dg and the per-segment sums.  x grows along the row, so the segment index only ever increases.
-//   kMode 0  the thread's 16 positions lie in at most two adjacent table segments [seg_first, seg_last] split at xb and
-//            touch no flagged cell: two register buckets, no per-position segment lookup (the common case);
-//   kMode 1  some lane of the warp crosses up to three boundaries or touches a flagged cell: per-position lookup in the
-//            shared-memory segment arrays, four register buckets seg_first .. seg_first + 3;
-//   kMode 2  anything else (more than kSegSmem segments, > 3 boundaries in 16 positions): per-position lookup through
-//            the global table, run-length merged with per-thread atomics.
+// The thread therefore knows its segment: bnd = (xb, xb2, xb3) are the next three boundaries after seg_first.
+//   kMode 0  the 16 positions lie in at most two adjacent segments [seg_first, seg_first + 1] split at xb: the two
+//            segments' coefficients (clo, chi) sit in registers, a position costs one compare and two selects - no table
+//            access at all - and the sums go to two register buckets (the common case);
+//   kMode 1  some lane of the warp crosses two or three boundaries: segment = seg_first + number of boundaries passed,
+//            coefficients from the shared-memory segment array, four register buckets;
+//   kMode 2  anything else (table with more than kSegSmem segments, > 3 boundaries in 16 positions): per-position
+//            lookup through the cell index / global table, run-length merged with per-thread reductions.
 // tS = TMEM address of the warp's first S^T column of this head (dP^T sits 64 columns further).
 template <bool kKeyMasked, int kMode>
 __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, uint32_t tS, uint32_t rowa, int head, float g_j,
-                                          bool key_valid, float sc2, int seg_first, int seg_last, float xb, float& dgacc, SegRun& run,
-                                          const SegSink& ssum, h16* dsp, long long* trc = nullptr) {
+                                          bool key_valid, float sc2, int seg_first, int seg_last, float3 bnd, float2 clo, float2 chi,
+                                          float& dgacc, SegRun& run, const SegSink& ssum, h16* dsp, long long* trc = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint32_t hoff = head ? 8u : 0u;
-  // xb (kMode 0): upper boundary of segment seg_first = the split between the two buckets
+  const float xb = bnd.x;
   float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};   // kMode 0: [0] whole tile, [1] at or above xb; kMode 1: per segment
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries
@@ -432,28 +434,6 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
     tmem_ld_fence();
     reg_fence(a); reg_fence(pa);
     uint32_t wp[4], ws[4];
-    int sg[8];                                            // kMode 1: segment and x of each position
-    float xs[8];
-    if (kMode == 1) {
-      // all 8 positions in lock step (no per-position loop, so their loads overlap): start from the segment at the
-      // beginning of the cell, then step over boundaries until no lane of the warp moves any more
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float pr = sq[e] - g_j;
-        xs[e] = copysignf(__log2f(fabsf(pr) + 1.0f), pr);
-        sg[e] = lds_s32(L.meta + (uint32_t)cell_index(L, xs[e]) * 4u) & 0xffff;
-      }
-      bool more;
-      do {
-        more = false;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool m = xs[e] >= lds_f32(SL.bp + (uint32_t)sg[e] * 4u);
-          sg[e] += m ? 1 : 0;
-          more |= m;
-        }
-      } while (__any_sync(0xffffffffu, more));
-    }
 #pragma unroll
     for (int e = 0; e < 8; e += 2) {
       float pp[2], dd[2];
@@ -461,14 +441,17 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
       for (int u = 0; u < 2; ++u) {
         const float pr = sq[e + u] - g_j;
         const float qa = fabsf(pr) + 1.0f;
-        const float x = kMode == 1 ? xs[e + u] : copysignf(__log2f(qa), pr);
+        const float x = copysignf(__log2f(qa), pr);
         int cell, seg = 0;
+        const bool above = x >= xb;
         float2 t;                                          // this head's (slope, intercept)
-        if (kMode == 1) {
-          seg = sg[e + u];
-          t = lds_f32x2(SL.coef + (uint32_t)seg * 16u + hoff);
+        if (kMode == 0) {
+          t = above ? chi : clo;
+        } else if (kMode == 1) {
+          seg = (above ? 1 : 0) + (x >= bnd.y ? 1 : 0) + (x >= bnd.z ? 1 : 0);      // relative to seg_first
+          t = lds_f32x2(SL.coef + (uint32_t)(seg_first + seg) * 16u + hoff);
         } else {
-          t = lookup2h<kMode == 2, kMode == 2>(L, x, hoff, cell, seg);
+          t = lookup2h<true, true>(L, x, hoff, cell, seg);
         }
         const float slope = t.x, icpt = t.y;
         float p0 = ex2(fmaf(__uint_as_float(a[e + u]), sc2, fmaf(slope, x, icpt)) - l0[e + u]);
@@ -481,15 +464,14 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
           if (seg != run.seg) { seg_flush(ssum, run, head); run.seg = seg; }
           run.a += s0; run.b = fmaf(s0, x, run.b);
         } else if (kMode == 1) {
-          const int k = seg - seg_first;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float m = k == q ? s0 : 0.f;      // select, not a branch: the positions stay interleaved
+            const float m = seg == q ? s0 : 0.f;    // select, not a branch: the positions stay interleaved
             ba[q] += m; bb[q] = fmaf(m, x, bb[q]);
           }
         } else {
           ba[0] += s0; bb[0] = fmaf(s0, x, bb[0]);
-          if (x >= xb) { ba[1] += s0; bb[1] = fmaf(s0, x, bb[1]); }
+          if (above) { ba[1] += s0; bb[1] = fmaf(s0, x, bb[1]); }
         }
       }
       wp[e >> 1] = pack_f16(pp[0], pp[1]);
@@ -694,24 +676,26 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       if (tr3) p.trace[t * 8 + 3] = clock64();
       const uint32_t rowa = sbase + kOffRow + st * kRowStride + half * 64;
       const uint32_t tS = tmem + lane_off + buf * 128 + head * 32 + half * 16;
-      // segments of this thread's first / last position -> which variant the whole warp takes (see dkv_sweep)
+      // segment of this thread's first position and the boundaries after it -> which variant the whole warp takes
       int seg_first, seg_last, mode;
-      float xb = __int_as_float(0x7f800000);
+      float3 bnd = make_float3(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000));
+      float2 clo = make_float2(0.f, 0.f), chi = clo;
       const float x_first = cpb_x(lds_f32(rowa) - g_j), x_last = cpb_x(lds_f32(rowa + 15 * 4) - g_j);
       if (SL.staged) {
-        // x only grows from tile to tile, so the first segment is found by stepping on from where the last tile ended
-        // (run.seg), and two boundaries decide the variant: xb = end of seg_first, and the one after it
+        // x only grows from tile to tile: step on from the segment the last tile ended in (run.seg)
         int sf = run.seg;
         if (sf < 0) { int c; lookup_seg(L, SL, x_first, c, sf); }
         else { while (x_first >= lds_f32(SL.bp + (uint32_t)sf * 4u)) ++sf; }
         seg_first = sf;
-        xb = lds_f32(SL.bp + (uint32_t)sf * 4u);
-        const float xb2 = lds_f32(SL.bp + (uint32_t)sf * 4u + 4u);
-        const bool dirty = tab_dirty_between(L, cell_index(L, x_first), cell_index(L, x_last)) != 0;
-        if (!__any_sync(0xffffffffu, x_last >= xb2 || dirty)) {
-          seg_last = sf + (x_last >= xb ? 1 : 0);
+        bnd.x = lds_f32(SL.bp + (uint32_t)sf * 4u);
+        bnd.y = lds_f32(SL.bp + (uint32_t)sf * 4u + 4u);
+        if (!__any_sync(0xffffffffu, x_last >= bnd.y)) {
+          seg_last = sf + (x_last >= bnd.x ? 1 : 0);
+          clo = lds_f32x2(SL.coef + (uint32_t)sf * 16u + (head ? 8u : 0u));
+          chi = lds_f32x2(SL.coef + (uint32_t)sf * 16u + 16u + (head ? 8u : 0u));
           mode = 0;
         } else {
+          bnd.z = lds_f32(SL.bp + (uint32_t)sf * 4u + 8u);
           int sl = sf;
           while (x_last >= lds_f32(SL.bp + (uint32_t)sl * 4u)) ++sl;
           seg_last = sl;
@@ -721,12 +705,10 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         int c0, c1;
         lookup2<true, true>(L, x_first, c0, seg_first);
         lookup2<true, true>(L, x_last, c1, seg_last);
-        const int span = seg_last - seg_first;
-        mode = __any_sync(0xffffffffu, span > 1 || tab_dirty_between(L, c0, c1) != 0) ? 2 : 0;
-        if (span == 1) xb = __ldg(reinterpret_cast<const float*>(L.gtab + kTabSegBp) + seg_first);
+        mode = 2;
       }
       h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;      // ds_row already points at this CTA's first tile
-#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, xb, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
+#define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, bnd, clo, chi, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
       if (!key_masked) {
         if (mode == 0) DML_DKV_SWEEP(false, 0);
         else if (mode == 1) DML_DKV_SWEEP(false, 1);

@@ -274,7 +274,7 @@ __device__ __forceinline__ SegLookup seg_stage(uint8_t* sgen, uint32_t saddr, co
   S.bp = saddr;
   S.coef = saddr + kSegSmem * 4;
   const int nseg = (int)__ldg(table);
-  S.staged = nseg < kSegSmem;      // strict: callers may read one boundary past the last segment
+  S.staged = nseg + 2 < kSegSmem;  // callers read up to three boundaries / one coefficient pair past the last segment
   if (S.staged) {
     float* bp = reinterpret_cast<float*>(sgen);
     float4* coef = reinterpret_cast<float4*>(sgen + kSegSmem * 4);
