@@ -44,10 +44,12 @@ struct BwdParams {
   float scale;
   h16* ds_ws;            // optional fp16 [(B H), n_kv_pad, n_pad]: dS^T (times s) written by the dK/dV kernel
   int n_pad, n_kv_pad;
+  int seg_limit;         // dK/dV kernel: tables with >= seg_limit - 2 segments are not staged (debug knob, default kSegSmem)
   int qsplit;            // dK/dV kernel: the query tiles of one key block are shared by this many CTAs (blockIdx.x % qsplit)
   long long* trace;      // debug: per-tile clock64() stamps of CTA (0,0,0) of the dQ kernel (nullptr = off)
 };
 static long long* g_trace = nullptr;
+static int g_seg_limit = kSegSmem;
 
 // D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (O fp32 as written by the forward, dO the fp16 tensor the MMAs consume)
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ o, const h16* __restrict__ d_o, int B, int n,
@@ -543,7 +545,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   const Lookup L = tab_stage(sgen + kOffTab, sbase + kOffTab, p.table, tid, kThreads);
-  const SegLookup SL = seg_stage(sgen + kOffSeg, sbase + kOffSeg, p.table, tid, kThreads);
+  const SegLookup SL = seg_stage(sgen + kOffSeg, sbase + kOffSeg, p.table, tid, kThreads, p.seg_limit);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tab_finish(sgen + kOffTab, lane);
@@ -894,6 +896,13 @@ size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
   return (size_t)B * H * (size_t)(dml::cdiv(n_kv, 128) * 128) * (size_t)(dml::cdiv(n, 32) * 32) * 2;
 }
 
+/* debug / test knob: tables with at least limit - 2 segments are treated as too large for the shared-memory segment
+ * arrays of the dK/dV kernel (its general per-position path); limit <= 0 restores the default */
+int dml_debug_set_seg_limit(int limit) {
+  dml::tc::g_seg_limit = limit > 0 ? limit : dml::tc::kSegSmem;
+  return 0;
+}
+
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
                            int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
@@ -938,6 +947,7 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   p.dq = dq; p.dk = dk; p.dv = dv; p.dg = dg; p.segsum = segsum;
   p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.n_seq = n_seq; p.scale = scale;
   p.trace = dml::tc::g_trace;
+  p.seg_limit = dml::tc::g_seg_limit;
   p.ds_ws = (h16*)ds_ws; p.n_pad = cdiv(n, 32) * 32; p.n_kv_pad = cdiv(n_kv, 128) * 128;
   CUtensorMap mds, mk64;
   if (ds_ws) {

@@ -263,18 +263,19 @@ __device__ __forceinline__ float4 lookup2(const Lookup& L, float x, int& cell, i
 }
 // ---- optional shared-memory copy of the first kSegSmem table segments (upper boundary, coefficients): the general
 // lookup for x ranges that touch flagged cells or several segment boundaries, without going to global memory ----
-constexpr int kSegSmem = 256;
+constexpr int kSegSmem = 512;      // 10 KB; tables with more segments (hidden 32: at most 1088) take the callers' slow paths
 constexpr uint32_t kSegSmemBytes = kSegSmem * 4 + kSegSmem * 16;
 struct SegLookup {
   uint32_t bp, coef;     // shared-space addresses: float[kSegSmem], float4[kSegSmem]
   bool staged;           // false: the table has more segments than fit (callers fall back to lookup2<true, .>)
 };
-__device__ __forceinline__ SegLookup seg_stage(uint8_t* sgen, uint32_t saddr, const uint32_t* __restrict__ table, int tid, int nthreads) {
+__device__ __forceinline__ SegLookup seg_stage(uint8_t* sgen, uint32_t saddr, const uint32_t* __restrict__ table, int tid, int nthreads,
+                                               int limit = kSegSmem) {   // limit < kSegSmem: tests force the callers' slow paths
   SegLookup S;
   S.bp = saddr;
   S.coef = saddr + kSegSmem * 4;
   const int nseg = (int)__ldg(table);
-  S.staged = nseg + 2 < kSegSmem;  // callers read up to three boundaries / one coefficient pair past the last segment
+  S.staged = nseg + 2 < min(limit, kSegSmem);  // callers read up to three boundaries / one coefficient pair past the last segment
   if (S.staged) {
     float* bp = reinterpret_cast<float*>(sgen);
     float4* coef = reinterpret_cast<float4*>(sgen + kSegSmem * 4);

@@ -138,6 +138,9 @@ int dml_gemm_nt_split(const void* a_hi, const void* a_lo, const void* b_hi, cons
 /* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
  * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
 int dml_debug_set_trace(void* buf);
+/* Test knob: bias tables with at least limit - 2 segments take the dK/dV kernel's general per-position path (as tables too
+ * large for its shared-memory segment arrays do); limit <= 0 restores the default.                                       */
+int dml_debug_set_seg_limit(int limit);
 
 /* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
 /* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]

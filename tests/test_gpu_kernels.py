@@ -102,7 +102,8 @@ def test_deform_attn_fwd_tcgen05_matches_torch(B, n, n_kv):
     H.assert_close(lse, lse2, 1e-5, "log-sum-exp (tcgen05 vs mma.sync)")
 
 
-@pytest.mark.parametrize("impl", ["mma", "tc", "tc_ws"])   # tc_ws: dS^T workspace + streaming dQ GEMM
+# tc_ws: dS^T workspace + streaming dQ GEMM; tc_general: the dK/dV kernel's path for tables with too many segments
+@pytest.mark.parametrize("impl", ["mma", "tc", "tc_ws", "tc_general"])
 # (1, 3100, 200): few key blocks, many query tiles -> the dK/dV kernel splits the query range across CTAs (reductions)
 @pytest.mark.parametrize("B,n,n_kv", [(1, 193, 48), (2, 130, 64), (1, 517, 129), (1, 64, 1), (1, 1100, 300), (1, 3100, 200)])
 def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv, impl):
@@ -145,6 +146,8 @@ def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv, impl):
              C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum), stream())
     else:
         ws = None
+        if impl == "tc_general":
+            _lib.load().dml_debug_set_seg_limit(3)
         if impl == "tc_ws":
             nbytes = _lib.load().dml_deform_attn_bwd_ws_bytes(B, Hh, n, n_kv)
             assert nbytes == B * Hh * (-(-n_kv // 128) * 128) * (-(-n // 32) * 32) * 2
@@ -152,6 +155,7 @@ def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv, impl):
         call("dml_deform_attn_bwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(r16), ptr(lse), B, Hh, d, n,
              n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq), ptr(dk), ptr(dv), ptr(dg), ptr(segsum),
              ptr(ws) if ws is not None else None, stream())
+        _lib.load().dml_debug_set_seg_limit(0)
     mg = torch.empty(ops.CPB_GRAD_FLOATS, device=DEV)
     call("dml_cpb_param_grad", *[ptr(a) for a in margs], 32, nout, ptr(table), ptr(segsum), ptr(mg), stream())
     tol = 3e-3     # fp16 P / dS operands in the MMAs; compared against exact fp32 maths
