@@ -7,15 +7,19 @@
 // One CTA = one (batch, offset group, 256 consecutive queries): the TWO heads of the group are processed together,
 // so the position x_ij, its log and its table cell are evaluated once per (i, j) and shared by both heads.
 //
-//   warp 8    TMA producer: Q tiles once, then a 4-stage ring of {K_h0, K_h1, V_h0, V_h1} 32-key tiles
+//   warp 16   TMA producer: Q tiles once, then a 4-stage ring of {K_h0, K_h1, V_h0, V_h1} 32-key tiles
 //             (cp.async.bulk.tensor, 128-byte swizzle) + the 32 sampling positions g of the tile
-//   warps 9,10 MMA issuers, one per query group (uniform datapath, one elected lane): S = Q K^T (SS form, operands in
+//   warps 17,18 MMA issuers, one per query group (uniform datapath, one elected lane): S = Q K^T (SS form, operands in
 //             shared memory) and O += P V (TS form: P is read from TMEM, V from shared memory as an MN-major operand);
-//             warp 9 owns the TMEM allocation
-//   warps 0-3 softmax group 0 = queries [i0, i0+128);  warps 4-7 softmax group 1 = queries [i0+128, i0+256).
-//             Thread t of a group owns query row t: TMEM lane t holds its S row and its O row, so the row maximum,
-//             the row sum and the position s_i are thread-private (no shuffles), and the 32 lanes of a warp look up
-//             nearly the same table cell (consecutive queries) -> broadcast shared-memory reads.
+//             warp 17 owns the TMEM allocation
+//   warps 0-7 softmax group 0 = queries [i0, i0+128);  warps 8-15 softmax group 1 = queries [i0+128, i0+256).
+//             Inside a group warp w takes TMEM lanes 32 (w & 3).. (query rows) and the key half (w >> 2) & 1 of every
+//             32-key tile: TMEM lane t holds query row t's S row and O row, and a row is shared by exactly two threads
+//             (one per key half, in two warps).  Each keeps a partial row sum; the row maximum of the raw S tile is
+//             exchanged through shared memory behind a 64-thread named barrier, after which both threads derive the
+//             same softmax reference.  Four softmax warps per scheduler instead of two hide the table-lookup / MUFU /
+//             TMEM latencies of each other.  The 32 lanes of a warp look up nearly the same table cell (consecutive
+//             queries) -> broadcast shared-memory reads.
 //
 // TMEM (512 columns x 128 lanes, fp32): group g at column 256 g:  two S buffers of 64 columns (S_h0 32 | S_h1 32) at 0 and
 // 64, O_h0 [128,192), O_h1 [192,256).  S of key tile j+1 is computed into the other buffer while the softmax warps work
@@ -39,7 +43,8 @@ constexpr int kBM = 128;          // query rows per softmax group (= TMEM lanes)
 constexpr int kGroups = 2;        // softmax groups per CTA
 constexpr int kBN = 32;           // keys per tile
 constexpr int kStages = 4;
-constexpr int kThreads = 32 * 11;   // 8 softmax warps, TMA producer, one MMA-issuing warp per group
+constexpr int kSoftWarps = 16;      // 2 groups x 4 lane quarters x 2 key halves
+constexpr int kThreads = 32 * (kSoftWarps + 3);   // + TMA producer + one MMA-issuing warp per group
 constexpr uint32_t kTileQ = kBM * kD * 2;   // 16384 B
 constexpr uint32_t kTileKV = kBN * kD * 2;  // 4096 B
 constexpr uint32_t kStageBytes = 4 * kTileKV;
@@ -51,13 +56,15 @@ constexpr uint32_t kOffKV = kOffQ + kGroups * 2 * kTileQ;            // [stage]{
 constexpr uint32_t kOffG = kOffKV + kStages * kStageBytes;           // [stage][32 g + gmin + gmax + pad] floats
 constexpr uint32_t kGStride = 40 * 4;
 constexpr uint32_t kOffRec = kOffG + kStages * kGStride;             // bias table image (tc_common.cuh), 16-B aligned
-constexpr uint32_t kOffBar = kOffRec + kTabSmemBytes;                // mbarriers (8 B each)
+constexpr uint32_t kOffPair = kOffRec + kTabSmemBytes;               // [slot 2][group 2][row 128][key half 2] float2: row-max exchange
+constexpr uint32_t kPairBytes = 2 * kGroups * kBM * 2 * 8;
+constexpr uint32_t kOffBar = kOffPair + kPairBytes;                  // mbarriers (8 B each)
 constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,   // [group][buffer]
               kBarPFull = kBarSFull + 2 * kGroups, kBarPvDone = kBarPFull + 2 * kGroups, kBarOFinal = kBarPvDone + kGroups,
               kNumBars = kBarOFinal + kGroups;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;             // + slack for the 1024-B alignment
-static_assert(kOffRec % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kOffRec % 16 == 0 && kOffPair % 8 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -72,44 +79,45 @@ struct Params {
 constexpr uint32_t kIdescS = idesc_f16(128, kBN, false, false);   // S = Q K^T: A, B K-major
 constexpr uint32_t kIdescPV = idesc_f16(128, 64, false, true);    // O += P V: A in TMEM, B (= V) MN-major
 
-// One 32-key tile of one query row, both heads, from registers: sa / sb = the row's 32 S values of head 0 / 1 (already
-// loaded from TMEM for the bound pass) -> P = exp2(S sc2 + bias - m) split into fp16 hi/lo pairs written over the S
-// columns (S_h0 at tS, S_h1 at tS + 32); l0/l1 accumulate the row sums.  kMasked: keys >= jrem are padding; kDirty: the
-// row's position window touches a table cell holding >= 2 breakpoints.
+// One key half (16 keys) of a 32-key tile of one query row, both heads, from registers: sa / sb = the row's 16 S values
+// of head 0 / 1 -> P = exp2(S sc2 + bias - m) split into fp16 hi/lo pairs written over the same S columns (S_h0 at tS,
+// S_h1 at tS + 32; tS already points at the half's first column); l0/l1 accumulate the partial row sums.  kMasked: keys
+// >= jrem (counted inside the half) are padding; kDirty: the row's position window touches a table cell holding >= 2
+// breakpoints.  gsa = shared address of the half's 16 sampling positions.
 template <bool kMasked, bool kDirty>
-__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tS, uint32_t gsa, const uint32_t (&sa)[32],
-                                       const uint32_t (&sb)[32], float s_i, float sc2, float m0, float m1, int jrem,
+__device__ __forceinline__ void sweep2(const Lookup& L, uint32_t tS, uint32_t gsa, const uint32_t (&sa)[16],
+                                       const uint32_t (&sb)[16], float s_i, float sc2, float m0, float m1, int jrem,
                                        float& l0, float& l1) {
+  float gq[16];
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    float gq[16];
-#pragma unroll
-    for (int e = 0; e < 16; e += 4) {
-      const float4 t = lds_f32x4(gsa + (uint32_t)(c * 16 + e) * 4);
-      gq[e] = t.x; gq[e + 1] = t.y; gq[e + 2] = t.z; gq[e + 3] = t.w;
-    }
-    uint32_t w0[16], w1[16];   // [0,8) = P_hi pairs, [8,16) = P_lo pairs
-#pragma unroll
-    for (int e = 0; e < 16; e += 2) {
-      float v0[2], v1[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float x = cpb_x(s_i - gq[e + u]);
-        int cdummy, sdummy;
-        const float4 t = lookup2<kDirty, false>(L, x, cdummy, sdummy);
-        v0[u] = ex2(fmaf(__uint_as_float(sa[c * 16 + e + u]), sc2, fmaf(t.x, x, t.y)) - m0);
-        v1[u] = ex2(fmaf(__uint_as_float(sb[c * 16 + e + u]), sc2, fmaf(t.z, x, t.w)) - m1);
-        if (kMasked && c * 16 + e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
-        l0 += v0[u];
-        l1 += v1[u];
-      }
-      split_f16(v0[0], v0[1], w0[e >> 1], w0[8 + (e >> 1)]);
-      split_f16(v1[0], v1[1], w1[e >> 1], w1[8 + (e >> 1)]);
-    }
-    tmem_st16(tS + c * 16, w0);
-    tmem_st16(tS + 32 + c * 16, w1);
+  for (int e = 0; e < 16; e += 4) {
+    const float4 t = lds_f32x4(gsa + (uint32_t)e * 4);
+    gq[e] = t.x; gq[e + 1] = t.y; gq[e + 2] = t.z; gq[e + 3] = t.w;
   }
+  uint32_t w0[16], w1[16];   // [0,8) = P_hi pairs, [8,16) = P_lo pairs
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float v0[2], v1[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float x = cpb_x(s_i - gq[e + u]);
+      int cdummy, sdummy;
+      const float4 t = lookup2<kDirty, false>(L, x, cdummy, sdummy);
+      v0[u] = ex2(fmaf(__uint_as_float(sa[e + u]), sc2, fmaf(t.x, x, t.y)) - m0);
+      v1[u] = ex2(fmaf(__uint_as_float(sb[e + u]), sc2, fmaf(t.z, x, t.w)) - m1);
+      if (kMasked && e + u >= jrem) { v0[u] = 0.f; v1[u] = 0.f; }
+      l0 += v0[u];
+      l1 += v1[u];
+    }
+    split_f16(v0[0], v0[1], w0[e >> 1], w0[8 + (e >> 1)]);
+    split_f16(v1[0], v1[1], w1[e >> 1], w1[8 + (e >> 1)]);
+  }
+  tmem_st16(tS, w0);
+  tmem_st16(tS + 32, w1);
 }
+
+// 64-thread named barrier of the two warps that share a lane quarter of a group (ids 1..8; id 0 is __syncthreads)
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
@@ -128,11 +136,11 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   if (tid == 0) {
     mbar_init(bar(kBarQ), 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), kGroups); }
-    for (int g = 0; g < 2 * kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), kBM); }
+    for (int g = 0; g < 2 * kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), 2 * kBM); }
     for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarPvDone + g), 1); mbar_init(bar(kBarOFinal + g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == kSoftWarps + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kOffTmemPtr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -144,7 +152,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kSoftWarps) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       mbar_expect_tx(bar(kBarQ), kGroups * 2 * kTileQ);
@@ -173,10 +181,10 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       if (lane == 0) { gs[32] = gmn; gs[33] = gmx; }
       mbar_arrive(bar(kBarKvFull + st));                     // 32 arrivals (release) + the TMA bytes complete the phase
     }
-  } else if (warp >= 9) {
-    // =========================== MMA issuers: warp 9 -> group 0, warp 10 -> group 1 ===========================
+  } else if (warp > kSoftWarps) {
+    // =========================== MMA issuers: one warp per query group ===========================
     // All 32 lanes run the loop (uniform operands); one elected lane executes each tcgen05 instruction.
-    const int g = warp - 9;
+    const int g = warp - (kSoftWarps + 1);
     const bool leader = elect_one();
     mbar_wait(bar(kBarQ), 0);
     auto issue_s = [&](int j) {
@@ -220,53 +228,51 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     tc_commit(bar(kBarOFinal + g), leader);            // one-shot: every MMA of the group has completed
   } else {
     // =========================== softmax groups ===========================
-    const int g = warp >> 2;                        // group
+    const int g = warp >> 3;                        // group
+    const int kh = (warp >> 2) & 1;                 // key half of every tile
     const int row = (warp & 3) * 32 + lane;         // TMEM lane = query row inside the group's tile
     const int gi = i0 + g * kBM + row;
+    const int pair_id = 1 + g * 4 + (warp & 3);     // named barrier shared with the warp of the other key half
     const uint32_t tbase = tmem + g * 256 + (((uint32_t)(warp & 3) * 32u) << 16);
     const float amax0 = __uint_as_float(__ldg(p.table + 6)), amax1 = __uint_as_float(__ldg(p.table + 7));
     const float s_i = seq_pos(min(gi, p.n_seq - 1), p.n_seq);     // rows past the end: any in-domain position
     const float sc2 = p.scale * kLog2e;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // m: common to both halves; l: this half's partial sum
+    // exchange slots: [slot][group][row][half] float2
+    auto pair_slot = [&](int slot, int half) { return sbase + kOffPair + (uint32_t)(((slot * kGroups + g) * kBM + row) * 2 + half) * 8u; };
 
     for (int j = 0; j < ntiles; ++j) {
       const int st = j % kStages;
       const uint32_t gsa = sbase + kOffG + st * kGStride;
       const int buf = j & 1;
-      const uint32_t tS = tbase + buf * 64;
+      const uint32_t tS = tbase + buf * 64 + kh * 16;
       mbar_wait(bar(kBarKvFull + st), (j / kStages) & 1);       // g tile visible to this thread
       mbar_wait(bar(kBarSFull + g * 2 + buf), (j >> 1) & 1);    // S(j) landed
       tc_fence_after();
-      const int jrem = p.n_kv - j * kBN;                        // valid keys in this tile (>= 1)
+      const int jrem = p.n_kv - j * kBN - kh * 16;              // valid keys in this half of the tile (may be <= 0)
 
-      // ---- the row's S tile (32 keys x 2 heads) into registers, once; bound of the row maximum ----
-      uint32_t sa[32], sb[32];
-      {
-        uint32_t t0[16], t1[16], t2[16], t3[16];
-        tmem_ld16(tS, t0);
-        tmem_ld16(tS + 16, t1);
-        tmem_ld16(tS + 32, t2);
-        tmem_ld16(tS + 48, t3);
-        tmem_ld_fence();
-        reg_fence(t0); reg_fence(t1); reg_fence(t2); reg_fence(t3);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) { sa[e] = t0[e]; sa[16 + e] = t1[e]; sb[e] = t2[e]; sb[16 + e] = t3[e]; }
-      }
+      // ---- this half of the row's S tile (16 keys x 2 heads) into registers, once; its maximum goes to the partner ----
+      uint32_t sa[16], sb[16];
+      tmem_ld16(tS, sa);
+      tmem_ld16(tS + 32, sb);
+      tmem_ld_fence();
+      reg_fence(sa); reg_fence(sb);
       float r0 = -INFINITY, r1 = -INFINITY;
-      if (jrem >= kBN) {
+      if (jrem >= 16) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int e = 0; e < 16; ++e) {
           r0 = fmaxf(r0, __uint_as_float(sa[e]));
           r1 = fmaxf(r1, __uint_as_float(sb[e]));
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
+        for (int e = 0; e < 16; ++e)
           if (e < jrem) {
             r0 = fmaxf(r0, __uint_as_float(sa[e]));
             r1 = fmaxf(r1, __uint_as_float(sb[e]));
           }
       }
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(pair_slot(buf, kh)), "f"(r0), "f"(r1) : "memory");
       float bh0, bh1;
       int ndirty;
       {
@@ -278,17 +284,25 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         bh1 = fmaxf(fmaf(e.z, xlo, e.w), fmaf(f.z, xhi, f.w)) + amax1 * half;
         ndirty = tab_dirty_between(L, clo, chi);
       }
+      pair_sync(pair_id);
+      {
+        const float2 o = lds_f32x2(pair_slot(buf, kh ^ 1));
+        r0 = fmaxf(r0, o.x);
+        r1 = fmaxf(r1, o.y);
+      }
+      // from here on both threads of the row hold identical r, bh, m: they take the same decisions
       const float ub0 = fmaf(r0, sc2, bh0), ub1 = fmaf(r1, sc2, bh1);
       const bool raise0 = ub0 > m0 + kRaise, raise1 = ub1 > m1 + kRaise;
       if (__any_sync(0xffffffffu, raise0 || raise1)) {
         const float f0 = raise0 ? ex2(m0 - ub0) : 1.0f, f1 = raise1 ? ex2(m1 - ub1) : 1.0f;   // ex2(-inf) = 0 on the first tile
         if (raise0) { m0 = ub0; l0 *= f0; }
         if (raise1) { m1 = ub1; l1 *= f1; }
-        if (j > 0) {                                           // rescale this warp's O rows in TMEM
+        if (j > 0) {                                           // rescale this warp's share of the O rows in TMEM
           mbar_wait(bar(kBarPvDone + g), (j - 1) & 1);          // O += P V of tile j-1 has completed
           tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c2 = 0; c2 < 4; ++c2) {
+            const int c = c2 * 2 + kh;                         // 16-column chunks of O_h0 (0..3) and O_h1 (4..7), alternating
             uint32_t a[16];
             tmem_ld16(tbase + 128 + c * 16, a);
             tmem_ld_wait(a);
@@ -302,24 +316,33 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
 
       // ---- sweep 2: P = exp2(S sc2 + bias - m), in place ----
       const bool dirty = __any_sync(0xffffffffu, ndirty != 0);
-      if (jrem >= kBN) {
-        if (!dirty) sweep2<false, false>(L, tS, gsa, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
-        else sweep2<false, true>(L, tS, gsa, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
+      const uint32_t gh = gsa + kh * 64;
+      if (jrem >= 16) {
+        if (!dirty) sweep2<false, false>(L, tS, gh, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
+        else sweep2<false, true>(L, tS, gh, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
       } else {
-        sweep2<true, true>(L, tS, gsa, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
+        sweep2<true, true>(L, tS, gh, sa, sb, s_i, sc2, m0, m1, jrem, l0, l1);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(kBarPFull + g * 2 + buf));
     }
 
-    // ---- epilogue: O / l -> global, log-sum-exp ----
+    // ---- epilogue: the two partial row sums -> l; O / l -> global, log-sum-exp ----
     // (a one-shot barrier: the per-tile kBarPvDone may still be several phases behind here, and a parity wait is only
     // meaningful when the waiter is at most one phase ahead)
+    {
+      const int slot = ntiles & 1;                             // the slot the last tile did not use
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(pair_slot(slot, kh)), "f"(l0), "f"(l1) : "memory");
+      pair_sync(pair_id);
+      const float2 o = lds_f32x2(pair_slot(slot, kh ^ 1));
+      l0 += o.x;
+      l1 += o.y;
+    }
     mbar_wait(bar(kBarOFinal + g), 0);
     tc_fence_after();
     const int h0 = grp * 2;
-    if (gi < p.n) {
+    if (gi < p.n && kh == 0) {
       float* lb = p.lse + ((size_t)b * p.H + h0) * p.n + gi;
       lb[0] = m0 + __log2f(l0);
       lb[p.n] = m1 + __log2f(l1);
@@ -327,7 +350,8 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     float* ob = p.o + ((size_t)b * p.n + gi) * p.ldo + h0 * kD;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c2 = 0; c2 < 4; ++c2) {
+      const int c = c2 * 2 + kh;
       uint32_t a[16];
       tmem_ld16(tbase + 128 + c * 16, a);      // warp-collective: every lane takes part, stores are predicated
       tmem_ld_wait(a);
@@ -345,7 +369,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kSoftWarps + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
