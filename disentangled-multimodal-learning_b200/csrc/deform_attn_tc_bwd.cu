@@ -20,6 +20,7 @@
 //                              and x_ij grows monotonically along the row: the per-segment sums are run-length merged
 //                              in registers and reach shared memory only when the segment changes.
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/dml_b200.h"
 #include "tc_common.cuh"
@@ -50,6 +51,7 @@ struct BwdParams {
 };
 static long long* g_trace = nullptr;
 static int g_seg_limit = kSegSmem;
+static int g_concurrency = 1;
 
 // D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (O fp32 as written by the forward, dO the fp16 tensor the MMAs consume)
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ o, const h16* __restrict__ d_o, int B, int n,
@@ -896,6 +898,13 @@ size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
   return (size_t)B * H * (size_t)(dml::cdiv(n_kv, 128) * 128) * (size_t)(dml::cdiv(n, 32) * 32) * 2;
 }
 
+/* scheduling hint: how many independent launches of the attention backward the caller keeps in flight on different streams
+ * (>= 1); only used to choose how the dK/dV kernel splits its work over CTAs */
+int dml_set_launch_concurrency(int n) {
+  dml::tc::g_concurrency = n > 0 ? n : 1;
+  return 0;
+}
+
 /* debug / test knob: tables with at least limit - 2 segments are treated as too large for the shared-memory segment
  * arrays of the dK/dV kernel (its general per-position path); limit <= 0 restores the default */
 int dml_debug_set_seg_limit(int limit) {
@@ -956,22 +965,30 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   const int rows = B * n;
   bwd_prep_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>((const float*)out, (const h16*)d_out, B, n, H, ldo, dsum_ws);
   {
-    // query split of the dK/dV kernel: the qsplit in 1..16 with the shortest estimated makespan
-    // ceil(items * qsplit / SMs) / qsplit, each extra part charged 8 % for its prologue (table staging, K/V load, pipeline
-    // fill) and reduction traffic - measured at n = 16385: 128 items on 148 SMs are faster unsplit (1.53 ms) than as
-    // 1024 parts in 7 waves (1.61 ms), so the split only pays when the items leave most of the SMs idle
+    // query split of the dK/dV kernel: the qsplit in 1..16 with the shortest estimated makespan of the `conc` identical
+    // launches the caller keeps in flight (dml_set_launch_concurrency; the two towers of DeformPathomicNet run their
+    // backward on two streams): ceil(conc * items * qsplit / SMs) / qsplit waves, each extra part charged 2.8 % for its
+    // prologue (table staging, K/V load, pipeline fill) and reduction traffic.  Measured at n = 16385 (128 items, 148
+    // SMs): alone 1 part is best (8 parts: +5 %); two launches in flight: 4 parts, 7 waves of quarter items instead of
+    // 2 waves of whole ones (+0.6 .. +2.3 % bags/s depending on the box).
     static int nsm = 0;
     if (!nsm) {
       int dev = 0;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
     }
-    const int items = cdiv(n_kv, dkvk::kBK) * G * B, ntiles = cdiv(n, dkvk::kBI);
+    const int items = cdiv(n_kv, dkvk::kBK) * G * B, ntiles = cdiv(n, dkvk::kBI), conc = dml::tc::g_concurrency;
     int best = 1;
-    double best_t = (double)cdiv(items, nsm);
+    double best_t = (double)cdiv(conc * items, nsm);
     for (int sp = 2; sp <= 16 && ntiles / sp >= 48; ++sp) {
-      const double t = (double)cdiv(items * sp, nsm) / sp * (1.0 + 0.08 * (sp - 1));
+      const double t = (double)cdiv(conc * items * sp, nsm) / sp * (1.0 + 0.028 * (sp - 1));
       if (t < best_t) { best_t = t; best = sp; }
     }
+    static int forced = -1;      // DML_B200_DKV_QSPLIT=<n> overrides the heuristic (tuning aid)
+    if (forced < 0) {
+      const char* ev = getenv("DML_B200_DKV_QSPLIT");
+      forced = ev ? atoi(ev) : 0;
+    }
+    if (forced > 0 && ntiles / forced >= 1) best = forced;
     p.qsplit = best;
     if (best > 1) {
       if ((e = cudaMemsetAsync(dk, 0, sizeof(float) * (size_t)B * n_kv * H * kD, st)) != cudaSuccess) return (int)e;
