@@ -65,12 +65,18 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 }
 
 // (x0, x1) -> packed fp16 pair `hi` and the packed fp16 residual pair `lo` (x ~= hi + lo to 22 bits)
+// The residual x - hi is one mixed-precision FMA per element (fma.rn.f32.f16: fp16 x fp16 + fp32, exact here) instead of an
+// unpack and a subtract.
 __device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  float r0, r1;
+  asm("{\n.reg .b16 h0, h1, m1;\n"
+      "cvt.rn.f16x2.f32 %0, %4, %3;\n"
+      "mov.b32 {h0, h1}, %0;\n"
+      "mov.b16 m1, 0xBC00;\n"                      // -1.0
+      "fma.rn.f32.f16 %1, h0, m1, %3;\n"
+      "fma.rn.f32.f16 %2, h1, m1, %4;\n}"
+      : "=&r"(hi), "=f"(r0), "=f"(r1) : "f"(x0), "f"(x1));
+  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(r0), "f"(r1));
 }
 
 // ---- cp.async (LDGSTS) 16-byte copies with zero-fill predicate ----
