@@ -176,10 +176,15 @@ struct Lookup {
   const uint32_t* gtab;       // table in global memory (slow path)
   float c1, c2;               // cell = floor(x c1 + c2)
   float c2m;                  // c2 - 0.5: cell_index() rounds on the FMA pipe instead of converting on the XU pipe
+  uint32_t bp_adj, piece_adj; // bp - 4 K, piece - 32 K (mod 2^32), K = 0x4B400000: the raw rounded float of cell_raw() scales
+                              // straight into an address, without first subtracting K
 };
 // floor(x c1 + c2) for 0 <= value < 2^22 without a float->int conversion: adding 1.5 * 2^23 leaves the integer part in the
 // low mantissa bits (round-to-nearest of value - 0.5 == floor(value) except on exact ties, where either neighbouring cell
 // describes the same continuous function).
+__device__ __forceinline__ uint32_t cell_raw(const Lookup& L, float x) {      // K + cell index
+  return __float_as_uint(fmaf(x, L.c1, L.c2m) + 12582912.0f);
+}
 __device__ __forceinline__ int cell_index(const Lookup& L, float x) {
   return __float_as_int(fmaf(x, L.c1, L.c2m) + 12582912.0f) - 0x4B400000;      // 12582912 = 1.5 * 2^23
 }
@@ -207,6 +212,8 @@ __device__ __forceinline__ Lookup tab_stage(uint8_t* sgen, uint32_t saddr, const
   L.c1 = inv;
   L.c2 = X * inv;
   L.c2m = X * inv - 0.5f;
+  L.bp_adj = L.bp - 0x4B400000u * 4u;
+  L.piece_adj = L.piece - 0x4B400000u * 32u;
   return L;
 }
 __device__ __forceinline__ void tab_finish(uint8_t* sgen, int lane) {   // one warp: running count of flagged cells
@@ -251,10 +258,13 @@ static __device__ __noinline__ float4 lookup_slow(const uint32_t* gtab, int cell
 // kSeg: also return the global segment index of x.
 template <bool kDirty, bool kSeg>
 __device__ __forceinline__ float4 lookup2(const Lookup& L, float x, int& cell, int& seg) {
-  cell = cell_index(L, x);
-  const float bpv = lds_f32(L.bp + (uint32_t)cell * 4u);
+  const uint32_t raw = cell_raw(L, x);
+  cell = (int)(raw - 0x4B400000u);
+  const float bpv = lds_f32(L.bp_adj + raw * 4u);
   const bool hi = x >= bpv;
-  float4 e = lds_f32x4(L.piece + (uint32_t)cell * 32u + (hi ? 16u : 0u));
+  uint32_t pa = L.piece_adj + raw * 32u;
+  if (hi) pa += 16u;
+  float4 e = lds_f32x4(pa);
   if (kSeg) seg = (lds_s32(L.meta + (uint32_t)cell * 4u) & 0xffff) + (hi ? 1 : 0);
   if (kDirty) {
     if (bpv != bpv) e = lookup_slow(L.gtab, cell, x, kSeg ? &seg : nullptr);
@@ -298,10 +308,13 @@ __device__ __forceinline__ float4 lookup_seg(const Lookup& L, const SegLookup& S
 // one head's (a, c) only: `hoff` = 8 * head selects the pair inside the 16-byte piece
 template <bool kDirty, bool kSeg>
 __device__ __forceinline__ float2 lookup2h(const Lookup& L, float x, uint32_t hoff, int& cell, int& seg) {
-  cell = cell_index(L, x);
-  const float bpv = lds_f32(L.bp + (uint32_t)cell * 4u);
+  const uint32_t raw = cell_raw(L, x);
+  cell = (int)(raw - 0x4B400000u);
+  const float bpv = lds_f32(L.bp_adj + raw * 4u);
   const bool hi = x >= bpv;
-  float2 e = lds_f32x2(L.piece + (uint32_t)cell * 32u + (hi ? 16u : 0u) + hoff);
+  uint32_t pa = L.piece_adj + raw * 32u + hoff;
+  if (hi) pa += 16u;
+  float2 e = lds_f32x2(pa);
   if (kSeg) seg = (lds_s32(L.meta + (uint32_t)cell * 4u) & 0xffff) + (hi ? 1 : 0);
   if (kDirty) {
     if (bpv != bpv) {
