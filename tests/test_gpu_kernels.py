@@ -102,6 +102,34 @@ def test_deform_attn_fwd_tcgen05_matches_torch(B, n, n_kv):
     H.assert_close(lse, lse2, 1e-5, "log-sum-exp (tcgen05 vs mma.sync)")
 
 
+def test_deform_attn_fwd_tcgen05_is_deterministic_with_large_scores():
+    """No atomics in the forward: repeated launches must agree bit for bit (a race between the two threads that share a
+    query row, or between the softmax warps and the MMA warps, would show up here).  Large |q|, |k| force the softmax
+    reference to be raised - and the O rows rescaled in TMEM - many times."""
+    B, n, n_kv, Hh, d, nout = 1, 3001, 750, 8, 64, 2
+    G, C = Hh // nout, Hh * d
+    seed = 77
+    q = (synth.normal((B, n, C), seed, "q") * 3.0).to(DEV).to(torch.float16)
+    k = (synth.normal((B, n_kv, C), seed, "k") * 3.0).to(DEV).to(torch.float16)
+    v = synth.normal((B, n_kv, C), seed, "v").to(DEV).to(torch.float16)
+    vgrid = torch.arange(n_kv, device=DEV)[None] + synth.uniform((B * G, n_kv), seed, "off", 2.0).to(DEV)
+    g = O.normalize_grid(vgrid).contiguous()
+    P = mlp_params(seed)
+    table, _ = build_table(P, math.log1p(2.0 + 4.0 / (n_kv - 1)) * 1.001 + 1e-3)
+    scale = d ** -0.5
+    outs = []
+    for _ in range(6):
+        o = torch.full((B, n, C), float("nan"), device=DEV)
+        lse = torch.full((B, Hh, n), float("nan"), device=DEV)
+        call("dml_deform_attn_fwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, n, C, C, C, C, nout,
+             scale, ptr(o), ptr(lse), stream())
+        outs.append((o, lse))
+    for o, lse in outs[1:]:
+        assert torch.equal(o, outs[0][0]) and torch.equal(lse, outs[0][1])
+    ref = attn_reference(q.float(), k.float(), v.float(), g, P, Hh, nout, scale, n)
+    H.assert_close(outs[0][0], ref, 2e-3, "attention output, peaked softmax")
+
+
 # tc_ws: dS^T workspace + streaming dQ GEMM; tc_general: the dK/dV kernel's path for tables with too many segments
 @pytest.mark.parametrize("impl", ["mma", "tc", "tc_ws", "tc_general"])
 # (1, 3100, 200): few key blocks, many query tiles -> the dK/dV kernel splits the query range across CTAs (reductions)
