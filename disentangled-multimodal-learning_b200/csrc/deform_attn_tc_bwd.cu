@@ -46,8 +46,16 @@ struct BwdParams {
   h16* ds_ws;            // optional fp16 [(B H), n_kv_pad, n_pad]: dS^T (times s) written by the dK/dV kernel
   int n_pad, n_kv_pad;
   int seg_limit;         // dK/dV kernel: tables with >= seg_limit - 2 segments are not staged (debug knob, default kSegSmem)
-  int qsplit;            // dK/dV kernel: the query tiles of one key block are shared by this many CTAs (blockIdx.x % qsplit)
+  int qsplit;            // dK/dV kernel without a work list: the query tiles of one item are shared by this many CTAs
   long long* trace;      // debug: per-tile clock64() stamps of CTA (0,0,0) of the dQ kernel (nullptr = off)
+};
+// Work list of the dK/dV kernel (kernel parameter, read through the constant bank): CTA i takes query tiles [t0, t1) of
+// item `item` = key block + nkb * (head pair + G * batch).  n == 0: no list, blockIdx.x = item * qsplit + part.
+struct DkvWork { uint16_t item, t0, t1, pad; };
+constexpr int kDkvWorkMax = 320;
+struct DkvWorkList {
+  int n;
+  DkvWork e[kDkvWorkMax];
 };
 static long long* g_trace = nullptr;
 static int g_seg_limit = kSegSmem;
@@ -519,19 +527,30 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
 __global__ void __launch_bounds__(dkvk::kThreads, 1)
 deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mdo,
                           const __grid_constant__ CUtensorMap mk, const __grid_constant__ CUtensorMap mv,
-                          const BwdParams p) {
+                          const BwdParams p, const __grid_constant__ DkvWorkList wl) {
   using namespace dkvk;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
-  // blockIdx.x = key block * qsplit + part: `part` takes the query tiles [t_begin, t_end) of the key block.  With 128 key
-  // blocks x head pairs on 148 SMs a whole-item decomposition leaves 20 SMs idle; qsplit CTAs per item fill the waves
-  // (the host picks qsplit) and add their dK / dV into the zeroed outputs with float4 reductions.
-  const int j0 = (blockIdx.x / p.qsplit) * kBK, grp = blockIdx.y, b = blockIdx.z;
-  const int G = p.H / 2, h0 = grp * 2;
-  const int t_begin = (int)((long long)cdiv(p.n, kBI) * (blockIdx.x % p.qsplit) / p.qsplit);
-  const int ntiles = (int)((long long)cdiv(p.n, kBI) * (blockIdx.x % p.qsplit + 1) / p.qsplit);      // end of this CTA's tile range
+  // A CTA takes the query tiles [t_begin, ntiles) of one item (batch, head pair, 128-key block).  With 128 items on 148
+  // SMs a one-CTA-per-item launch leaves 20 SMs idle, so the host cuts the items' tile ranges into pieces of about equal
+  // estimated cost, lists them longest first (the work list) and the pieces of an item add their dK / dV into the zeroed
+  // outputs with float4 reductions; without a list blockIdx.x = item * qsplit + part.
+  int item, t_begin, ntiles;      // ntiles = END of this CTA's tile range
+  if (wl.n > 0) {
+    const DkvWork w = wl.e[blockIdx.x];
+    item = w.item; t_begin = w.t0; ntiles = w.t1;
+  } else {
+    const int part = blockIdx.x % p.qsplit;
+    item = blockIdx.x / p.qsplit;
+    t_begin = (int)((long long)cdiv(p.n, kBI) * part / p.qsplit);
+    ntiles = (int)((long long)cdiv(p.n, kBI) * (part + 1) / p.qsplit);
+  }
+  const bool whole = t_begin == 0 && ntiles == cdiv(p.n, kBI);      // the only CTA of its item: plain stores
+  const int G = p.H / 2, nkb = cdiv(p.n_kv, kBK);
+  const int j0 = (item % nkb) * kBK, grp = (item / nkb) % G, b = item / (nkb * G);
+  const int h0 = grp * 2;
   auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
 
@@ -611,7 +630,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       tc_fence_after();
       issue_sd(0);
 #ifdef DML_TRACE
-      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
 #else
       constexpr bool tr = false;
 #endif
@@ -665,8 +684,8 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
     const SegSink ssum{p.segsum, inv_s};
 
 #ifdef DML_TRACE      // clock64() stamps of CTA 0 for scripts/trace_dkv.py (build with -DDML_TRACE)
-    const bool tr0 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 0;
-    const bool tr3 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && warp == 3;
+    const bool tr0 = p.trace && blockIdx.x == 0 && lane == 0 && warp == 0;
+    const bool tr3 = p.trace && blockIdx.x == 0 && lane == 0 && warp == 3;
 #else
     constexpr bool tr0 = false, tr3 = false;
 #endif
@@ -754,7 +773,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
             const float4 v = make_float4(__uint_as_float(a[e]) * f, __uint_as_float(a[e + 1]) * f, __uint_as_float(a[e + 2]) * f,
                                          __uint_as_float(a[e + 3]) * f);
             float4* o = reinterpret_cast<float4*>(dst + c * 16 + e);
-            if (p.qsplit == 1) *o = v;
+            if (whole) *o = v;
             else atomicAdd(o, v);
           }
         }
@@ -899,7 +918,7 @@ size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
 }
 
 /* scheduling hint: how many independent launches of the attention backward the caller keeps in flight on different streams
- * (>= 1); only used to choose how the dK/dV kernel splits its work over CTAs */
+ * (>= 1).  Recorded only: the work-list decomposition of the dK/dV kernel fills the SMs for one launch as for two. */
 int dml_set_launch_concurrency(int n) {
   dml::tc::g_concurrency = n > 0 ? n : 1;
   return 0;
@@ -965,36 +984,88 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   const int rows = B * n;
   bwd_prep_kernel<<<min(cdiv(rows, 8), 148 * 8), 256, 0, st>>>((const float*)out, (const h16*)d_out, B, n, H, ldo, dsum_ws);
   {
-    // query split of the dK/dV kernel: the qsplit in 1..16 with the shortest estimated makespan of the `conc` identical
-    // launches the caller keeps in flight (dml_set_launch_concurrency; the two towers of DeformPathomicNet run their
-    // backward on two streams): ceil(conc * items * qsplit / SMs) / qsplit waves, each extra part charged 2.8 % for its
-    // prologue (table staging, K/V load, pipeline fill) and reduction traffic.  Measured at n = 16385 (128 items, 148
-    // SMs): alone 1 part is best (8 parts: +5 %); two launches in flight: 4 parts, 7 waves of quarter items instead of
-    // 2 waves of whole ones (+0.6 .. +2.3 % bags/s depending on the box).
+    // Decomposition of the dK/dV kernel.  One CTA per item (batch, head pair, 128-key block) is right when the items fill
+    // the SMs several times over.  With few items (128 on 148 SMs at the north-star size) the items' query-tile ranges
+    // are cut into pieces of about equal estimated cost - one cut per SM, so a piece never spans two items - and listed
+    // longest first; the hardware hands CTAs to SMs in index order, which makes this the longest-processing-time rule
+    // (a simulation with the cost model below: makespan 527 vs 599 tile units unsplit, 502 ideal).  Cost model: tiles
+    // within 0.16 n positions of the item's diagonal - where the table segments are dense - count 1.45, each piece pays
+    // a prologue of 12 tiles.  DML_B200_DKV_QSPLIT=<q> forces q equal parts per item instead (tuning aid; 1 = unsplit).
     static int nsm = 0;
     if (!nsm) {
       int dev = 0;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
     }
-    const int items = cdiv(n_kv, dkvk::kBK) * G * B, ntiles = cdiv(n, dkvk::kBI), conc = dml::tc::g_concurrency;
-    int best = 1;
-    double best_t = (double)cdiv(conc * items, nsm);
-    for (int sp = 2; sp <= 16 && ntiles / sp >= 48; ++sp) {
-      const double t = (double)cdiv(conc * items * sp, nsm) / sp * (1.0 + 0.028 * (sp - 1));
-      if (t < best_t) { best_t = t; best = sp; }
-    }
-    static int forced = -1;      // DML_B200_DKV_QSPLIT=<n> overrides the heuristic (tuning aid)
+    static int forced = -1;
     if (forced < 0) {
       const char* ev = getenv("DML_B200_DKV_QSPLIT");
       forced = ev ? atoi(ev) : 0;
     }
-    if (forced > 0 && ntiles / forced >= 1) best = forced;
-    p.qsplit = best;
-    if (best > 1) {
+    const int nkb = cdiv(n_kv, dkvk::kBK), items = nkb * G * B, ntiles = cdiv(n, dkvk::kBI);
+    // the list only depends on the problem shape: each host thread keeps the last one it built (65 k cost evaluations
+    // would otherwise sit between the prep kernel and this launch on every eager call)
+    thread_local DkvWorkList wl;
+    thread_local long long wl_key[5] = {-1, -1, -1, -1, -1};
+    const long long key[5] = {B, G, n, n_kv, nsm};
+    const bool cached = forced <= 0 && key[0] == wl_key[0] && key[1] == wl_key[1] && key[2] == wl_key[2] && key[3] == wl_key[3] && key[4] == wl_key[4];
+    int ncta = items;
+    p.qsplit = 1;
+    if (cached) {
+      if (wl.n > 0) ncta = wl.n;
+    } else if (forced > 0) {
+      wl.n = 0;
+      wl_key[0] = -1;
+      p.qsplit = ntiles / forced >= 1 ? forced : 1;
+      ncta = items * p.qsplit;
+    } else if (!(items <= nsm && 2 * nsm <= kDkvWorkMax && ntiles >= 96 && items < 65536 && ntiles < 65536)) {
+      wl.n = 0;
+      for (int q = 0; q < 5; ++q) wl_key[q] = key[q];
+    } else {
+      const double kDense = 1.45, half = 0.16 * n / dkvk::kBI;
+      auto cost = [&](int item, int t) {
+        const double tdiag = ((item % nkb) * dkvk::kBK + 0.5 * dkvk::kBK) * ((double)n / n_kv) / dkvk::kBI;
+        return fabs(t - tdiag) < half ? kDense : 1.0;
+      };
+      double total = 0.0;
+      for (int i = 0; i < items; ++i)
+        for (int t = 0; t < ntiles; ++t) total += cost(i, t);
+      const double target = total / nsm;
+      double acc = 0.0, pc[kDkvWorkMax];
+      int k = 1, np = 0;
+      for (int i = 0; i < items && np < kDkvWorkMax; ++i) {
+        int t0 = 0;
+        double c = 0.0;
+        for (int t = 0; t < ntiles; ++t) {
+          const double ct = cost(i, t);
+          acc += ct; c += ct;
+          if (acc >= k * target - 1e-9 && k < nsm) {
+            ++k;
+            // cut here unless it would leave a sliver (each piece pays a ~10 us prologue): then the item boundary or the
+            // previous cut stands in for it
+            if (t + 1 - t0 >= 24 && ntiles - (t + 1) >= 24 && np < kDkvWorkMax - 1) {
+              wl.e[np] = DkvWork{(uint16_t)i, (uint16_t)t0, (uint16_t)(t + 1), 0}; pc[np++] = c;
+              t0 = t + 1; c = 0.0;
+            }
+          }
+        }
+        wl.e[np] = DkvWork{(uint16_t)i, (uint16_t)t0, (uint16_t)ntiles, 0}; pc[np++] = c;
+      }
+      for (int a = 1; a < np; ++a) {      // insertion sort, longest first (np <= 320)
+        const DkvWork w = wl.e[a];
+        const double c = pc[a];
+        int q = a - 1;
+        for (; q >= 0 && pc[q] < c; --q) { wl.e[q + 1] = wl.e[q]; pc[q + 1] = pc[q]; }
+        wl.e[q + 1] = w; pc[q + 1] = c;
+      }
+      wl.n = np;
+      ncta = np;
+      for (int q = 0; q < 5; ++q) wl_key[q] = key[q];
+    }
+    if (ncta != items) {
       if ((e = cudaMemsetAsync(dk, 0, sizeof(float) * (size_t)B * n_kv * H * kD, st)) != cudaSuccess) return (int)e;
       if ((e = cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)B * n_kv * H * kD, st)) != cudaSuccess) return (int)e;
     }
-    deform_attn_dkv_tc_kernel<<<dim3(cdiv(n_kv, dkvk::kBK) * best, G, B), dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p);
+    deform_attn_dkv_tc_kernel<<<ncta, dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p, wl);
   }
   if (ds_ws)
     deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), G, B), dqg::kThreads, dqg::kSmemBytes, st>>>(mds, mk64, p);
