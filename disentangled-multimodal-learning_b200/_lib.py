@@ -41,7 +41,6 @@ SIGNATURES = {
     "dml_split_f16": (_i, [_fp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _fp, _vp, _vp]),
     "dml_gemm_nt_split": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _fp, _i, _ll, _vp]),
     "dml_debug_set_trace": (_i, [_vp]),
-    "dml_set_launch_concurrency": (_i, [_i]),
     "dml_debug_set_seg_limit": (_i, [_i]),
     "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),

@@ -59,7 +59,6 @@ struct DkvWorkList {
 };
 static long long* g_trace = nullptr;
 static int g_seg_limit = kSegSmem;
-static int g_concurrency = 1;
 
 // D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (O fp32 as written by the forward, dO the fp16 tensor the MMAs consume)
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ o, const h16* __restrict__ d_o, int B, int n,
@@ -915,13 +914,6 @@ int dml_debug_set_trace(void* buf) {
 size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
   if (B <= 0 || H <= 0 || n <= 0 || n_kv <= 0) return 0;
   return (size_t)B * H * (size_t)(dml::cdiv(n_kv, 128) * 128) * (size_t)(dml::cdiv(n, 32) * 32) * 2;
-}
-
-/* scheduling hint: how many independent launches of the attention backward the caller keeps in flight on different streams
- * (>= 1).  Recorded only: the work-list decomposition of the dK/dV kernel fills the SMs for one launch as for two. */
-int dml_set_launch_concurrency(int n) {
-  dml::tc::g_concurrency = n > 0 ? n : 1;
-  return 0;
 }
 
 /* debug / test knob: tables with at least limit - 2 segments are treated as too large for the shared-memory segment

@@ -12,7 +12,6 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn import Parameter
 
-from . import _lib
 from .DeformCrossTransMIL import DeformCrossTransMIL
 from .mil import TransMIL
 
@@ -91,8 +90,6 @@ class DeformPathomicNet(nn.Module):
         # versa; autograd replays each backward node on the stream of its forward, so the backward overlaps the same way.
         x_path = kwargs['x_path']
         two_streams = x_path.is_cuda and getattr(self.args, "overlap_towers", True)
-        if x_path.is_cuda:      # scheduling hint for the attention backward: two launches in flight when the towers overlap
-            _lib.load().dml_set_launch_concurrency(2 if two_streams else 1)
         if two_streams:
             cur = torch.cuda.current_stream()
             side = _tower_stream(x_path.device)

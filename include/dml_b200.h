@@ -107,10 +107,6 @@ int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float
  * undefined afterwards).  With it the dK/dV kernel also stores dS^T in fp16 and dQ = dS.K runs as a streaming GEMM
  * over that buffer; without it dQ recomputes P and dS from q, k, lse (no n x n_kv memory).  Same results either way. */
 size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv);
-/* Scheduling hint (process-wide, default 1): the number of independent dml_deform_attn_bwd_tc launches the caller keeps
- * in flight on different streams (the two towers of DeformPathomicNet: 2).  Results never depend on it; the current
- * kernels' work decomposition does not either (kept so that callers can state it).                                    */
-int dml_set_launch_concurrency(int n);
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
                            int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
