@@ -88,6 +88,10 @@ class DeformCrossTransMIL(nn.Module):
             path = F.relu(ops.LinearBf16BagFn.apply(path.reshape(B_ * N_, K_), fc1.weight, fc1.bias).reshape(B_, N_, -1))
         else:
             path = F.relu(ops.mm_tf32(path.float(), fc1.weight.t()) + fc1.bias)
+        ready = getattr(omic, "_dml_ready", None)      # omic vector produced on another stream (model._omic_ahead)
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+            omic.record_stream(torch.cuda.current_stream())
         h = self.fusion_layer(path, omic.float())
         B = h.shape[0]
         cls_tokens = self.cls_token.expand(B, -1, -1).to(h.device)

@@ -51,11 +51,24 @@ class MaxNet(nn.Module):
 _TOWER_STREAMS = {}
 
 
-def _tower_stream(dev):
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+def _tower_stream(dev, which=0):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _TOWER_STREAMS:
-        _TOWER_STREAMS[key] = torch.cuda.Stream(device=key)
+        _TOWER_STREAMS[key] = torch.cuda.Stream(device=key[0])
     return _TOWER_STREAMS[key]
+
+
+def _omic_ahead(net, x_omic, which):
+    """The small omic MLP (some 40 microsecond-sized kernels, and 60 more in the backward) on its own stream, next to the
+    tower's fc1 GEMM which does not depend on it.  The result carries the event the tower waits for right before its
+    first use (DeformCrossTransMIL.forward); autograd replays the backward on the same streams."""
+    cur = torch.cuda.current_stream()
+    so = _tower_stream(x_omic.device, which)
+    so.wait_stream(cur)
+    with torch.cuda.stream(so):
+        vec = net(x_omic=x_omic)[0]
+        vec._dml_ready = so.record_event()
+    return vec
 
 
 class DeformPathomicNet(nn.Module):
@@ -95,9 +108,11 @@ class DeformPathomicNet(nn.Module):
             side = _tower_stream(x_path.device)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                omic_vec_immune, _, _ = self.omic_net_immune(x_omic=kwargs['x_omic_immune'])
+                omic_vec_immune = _omic_ahead(self.omic_net_immune, kwargs['x_omic_immune'], 2)
                 vec_immune, _, grads_immune = self.pathomic_net_immune(path=x_path, omic=omic_vec_immune)
-        omic_vec_tumor, _, _ = self.omic_net_tumor(x_omic=kwargs['x_omic_tumor'])
+            omic_vec_tumor = _omic_ahead(self.omic_net_tumor, kwargs['x_omic_tumor'], 3)
+        else:
+            omic_vec_tumor, _, _ = self.omic_net_tumor(x_omic=kwargs['x_omic_tumor'])
         vec_tumor, _, grads_tumor = self.pathomic_net_tumor(path=x_path, omic=omic_vec_tumor)
         if two_streams:
             cur.wait_stream(side)
