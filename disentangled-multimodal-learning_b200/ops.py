@@ -66,11 +66,13 @@ _SIDE_STREAMS = {}
 
 
 def side_stream(dev) -> torch.cuda.Stream:
-    """One auxiliary stream per device for small kernels that only depend on the weights (the bias-table build):
-    they run next to the projections instead of in front of the attention."""
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    """The auxiliary stream of the CURRENT stream (one per device and calling stream, so that the two towers of
+    DeformPathomicNet, which run on two streams, do not serialise through a shared one): small kernels off the critical
+    chain - the bias-table build in the forward, the weight gradients in the backward - run on it next to the chain."""
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx)
     return _SIDE_STREAMS[key]
 
 
@@ -180,9 +182,13 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         # dO feeds dS = P (dP - D) directly: fp32-class product, one fp16 rounding below
         d_o = gemm_nt(SplitOperand(dout.reshape(1, -1, dim), True), SplitOperand(Wo2[None], False),
                       (1, dout.shape[0] * dout.shape[1], C)).reshape(dout.shape[0], dout.shape[1], C)   # [B,n,C] fp32
-        with tf32_matmul():
+        # weight gradients are leaves of this backward: they run on the auxiliary stream, next to the chain
+        # dO -> attention backward -> offsets / gather backward -> input gradients, and join it at the end
+        cur, side = torch.cuda.current_stream(), side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), tf32_matmul():
             dWo = dout.reshape(-1, dim).t() @ o.reshape(-1, C)             # [dim, C]
-        dbo = dout.sum(dim=(0, 1))
+            dbo = dout.sum(dim=(0, 1))
         dscale = grad_scale(d_o)
         d_o16 = (d_o * dscale[0]).to(F16)
 
@@ -204,13 +210,14 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
             full = torch.zeros(B, n, C, device=dev, dtype=F32)
             full[:, :n_out] = dq_attn
             dq_attn = full
-        mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
-        call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), st)
-
-        with tf32_matmul():
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), tf32_matmul():
+            mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
+            call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), stream())
             kvf = kv.reshape(-1, dim)
             dWk = dk.reshape(-1, C).t() @ kvf
             dWv = dv.reshape(-1, C).t() @ kvf
+        with tf32_matmul():
             dkv = (dk @ Wk2 + dv @ Wv2).contiguous()                       # [B,n_kv,dim]
         dcentre = torch.empty(B, dim, device=dev, dtype=F32)
         call("dml_kv_gather_bwd", ptr(x2f), ptr(g), ptr(dkv), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(dcentre),
@@ -229,9 +236,16 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dq = torch.empty(B, n, C, device=dev, dtype=F32)
         call("dml_offsets_bwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), ptr(dq_attn), scale, B, n, C, G, ks,
              stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), ptr(dq), st)
-        with tf32_matmul():
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), tf32_matmul():
             dWq = dq.reshape(-1, C).t() @ x1f.reshape(-1, dim)             # [C, dim]
+        with tf32_matmul():
             dx1t = torch.matmul(dq, Wq2)
+        cur.wait_stream(side)
+        for t in (dWo, dbo, mlp_g, dWk, dWv, dWq):                         # allocated on the auxiliary stream, consumed on this one
+            t.record_stream(cur)
+        for t in (dout, o, segsum, dk, dv, dq):                            # allocated here, read there
+            t.record_stream(side)
 
         dw0 = wgrad[: Cg * ks].reshape(Cg, 1, ks)
         db0 = wgrad[Cg * ks: Cg * ks + Cg]
