@@ -22,10 +22,18 @@ class GraphedTrainStep:
     static device buffers, replays the captured forward + loss + backward, all-reduces the flat gradient buffer when a
     process group is initialised, then runs `optimizer.step()`.
 
-    net: module called as net(**inputs_without_label_keys); loss_fn(outputs, inputs) -> scalar."""
+    net: module called as net(**inputs_without_label_keys); loss_fn(outputs, inputs) -> scalar.
+
+    flat_optimizer: instead of `optimizer`, a callable `params -> optimizer`.  The parameters are then moved into one
+    flat buffer laid out like the flat gradient buffer (each parameter becomes a view of it, values unchanged) and the
+    optimizer is built over the few contiguous runs of parameters that receive gradients - an element-wise optimizer
+    with uniform hyper-parameters (AdamW here) computes exactly the same update in one small launch instead of one
+    multi-tensor launch chain over ~120 tensors (85 us per step for DeformPathomicNet).  Parameters that never receive a
+    gradient are left out, as torch's optimizers skip parameters whose grad is None."""
 
     def __init__(self, net: torch.nn.Module, loss_fn: Callable, example: Dict[str, torch.Tensor],
-                 optimizer: Optional[torch.optim.Optimizer] = None, model_keys=None, warmup: int = 3):
+                 optimizer: Optional[torch.optim.Optimizer] = None, model_keys=None, warmup: int = 3,
+                 flat_optimizer: Optional[Callable] = None):
         self.net, self.loss_fn, self.optimizer = net, loss_fn, optimizer
         dev = next(net.parameters()).device
         self.static = {k: v.to(dev).clone() for k, v in example.items()}
@@ -44,12 +52,41 @@ class GraphedTrainStep:
                     p.grad = None
                 self._fwd_bwd()
             self.reducer.attach()              # p.grad := views of the flat buffer (None for never-used parameters)
+            if flat_optimizer is not None:
+                self.optimizer = flat_optimizer(self._flatten_params())
             self._zero_and_fwd_bwd()           # once more on the attached layout
         cur.wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._zero_and_fwd_bwd()
+
+    def _flatten_params(self):
+        """Parameters -> views of one flat buffer (same layout as reducer.flat); returns one Parameter per contiguous
+        run of parameters that receive gradients, its .grad the matching slice of the flat gradient buffer."""
+        r = self.reducer
+        self.flat_params = torch.empty(r.total, dtype=torch.float32, device=r.flat.device)
+        segs, run = [], None
+        self.flat_params.zero_()
+        for p, offs, n, has in zip(r.params, r.offsets, r.sizes, r._present):
+            assert p.dtype == torch.float32, "flat optimizer: fp32 parameters only"
+            slot = self.flat_params[offs: offs + n]
+            slot.copy_(p.data.reshape(-1))
+            p.data = slot.view_as(p)
+            end = offs + (n + 31) // 32 * 32          # the padding rides along (zero parameter, zero gradient: stays zero)
+            if has:
+                run = [offs, end] if run is None else [run[0], end]
+            elif run is not None:
+                segs.append(run)
+                run = None
+        if run is not None:
+            segs.append(run)
+        out = []
+        for a, b in segs:
+            q = torch.nn.Parameter(self.flat_params[a:b])
+            q.grad = r.flat[a:b]
+            out.append(q)
+        return out
 
     def _fwd_bwd(self):
         out = self.net(**{k: self.static[k] for k in self.model_keys})

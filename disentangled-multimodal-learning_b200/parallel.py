@@ -58,16 +58,25 @@ class FlatGradAllReducer:
         self._present = None
         self.params = [p for p in params if p.requires_grad]
         self.sizes = [p.numel() for p in self.params]
-        self.total = sum(self.sizes)
+        # every slot starts on a 128-byte boundary: the flat buffers may also hold the parameters themselves
+        # (graph.GraphedTrainStep flat_optimizer), and kernels read weights with 16-byte vector loads
+        self.offsets, off = [], 0
+        for n in self.sizes:
+            self.offsets.append(off)
+            off += (n + 31) // 32 * 32
+        self.total = off
         p0 = self.params[0]
         self.flat = torch.zeros(self.total + len(self.params), dtype=torch.float32, device=p0.device)
 
     # ---- attached mode: parameters accumulate their gradients directly into views of the flat buffer ----
+    def _views(self, flat):
+        return [flat[o: o + n] for o, n in zip(self.offsets, self.sizes)]
+
     def attach(self) -> None:
         """Call after one backward pass: parameters that received a gradient get p.grad = a view of the flat buffer
         (autograd accumulates in place from then on), the others keep grad = None.  Afterwards use zero_grad() instead
         of optimizer.zero_grad(); allreduce() is then a single collective with no copies."""
-        views = self.flat[: self.total].split(self.sizes)
+        views = self._views(self.flat)
         self._present = [p.grad is not None for p in self.params]
         for p, v, has in zip(self.params, views, self._present):
             if has:
@@ -78,7 +87,7 @@ class FlatGradAllReducer:
 
     def attach_views(self) -> None:
         """Re-point p.grad at this reducer's flat buffer (after another reducer / optimizer call replaced them)."""
-        views = self.flat[: self.total].split(self.sizes)
+        views = self._views(self.flat)
         for p, v, has in zip(self.params, views, self._present):
             p.grad = v.view_as(p) if has else None
 
@@ -95,7 +104,7 @@ class FlatGradAllReducer:
             flat[: self.total].div_(world)
             return
         flat.zero_()
-        views = flat[: self.total].split(self.sizes)
+        views = self._views(flat)
         flags = flat[self.total:]
         for i, (p, v) in enumerate(zip(self.params, views)):
             if p.grad is not None:

@@ -273,3 +273,38 @@ def test_backward_workspace_and_recompute_paths_agree(monkeypatch):
             assert float((a - b).abs().max()) <= 1e-3 * max(1e-6, float(grads[0][names.index("rel_pos_bias.mlp.2.weight")].abs().max()))
             continue
         H.assert_close(a, b, 2e-4, f"grad {nm}: workspace vs recompute")
+
+
+def test_flat_optimizer_step_equals_per_parameter_adamw():
+    """GraphedTrainStep(flat_optimizer=...) moves the parameters into one buffer and runs AdamW over its contiguous runs:
+    bit-identical to torch's per-parameter fused AdamW (pure-torch model, so nothing else differs between the runs)."""
+    import copy
+    from dml_b200.graph import GraphedTrainStep
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Linear(24, 40)
+            self.unused = torch.nn.Linear(7, 5)          # never receives a gradient: must stay untouched
+            self.b = torch.nn.Linear(40, 3)
+
+        def forward(self, x):
+            return self.b(torch.tanh(self.a(x)))
+
+    torch.manual_seed(3)
+    n0 = Net().to(DEV)
+    n1 = copy.deepcopy(n0)
+    x = torch.randn(64, 24, device=DEV)
+    y = torch.randn(64, 3, device=DEV)
+    mk = lambda ps: torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.05, fused=True)   # noqa: E731
+    loss_fn = lambda out, b: ((out - b["y"]) ** 2).mean()                          # noqa: E731
+    s0 = GraphedTrainStep(n0, loss_fn, {"x": x, "y": y}, optimizer=mk([p for p in n0.parameters()]), model_keys=("x",))
+    s1 = GraphedTrainStep(n1, loss_fn, {"x": x, "y": y}, flat_optimizer=mk, model_keys=("x",))
+    for _ in range(5):
+        l0 = s0({"x": x, "y": y})
+        l1 = s1({"x": x, "y": y})
+    torch.cuda.synchronize()
+    assert torch.equal(l0, l1)
+    for (k, a), (_, b) in zip(n0.state_dict().items(), n1.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert len(s1.optimizer.param_groups[0]["params"]) == 2       # two runs: a.*, b.* (unused.* sits between them)
