@@ -19,7 +19,8 @@ b = synth.synthetic_bag(N, seed=1000)
 bag = {"x_path": b["x_path"].to(torch.bfloat16).to(dev), "x_omic_tumor": b["x_omic_tumor"].to(dev),
        "x_omic_immune": b["x_omic_immune"].to(dev), "label": b["label_diag"].to(dev)}
 keys = ("x_path", "x_omic_tumor", "x_omic_immune")
-step = GraphedTrainStep(net, lambda out, bb: bag_loss(out[3], bb["label"], "diag2021"), bag, optimizer=opt, model_keys=keys)
+step = GraphedTrainStep(net, lambda out, bb: bag_loss(out[3], bb["label"], "diag2021"), bag, model_keys=keys,
+                        flat_optimizer=lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=0.01, fused=True))
 for _ in range(5):
     step(bag)
 torch.cuda.synchronize()
