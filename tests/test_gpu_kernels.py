@@ -133,7 +133,8 @@ def test_deform_attn_fwd_tcgen05_is_deterministic_with_large_scores():
 # tc_ws: dS^T workspace + streaming dQ GEMM; tc_general: the dK/dV kernel's path for tables with too many segments
 @pytest.mark.parametrize("impl", ["mma", "tc", "tc_ws", "tc_general"])
 # (1, 3100, 200): few key blocks, many query tiles -> the dK/dV kernel splits the query range across CTAs (reductions)
-@pytest.mark.parametrize("B,n,n_kv", [(1, 193, 48), (2, 130, 64), (1, 517, 129), (1, 64, 1), (1, 1100, 300), (1, 3100, 200)])
+@pytest.mark.parametrize("B,n,n_kv", [(1, 193, 48), (2, 130, 64), (1, 517, 129), (1, 64, 1), (1, 1100, 300), (1, 3100, 200),
+                                      (2, 3200, 129)])      # batch 2 + work list + a mostly padded second key block
 def test_deform_attn_fwd_bwd_matches_torch(B, n, n_kv, impl):
     Hh, d, nout = 8, 64, 2
     G, C = Hh // nout, Hh * d
