@@ -387,6 +387,37 @@ def main():
                 "dense_math_roofline_ms": dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3,
                 "time_vs_dense_math_roofline": kavg[top] / (dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3)}
 
+    # ---- the HBM-bound kernel of the path on its own: dQ = dS K streamed from the fp16 dS^T workspace ----
+    roof_hbm = None
+    if rank == 0 and N == N_PATCHES:
+        try:
+            Hh, dh = 8, 64
+            n_pad, n_kv_pad = -(-n // 32) * 32, -(-n_kv // 128) * 128
+            ws = torch.randn(Hh, n_kv_pad, n_pad, device=dev, dtype=torch.float16)      # 1.08 GB > L2: every launch streams it from HBM
+            kk = torch.randn(1, n_kv, Hh * dh, device=dev, dtype=torch.float16)
+            dsc = torch.tensor([1.0, 1.0], device=dev)
+            dqo = torch.empty(1, n, Hh * dh, device=dev)
+            args_ = (_lib.ptr(ws), _lib.ptr(kk), _lib.ptr(dsc), 1, Hh, dh, n, n_kv, Hh * dh, _lib.ptr(dqo), _lib.stream())
+            for _ in range(3):
+                _lib.call("dml_deform_attn_dq_from_ds", *args_)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            reps = 10
+            for _ in range(reps):
+                _lib.call("dml_deform_attn_dq_from_ds", *args_)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_g = e0.elapsed_time(e1) / reps
+            alg = ws.numel() * 2 + kk.numel() * 2 + dqo.numel() * 4                      # workspace + K read, dQ written
+            roof_hbm = {"kernel": "deform_attn_dq_gemm_kernel (dml_deform_attn_dq_from_ds, last stage of the backward)",
+                        "bound": "hbm", "achieved": alg / (ms_g * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": alg / (ms_g * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": 1115e6, "ms_per_launch": ms_g,
+                        "peak_source": pk_kind, "note": "algorithmic bytes = fp16 dS^T workspace + K read once, fp32 dQ "
+                        "written once; traffic = ncu dram bytes of the same launch (profiles/r1_c_launches_prof_attn_n16385.csv)"}
+            del ws, kk, dqo
+        except Exception as ex:      # never lose the headline line to the side measurement
+            roof_hbm = {"error": repr(ex)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec, scale, n_used = cpu_reference_bags_per_s(args.cpu_sample, repeats=1)
@@ -405,7 +436,7 @@ def main():
                                    (" + flat NCCL grad all-reduce" if world > 1 else "") +
                                    (" + fused AdamW over the flat parameter buffer" if use_graph else " + fused AdamW"),
                            "parallelism": f"bag-sharded dp{world}", "l2": f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"},
-                "clocks": clk.summary(),
+                "clocks": clk.summary(), "roofline_hbm_kernel": roof_hbm,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,

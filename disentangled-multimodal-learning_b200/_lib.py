@@ -36,6 +36,7 @@ SIGNATURES = {
     "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
     "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp, _vp]),
     "dml_deform_attn_bwd_ws_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "dml_deform_attn_dq_from_ds": (_i, [_vp, _vp, _fp] + [_i] * 6 + [_fp, _vp]),
     "dml_layernorm_fwd": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _fp, _fp, _vp]),
     "dml_layernorm_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
     "dml_split_f16": (_i, [_fp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _fp, _vp, _vp]),
@@ -90,7 +91,7 @@ _ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace t
 # kernels launched per entry point (memsets not counted) - bench.py reports the total as gpu_launches
 KERNELS_PER_CALL = {
     "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2,
-    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3,
+    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
     "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
     "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1, "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1, "dml_split_f16": 2, "dml_gemm_nt_split": 1,
 }

@@ -1066,4 +1066,32 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   DML_RETURN_LAUNCH();
 }
 
+/* The last stage of the workspace backward on its own: dq [B, n, H*64] (fp32) = (1/s) * dS . K from a dS^T workspace laid
+ * out as dml_deform_attn_bwd_tc writes it (fp16 [(B H), ceil128(n_kv), ceil32(n)], times the loss scale s = dscale[0]).
+ * A streaming GEMM: reads the workspace once - the HBM-bound kernel of the path (bench.py times it against the copy
+ * bandwidth).                                                                                                          */
+int dml_deform_attn_dq_from_ds(const void* ds_ws, const void* k, const float* dscale, int B, int H, int dim_head, int n,
+                               int n_kv, int ldk, float* dq, void* stream) {
+  using namespace dml;
+  using namespace dml::tc;
+  DML_CHECK_ARG(ds_ws && k && dscale && dq && B > 0 && H > 0 && n > 0 && n_kv > 0);
+  if (dim_head != kD || (H & 1)) return DML_EUNSUPPORTED;
+  if ((ldk % 8) || ldk < H * kD) return DML_EINVAL;
+  if ((((uintptr_t)ds_ws) | ((uintptr_t)k) | ((uintptr_t)dq)) & 15) return DML_EINVAL;
+  BwdParams p{};
+  p.dscale = dscale; p.dq = dq; p.B = B; p.H = H; p.n = n; p.n_kv = n_kv;
+  p.ds_ws = (h16*)ds_ws; p.n_pad = cdiv(n, 32) * 32; p.n_kv_pad = cdiv(n_kv, 128) * 128;
+  CUtensorMap mds, mk64;
+  int rc;
+  if ((rc = make_map(&mds, ds_ws, B * H, p.n_kv_pad, p.n_pad, 64)) || (rc = make_map(&mk64, k, B, n_kv, ldk, 64))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(deform_attn_dq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dqg::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), H / 2, B), dqg::kThreads, dqg::kSmemBytes, (cudaStream_t)stream>>>(mds, mk64, p);
+  DML_RETURN_LAUNCH();
+}
+
 }  // extern "C"

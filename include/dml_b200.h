@@ -113,6 +113,12 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
                            const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
                            float* segsum, void* ds_ws, void* stream);
 
+/* The last stage of the workspace backward on its own: dq float [B, n, H*dim_head] = (1/s) * dS . K from a dS^T workspace
+ * in the layout dml_deform_attn_bwd_tc writes (fp16 [(B*H), ceil128(n_kv), ceil32(n)], times s = dscale[0]); k as above.
+ * Streams the workspace once: the HBM-bound kernel of the path.                                                        */
+int dml_deform_attn_dq_from_ds(const void* ds_ws, const void* k, const float* dscale, int B, int H, int dim_head, int n,
+                               int n_kv, int ldk, float* dq, void* stream);
+
 /* ---- row LayerNorm (DeformCrossTransLayer.norm, models/DeformCrossTransMIL.py:44,66; TransLayer.norm, mil.py:174,186) -- */
 /* x, y, dy, dx: float [rows, D] (D in {128, 256, 512}); w, b, dw, db: float [D]; mean, rstd: float [rows] saved by the
  * forward.  Biased variance, eps inside the square root (torch.nn.LayerNorm).  dw / db are overwritten.              */

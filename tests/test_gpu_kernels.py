@@ -102,6 +102,26 @@ def test_deform_attn_fwd_tcgen05_matches_torch(B, n, n_kv):
     H.assert_close(lse, lse2, 1e-5, "log-sum-exp (tcgen05 vs mma.sync)")
 
 
+@pytest.mark.parametrize("B,n,n_kv", [(1, 300, 70), (2, 1000, 257)])
+def test_dq_from_ds_workspace_matches_matmul(B, n, n_kv):
+    """The streaming dQ GEMM on its own: dq = (1/s) dS K from a dS^T workspace in the backward's layout."""
+    Hh, d = 8, 64
+    C = Hh * d
+    n_pad, n_kv_pad = -(-n // 32) * 32, -(-n_kv // 128) * 128
+    seed = 900 + n
+    ds = synth.normal((B * Hh, n_kv, n), seed, "ds").to(DEV)
+    ws = torch.zeros(B * Hh, n_kv_pad, n_pad, device=DEV, dtype=torch.float16)
+    ws[:, :n_kv, :n] = ds.to(torch.float16)
+    k = synth.normal((B, n_kv, C), seed, "k").to(DEV).to(torch.float16)
+    dscale = torch.tensor([4.0, 0.25], device=DEV)
+    dq = torch.full((B, n, C), float("nan"), device=DEV)
+    call("dml_deform_attn_dq_from_ds", ptr(ws), ptr(k), ptr(dscale), B, Hh, d, n, n_kv, C, ptr(dq), stream())
+    dsf = ws[:, :n_kv, :n].float().reshape(B, Hh, n_kv, n)
+    kf = k.float().reshape(B, n_kv, Hh, d).permute(0, 2, 1, 3)
+    ref = 0.25 * torch.einsum("bhji,bhjd->bihd", dsf, kf).reshape(B, n, C)
+    H.assert_close(dq, ref, 1e-5, "dq from dS^T")
+
+
 def test_deform_attn_fwd_tcgen05_is_deterministic_with_large_scores():
     """No atomics in the forward: repeated launches must agree bit for bit (a race between the two threads that share a
     query row, or between the softmax warps and the MMA warps, would show up here).  Large |q|, |k| force the softmax
