@@ -177,25 +177,29 @@ __global__ void __launch_bounds__(256)
 offsets_dq_combine_kernel(const float* __restrict__ dq_attn, const float* __restrict__ dy,
                           const float* __restrict__ w0, int B, int n, int C, int G, int ks, int stride, int pad,
                           int n_kv, float scale, float* __restrict__ dq) {
+  // C / 4 threads per token (host guarantees that C / 4 divides the block size): the channel of a thread never changes,
+  // tokens advance by whole blocks - no per-element divisions (they made the first version compute-bound: 30 us for a
+  // 67 MB pass)
   const int Cg = C / G;
-  const size_t total4 = (size_t)B * n * C / 4;
-  for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (size_t)gridDim.x * blockDim.x) {
-    const size_t i = i4 * 4;
-    const int c = (int)(i % C);
-    const int p = (int)((i / C) % n);
-    const int b = (int)(i / ((size_t)C * n));
-    const int g = c / Cg, cc = c % Cg;
-    float4 a = *reinterpret_cast<const float4*>(dq_attn + i);
+  const int tpt = C >> 2;                                  // threads per token
+  const int c = (threadIdx.x % tpt) * 4;
+  const int g = c / Cg, cc = c % Cg;
+  const int tok_per_blk = blockDim.x / tpt;
+  const long long rows = (long long)B * n;
+  for (long long row = (long long)blockIdx.x * tok_per_blk + threadIdx.x / tpt; row < rows; row += (long long)gridDim.x * tok_per_blk) {
+    const int b = (int)(row / n), p = (int)(row - (long long)b * n);
+    const size_t i = (size_t)row * C + c;
+    const float4 a = *reinterpret_cast<const float4*>(dq_attn + i);
     float r[4] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale};
     const int jhi = min((p + pad) / stride, n_kv - 1);
-    for (int j = jhi; j >= 0; --j) {
+    for (int j = jhi; j >= 0; --j) {                     // at most ceil(ks / stride) keys see this token
       const int t = p + pad - stride * j;
       if (t >= ks) break;
       const float4 d = *reinterpret_cast<const float4*>(dy + ((size_t)(b * G + g) * n_kv + j) * Cg + cc);
-      r[0] = fmaf(d.x, w0[(cc + 0) * ks + t], r[0]);
-      r[1] = fmaf(d.y, w0[(cc + 1) * ks + t], r[1]);
-      r[2] = fmaf(d.z, w0[(cc + 2) * ks + t], r[2]);
-      r[3] = fmaf(d.w, w0[(cc + 3) * ks + t], r[3]);
+      r[0] = fmaf(d.x, __ldg(w0 + (cc + 0) * ks + t), r[0]);
+      r[1] = fmaf(d.y, __ldg(w0 + (cc + 1) * ks + t), r[1]);
+      r[2] = fmaf(d.z, __ldg(w0 + (cc + 2) * ks + t), r[2]);
+      r[3] = fmaf(d.w, __ldg(w0 + (cc + 3) * ks + t), r[3]);
     }
     *reinterpret_cast<float4*>(dq + i) = make_float4(r[0], r[1], r[2], r[3]);
   }
@@ -334,6 +338,7 @@ int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float
   const int blocks = min(dml::cdiv(warps, 8), 148 * 2);
   dml::offsets_bwd_kernel<<<blocks, 256, 0, st>>>((const dml::h16*)q, w0, b0, w2, d_off, B, n, C, G, ksize, stride, pad,
                                                  n_kv, offset_scale, dy_ws, wgrad);
+  if (C % 4 != 0 || 256 % (C / 4) != 0 || ((C / G) % 4) != 0) return DML_EUNSUPPORTED;
   const size_t total4 = (size_t)B * n * C / 4;
   const int blocks2 = (int)min((total4 + 255) / 256, (size_t)148 * 16);
   dml::offsets_dq_combine_kernel<<<blocks2, 256, 0, st>>>(dq_attn, dy_ws, w0, B, n, C, G, ksize, stride, pad, n_kv,
