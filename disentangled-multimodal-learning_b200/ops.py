@@ -236,7 +236,8 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
             dWo = wgrad_mm(dout.reshape(-1, dim), o.reshape(-1, C))        # [dim, C]
             dbo = colsum(dout.reshape(-1, dim))
         dscale = grad_scale(d_o)
-        d_o16 = (d_o * dscale[0]).to(F16)
+        d_o16 = torch.empty(d_o.shape, device=dev, dtype=F16)
+        torch.mul(d_o, dscale[0], out=d_o16)                               # scale and round in one pass
 
         dq_attn = torch.empty(B, n_out, C, device=dev, dtype=F32)
         dk = torch.empty(B, n_kv, C, device=dev, dtype=F32)
