@@ -185,6 +185,15 @@ def main():
     from dml_b200 import _lib, synth
     from dml_b200.model import Args, bag_loss, define_net
 
+    if not os.path.exists(_lib.LIB_PATH):          # snapshot without the built library: build it (one rank), never fall back
+        if local_rank == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        else:
+            while not os.path.exists(_lib.LIB_PATH):
+                time.sleep(1.0)
+            time.sleep(2.0)
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
