@@ -59,7 +59,10 @@ def _worker(rank, port, q):
         full = torch.cat(parts, dim=0)
         w = torch.arange(full.numel(), dtype=torch.float32).reshape(full.shape) * (rank + 1)
         (full * w).sum().backward()
-        q.put((rank, mine, grads, full.detach().clone(), t.grad.clone(), w[2 * rank: 2 * rank + 2].clone()))
+        # plain numpy payloads: tensors on an mp.Queue are shared through the sender's resource sharer, which is gone
+        # if this worker exits before the parent unpickles them (an intermittent FileNotFoundError in the parent)
+        q.put((rank, mine, {k: (None if v is None else v.numpy()) for k, v in grads.items()}, full.detach().numpy().copy(),
+               t.grad.numpy().copy(), w[2 * rank: 2 * rank + 2].numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -74,7 +77,8 @@ def test_world2_sharding_allreduce_gather():
     res = {}
     for _ in range(WORLD):
         r = q.get(timeout=180)                  # a crashed worker fails the test instead of hanging it
-        res[r[0]] = r[1:]
+        res[r[0]] = (r[1], {k: (None if v is None else torch.from_numpy(v)) for k, v in r[2].items()},
+                     torch.from_numpy(r[3]), torch.from_numpy(r[4]), torch.from_numpy(r[5]))
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
