@@ -198,6 +198,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL prints its version banner on stdout, where the
+            os.environ["NCCL_DEBUG"] = "WARN"                          # driver expects exactly one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     N = args.n_patches
     net = define_net(Args(task_type=TASK))
