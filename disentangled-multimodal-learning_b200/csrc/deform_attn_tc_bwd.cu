@@ -9,16 +9,20 @@
 // dS workspace (dml_deform_attn_bwd_ws_bytes) the dK/dV kernel also writes dS^T (fp16, [head][key][query]) and dQ = dS K
 // becomes a plain streaming GEMM over it (deform_attn_dq_gemm_kernel) instead of a second recomputation.
 //
-//   deform_attn_dq_tc_kernel   query-stationary (TMEM lane = query), the forward's structure: two 128-query groups per
-//                              CTA alternate on the tensor pipe; per 32-key tile S = Q K^T and dP = dO V^T (SS MMAs),
-//                              dS (fp16) overwrites S in TMEM, dQ += dS K (TS MMA, K as an MN-major operand).
 //   deform_attn_dkv_tc_kernel  key-stationary (TMEM lane = key): one 128-key tile and both heads of the group per CTA,
 //                              streaming 32-query tiles through a 4-stage TMA ring; S^T = K Q^T and dP^T = V dO^T are
 //                              double-buffered in TMEM, P^T and dS^T (fp16) overwrite them in place and feed
-//                              dV += P^T dO, dK += dS^T Q (TS MMAs, dO / Q tiles re-read as MN-major operands).  A
-//                              thread owns one key for all queries, so g_j is a register, dg_j accumulates privately
-//                              and x_ij grows monotonically along the row: the per-segment sums are run-length merged
-//                              in registers and reach shared memory only when the segment changes.
+//                              dV += P^T dO, dK += dS^T Q (TS MMAs, dO / Q tiles re-read as MN-major operands).  16
+//                              elementwise warps: one head, one TMEM lane quarter and one 16-query half of the tile
+//                              each.  A thread owns one key for all queries, so g_j is a register, dg_j accumulates
+//                              privately and x_ij grows monotonically along the row: the thread carries its table
+//                              segment from tile to tile (coefficients in registers, no per-position table access) and
+//                              the per-segment sums leave as warp-reduced global reductions when the segment changes.
+//                              CTAs take pieces of items from a cost-balanced work list (host wrapper below).
+//   deform_attn_dq_gemm_kernel with the workspace: dQ = dS K streamed from the stored dS^T (MN-major A operand).
+//   deform_attn_dq_tc_kernel   without it: query-stationary (TMEM lane = query), two 128-query groups per CTA alternate
+//                              on the tensor pipe; per 32-key tile S = Q K^T and dP = dO V^T (SS MMAs), dS (fp16)
+//                              overwrites S in TMEM, dQ += dS K (TS MMA, K as an MN-major operand).
 #include <math.h>
 #include <stdlib.h>
 
