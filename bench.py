@@ -383,10 +383,10 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's kernels at N = 16 384 from
-                # ncu (profiles/r1_c_launches_prof_attn_n16385.csv).  Backward: 50 MB (D = dO.O) + 64 MB + 1044 MB (dK/dV
+                # ncu (profiles/r1_c_launches_prof_attn_n16385.csv).  Backward: 50 MB (D = dO.O) + 214 MB + 1058 MB (dK/dV
                 # kernel, writes the fp16 dS^T workspace: 8 heads x 4096 x 16416 x 2 B = 1.08 GB) + 1086 MB + 29 MB (dQ
                 # GEMM, reads it back); algorithmic without the workspace: q,k,v,dO fp16 + O, dQ, dK, dV fp32 = 97 MB
-                "traffic": ({"dml_deform_attn_fwd_tc": 25.4e6, "dml_deform_attn_bwd_tc": 2273e6}.get(top)
+                "traffic": ({"dml_deform_attn_fwd_tc": 25.4e6, "dml_deform_attn_bwd_tc": 2438e6}.get(top)
                             if N == N_PATCHES else None),
                 "peak_source": pk_kind + " (sustained)",
                 "ms_per_launch": kavg[top],
