@@ -58,13 +58,15 @@ constexpr uint32_t kGStride = 40 * 4;
 constexpr uint32_t kOffRec = kOffG + kStages * kGStride;             // bias table image (tc_common.cuh), 16-B aligned
 constexpr uint32_t kOffPair = kOffRec + kTabSmemBytes;               // [slot 2][group 2][row 128][key half 2] float2: row-max exchange
 constexpr uint32_t kPairBytes = 2 * kGroups * kBM * 2 * 8;
-constexpr uint32_t kOffBar = kOffPair + kPairBytes;                  // mbarriers (8 B each)
+constexpr uint32_t kOffPairBh = kOffPair + kPairBytes;               // [slot 2][group 2][row 128] float4: bias bound + flagged-cell count
+constexpr uint32_t kPairBhBytes = 2 * kGroups * kBM * 16;
+constexpr uint32_t kOffBar = kOffPairBh + kPairBhBytes;              // mbarriers (8 B each)
 constexpr int kBarQ = 0, kBarKvFull = 1, kBarKvEmpty = kBarKvFull + kStages, kBarSFull = kBarKvEmpty + kStages,   // [group][buffer]
               kBarPFull = kBarSFull + 2 * kGroups, kBarPvDone = kBarPFull + 2 * kGroups, kBarOFinal = kBarPvDone + kGroups,
               kNumBars = kBarOFinal + kGroups;
 constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;             // + slack for the 1024-B alignment
-static_assert(kOffRec % 16 == 0 && kOffPair % 8 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kOffRec % 16 == 0 && kOffPair % 8 == 0 && kOffPairBh % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 struct Params {
@@ -273,9 +275,12 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           }
       }
       asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(pair_slot(buf, kh)), "f"(r0), "f"(r1) : "memory");
-      float bh0, bh1;
-      int ndirty;
-      {
+      // the bias bound over the tile's position window is the same for both halves of the row: the kh = 0 thread works
+      // it out and hands it over with the maximum (the two warps share a scheduler: the issue slots go to the partner)
+      const uint32_t bh_slot = sbase + kOffPairBh + (uint32_t)((buf * kGroups + g) * kBM + row) * 16u;
+      float bh0 = 0.f, bh1 = 0.f;
+      int ndirty = 0;
+      if (kh == 0) {
         const float xlo = cpb_x(s_i - lds_f32(gsa + 33 * 4)), xhi = cpb_x(s_i - lds_f32(gsa + 32 * 4));
         int clo, chi, sdummy;
         const float4 e = lookup2<true, false>(L, xlo, clo, sdummy), f = lookup2<true, false>(L, xhi, chi, sdummy);
@@ -283,12 +288,17 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
         bh0 = fmaxf(fmaf(e.x, xlo, e.y), fmaf(f.x, xhi, f.y)) + amax0 * half;
         bh1 = fmaxf(fmaf(e.z, xlo, e.w), fmaf(f.z, xhi, f.w)) + amax1 * half;
         ndirty = tab_dirty_between(L, clo, chi);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bh_slot), "f"(bh0), "f"(bh1), "f"(__int_as_float(ndirty)), "f"(0.f) : "memory");
       }
       pair_sync(pair_id);
       {
         const float2 o = lds_f32x2(pair_slot(buf, kh ^ 1));
         r0 = fmaxf(r0, o.x);
         r1 = fmaxf(r1, o.y);
+        if (kh == 1) {
+          const float4 v = lds_f32x4(bh_slot);
+          bh0 = v.x; bh1 = v.y; ndirty = __float_as_int(v.z);
+        }
       }
       // from here on both threads of the row hold identical r, bh, m: they take the same decisions
       const float ub0 = fmaf(r0, sc2, bh0), ub1 = fmaf(r1, sc2, bh1);
