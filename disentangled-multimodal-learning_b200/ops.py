@@ -78,7 +78,7 @@ def side_stream(dev) -> torch.cuda.Stream:
 
 def grad_scale(t: torch.Tensor) -> torch.Tensor:
     """Device-side power-of-two loss scale for an fp16 operand: float[2] = (s, 1/s) with
-    8 <= s * max|t| < 16 (no host sync; s = 1 for an all-zero tensor)."""
+    4 < s * max|t| <= 8 (no host sync; s = 1 for an all-zero tensor)."""
     lo, hi = torch.aminmax(t.detach())          # one pass, no |t| temporary
     amax = torch.maximum(hi, -lo).float()
     s = torch.exp2(torch.floor(torch.log2(8.0 / amax.clamp_min(1e-30))).clamp(-60.0, 60.0))
