@@ -43,6 +43,7 @@ SIGNATURES = {
     "dml_gemm_nt_split": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _fp, _i, _ll, _vp]),
     "dml_debug_set_trace": (_i, [_vp]),
     "dml_debug_set_seg_limit": (_i, [_i]),
+    "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
     "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
     "dml_softmax_rows_fwd": (_i, [_fp, _fp, _ll, _i, _vp]),

@@ -906,6 +906,55 @@ deform_attn_dq_gemm_kernel(const __grid_constant__ CUtensorMap mds, const __grid
 }  // namespace tc
 }  // namespace dml
 
+// ---- host: work list of the dK/dV kernel (see the launch in dml_deform_attn_bwd_tc) ----------------------------------
+static bool dkv_worklist_applies(int items, int ntiles, int nsm) {
+  return items <= nsm && 2 * nsm <= dml::tc::kDkvWorkMax && ntiles >= 96 && items < 65536 && ntiles < 65536;
+}
+// Cuts the items' query-tile ranges into pieces of about equal estimated cost (one cut per SM, never inside the first or
+// last 24 tiles of what it would split) and lists them longest first; returns the number of pieces.
+static int plan_dkv_worklist(int B, int G, int n, int n_kv, int nsm, dml::tc::DkvWorkList& wl) {
+  using namespace dml;
+  using namespace dml::tc;
+  const int nkb = cdiv(n_kv, dkvk::kBK), items = nkb * G * B, ntiles = cdiv(n, dkvk::kBI);
+  const double kDense = 1.45, half = 0.16 * n / dkvk::kBI;
+  auto cost = [&](int item, int t) {
+    const double tdiag = ((item % nkb) * dkvk::kBK + 0.5 * dkvk::kBK) * ((double)n / n_kv) / dkvk::kBI;
+    return fabs(t - tdiag) < half ? kDense : 1.0;
+  };
+  double total = 0.0;
+  for (int i = 0; i < items; ++i)
+    for (int t = 0; t < ntiles; ++t) total += cost(i, t);
+  const double target = total / nsm;
+  double acc = 0.0, pc[kDkvWorkMax];
+  int k = 1, np = 0;
+  for (int i = 0; i < items && np < kDkvWorkMax; ++i) {
+    int t0 = 0;
+    double c = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+      const double ct = cost(i, t);
+      acc += ct; c += ct;
+      if (acc >= k * target - 1e-9 && k < nsm) {
+        ++k;
+        // cut here unless it would leave a sliver (each piece pays a ~10 us prologue): then the item boundary or the
+        // previous cut stands in for it
+        if (t + 1 - t0 >= 24 && ntiles - (t + 1) >= 24 && np < kDkvWorkMax - 1) {
+          wl.e[np] = DkvWork{(uint16_t)i, (uint16_t)t0, (uint16_t)(t + 1), 0}; pc[np++] = c;
+          t0 = t + 1; c = 0.0;
+        }
+      }
+    }
+    wl.e[np] = DkvWork{(uint16_t)i, (uint16_t)t0, (uint16_t)ntiles, 0}; pc[np++] = c;
+  }
+  for (int a = 1; a < np; ++a) {      // insertion sort, longest first (np <= 320)
+    const DkvWork w = wl.e[a];
+    const double c = pc[a];
+    int q = a - 1;
+    for (; q >= 0 && pc[q] < c; --q) { wl.e[q + 1] = wl.e[q]; pc[q + 1] = pc[q]; }
+    wl.e[q + 1] = w; pc[q + 1] = c;
+  }
+  return np;
+}
+
 extern "C" {
 
 /* debug: device buffer of long long[4 * 2 * ntiles] that the next dQ launches fill with clock64() stamps (NULL = off) */
@@ -918,6 +967,22 @@ int dml_debug_set_trace(void* buf) {
 size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
   if (B <= 0 || H <= 0 || n <= 0 || n_kv <= 0) return 0;
   return (size_t)B * H * (size_t)(dml::cdiv(n_kv, 128) * 128) * (size_t)(dml::cdiv(n, 32) * 32) * 2;
+}
+
+/* test aid (host only, no device needed): the dK/dV work list for a problem shape on a device with `nsm` SMs as
+ * (item, t0, t1) triples in launch order; returns the number of pieces (0: one CTA per item), at most cap are written */
+int dml_debug_dkv_worklist(int B, int H, int n, int n_kv, int nsm, int* out, int cap) {
+  using namespace dml;
+  using namespace dml::tc;
+  if (B <= 0 || H < 2 || n <= 0 || n_kv <= 0 || nsm <= 0 || !out) return DML_EINVAL;
+  const int G = H / 2, items = cdiv(n_kv, dkvk::kBK) * G * B, ntiles = cdiv(n, dkvk::kBI);
+  if (!dkv_worklist_applies(items, ntiles, nsm)) return 0;
+  DkvWorkList wl;
+  const int np = plan_dkv_worklist(B, G, n, n_kv, nsm, wl);
+  for (int i = 0; i < np && i < cap; ++i) {
+    out[3 * i] = wl.e[i].item; out[3 * i + 1] = wl.e[i].t0; out[3 * i + 2] = wl.e[i].t1;
+  }
+  return np;
 }
 
 /* debug / test knob: tables with at least limit - 2 segments are treated as too large for the shared-memory segment
@@ -1013,46 +1078,11 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
       wl_key[0] = -1;
       p.qsplit = ntiles / forced >= 1 ? forced : 1;
       ncta = items * p.qsplit;
-    } else if (!(items <= nsm && 2 * nsm <= kDkvWorkMax && ntiles >= 96 && items < 65536 && ntiles < 65536)) {
+    } else if (!dkv_worklist_applies(items, ntiles, nsm)) {
       wl.n = 0;
       for (int q = 0; q < 5; ++q) wl_key[q] = key[q];
     } else {
-      const double kDense = 1.45, half = 0.16 * n / dkvk::kBI;
-      auto cost = [&](int item, int t) {
-        const double tdiag = ((item % nkb) * dkvk::kBK + 0.5 * dkvk::kBK) * ((double)n / n_kv) / dkvk::kBI;
-        return fabs(t - tdiag) < half ? kDense : 1.0;
-      };
-      double total = 0.0;
-      for (int i = 0; i < items; ++i)
-        for (int t = 0; t < ntiles; ++t) total += cost(i, t);
-      const double target = total / nsm;
-      double acc = 0.0, pc[kDkvWorkMax];
-      int k = 1, np = 0;
-      for (int i = 0; i < items && np < kDkvWorkMax; ++i) {
-        int t0 = 0;
-        double c = 0.0;
-        for (int t = 0; t < ntiles; ++t) {
-          const double ct = cost(i, t);
-          acc += ct; c += ct;
-          if (acc >= k * target - 1e-9 && k < nsm) {
-            ++k;
-            // cut here unless it would leave a sliver (each piece pays a ~10 us prologue): then the item boundary or the
-            // previous cut stands in for it
-            if (t + 1 - t0 >= 24 && ntiles - (t + 1) >= 24 && np < kDkvWorkMax - 1) {
-              wl.e[np] = DkvWork{(uint16_t)i, (uint16_t)t0, (uint16_t)(t + 1), 0}; pc[np++] = c;
-              t0 = t + 1; c = 0.0;
-            }
-          }
-        }
-        wl.e[np] = DkvWork{(uint16_t)i, (uint16_t)t0, (uint16_t)ntiles, 0}; pc[np++] = c;
-      }
-      for (int a = 1; a < np; ++a) {      // insertion sort, longest first (np <= 320)
-        const DkvWork w = wl.e[a];
-        const double c = pc[a];
-        int q = a - 1;
-        for (; q >= 0 && pc[q] < c; --q) { wl.e[q + 1] = wl.e[q]; pc[q + 1] = pc[q]; }
-        wl.e[q + 1] = w; pc[q + 1] = c;
-      }
+      const int np = plan_dkv_worklist(B, G, n, n_kv, nsm, wl);
       wl.n = np;
       ncta = np;
       for (int q = 0; q < 5; ++q) wl_key[q] = key[q];

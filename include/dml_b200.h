@@ -147,6 +147,10 @@ int dml_debug_set_trace(void* buf);
 /* Test knob: bias tables with at least limit - 2 segments take the dK/dV kernel's general per-position path (as tables too
  * large for its shared-memory segment arrays do); limit <= 0 restores the default.                                       */
 int dml_debug_set_seg_limit(int limit);
+/* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
+ * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
+ * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */
+int dml_debug_dkv_worklist(int B, int H, int n, int n_kv, int nsm, int* out, int cap);
 
 /* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
 /* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]

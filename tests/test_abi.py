@@ -69,3 +69,39 @@ def test_state_dict_contract():
     sd = define_net(Args(mode="path", label_dim=4)).state_dict()
     assert {k: tuple(v.shape) for k, v in sd.items()} == H.transmil_shapes(label_dim=4)
     assert len(sd) == 27 and sum(v.numel() for v in sd.values()) == 2738836
+
+
+def test_dkv_worklist_partitions_every_item():
+    """Host logic of the attention backward (no device needed): the work list handed to the dK/dV kernel covers every
+    item's query-tile range exactly once, has no slivers, and is ordered longest first."""
+    import ctypes as C
+    from dml_b200 import _lib
+    lib = _lib.load()
+    cap = 400
+    buf = (C.c_int * (3 * cap))()
+    # north-star shape: 32 key blocks x 4 head pairs on 148 SMs
+    B, H, n, n_kv, nsm = 1, 8, 16385, 4096, 148
+    npieces = lib.dml_debug_dkv_worklist(B, H, n, n_kv, nsm, buf, cap)
+    items, ntiles = 32 * 4, (n + 31) // 32
+    assert items < npieces <= 2 * nsm
+    pieces = [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(npieces)]
+    cover = {}
+    for it, t0, t1 in pieces:
+        assert 0 <= it < items and 0 <= t0 < t1 <= ntiles
+        assert t1 - t0 >= 24 or (t0 == 0 and t1 == ntiles)
+        cover.setdefault(it, []).append((t0, t1))
+    assert sorted(cover) == list(range(items))
+    for it, rs in cover.items():
+        rs.sort()
+        assert rs[0][0] == 0 and rs[-1][1] == ntiles and all(a[1] == b[0] for a, b in zip(rs, rs[1:])), (it, rs)
+    # pieces of a similar size near the front, the small remainders at the back (cost-ordered)
+    lens = [t1 - t0 for _, t0, t1 in pieces]
+    assert max(lens[: nsm // 2]) <= ntiles and min(lens[: nsm // 2]) > max(lens[-8:])
+    # many items / short sequences: one CTA per item
+    assert lib.dml_debug_dkv_worklist(1, 8, 100000, 25000, nsm, buf, cap) == 0
+    assert lib.dml_debug_dkv_worklist(1, 8, 2000, 512, nsm, buf, cap) == 0
+    # batch 2, few key blocks: still an exact partition
+    npieces = lib.dml_debug_dkv_worklist(2, 8, 6400, 300, nsm, buf, cap)
+    assert npieces > 0
+    tot = sum(buf[3 * i + 2] - buf[3 * i + 1] for i in range(npieces))
+    assert tot == (3 * 4 * 2) * ((6400 + 31) // 32)
