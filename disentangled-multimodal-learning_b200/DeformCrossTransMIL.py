@@ -88,7 +88,7 @@ class DeformCrossTransMIL(nn.Module):
         fc1 = self._fc1[0]
         if path.dtype == torch.bfloat16:      # bf16 bags: fc1 on the bf16 tensor-core path (fp32 accumulate/output)
             B_, N_, K_ = path.shape
-            path = F.relu(ops.LinearBf16BagFn.apply(path.reshape(B_ * N_, K_), fc1.weight, fc1.bias).reshape(B_, N_, -1))
+            path = ops.fc1_bf16_bag(path.reshape(B_ * N_, K_), fc1.weight, fc1.bias).reshape(B_, N_, -1)
         else:
             path = F.relu(ops.mm_tf32(path.float(), fc1.weight.t()) + fc1.bias)
         ready = getattr(omic, "_dml_ready", None)      # omic vector produced on another stream (model._omic_ahead)

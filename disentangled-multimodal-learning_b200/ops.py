@@ -444,6 +444,11 @@ class LinearBf16BagFn(torch.autograd.Function):
         return dx, dW, colsum(dy)
 
 
+def fc1_bf16_bag(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """relu(x @ W^T + b) for a bf16 bag x [M, K] (DeformCrossTransMIL.py:100 on `path.float()`), fp32 output."""
+    return torch.relu(LinearBf16BagFn.apply(x, W, b))
+
+
 class LayerNormFn(torch.autograd.Function):
     """LayerNorm over the last dim (128 / 256 / 512) of a contiguous fp32 tensor: one warp per row, statistics saved
     for the backward, weight / bias gradients reduced per CTA (DeformCrossTransLayer.norm, TransLayer.norm)."""

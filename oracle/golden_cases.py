@@ -11,9 +11,19 @@ NYSTROM_CASES = [
     dict(name="nystrom_d64_m16_n100_b2", b=2, n=100, dim=64, dim_head=8, m=16, seed=21),
     dict(name="nystrom_d512_m256_n300_b1", b=1, n=300, dim=512, dim_head=64, m=256, seed=22),
     dict(name="nystrom_d128_m64_n256_b1_nopad", b=1, n=256, dim=128, dim_head=16, m=64, seed=23),
+    # B = 2 at head sizes the GPU library supports (H * d >= 128): pins the cross-bag coupling of the pinv init (T3)
+    dict(name="nystrom_d128_m64_n200_b2", b=2, n=200, dim=128, dim_head=16, m=64, seed=24),
+    # CMTA's Nystrom configuration (cmta_utils.py:858-874: dim 256, dim_head 32, 128 landmarks), B = 2, front pad 84
+    dict(name="nystrom_d256_m128_n300_b2_cmta", b=2, n=300, dim=256, dim_head=32, m=128, seed=25),
 ]
 TOWER_CASES = [dict(name="dctmil_n301_b1", B=1, N=300, seed=31)]
-TRANSMIL_CASES = [dict(name="transmil_n150_b1", B=1, N=150, seed=41)]
+TRANSMIL_CASES = [
+    dict(name="transmil_n150_b1", B=1, N=150, seed=41),
+    # BASELINE.json config 1 (N = 6 000: grid 78^2, n = 6 085, front pad 59, l = 24) and the 16k bag (pad 255, l = 65):
+    # the reference itself runs these in seconds on the CPU, so the goldens come from it, not from the oracle
+    dict(name="transmil_n6000_b1", B=1, N=6000, seed=42),
+    dict(name="transmil_n16384_b1", B=1, N=16384, seed=43),
+]
 PATHOMIC_CASES = [
     dict(name="pathomic_diag_n260_b2", B=2, N=260, seed=51, task="diag2021"),
     dict(name="pathomic_surv_n132_b1", B=1, N=132, seed=52, task="survival"),

@@ -192,7 +192,11 @@ def gen_towers():
 
 
 def main():
+    """python -m oracle.make_goldens [--missing]   (--missing: only write fixtures that do not exist yet)"""
     os.makedirs(OUT, exist_ok=True)
+    if "--missing" in sys.argv:
+        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES):
+            cases[:] = [c for c in cases if not os.path.exists(os.path.join(OUT, c["name"] + ".npz"))]
     sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
     install_reference_shims()
     torch.manual_seed(0)

@@ -308,3 +308,67 @@ def test_flat_optimizer_step_equals_per_parameter_adamw():
     for (k, a), (_, b) in zip(n0.state_dict().items(), n1.state_dict().items()):
         assert torch.equal(a, b), k
     assert len(s1.optimizer.param_groups[0]["params"]) == 2       # two runs: a.*, b.* (unused.* sits between them)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the code path bench.py times: bf16 bags (DeformCrossTransMIL.forward takes the bf16 fc1 branch) at N = 16 384
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,N", [(777, 1024), (16384, 1024)])
+def test_fc1_on_a_bf16_bag_matches_fp32_linear(rows, N):
+    """fc1 of the towers on a bf16 bag (DeformCrossTransMIL.py:100 applied to `path.float()`): y, dW and db against an
+    fp64 linear on the same bf16-rounded input (the bag is GIVEN in bf16: its rounding is not an error of the path)."""
+    from dml_b200 import ops
+    x = synth.normal((rows, N), 3, "x").to(DEV).to(torch.bfloat16)
+    W = (synth.uniform((128, N), 3, "W", 1.0 / 32)).to(DEV).requires_grad_()
+    b = synth.uniform((128,), 3, "b", 0.1).to(DEV).requires_grad_()
+    r = synth.normal((rows, 128), 3, "r").to(DEV)
+    y = ops.fc1_bf16_bag(x, W, b)
+    gW, gb = torch.autograd.grad((y * r).sum(), (W, b))
+    xd, Wd, bd = x.double(), W.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    yd = torch.relu(xd @ Wd.t() + bd)
+    gWd, gbd = torch.autograd.grad((yd * r.double()).sum(), (Wd, bd))
+    H.assert_close(y, yd, 1e-4, "fc1(bf16 bag)")
+    H.assert_close(gW, gWd, 1e-4, "dW fc1")
+    H.assert_close(gb, gbd, 1e-4, "db fc1")
+
+
+@pytest.mark.parametrize("task", ["diag2021", "survival"])
+def test_deform_pathomic_net_16k_bf16_bag_against_chunked_oracle(task):
+    """BASELINE.json configs[1] / [2] exactly as bench.py runs them: DeformPathomicNet, one 16 384-patch bf16 bag,
+    weighted CE (diag2021) / NLL hazard loss (survival): logits / hazards, loss and EVERY parameter gradient against the
+    row-chunked oracle (same maths as the reference, which needs ~190 GB here) on the same bf16-rounded bag, at 5e-3."""
+    seed, N = 88, 16384
+    mod = load(define_net(Args(task_type=task)), H.pathomic_shapes(), seed).eval()
+    bag = {k: v.to(DEV) for k, v in synth.synthetic_bag(N, seed, 1).items()}
+    x_bf16 = bag["x_path"].to(torch.bfloat16)
+    feats, vt, vi, logits, *_ = mod(x_path=x_bf16, x_omic_tumor=bag["x_omic_tumor"], x_omic_immune=bag["x_omic_immune"])
+    label = bag["label_diag"] if task == "diag2021" else bag["label_surv"]
+    loss = bag_loss(logits, label, task, bag["censor"])
+    names = [k for k, p in mod.named_parameters() if p.requires_grad]
+    grads = torch.autograd.grad(loss, [p for _, p in mod.named_parameters() if p.requires_grad], allow_unused=True)
+
+    P = _oracle_params(mod)
+    rf, rvt, rvi, rlogits = towers.deform_pathomic_net(x_bf16.float(), bag["x_omic_tumor"], bag["x_omic_immune"], P,
+                                                       task_type=task, row_block=1024)
+    rloss = towers.bag_loss(rlogits, label, task, bag["censor"])
+    rgrads = torch.autograd.grad(rloss, [P[k] for k in names], allow_unused=True)
+    H.assert_close(feats, rf, TOL_BF16, "features")
+    for i, nm in enumerate(("hazard_tumor", "hazard_immune", "hazard")):
+        H.assert_close(logits[i], rlogits[i], TOL_BF16, nm)
+    H.assert_close(loss, rloss, TOL_BF16, "loss")
+    seen = 0
+    for k, a, b in zip(names, grads, rgrads):
+        if b is None:
+            assert a is None or float(a.abs().max()) == 0.0, f"unexpected gradient for {k}"
+            continue
+        assert a is not None, f"missing gradient for {k}"
+        if float(b.abs().max()) == 0.0:
+            assert float(a.abs().max()) <= 1e-6, k
+            continue
+        zero_tol = 0.0
+        if k.endswith("rel_pos_bias.mlp.2.bias"):     # analytically zero (softmax shift invariance): rounding only
+            w = rgrads[names.index(k.replace("mlp.2.bias", "mlp.2.weight"))]
+            zero_tol = max(1e-6, 2e-3 * float(w.abs().max()))
+        H.assert_close(a, b, TOL_BF16, "grad " + k, atol=zero_tol)
+        seen += 1
+    assert seen > 60
