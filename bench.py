@@ -105,56 +105,283 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference path on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_bags_per_s(n_sample, repeats=1, seed=42):
-    """fwd + loss + bwd of DeformPathomicNet (oracle restatement of the reference, fp32, all host threads)
-    on one N=n_sample bag; the pair-count-dominated cost is extrapolated to N_PATCHES by (N/n_sample)^2."""
+def _oracle_deform_setup(seed=42):
+    from dml_b200 import synth
+    from dml_b200.model import Args, define_net
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = define_net(Args(task_type=TASK))
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    return {k: v.requires_grad_(v.is_floating_point()) for k, v in synth.fill_like(shapes, seed).items()}
+
+
+def _oracle_deform_pass(P, n_bag, seed=42, row_block=512):
+    """One fwd + weighted-CE + bwd of DeformPathomicNet through the oracle restatement of the reference (fp32, all host
+    threads) on one n_bag-patch bag; returns seconds."""
+    from dml_b200 import synth
+    from oracle import towers
+    bag = synth.synthetic_bag(n_bag, seed)
+    x = bag["x_path"].to(torch.bfloat16).float()              # the same bf16-rounded bag the GPU arm consumes
+    t0 = time.perf_counter()
+    _, _, _, logits = towers.deform_pathomic_net(x, bag["x_omic_tumor"], bag["x_omic_immune"], P, task_type=TASK,
+                                                 row_block=row_block)
+    loss = towers.bag_loss(logits, bag["label_diag"], TASK)
+    torch.autograd.grad(loss, [p for p in P.values() if p.requires_grad], allow_unused=True)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_deform(N, budget_s, max_passes=1):
+    """The reference algorithm (oracle port) on the host cores at the benched size.  A TRUE N-patch pass (row-chunked CPB
+    attention: the shipped module needs ~190 GB at 16k) is timed whenever a 2048-patch probe predicts that it fits the
+    budget; otherwise a bounded sample is timed and scaled by the pair count, and the result says so."""
+    P = _oracle_deform_setup()
+    _oracle_deform_pass(P, 128, row_block=64)                  # warm-up (thread pool, autograd / checkpoint import)
+    probe_n = min(2048, N)
+    t_probe = _oracle_deform_pass(P, probe_n)
+    predicted = t_probe * (N / probe_n) ** 2
+    cores = os.cpu_count()
+    if predicted <= budget_s or probe_n == N:
+        times = []
+        t_all = time.perf_counter()
+        while len(times) < max(1, max_passes):
+            times.append(_oracle_deform_pass(P, N))
+            if time.perf_counter() - t_all + times[-1] > budget_s:
+                break
+        best = min(times)
+        return {"value": 1.0 / best, "seconds_per_pass": best, "passes": len(times), "measured_at": N, "extrapolated": False,
+                "cores": cores,
+                "sample": f"oracle port of the reference (torch fp32, CPB attention evaluated in 512-row query blocks), "
+                          f"{len(times)} TRUE N={N}-patch bag(s) fwd+loss+bwd, best {best:.1f} s on {cores} host threads "
+                          f"(no extrapolation)",
+                "side": {"probe_n": probe_n, "probe_seconds": t_probe, "pair_count_extrapolation_s": predicted}}
+    n_s = 4096 if t_probe * 4 <= max(budget_s, 30) else probe_n
+    t_s = _oracle_deform_pass(P, n_s) if n_s != probe_n else t_probe
+    scale = (N / n_s) ** 2
+    return {"value": 1.0 / (t_s * scale), "seconds_per_pass": t_s * scale, "passes": 1, "measured_at": n_s,
+            "extrapolated": True, "cores": cores,
+            "sample": f"EXTRAPOLATED: oracle port, one N={n_s}-patch bag fwd+loss+bwd = {t_s:.2f} s on {cores} host threads, "
+                      f"scaled x{scale:.0f} (pair count) to N={N} (a true pass was predicted at {predicted:.0f} s > budget)",
+            "side": {"probe_n": probe_n, "probe_seconds": t_probe}}
+
+
+def cpu_reference_transmil(N, repeats=3, seed=42):
+    """TransMIL (NystromAttention) fwd + weighted-CE + bwd through the oracle restatement at the true size (seconds)."""
     from dml_b200 import synth
     from dml_b200.model import Args, define_net
     from oracle import towers
     torch.set_num_threads(os.cpu_count() or 1)
-    net = define_net(Args(task_type=TASK))
+    net = define_net(Args(mode="path", label_dim=3))
     shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
     P = {k: v.requires_grad_(v.is_floating_point()) for k, v in synth.fill_like(shapes, seed).items()}
-    def one_pass(n_bag, row_block=512):
-        bag = synth.synthetic_bag(n_bag, seed)
+    bag = synth.synthetic_bag(N, seed)
+    x = bag["x_path"].to(torch.bfloat16).float()
+    label = bag["label_grade"]
+    w = torch.tensor([1.47, 1.51, 1.0])
+
+    def one():
         t0 = time.perf_counter()
-        _, _, _, logits = towers.deform_pathomic_net(bag["x_path"], bag["x_omic_tumor"], bag["x_omic_immune"], P,
-                                                     task_type=TASK, row_block=row_block)
-        loss = towers.bag_loss(logits, bag["label_diag"], TASK)
+        _, logits = towers.trans_mil(x, P)                     # torch's default CPU backends (oneDNN on), as a user runs it
+        loss = torch.nn.functional.cross_entropy(logits, label, weight=w)
         torch.autograd.grad(loss, [p for p in P.values() if p.requires_grad], allow_unused=True)
         return time.perf_counter() - t0
 
-    one_pass(128, row_block=64)                    # warm-up (thread pool, autograd/checkpoint import)
-    if n_sample <= 0:                              # auto: the largest of 1024/2048/4096 predicted to stay under ~30 s
-        t1k = one_pass(1024)
-        n_sample = 4096 if t1k * 16 < 30 else (2048 if t1k * 4 < 30 else 1024)
-    best = min(one_pass(n_sample) for _ in range(max(1, repeats)))
-    scale = (N_PATCHES / n_sample) ** 2
-    return 1.0 / (best * scale), best, scale, n_sample
+    one()
+    best = min(one() for _ in range(max(1, repeats)))
+    cores = os.cpu_count()
+    return {"value": 1.0 / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle port of TransMIL (torch fp32), TRUE N={N}-patch bag fwd+loss+bwd, best of {repeats}: "
+                      f"{best:.2f} s on {cores} host threads"}
+
+
+def deform_config(N, world, use_graph=True):
+    return {"precision": "bf16 bags; attention MMAs fp16 operands (P as an fp16 hi+lo pair), fp32 accumulate and "
+                         "fp32 softmax/bias/outputs; projections fp32-class (fp16 hi+lo pairs on tcgen05)",
+            "workload": workload_name(N),
+            "step": ("CUDA-graph replay of " if use_graph else "") + "fwd + weighted-CE + bwd" +
+                    (" + flat NCCL grad all-reduce" if world > 1 else "") + " + fused AdamW",
+            "parallelism": f"bag-sharded dp{world}"}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, args.steps)):
-        v, sec, scale, n_sample = cpu_reference_bags_per_s(args.cpu_sample, repeats=1)
-        vals.append(v)
-        if time.perf_counter() - t0 > 150:
-            break
-    v = max(vals)
-    cores = os.cpu_count()
-    sample = (f"oracle port of the reference (torch fp32, row-chunked CPB attention), one N={n_sample}-patch bag fwd+loss+bwd "
-              f"= {sec:.2f} s on {cores} host threads, scaled x{scale:.0f} (pair count) to N={N_PATCHES}")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-            "warmup": 1, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(N_PATCHES), "step": "fwd + weighted-CE + bwd (no optimizer step)",
-                       "impl": "reference algorithm (oracle port, torch fp32) on the host cores"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    N = args.n_patches
+    if args.workload == "transmil":
+        r = cpu_reference_transmil(N, repeats=max(1, min(args.steps, 5)))
+        v = r["value"]
+        line = {"impl": "reference", "metric": transmil_metric(N), "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": transmil_config(N, args.gpus), "cpu_baseline": r,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+    r = cpu_reference_deform(N, budget_s=args.cpu_budget, max_passes=max(1, args.steps))
+    v = r["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            # steps / ms_per_step describe what was actually timed: TRUE N-patch passes of the reference algorithm
+            "steps": r["passes"], "steps_requested": args.steps, "warmup": 1, "ms_per_step": 1000.0 * r["seconds_per_pass"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": deform_config(N, args.gpus),
+            "reference_impl": "reference algorithm (oracle port, torch fp32, no optimizer step) on the host cores; "
+                              "/root/reference is pure Python and absent on the GPU box",
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                             "extrapolated": r["extrapolated"], "side": r["side"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def transmil_metric(N):
+    return f"WSI bags/sec fwd+bwd (TransMIL / NystromAttention, N={N} patches)"
+
+
+def transmil_geometry(N):
+    import math
+    side = int(math.ceil(math.sqrt(N)))
+    n = side * side + 1
+    m = 256
+    pad = (m - n % m) % m
+    return side, n, pad, n + pad, -(-n // m)
+
+
+def transmil_config(N, world):
+    side, n, pad, n_pad, l = transmil_geometry(N)
+    return {"workload": f"TransMIL (mil.py:209-259, 2 x NystromAttention dim 512 / 8 heads / 256 landmarks + PPEG), 1 bag x {N} "
+                        f"patches x 1024 bf16 feats per GPU per step (grid {side}^2, n={n} tokens, front pad {pad}, l={l})",
+            "step": "CUDA-graph replay of fwd + weighted-CE (grade) + bwd + fused AdamW, train() mode (to_out dropout 0.1 live)",
+            "precision": "bf16 bags; every contraction fp32-class (fp16 hi+lo operand pairs on tcgen05, fp32 accumulate)",
+            "parallelism": f"bag-sharded dp{world}"}
+
+
+def transmil_flops(N):
+    """Dense maths of the reference for one fwd: fc1 + 2 Nystrom layers + PPEG; bwd = 2 x fwd."""
+    side, n, pad, n_pad, l = transmil_geometry(N)
+    H, d, m, dim = 8, 64, 256, 512
+    layer = (2.0 * n_pad * dim * 3 * dim                      # to_qkv
+             + 2.0 * H * n_pad * m * d * 2                    # sim1, sim3
+             + 2.0 * H * m * m * d                            # sim2
+             + 24 * 2.0 * H * m ** 3                          # pinv: 6 iterations x 4 products
+             + 2.0 * H * n_pad * m * m                        # attn1 @ attn2_inv
+             + 2.0 * H * m * n_pad * d                        # attn3 @ v
+             + 2.0 * H * n_pad * m * d                        # (.) @ (attn3 v)
+             + 2.0 * H * n_pad * d * 33                       # res_conv
+             + 2.0 * n_pad * dim * dim)                       # to_out
+    fc1 = 2.0 * N * 1024 * dim
+    ppeg = 2.0 * side * side * dim * (49 + 25 + 9)
+    return fc1 + 2 * layer + ppeg
+
+
+def bench_transmil(N, args, dev, rank, world, cpu=True):
+    """TransMIL fwd + loss + bwd + AdamW on one N-patch bf16 bag per rank: device-resident value, e2e with host bags, the
+    launches of our library per step, per-entry-point device times and the whole-step dense-math roofline."""
+    import torch.distributed as dist
+    from dml_b200 import _lib, synth
+    from dml_b200.graph import GraphedTrainStep
+    from dml_b200.model import Args, define_net
+    net = define_net(Args(mode="path", label_dim=3))
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(synth.fill_like(shapes, 42), strict=True)
+    net.to(dev).train()
+    w_ce = torch.tensor([1.47, 1.51, 1.0], device=dev)          # train_test.py:791
+    nb = max(2, args.bags_resident)
+    host_bags, dev_bags = [], []
+    for i in range(nb):
+        b = synth.synthetic_bag(N, seed=2000 + rank * 64 + i)
+        hb = {"x": b["x_path"].to(torch.bfloat16).pin_memory(), "label": b["label_grade"].pin_memory()}
+        host_bags.append(hb)
+        dev_bags.append({k: v.to(dev) for k, v in hb.items()})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_bags[0].values())
+    loss_fn = lambda out, b: torch.nn.functional.cross_entropy(out[1], b["label"], weight=w_ce)   # noqa: E731
+    flat_adamw = lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=0.01, fused=True)         # noqa: E731
+
+    launches0 = _lib.launch_count
+    out = net(dev_bags[0]["x"])
+    loss_fn(out, dev_bags[0]).backward()
+    launches_per_step = _lib.launch_count - launches0
+    net.zero_grad(set_to_none=True)
+    gstep = GraphedTrainStep(net, loss_fn, dev_bags[0], flat_optimizer=flat_adamw, model_keys=("x",), warmup=2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(steps)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def resident(steps):
+        for s_ in range(steps):
+            gstep(dev_bags[s_ % nb])
+
+    resident(args.warmup)
+    with Clocks(dev.index or 0) as clk:
+        ms = timed(resident, args.steps)
+    value = world * args.steps / (ms / 1000.0)
+
+    losses_host = torch.zeros(max(args.steps, args.warmup), dtype=torch.float32).pin_memory()
+
+    def e2e(steps):
+        for s_ in range(steps):
+            loss = gstep(host_bags[s_ % nb])                   # pinned host bag -> static graph inputs (H2D inside the step)
+            losses_host[s_].copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e(args.warmup)
+    ms_e2e = timed(e2e, args.steps)
+    e2e_value = world * args.steps / (ms_e2e / 1000.0)
+
+    # per-entry-point device times of our library (eager pass, CUDA events around each call)
+    events = []
+
+    def hook(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        events.append((name, phase, ev))
+
+    net.zero_grad(set_to_none=True)
+    gstep.reducer.attach_views()
+    _lib._timing_hook = hook
+    out = net(dev_bags[0]["x"])
+    loss_fn(out, dev_bags[0]).backward()
+    torch.cuda.synchronize()
+    _lib._timing_hook = None
+    ktime = {}
+    for i in range(0, len(events), 2):
+        (nm, _, a), (_, _, b) = events[i], events[i + 1]
+        ktime.setdefault(nm, []).append(a.elapsed_time(b))
+    kms = {k: round(sum(v), 4) for k, v in sorted(ktime.items(), key=lambda kv: -sum(kv[1]))}
+    kcalls = {k: len(v) for k, v in ktime.items()}
+
+    pk, pk_kind = peaks()
+    fl = 3.0 * transmil_flops(N)
+    ms_step = ms / args.steps
+    roof = {"kernel": "whole TransMIL step (fwd+bwd), dense maths of the reference", "bound": "tensor",
+            "achieved": fl / (ms_step * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": fl / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "traffic": None,
+            "dense_math_tflop": fl / 1e12, "dense_math_roofline_ms": fl / (pk["bf16_tflops_sustained"] * 1e12) * 1e3,
+            "peak_source": pk_kind + " (sustained)",
+            "note": "fp32-class parity (1e-3) makes every product three fp16 MMAs (hi.hi + hi.lo + lo.hi): the issued tensor "
+                    "work is 3x the dense figure used here"}
+    line = {"metric": transmil_metric(N), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16", "data": "synthetic", "config": dict(transmil_config(N, world),
+                                                               l2=f"{nb} distinct bags rotated ({nb * h2d_bytes / 1e6:.0f} MB)"),
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+            "kernel_ms_per_step": kms, "kernel_calls_per_step": kcalls, "roofline": roof,
+            "cpu_baseline": cpu_reference_transmil(N) if cpu else None}
+    del gstep
+    return line
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,7 +394,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-patches", type=int, default=N_PATCHES)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="bag size of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--workload", default="deform", choices=["deform", "transmil"],
+                    help="deform = BASELINE configs[1] (DeformPathomicNet, headline); transmil = configs[0]'s TransMIL / NystromAttention")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the CPU reference may spend on true-size passes")
+    ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the additional sustained-loop record")
+    ap.add_argument("--no-transmil", action="store_true", help="skip the TransMIL sub-record of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cls-row-only", action="store_true", help="skip the separately reported exact cls-row-only arm")
@@ -198,10 +429,15 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL prints its version banner on stdout, where the
-            os.environ["NCCL_DEBUG"] = "WARN"                          # driver expects exactly one JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     N = args.n_patches
+    if args.workload == "transmil":
+        r = bench_transmil(N, args, dev, rank, world, cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+        if rank == 0:
+            print(json.dumps(r), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     net = define_net(Args(task_type=TASK))
     shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
     net.load_state_dict(synth.fill_like(shapes, 42), strict=True)
@@ -283,6 +519,15 @@ def main():
         ms = timed(resident, args.steps)
     launches = launches_per_step * args.steps
     value = world * args.steps / (ms / 1000.0)
+
+    # ---- sustained record: the same step looped for >= --sustain-seconds (power / clock behaviour of a long run) ----
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1000.0 / (ms / args.steps)) + 1)
+        with Clocks(local_rank) as clk_s:
+            ms_s = timed(resident, n_sus)
+        sustained = {"steps": n_sus, "seconds": ms_s / 1000.0, "ms_per_step": ms_s / n_sus,
+                     "value": world * n_sus / (ms_s / 1000.0), "unit": UNIT, "clocks": clk_s.summary()}
 
     # ---- end-to-end arm: host (pinned) bags -> H2D on a copy stream (double-buffered) -> step -> D2H loss ----
     copy_stream = torch.cuda.Stream(device=dev)
@@ -431,28 +676,32 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, scale, n_used = cpu_reference_bags_per_s(args.cpu_sample, repeats=1)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"oracle port, one N={n_used}-patch bag fwd+loss+bwd = {sec:.2f} s on {os.cpu_count()} host "
-                         f"threads, scaled x{scale:.0f} (pair count) to N={N}"}
+        r = cpu_reference_deform(N, budget_s=args.cpu_budget, max_passes=1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "extrapolated": r["extrapolated"], "side": r["side"]}
+
+    # ---- TransMIL / NystromAttention (BASELINE configs[0]'s model) at N = 6 000 and 16 384: its own sub-records ----
+    transmil = None
+    if rank == 0 and world == 1 and not args.no_transmil:
+        transmil = {}
+        for n_t in (6000, 16384):
+            try:
+                transmil[f"n{n_t}"] = bench_transmil(n_t, args, dev, rank, world, cpu=not args.no_cpu_baseline)
+            except Exception as ex:      # never lose the headline line to the side measurement
+                transmil[f"n{n_t}"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "fp16", "data": "synthetic",
-                "config": {"precision": "bf16 bags; attention MMAs fp16 operands (P as an fp16 hi+lo pair), fp32 accumulate and "
-                                        "fp32 softmax/bias/outputs; projections fp32/TF32 library GEMMs",
-                           "workload": workload_name(N),
-                           "step": ("CUDA-graph replay of " if use_graph else "") + "fwd + weighted-CE + bwd" +
-                                   (" + flat NCCL grad all-reduce" if world > 1 else "") +
-                                   (" + fused AdamW over the flat parameter buffer" if use_graph else " + fused AdamW"),
-                           "parallelism": f"bag-sharded dp{world}", "l2": f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"},
+                "config": dict(deform_config(N, world, use_graph),
+                               l2=f"{nb} distinct bags rotated (inputs {nb * h2d_bytes / 1e6:.0f} MB > L2)"),
                 "clocks": clk.summary(), "roofline_hbm_kernel": roof_hbm,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
                 "kernel_ms_per_step": {k: round(kavg[k] * kcalls[k], 4) for k in sorted(kavg, key=lambda k: -kavg[k] * kcalls[k])},
-                "roofline": roof, "cpu_baseline": cpu, "cls_row_only": cls_only}
+                "roofline": roof, "cpu_baseline": cpu, "cls_row_only": cls_only, "sustained": sustained, "transmil": transmil}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -298,11 +298,9 @@ extern "C" {
 
 int dml_cpb_eval(const void* table, const float* t, int count, float* out, int* seg, void* stream) {
   DML_CHECK_ARG(table && t && out && count > 0);
-  static bool attr = false;
-  if (!attr) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(dml::cpb_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dml::kCpbSmemBwdBytes);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   dml::cpb_eval_kernel<<<dml::cdiv(count, 256) < 296 ? dml::cdiv(count, 256) : 296, 256, dml::kCpbSmemBwdBytes,
                          (cudaStream_t)stream>>>((const uint32_t*)table, t, count, out, seg);

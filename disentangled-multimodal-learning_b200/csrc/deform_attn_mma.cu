@@ -648,11 +648,9 @@ int dml_deform_attn_fwd(const void* q, const void* k, const void* v, const float
   p.scale = scale;
   int rc = check_common(p);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(deform_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   dim3 grid(cdiv(n, kBM), H, B);
   deform_attn_fwd_kernel<<<grid, 128, kFwdSmem, (cudaStream_t)stream>>>(p);
@@ -677,13 +675,11 @@ int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float
   if (rc) return rc;
   if (ldo != H * kD) return DML_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(deform_attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(deform_attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkvSmem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int G = H / heads_per_group;
   cudaError_t e = cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)B * G * n_kv, st);

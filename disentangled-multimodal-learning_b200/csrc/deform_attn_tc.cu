@@ -407,11 +407,9 @@ int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const fl
   if (rc) return rc;
   rc = make_map(&mv, v, B, n_kv, ldv, kBN);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(deform_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   Params p{};
   p.g = g; p.table = (const uint32_t*)table; p.o = (float*)out; p.lse = lse;

@@ -1016,15 +1016,13 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
       (rc = make_map(&mq32, q, B, n, ldq, 32)) || (rc = make_map(&mdo32, d_out, B, n, ldo, 32)) ||
       (rc = make_map(&mk128, k, B, n_kv, ldk, 128)) || (rc = make_map(&mv128, v, B, n_kv, ldv, 128)))
     return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(deform_attn_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dqk::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(deform_attn_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkvk::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(deform_attn_dq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dqg::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int G = H / 2;
   cudaError_t e = cudaMemsetAsync(dg, 0, sizeof(float) * (size_t)B * G * n_kv, st);
@@ -1052,8 +1050,8 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
     // (a simulation with the cost model below: makespan 527 vs 599 tile units unsplit, 502 ideal).  Cost model: tiles
     // within 0.16 n positions of the item's diagonal - where the table segments are dense - count 1.45, each piece pays
     // a prologue of 12 tiles.  DML_B200_DKV_QSPLIT=<q> forces q equal parts per item instead (tuning aid; 1 = unsplit).
-    static int nsm = 0;
-    if (!nsm) {
+    int nsm = 0;       // per device (the current one), not cached process-wide; it is part of the work-list cache key below
+    {
       int dev = 0;
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0) nsm = 148;
     }
@@ -1118,11 +1116,9 @@ int dml_deform_attn_dq_from_ds(const void* ds_ws, const void* k, const float* ds
   CUtensorMap mds, mk64;
   int rc;
   if ((rc = make_map(&mds, ds_ws, B * H, p.n_kv_pad, p.n_pad, 64)) || (rc = make_map(&mk64, k, B, n_kv, ldk, 64))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(deform_attn_dq_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dqg::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), H / 2, B), dqg::kThreads, dqg::kSmemBytes, (cudaStream_t)stream>>>(mds, mk64, p);
   DML_RETURN_LAUNCH();

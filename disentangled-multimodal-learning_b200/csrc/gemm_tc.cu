@@ -269,13 +269,11 @@ int dml_gemm_nt_split(const void* a_hi, const void* a_lo, const void* b_hi, cons
   Params p{};
   p.c = c; p.scale_a = scale_a; p.scale_b = scale_b; p.alpha = alpha; p.c_batch_stride = c_batch_stride;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(gemm_nt_split_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(gemm_nt_split_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   dim3 grid(cdiv(M, kBM), cdiv(N, BN), batch);
   if (BN == 128)

@@ -269,7 +269,7 @@ res_conv_merge_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
   __syncthreads();
   const int c = threadIdx.x % kRcCols, rg = threadIdx.x / kRcCols;
   const int col = cb + c, h = col / d, cc = col % d;
-  const int hl = c / d;  // head slot inside this 128-column block (d >= 32 -> at most kRcHeadSlots)
+  const int hl = (cb + c) / d - cb / d;  // head slot inside this 128-column block (heads may straddle block boundaries)
   float wk[kRcKMax], gw[kRcKMax];
 #pragma unroll
   for (int t = 0; t < kRcKMax; ++t) { wk[t] = t < K ? w[h * K + t] : 0.f; gw[t] = 0.f; }
@@ -390,11 +390,9 @@ int dml_res_conv_merge_fwd(const float* a, const float* v, int ldv, int col0, co
   int rc = res_conv_check(K, H, d, ldv, col0);
   if (rc) return rc;
   const size_t smem = sizeof(float) * (size_t)(dml::kRcRows + K - 1) * dml::kRcCols;
-  static bool attr = false;
-  if (!attr) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     cudaError_t e = cudaFuncSetAttribute(dml::res_conv_merge_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   dim3 grid(dml::cdiv(n_pad, dml::kRcRows), (H * d) / dml::kRcCols, B);
   dml::res_conv_merge_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, v, ldv, col0, w, K, n_pad, H, d, y);
@@ -410,11 +408,9 @@ int dml_res_conv_merge_bwd(const float* dy, const float* v, int ldv, int col0, c
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)H * K, st);
   if (e != cudaSuccess) return (int)e;
   const size_t smem = sizeof(float) * ((size_t)2 * (dml::kRcRows + K - 1) * dml::kRcCols + dml::kRcHeadSlots * dml::kRcKMax);
-  static bool attr = false;
-  if (!attr) {
+  {   // per-device attribute: set on every call (cheap, no process-global flag)
     e = cudaFuncSetAttribute(dml::res_conv_merge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
   }
   dim3 grid(dml::cdiv(n_pad, dml::kRcRows), (H * d) / dml::kRcCols, B);
   dml::res_conv_merge_bwd_kernel<<<grid, 256, smem, st>>>(dy, v, ldv, col0, w, K, n_pad, H, d, da, dv, dw);

@@ -96,7 +96,14 @@ def colsum(x2d: torch.Tensor) -> torch.Tensor:
     key = (x2d.device, rows)
     ones = _ONES.get(key)
     if ones is None:
-        ones = _ONES[key] = torch.ones(rows, device=x2d.device, dtype=F32)
+        # the cached vector is read from several streams (towers, auxiliary streams): it must be complete before any of
+        # them can see it, so the fill is synchronised once here (never inside a graph capture: shapes are first seen in
+        # the eager warm-up passes; a shape first met while capturing gets an uncached, capture-local vector)
+        ones = torch.ones(rows, device=x2d.device, dtype=F32)
+        if torch.cuda.is_current_stream_capturing():
+            return torch.mv(x2d.t(), ones)
+        torch.cuda.current_stream(x2d.device).synchronize()
+        _ONES[key] = ones
     return torch.mv(x2d.t(), ones)
 
 
