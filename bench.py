@@ -298,7 +298,28 @@ def bench_transmil(N, args, dev, rank, world, cpu=True):
     loss_fn(out, dev_bags[0]).backward()
     launches_per_step = _lib.launch_count - launches0
     net.zero_grad(set_to_none=True)
-    gstep = GraphedTrainStep(net, loss_fn, dev_bags[0], flat_optimizer=flat_adamw, model_keys=("x",), warmup=2)
+    graph_error = None
+    try:
+        gstep = GraphedTrainStep(net, loss_fn, dev_bags[0], flat_optimizer=flat_adamw, model_keys=("x",), warmup=2)
+    except Exception as ex:                                    # not capturable: time the eager step and say so
+        graph_error = repr(ex)[:300]
+        torch.cuda.synchronize()
+        opt_e = torch.optim.AdamW([p_ for p_ in net.parameters() if p_.requires_grad], lr=2e-4, weight_decay=0.01, fused=True)
+        static = {k: v.clone() for k, v in dev_bags[0].items()}
+
+        class _Eager:
+            reducer = None
+
+            def __call__(self, inputs):
+                for k, v in inputs.items():
+                    static[k].copy_(v, non_blocking=True)
+                opt_e.zero_grad(set_to_none=True)
+                loss = loss_fn(net(static["x"]), static)
+                loss.backward()
+                opt_e.step()
+                return loss.detach()
+
+        gstep = _Eager()
 
     def barrier():
         if world > 1:
@@ -347,7 +368,8 @@ def bench_transmil(N, args, dev, rank, world, cpu=True):
         events.append((name, phase, ev))
 
     net.zero_grad(set_to_none=True)
-    gstep.reducer.attach_views()
+    if gstep.reducer is not None:
+        gstep.reducer.attach_views()
     _lib._timing_hook = hook
     out = net(dev_bags[0]["x"])
     loss_fn(out, dev_bags[0]).backward()
@@ -380,6 +402,9 @@ def bench_transmil(N, args, dev, rank, world, cpu=True):
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "kernel_ms_per_step": kms, "kernel_calls_per_step": kcalls, "roofline": roof,
             "cpu_baseline": cpu_reference_transmil(N) if cpu else None}
+    if graph_error:
+        line["graph_capture_error"] = graph_error
+        line["config"]["step"] = "EAGER " + line["config"]["step"].replace("CUDA-graph replay of ", "")
     del gstep
     return line
 

@@ -41,6 +41,9 @@ SIGNATURES = {
     "dml_layernorm_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
     "dml_split_f16": (_i, [_fp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _fp, _vp, _vp]),
     "dml_gemm_nt_split": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _fp, _i, _ll, _vp]),
+    "dml_pgemm": (_i, [C.c_void_p, _vp]),
+    "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
+    "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
     "dml_debug_set_trace": (_i, [_vp]),
     "dml_debug_set_seg_limit": (_i, [_i]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
@@ -51,6 +54,33 @@ SIGNATURES = {
     "dml_res_conv_merge_fwd": (_i, [_fp, _fp, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _vp]),
     "dml_res_conv_merge_bwd": (_i, [_fp, _fp, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _vp]),
 }
+
+
+
+class PgOperand(C.Structure):
+    """dml_pg_operand (include/dml_b200.h)."""
+    _fields_ = [("base", C.c_void_p), ("plane_stride", C.c_longlong), ("bs_inner", C.c_longlong), ("bs_outer", C.c_longlong),
+                ("layout", C.c_int), ("ld", C.c_int), ("rows", C.c_int), ("row_offset", C.c_int), ("k_offset", C.c_int),
+                ("k_mem", C.c_int)]
+
+
+class PgemmArgs(C.Structure):
+    """dml_pgemm_args (include/dml_b200.h)."""
+    _fields_ = [("A", PgOperand), ("B", PgOperand),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("nb_inner", C.c_int), ("nb_outer", C.c_int), ("splits", C.c_int),
+                ("alpha", C.c_float), ("alpha2", C.c_float), ("ncol_split", C.c_int),
+                ("alpha_dev", C.c_void_p), ("bias", C.c_void_p), ("bias_bs_inner", C.c_longlong), ("bias_bs_outer", C.c_longlong),
+                ("relu", C.c_int), ("use_diag", C.c_int), ("diag", C.c_float),
+                ("resid", C.c_void_p), ("ldr", C.c_int), ("r_bs_inner", C.c_longlong), ("r_bs_outer", C.c_longlong),
+                ("accumulate", C.c_int),
+                ("c", C.c_void_p), ("ldc", C.c_int), ("c_bs_inner", C.c_longlong), ("c_bs_outer", C.c_longlong),
+                ("pair", C.c_void_p), ("ldp", C.c_int), ("p_bs_inner", C.c_longlong), ("p_bs_outer", C.c_longlong),
+                ("p_plane", C.c_longlong),
+                ("half_out", C.c_void_p), ("ldh", C.c_int), ("h_bs_inner", C.c_longlong), ("h_bs_outer", C.c_longlong),
+                ("half_scale_dev", C.c_void_p), ("absmax", C.c_void_p), ("softmax", C.c_int),
+                ("aux", C.c_void_p), ("ldx", C.c_int), ("x_bs_inner", C.c_longlong), ("x_bs_outer", C.c_longlong),
+                ("x_plane", C.c_longlong)]
+
 
 _lock = threading.Lock()
 _lib = None

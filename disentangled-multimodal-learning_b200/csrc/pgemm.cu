@@ -1,0 +1,554 @@
+// dml_pgemm: batched GEMM on tcgen05 / TMEM / TMA with fp32-class accuracy from bf16 operand PAIRS (sm_100a).
+//
+// Every fp32 tensor x that enters a contraction of the path is held as two bf16 planes, x ~= hi + lo (hi = bf16(x),
+// lo = bf16(x - hi): 16 significant bits, the fp32 exponent range - no scale factors, no absmax pass), and a product is
+// accumulated in fp32 in TMEM as hi.hi + hi.lo + lo.hi (three tcgen05.mma per k-step; an operand that is exact in bf16,
+// such as the bf16 bag, has one plane and costs two).  Against the reference (fp32 torch) this gives 6-9e-6 relative error
+// through the whole NystromAttention forward and backward, pseudo-inverse recurrence included (TF32: 2e-3, outside the
+// 1e-3 bar) - measured on the reference's own goldens, DESIGN.md section 3.
+//
+// One kernel serves every contraction of NystromAttention (models/NystromAttention.py:89,122-125,138-140,150), TransMIL's
+// fc1 (models/mil.py:229) and the projections of DeformCrossTransMIL / DeformCrossAttention1D
+// (models/DeformCrossTransMIL.py:100,111; models/DeformableAttention1D.py:175,199,233) and all of their gradients:
+//   * either operand may be K-major (memory [rows][K]) or MN-major (memory [K][rows]) - the instruction descriptor's
+//     major bits - so C = A B^T, A B, A^T B all read the row-major tensors as they are (no transposes, no copies);
+//   * row / k offsets with TMA zero fill give the FRONT padding of NystromAttention (:79-85) without a padded copy;
+//   * two batch dimensions with arbitrary element strides address head slices inside a fused [n, 3 H d] qkv buffer;
+//   * the epilogue (TMEM lane = output row, one thread per row) fuses: alpha (with a second factor for a leading column
+//     range: q * scale), per-column bias, residual add, accumulate, ReLU, "diag I - C" (the pinv polynomial terms), the row
+//     softmax of the landmark similarity products and its backward, and writes fp32 and / or the bf16 pair of the result
+//     and / or fp16 (the operand type of the fused attention kernels), plus an optional |C| maximum;
+//   * split-K (fp32 reductions into a zeroed C) for the token-reduction products (weight gradients, attn3 @ v).
+//
+// CTA = one 128 x BN tile (BN = 64 / 128 / 256); warp 4 = TMA producer (ring of {A planes, B planes} 64-wide k-blocks,
+// 128-byte swizzle), warp 5 = MMA issuer + TMEM owner, warps 0-3 = epilogue.
+#include <math.h>
+
+#include "../../include/dml_b200.h"
+#include "tc_common.cuh"
+
+namespace dml {
+namespace tc {
+namespace pg {
+
+constexpr int kBM = 128, kBK = 64, kThreads = 32 * 6;
+constexpr uint32_t kTileA = kBM * kBK * 2;   // 16 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN == 64 ? 4 : (BN == 128 ? 3 : 2);
+  static constexpr uint32_t kTileB = BN * kBK * 2;
+  static constexpr uint32_t kStageBytes = 2 * kTileA + 2 * kTileB;
+  static constexpr uint32_t kOffBar = kStages * kStageBytes;
+  static constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAcc = 2 * kStages, kNumBars = 2 * kStages + 1;
+  static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
+  static constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+struct Params {
+  int M, N, K;
+  int nb_inner, splits;
+  int a_layout, b_layout, a_planes, b_planes;
+  int a_row_off, a_k_off, b_row_off, b_k_off;
+  int a_bi, a_bo, b_bi, b_bo;                 // 1: the operand is indexed by that batch dimension, 0: shared
+  float alpha, alpha2;
+  int ncol_split;
+  const float* alpha_dev;
+  const float* bias; long long bias_bi, bias_bo;
+  int relu, use_diag;
+  float diag;
+  const float* resid; int ldr; long long r_bi, r_bo;
+  int accumulate;
+  float* c; int ldc; long long c_bi, c_bo;
+  bf16* pair; int ldp; long long p_bi, p_bo, p_plane;
+  h16* half_out; int ldh; long long h_bi, h_bo;
+  const float* half_scale_dev;
+  uint32_t* absmax;
+  int softmax;
+  const bf16* aux; int ldx; long long x_bi, x_bo, x_plane;
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// MN-major operand: 64-element spans of the M / N index 8 KB apart (leading-dimension byte offset), 8-row k groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// (x0, x1) -> packed bf16 pair `hi` and packed bf16 residual pair `lo`
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - bf16_lo_f(hi), r1 = x1 - bf16_hi_f(hi);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb, const Params p) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  const int split = blockIdx.z % p.splits, batch = blockIdx.z / p.splits;
+  const int bi = batch % p.nb_inner, bo = batch / p.nb_inner;
+  const int nk_all = cdiv(p.K, kBK);
+  const int kb_per = cdiv(nk_all, p.splits);
+  const int kb0 = split * kb_per, kb1 = min(nk_all, kb0 + kb_per);
+  const int nk = max(kb1 - kb0, 0);
+  auto bar = [&](int i) { return sbase + C::kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + C::kOffTmemPtr);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(C::kBarFull + s), 1); mbar_init(bar(C::kBarEmpty + s), 1); }
+    mbar_init(bar(C::kBarAcc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)p.a_planes * kTileA + (uint32_t)p.b_planes * C::kTileB;
+      const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0, bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % kStages;
+        mbar_wait(bar(C::kBarEmpty + st), ((kb / kStages) & 1) ^ 1);
+        const uint32_t dst = sbase + st * C::kStageBytes;
+        const uint32_t fb = bar(C::kBarFull + st);
+        mbar_expect_tx(fb, bytes);
+        const int k0 = (kb0 + kb) * kBK;
+        for (int pl = 0; pl < p.a_planes; ++pl) {
+          const uint32_t d = dst + pl * kTileA;
+          if (p.a_layout == 0) {
+            tma_load_5d(d, &ma, fb, k0 + p.a_k_off, m0 + p.a_row_off, abi, abo, pl);
+          } else {
+            tma_load_5d(d, &ma, fb, m0 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+            tma_load_5d(d + 8192, &ma, fb, m0 + 64 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+          }
+        }
+        for (int pl = 0; pl < p.b_planes; ++pl) {
+          const uint32_t d = dst + 2 * kTileA + pl * C::kTileB;
+          if (p.b_layout == 0) {
+            tma_load_5d(d, &mb, fb, k0 + p.b_k_off, n0 + p.b_row_off, bbi, bbo, pl);
+          } else {
+#pragma unroll
+            for (int s = 0; s < BN / 64; ++s)
+              tma_load_5d(d + s * 8192, &mb, fb, n0 + 64 * s + p.b_row_off, k0 + p.b_k_off, bbi, bbo, pl);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---- MMA issuer (uniform datapath, one elected lane) ----
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16(128, BN, p.a_layout != 0, p.b_layout != 0);
+    const uint32_t ka = p.a_layout ? 128u : 2u, kbs = p.b_layout ? 128u : 2u;   // descriptor advance per 16 k (16-byte units)
+    for (int kb = 0; kb < nk; ++kb) {
+      const int st = kb % kStages;
+      mbar_wait(bar(C::kBarFull + st), (kb / kStages) & 1);
+      tc_fence_after();
+      const uint32_t base = sbase + st * C::kStageBytes;
+      const uint64_t a0 = p.a_layout ? desc_mn(base) : smem_desc(base);
+      const uint64_t a1 = p.a_layout ? desc_mn(base + kTileA) : smem_desc(base + kTileA);
+      const uint64_t b0 = p.b_layout ? desc_mn(base + 2 * kTileA) : smem_desc(base + 2 * kTileA);
+      const uint64_t b1 = p.b_layout ? desc_mn(base + 2 * kTileA + C::kTileB) : smem_desc(base + 2 * kTileA + C::kTileB);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) {
+        mma_ss(tmem, a0 + ka * k, b0 + kbs * k, idesc, (kb > 0) || (k > 0), leader);
+        if (p.b_planes > 1) mma_ss(tmem, a0 + ka * k, b1 + kbs * k, idesc, 1, leader);
+        if (p.a_planes > 1) mma_ss(tmem, a1 + ka * k, b0 + kbs * k, idesc, 1, leader);
+      }
+      tc_commit(bar(C::kBarEmpty + st), leader);
+    }
+    tc_commit(bar(C::kBarAcc), leader);
+  } else {
+    // ---- epilogue: TMEM lane = output row ----
+    const int row = m0 + warp * 32 + lane;
+    const bool rv = row < p.M;
+    float alpha = p.alpha;
+    if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+    const float alpha_q = alpha * p.alpha2;
+    const size_t rowl = (size_t)(rv ? row : 0);
+    const float* biasp = p.bias ? p.bias + (size_t)bo * p.bias_bo + (size_t)bi * p.bias_bi : nullptr;
+    const float* resp = p.resid ? p.resid + (size_t)bo * p.r_bo + (size_t)bi * p.r_bi + rowl * p.ldr : nullptr;
+    float* cp = p.c ? p.c + (size_t)bo * p.c_bo + (size_t)bi * p.c_bi + rowl * p.ldc : nullptr;
+    bf16* pp = p.pair ? p.pair + (size_t)bo * p.p_bo + (size_t)bi * p.p_bi + rowl * p.ldp : nullptr;
+    h16* hp = p.half_out ? p.half_out + (size_t)bo * p.h_bo + (size_t)bi * p.h_bi + rowl * p.ldh : nullptr;
+    const bf16* xp = p.aux ? p.aux + (size_t)bo * p.x_bo + (size_t)bi * p.x_bi + rowl * p.ldx : nullptr;
+    const float hscale = (p.half_out && p.half_scale_dev) ? __ldg(p.half_scale_dev) : 1.0f;
+    const uint32_t tb = tmem + (((uint32_t)warp * 32u) << 16);
+    if (nk > 0) {
+      mbar_wait(bar(C::kBarAcc), 0);
+      tc_fence_after();
+    }
+    // value of output element (row, col0 + e) before the softmax stage
+    auto load_chunk = [&](int c, float (&v)[16]) {
+      uint32_t a[16];
+      if (nk > 0) {
+        tmem_ld16(tb + c * 16, a);
+        tmem_ld_wait(a);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) a[e] = 0u;
+      }
+      const int col0 = n0 + c * 16;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int col = col0 + e;
+        float x = __uint_as_float(a[e]) * (col < p.ncol_split ? alpha_q : alpha);
+        if (rv && col < p.N) {
+          if (biasp) x += __ldg(biasp + col);
+          if (resp) x += __ldg(resp + col);
+          if (p.accumulate) x += cp[col];
+        }
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.use_diag) x = (row == col ? p.diag : 0.f) - x;
+        v[e] = x;
+      }
+    };
+    auto store_chunk = [&](int c, const float (&v)[16]) {
+      if (!rv) return;
+      const int col0 = n0 + c * 16;
+      if (col0 >= p.N) return;
+      const bool full = col0 + 16 <= p.N;
+      if (cp) {
+        if (full && ((p.ldc & 3) == 0) && ((((uintptr_t)(cp + col0)) & 15) == 0)) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(cp + col0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (col0 + e < p.N) cp[col0 + e] = v[e];
+        }
+      }
+      if (pp) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        bf16* ph = pp + col0;
+        bf16* pl = pp + p.p_plane + col0;
+        if (full && ((((uintptr_t)ph) | ((uintptr_t)pl)) & 15) == 0) {
+          *reinterpret_cast<uint4*>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(ph + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(pl + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (col0 + e < p.N) {
+              const uint32_t wh = hi[e >> 1], wl = lo[e >> 1];
+              reinterpret_cast<uint16_t*>(ph)[e] = (uint16_t)((e & 1) ? (wh >> 16) : (wh & 0xffffu));
+              reinterpret_cast<uint16_t*>(pl)[e] = (uint16_t)((e & 1) ? (wl >> 16) : (wl & 0xffffu));
+            }
+        }
+      }
+      if (hp) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = pack_f16(v[2 * e] * hscale, v[2 * e + 1] * hscale);
+        h16* ph = hp + col0;
+        if (full && (((uintptr_t)ph) & 15) == 0) {
+          *reinterpret_cast<uint4*>(ph) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(ph + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (col0 + e < p.N) reinterpret_cast<uint16_t*>(ph)[e] = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+        }
+      }
+    };
+    float amax = 0.f;
+    if (p.splits > 1) {
+      // split-K: reduce alpha * partial into the zeroed C
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        if (n0 + c * 16 >= p.N) break;
+        float v[16];
+        load_chunk(c, v);
+        if (rv && nk > 0) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (n0 + c * 16 + e < p.N) atomicAdd(cp + n0 + c * 16 + e, v[e]);
+        }
+      }
+    } else if (p.softmax == 0) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        if (n0 + c * 16 >= p.N) break;
+        float v[16];
+        load_chunk(c, v);
+        if (p.absmax) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (rv && n0 + c * 16 + e < p.N) amax = fmaxf(amax, fabsf(v[e]));
+        }
+        store_chunk(c, v);
+      }
+    } else if (p.softmax == 1) {
+      // row softmax over the N columns of this tile (host guarantees one column tile)
+      const int nch = cdiv(p.N, 16);
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        float v[16];
+        load_chunk(c, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (c * 16 + e < p.N) mx = fmaxf(mx, v[e]);
+      }
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        float v[16];
+        load_chunk(c, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (c * 16 + e < p.N) sum += __expf(v[e] - mx);
+      }
+      const float inv = 1.0f / sum;
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        float v[16];
+        load_chunk(c, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = __expf(v[e] - mx) * inv;
+        store_chunk(c, v);
+      }
+    } else {
+      // softmax backward: C = dA (this product), aux = A (pair): dS = A * (dA - sum_j dA_j A_j)
+      const int nch = cdiv(p.N, 16);
+      float dot = 0.f;
+      auto load_aux = [&](int c, float (&a)[16]) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c * 16 + e;
+          a[e] = (rv && col < p.N) ? __bfloat162float(xp[col]) + __bfloat162float(xp[p.x_plane + col]) : 0.f;
+        }
+      };
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        float v[16], a[16];
+        load_chunk(c, v);
+        load_aux(c, a);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dot = fmaf(v[e], a[e], dot);
+      }
+#pragma unroll 1
+      for (int c = 0; c < nch; ++c) {
+        float v[16], a[16];
+        load_chunk(c, v);
+        load_aux(c, a);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = a[e] * (v[e] - dot);
+        store_chunk(c, v);
+      }
+    }
+    if (p.absmax) {
+      amax = warp_max(amax);
+      if (lane == 0 && amax > 0.f) atomicMax(p.absmax, __float_as_uint(amax));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
+  }
+}
+
+// fp32 [rows, cols] (row stride ld) -> bf16 pair planes [rows, ldp]; optional per-call factor
+__global__ void __launch_bounds__(256)
+pair_from_f32_kernel(const float* __restrict__ x, long long rows, int cols, int ld, float mult, bf16* __restrict__ out, int ldp,
+                     long long plane) {
+  const int cols4 = (cols + 3) >> 2;
+  const long long total = rows * cols4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float v[4];
+    const float* src = x + r * ld + c;
+    if (c + 4 <= cols && ((ld & 3) == 0) && ((((uintptr_t)x) & 15) == 0)) {
+      const float4 f = *reinterpret_cast<const float4*>(src);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = c + e < cols ? src[e] : 0.f;
+    }
+    uint32_t hi[2], lo[2];
+    split_bf16x2(v[0] * mult, v[1] * mult, hi[0], lo[0]);
+    split_bf16x2(v[2] * mult, v[3] * mult, hi[1], lo[1]);
+    bf16* oh = out + r * ldp + c;
+    bf16* ol = oh + plane;
+    if (c + 4 <= ldp) {
+      *reinterpret_cast<uint2*>(oh) = make_uint2(hi[0], hi[1]);
+      *reinterpret_cast<uint2*>(ol) = make_uint2(lo[0], lo[1]);
+    } else {
+      for (int e = 0; e < 4 && c + e < ldp; ++e) {
+        reinterpret_cast<uint16_t*>(oh)[e] = (uint16_t)((e & 1) ? (hi[e >> 1] >> 16) : (hi[e >> 1] & 0xffffu));
+        reinterpret_cast<uint16_t*>(ol)[e] = (uint16_t)((e & 1) ? (lo[e >> 1] >> 16) : (lo[e >> 1] & 0xffffu));
+      }
+    }
+  }
+}
+
+// column sums of a [rows, cols] fp32 matrix (bias gradients): 32 x 8 threads per CTA over row chunks, atomics into zeroed out
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ld, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long rpb = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * rpb, r1 = min(rows, r0 + rpb);
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + ty; r < r1; r += 8) s += x[r * ld + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][tx];
+    if (c < cols) atomicAdd(out + c, s);
+  }
+}
+
+static int make_map5(CUtensorMap* m, const dml_pg_operand& o, int K, int nb_inner, int nb_outer, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return DML_EUNSUPPORTED;
+  const int planes = o.plane_stride ? 2 : 1;
+  const cuuint64_t nbi = o.bs_inner ? (cuuint64_t)nb_inner : 1, nbo = o.bs_outer ? (cuuint64_t)nb_outer : 1;
+  const cuuint64_t k_mem = (cuuint64_t)(o.k_mem > 0 ? o.k_mem : K);
+  cuuint64_t dims[5];
+  cuuint32_t box[5] = {64, 64, 1, 1, 1};
+  if (o.layout == 0) { dims[0] = k_mem; dims[1] = (cuuint64_t)o.rows; box[1] = (cuuint32_t)box_rows; }
+  else { dims[0] = (cuuint64_t)o.rows; dims[1] = k_mem; }
+  dims[2] = nbi; dims[3] = nbo; dims[4] = (cuuint64_t)planes;
+  // strides of dimensions that are never stepped (extent 1) only have to be legal
+  const cuuint64_t dflt = (cuuint64_t)o.ld * 2 * dims[1];
+  cuuint64_t strides[4] = {(cuuint64_t)o.ld * 2, o.bs_inner ? (cuuint64_t)o.bs_inner * 2 : dflt,
+                           o.bs_outer ? (cuuint64_t)o.bs_outer * 2 : dflt, o.plane_stride ? (cuuint64_t)o.plane_stride * 2 : dflt};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(o.base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DML_OK : DML_EINVAL;
+}
+
+static bool operand_ok(const dml_pg_operand& o) {
+  if (!o.base || (((uintptr_t)o.base) & 15)) return false;
+  if (o.ld <= 0 || (o.ld % 8) || o.rows <= 0) return false;
+  if ((o.bs_inner % 8) || (o.bs_outer % 8) || (o.plane_stride % 8)) return false;
+  if (o.bs_inner < 0 || o.bs_outer < 0 || o.plane_stride < 0) return false;
+  return o.layout == 0 || o.layout == 1;
+}
+
+}  // namespace pg
+}  // namespace tc
+}  // namespace dml
+
+extern "C" {
+
+int dml_pgemm(const dml_pgemm_args* a, void* stream) {
+  using namespace dml;
+  using namespace dml::tc;
+  using namespace dml::tc::pg;
+  DML_CHECK_ARG(a && a->M > 0 && a->N > 0 && a->K > 0 && a->nb_inner > 0 && a->nb_outer > 0);
+  if (!operand_ok(a->A) || !operand_ok(a->B)) return DML_EINVAL;
+  const int splits = a->splits > 1 ? a->splits : 1;
+  const int softmax = a->softmax;
+  DML_CHECK_ARG(softmax >= 0 && softmax <= 2);
+  DML_CHECK_ARG(a->c || a->pair || a->half_out);
+  if (splits > 1) {
+    // split-K reduces alpha * partial products into a C the CALLER has zeroed: no other epilogue stage applies
+    if (!a->c || a->pair || a->half_out || a->bias || a->resid || a->accumulate || a->relu || a->use_diag || softmax || a->absmax)
+      return DML_EINVAL;
+  }
+  if (a->accumulate && !a->c) return DML_EINVAL;
+  if (softmax == 2 && !a->aux) return DML_EINVAL;
+  if (softmax && a->N > 256) return DML_EUNSUPPORTED;
+  if (a->pair && ((a->ldp % 8) || (a->p_plane % 8) || (((uintptr_t)a->pair) & 15))) return DML_EINVAL;
+  const int BN = softmax ? (a->N > 128 ? 256 : (a->N > 64 ? 128 : 64)) : (a->N > 64 ? 128 : 64);
+  CUtensorMap ma, mb;
+  int rc;
+  if ((rc = make_map5(&ma, a->A, a->K, a->nb_inner, a->nb_outer, kBM)) || (rc = make_map5(&mb, a->B, a->K, a->nb_inner, a->nb_outer, BN)))
+    return rc;
+  Params p{};
+  p.M = a->M; p.N = a->N; p.K = a->K; p.nb_inner = a->nb_inner; p.splits = splits;
+  p.a_layout = a->A.layout; p.b_layout = a->B.layout;
+  p.a_planes = a->A.plane_stride ? 2 : 1; p.b_planes = a->B.plane_stride ? 2 : 1;
+  p.a_row_off = a->A.row_offset; p.a_k_off = a->A.k_offset; p.b_row_off = a->B.row_offset; p.b_k_off = a->B.k_offset;
+  p.a_bi = a->A.bs_inner != 0; p.a_bo = a->A.bs_outer != 0; p.b_bi = a->B.bs_inner != 0; p.b_bo = a->B.bs_outer != 0;
+  p.alpha = a->alpha; p.alpha2 = a->ncol_split > 0 ? a->alpha2 : 1.0f; p.ncol_split = a->ncol_split > 0 ? a->ncol_split : 0;
+  p.alpha_dev = a->alpha_dev;
+  p.bias = a->bias; p.bias_bi = a->bias_bs_inner; p.bias_bo = a->bias_bs_outer;
+  p.relu = a->relu; p.use_diag = a->use_diag; p.diag = a->diag;
+  p.resid = a->resid; p.ldr = a->ldr; p.r_bi = a->r_bs_inner; p.r_bo = a->r_bs_outer;
+  p.accumulate = a->accumulate;
+  p.c = a->c; p.ldc = a->ldc; p.c_bi = a->c_bs_inner; p.c_bo = a->c_bs_outer;
+  p.pair = (bf16*)a->pair; p.ldp = a->ldp; p.p_bi = a->p_bs_inner; p.p_bo = a->p_bs_outer; p.p_plane = a->p_plane;
+  p.half_out = (h16*)a->half_out; p.ldh = a->ldh; p.h_bi = a->h_bs_inner; p.h_bo = a->h_bs_outer; p.half_scale_dev = a->half_scale_dev;
+  p.absmax = (uint32_t*)a->absmax;
+  p.softmax = softmax;
+  p.aux = (const bf16*)a->aux; p.ldx = a->ldx; p.x_bi = a->x_bs_inner; p.x_bo = a->x_bs_outer; p.x_plane = a->x_plane;
+  const long long nz = (long long)a->nb_inner * a->nb_outer * splits;
+  if (nz > 65535) return DML_EUNSUPPORTED;
+  dim3 grid(cdiv(a->M, kBM), cdiv(a->N, BN), (unsigned)nz);
+  if (grid.y > 65535) return DML_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (BN == 64) {
+    if ((e = cudaFuncSetAttribute(pgemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmemBytes)) != cudaSuccess) return (int)e;
+    pgemm_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, st>>>(ma, mb, p);
+  } else if (BN == 128) {
+    if ((e = cudaFuncSetAttribute(pgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmemBytes)) != cudaSuccess) return (int)e;
+    pgemm_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(ma, mb, p);
+  } else {
+    if ((e = cudaFuncSetAttribute(pgemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmemBytes)) != cudaSuccess) return (int)e;
+    pgemm_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(ma, mb, p);
+  }
+  DML_RETURN_LAUNCH();
+}
+
+int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mult, void* pair, int ldp, long long plane_stride,
+                      void* stream) {
+  using namespace dml;
+  DML_CHECK_ARG(x && pair && rows > 0 && cols > 0 && ld >= cols && ldp >= cols && (ldp % 4) == 0 && (plane_stride % 4) == 0);
+  DML_CHECK_ARG((((uintptr_t)pair) & 7) == 0);
+  const long long total = rows * ((cols + 3) / 4);
+  const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
+  tc::pg::pair_from_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, mult, (bf16*)pair, ldp, plane_stride);
+  DML_RETURN_LAUNCH();
+}
+
+int dml_colsum(const float* x, long long rows, int cols, int ld, float* out, void* stream) {
+  using namespace dml;
+  DML_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st);
+  if (e != cudaSuccess) return (int)e;
+  const int gy = (int)max(1LL, min((long long)148 * 4 / cdiv(cols, 32), (rows + 63) / 64));
+  tc::pg::colsum_kernel<<<dim3(cdiv(cols, 32), gy), 256, 0, st>>>(x, rows, cols, ld, out);
+  DML_RETURN_LAUNCH();
+}
+
+}  // extern "C"

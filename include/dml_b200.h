@@ -141,6 +141,68 @@ int dml_gemm_nt_split(const void* a_hi, const void* a_lo, const void* b_hi, cons
                       const float* scale_b, float alpha, int batch, int M, int N, int K, int lda, int ldb, float* c,
                       int ldc, long long c_batch_stride, void* stream);
 
+/* ---- fp32-class batched GEMM from bf16 operand pairs (csrc/pgemm.cu) ----------------------------------------------
+ * Replaces every plain contraction of the path: NystromAttention (models/NystromAttention.py:89 to_qkv, :122-125 the
+ * three similarity products, :31-33 the pseudo-inverse recurrence, :140 the aggregation products, :150 to_out), TransMIL's
+ * fc1 (models/mil.py:229), DeformCrossTransMIL's fc1 / FusionNet (models/DeformCrossTransMIL.py:100,111) and the 1x1
+ * convolutions of DeformCrossAttention1D (models/DeformableAttention1D.py:175,199,233), forward and backward.
+ *
+ * An operand is a bf16 PAIR x ~= hi + lo: two planes `plane_stride` elements apart (plane_stride = 0: one plane, for data
+ * that is exact in bf16).  layout 0: memory [rows][K], K contiguous; layout 1: memory [K][rows], rows contiguous ("rows" is
+ * the operand's M (A) or N (B) index).  Logical row r reads memory row r + row_offset, logical k reads memory k + k_offset;
+ * reads outside [0, rows) x [0, k_mem) are zero (k_mem = 0: K).  Batch index = outer * nb_inner + inner; an operand with
+ * batch stride 0 is shared along that batch dimension.  ld, batch strides and plane_stride are in elements, multiples of 8;
+ * base 16-byte aligned.                                                                                                 */
+typedef struct dml_pg_operand {
+  const void* base;
+  long long plane_stride;
+  long long bs_inner, bs_outer;
+  int layout, ld, rows, row_offset, k_offset, k_mem;
+} dml_pg_operand;
+
+/* value(m, n) = alpha [* *alpha_dev] [* alpha2 if n < ncol_split] * sum_k A[m, k] B[n, k]
+ *               [+ bias[n]] [+ resid[m, n]] [+ c[m, n] if accumulate] -> [ReLU] -> [diag * (m == n) - value if use_diag]
+ * softmax = 1: value := softmax over n (N <= 256);  softmax = 2: value := aux * (value - sum_n value * aux), aux = bf16 pair
+ * (the backward of that softmax).  Outputs (any subset): c float [M, ldc]; pair bf16 planes [M, ldp] (p_plane apart);
+ * half_out fp16 [M, ldh] (times *half_scale_dev if given); absmax: device uint32 atomicMax of the bit pattern of |value|.
+ * splits > 1: split-K, alpha * partial sums are REDUCED into c, which the caller has zeroed; no other epilogue stage.     */
+typedef struct dml_pgemm_args {
+  dml_pg_operand A, B;
+  int M, N, K, nb_inner, nb_outer, splits;
+  float alpha, alpha2;
+  int ncol_split;
+  const float* alpha_dev;
+  const float* bias;
+  long long bias_bs_inner, bias_bs_outer;
+  int relu, use_diag;
+  float diag;
+  const float* resid;
+  int ldr;
+  long long r_bs_inner, r_bs_outer;
+  int accumulate;
+  float* c;
+  int ldc;
+  long long c_bs_inner, c_bs_outer;
+  void* pair;
+  int ldp;
+  long long p_bs_inner, p_bs_outer, p_plane;
+  void* half_out;
+  int ldh;
+  long long h_bs_inner, h_bs_outer;
+  const float* half_scale_dev;
+  void* absmax;
+  int softmax;
+  const void* aux;
+  int ldx;
+  long long x_bs_inner, x_bs_outer, x_plane;
+} dml_pgemm_args;
+int dml_pgemm(const dml_pgemm_args* args, void* stream);
+/* x float [rows, cols] (row stride ld) * mult -> bf16 pair planes [rows, ldp], plane_stride elements apart.              */
+int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mult, void* pair, int ldp,
+                      long long plane_stride, void* stream);
+/* out[c] = sum_r x[r, c] (bias gradients over the tokens); out float [cols] is overwritten.                              */
+int dml_colsum(const float* x, long long rows, int cols, int ld, float* out, void* stream);
+
 /* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
  * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
 int dml_debug_set_trace(void* buf);
