@@ -356,7 +356,7 @@ def test_deform_pathomic_net_16k_bf16_bag_against_chunked_oracle(task):
     for i, nm in enumerate(("hazard_tumor", "hazard_immune", "hazard")):
         H.assert_close(logits[i], rlogits[i], TOL_BF16, nm)
     H.assert_close(loss, rloss, TOL_BF16, "loss")
-    seen = 0
+    seen, bad = 0, []
     for k, a, b in zip(names, grads, rgrads):
         if b is None:
             assert a is None or float(a.abs().max()) == 0.0, f"unexpected gradient for {k}"
@@ -365,10 +365,18 @@ def test_deform_pathomic_net_16k_bf16_bag_against_chunked_oracle(task):
         if float(b.abs().max()) == 0.0:
             assert float(a.abs().max()) <= 1e-6, k
             continue
-        zero_tol = 0.0
-        if k.endswith("rel_pos_bias.mlp.2.bias"):     # analytically zero (softmax shift invariance): rounding only
-            w = rgrads[names.index(k.replace("mlp.2.bias", "mlp.2.weight"))]
-            zero_tol = max(1e-6, 2e-3 * float(w.abs().max()))
-        H.assert_close(a, b, TOL_BF16, "grad " + k, atol=zero_tol)
         seen += 1
+        if k.endswith("rel_pos_bias.mlp.2.bias"):
+            # analytically zero (softmax shift invariance: sum_j dS_ij = 0): BOTH sides only hold the rounding of a sum of
+            # ~5e8 signed terms.  Bound it against the same sum taken without the cancellation, which the neighbouring
+            # d mlp.2.weight = sum_ij dS_ij h_ij approximates from below (|h| <= ~1).
+            w = rgrads[names.index(k.replace("mlp.2.bias", "mlp.2.weight"))]
+            lim = 5e-2 * float(w.abs().max()) + 1e-7
+            if float(a.abs().max()) > lim:
+                bad.append(f"{k}: |g| = {float(a.abs().max()):.3e} (oracle {float(b.abs().max()):.3e}) > {lim:.3e}")
+            continue
+        e1, e2 = H.rel_l2(a, b), H.max_rel(a, b)
+        if not (e1 <= TOL_BF16 and e2 <= TOL_BF16):
+            bad.append(f"{k}: rel_l2={e1:.3e} max_rel={e2:.3e} (max|ref| = {float(b.abs().max()):.3e})")
+    assert not bad, "\n".join(bad)
     assert seen > 60
