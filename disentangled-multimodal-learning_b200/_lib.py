@@ -44,6 +44,15 @@ SIGNATURES = {
     "dml_pgemm": (_i, [C.c_void_p, _vp]),
     "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
     "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
+    "dml_layernorm_fwd_pair": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _vp, _ll, _fp, _fp, _vp]),
+    "dml_ny_landmark_pool": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _ll, _vp]),
+    "dml_ny_softmax_rows_fwd": (_i, [_fp, _ll, _i, _vp, _ll, _vp]),
+    "dml_ny_softmax_rows_bwd": (_i, [_vp, _ll, _fp, _ll, _i, _vp, _ll, _vp]),
+    "dml_ny_res_conv_fwd": (_i, [_fp, _vp, _ll, _i, _i, _fp, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "dml_ny_res_conv_bwd": (_i, [_fp, _vp, _ll, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _i, _i, _fp, _vp]),
+    "dml_ny_dqkv_finalize": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
+    "dml_ppeg_stencil": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _vp]),
+    "dml_ppeg_wgrad": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
     "dml_debug_set_trace": (_i, [_vp]),
     "dml_debug_set_seg_limit": (_i, [_i]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
@@ -72,7 +81,7 @@ class PgemmArgs(C.Structure):
                 ("alpha_dev", C.c_void_p), ("bias", C.c_void_p), ("bias_bs_inner", C.c_longlong), ("bias_bs_outer", C.c_longlong),
                 ("relu", C.c_int), ("use_diag", C.c_int), ("diag", C.c_float),
                 ("resid", C.c_void_p), ("ldr", C.c_int), ("r_bs_inner", C.c_longlong), ("r_bs_outer", C.c_longlong),
-                ("accumulate", C.c_int),
+                ("resid_scale", C.c_float), ("accumulate", C.c_int),
                 ("c", C.c_void_p), ("ldc", C.c_int), ("c_bs_inner", C.c_longlong), ("c_bs_outer", C.c_longlong),
                 ("pair", C.c_void_p), ("ldp", C.c_int), ("p_bs_inner", C.c_longlong), ("p_bs_outer", C.c_longlong),
                 ("p_plane", C.c_longlong),

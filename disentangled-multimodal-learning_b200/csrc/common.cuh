@@ -79,6 +79,30 @@ __device__ __forceinline__ void split_f16(float x0, float x1, uint32_t& hi, uint
   asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(r0), "f"(r1));
 }
 
+// ---- bf16 operand pairs (x ~= hi + lo, 16 significant bits, fp32 exponent range: no scale) -------------------------
+__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }          // low half of a packed pair
+__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }  // high half
+// (x0, x1) -> packed bf16 pair `hi` and packed bf16 residual pair `lo`
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float r0 = x0 - bf16_lo_f(hi), r1 = x1 - bf16_hi_f(hi);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+// four consecutive values -> 8 bytes into each plane
+__device__ __forceinline__ void store_pair4(bf16* hi_ptr, bf16* lo_ptr, float a, float b, float c, float d) {
+  uint32_t h0, l0, h1, l1;
+  split_bf16x2(a, b, h0, l0);
+  split_bf16x2(c, d, h1, l1);
+  *reinterpret_cast<uint2*>(hi_ptr) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo_ptr) = make_uint2(l0, l1);
+}
+// four consecutive values of a pair (8-byte aligned) -> fp32
+__device__ __forceinline__ float4 load_pair4(const bf16* hi_ptr, const bf16* lo_ptr) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi_ptr), l = *reinterpret_cast<const uint2*>(lo_ptr);
+  return make_float4(bf16_lo_f(h.x) + bf16_lo_f(l.x), bf16_hi_f(h.x) + bf16_hi_f(l.x), bf16_lo_f(h.y) + bf16_lo_f(l.y),
+                     bf16_hi_f(h.y) + bf16_hi_f(l.y));
+}
+
 // ---- cp.async (LDGSTS) 16-byte copies with zero-fill predicate ----
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
   int sz = pred ? 16 : 0;

@@ -12,7 +12,8 @@ namespace dml {
 template <int V>   // float4 vectors per lane: D = 128 * V
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, long long rows,
-                     float eps, float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+                     float eps, float* __restrict__ y, bf16* __restrict__ pair, long long plane, float* __restrict__ mean,
+                     float* __restrict__ rstd) {
   constexpr int D = 128 * V;
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -40,7 +41,6 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
     }
     const float rs = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
-    float* yr = y + r * D;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       float4 o;
@@ -48,7 +48,11 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, c
       o.y = fmaf(v[k].y * rs, wv[k].y, bv[k].y);
       o.z = fmaf(v[k].z * rs, wv[k].z, bv[k].z);
       o.w = fmaf(v[k].w * rs, wv[k].w, bv[k].w);
-      *reinterpret_cast<float4*>(yr + k * 128 + lane * 4) = o;
+      if (y) *reinterpret_cast<float4*>(y + r * D + k * 128 + lane * 4) = o;
+      if (pair) {      // the GEMM that consumes the normalised rows takes them as a bf16 pair: written here, not in a pass of its own
+        bf16* ph = pair + r * D + k * 128 + lane * 4;
+        store_pair4(ph, ph + plane, o.x, o.y, o.z, o.w);
+      }
     }
     if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
@@ -116,16 +120,24 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 
 extern "C" {
 
-int dml_layernorm_fwd(const float* x, const float* w, const float* b, long long rows, int D, float eps, float* y,
-                      float* mean, float* rstd, void* stream) {
-  DML_CHECK_ARG(x && w && b && y && mean && rstd && rows > 0);
+int dml_layernorm_fwd_pair(const float* x, const float* w, const float* b, long long rows, int D, float eps, float* y,
+                           void* pair, long long plane_stride, float* mean, float* rstd, void* stream) {
+  DML_CHECK_ARG(x && w && b && (y || pair) && mean && rstd && rows > 0);
   if (D != 128 && D != 256 && D != 512) return DML_EUNSUPPORTED;
+  if (pair && ((((uintptr_t)pair) & 7) || (plane_stride & 3))) return DML_EINVAL;
   const int blocks = (int)min((rows + 7) / 8, (long long)148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 128) dml::layernorm_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, w, b, rows, eps, y, mean, rstd);
-  else if (D == 256) dml::layernorm_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, w, b, rows, eps, y, mean, rstd);
-  else dml::layernorm_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, w, b, rows, eps, y, mean, rstd);
+  dml::bf16* pp = (dml::bf16*)pair;
+  if (D == 128) dml::layernorm_fwd_kernel<1><<<blocks, 256, 0, st>>>(x, w, b, rows, eps, y, pp, plane_stride, mean, rstd);
+  else if (D == 256) dml::layernorm_fwd_kernel<2><<<blocks, 256, 0, st>>>(x, w, b, rows, eps, y, pp, plane_stride, mean, rstd);
+  else dml::layernorm_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, w, b, rows, eps, y, pp, plane_stride, mean, rstd);
   DML_RETURN_LAUNCH();
+}
+
+int dml_layernorm_fwd(const float* x, const float* w, const float* b, long long rows, int D, float eps, float* y,
+                      float* mean, float* rstd, void* stream) {
+  DML_CHECK_ARG(y);
+  return dml_layernorm_fwd_pair(x, w, b, rows, D, eps, y, nullptr, 0, mean, rstd, stream);
 }
 
 int dml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,

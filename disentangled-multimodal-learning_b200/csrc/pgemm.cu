@@ -58,7 +58,7 @@ struct Params {
   const float* bias; long long bias_bi, bias_bo;
   int relu, use_diag;
   float diag;
-  const float* resid; int ldr; long long r_bi, r_bo;
+  const float* resid; int ldr; long long r_bi, r_bo; float resid_scale;
   int accumulate;
   float* c; int ldc; long long c_bi, c_bo;
   bf16* pair; int ldp; long long p_bi, p_bo, p_plane;
@@ -83,15 +83,6 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool 
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-// (x0, x1) -> packed bf16 pair `hi` and packed bf16 residual pair `lo`
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-  const float r0 = x0 - bf16_lo_f(hi), r1 = x1 - bf16_hi_f(hi);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
-}
-
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb, const Params p) {
@@ -218,7 +209,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
         float x = __uint_as_float(a[e]) * (col < p.ncol_split ? alpha_q : alpha);
         if (rv && col < p.N) {
           if (biasp) x += __ldg(biasp + col);
-          if (resp) x += __ldg(resp + col);
+          if (resp) x = fmaf(p.resid_scale, __ldg(resp + col), x);
           if (p.accumulate) x += cp[col];
         }
         if (p.relu) x = fmaxf(x, 0.f);
@@ -502,7 +493,7 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   p.alpha_dev = a->alpha_dev;
   p.bias = a->bias; p.bias_bi = a->bias_bs_inner; p.bias_bo = a->bias_bs_outer;
   p.relu = a->relu; p.use_diag = a->use_diag; p.diag = a->diag;
-  p.resid = a->resid; p.ldr = a->ldr; p.r_bi = a->r_bs_inner; p.r_bo = a->r_bs_outer;
+  p.resid = a->resid; p.ldr = a->ldr; p.r_bi = a->r_bs_inner; p.r_bo = a->r_bs_outer; p.resid_scale = a->resid_scale;
   p.accumulate = a->accumulate;
   p.c = a->c; p.ldc = a->ldc; p.c_bi = a->c_bs_inner; p.c_bo = a->c_bs_outer;
   p.pair = (bf16*)a->pair; p.ldp = a->ldp; p.p_bi = a->p_bs_inner; p.p_bo = a->p_bs_outer; p.p_plane = a->p_plane;

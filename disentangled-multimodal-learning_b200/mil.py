@@ -9,6 +9,7 @@ from torch import nn
 
 from . import ops
 from .NystromAttention import NystromAttention
+from .nystrom_fn import PPEGFn
 
 
 class TransLayer(nn.Module):
@@ -19,7 +20,7 @@ class TransLayer(nn.Module):
                                      residual=True, dropout=0.1)
 
     def forward(self, x):
-        return x + self.attn(ops.layer_norm(x, self.norm))
+        return x + self.attn(x, _norm=self.norm)      # LayerNorm fused into the attention function (mil.py:186)
 
 
 class PPEG(nn.Module):
@@ -30,12 +31,15 @@ class PPEG(nn.Module):
         self.proj2 = nn.Conv2d(dim, dim, 3, 1, 3 // 2, groups=dim)
 
     def forward(self, x, H, W):
-        B, _, C = x.shape
-        cls_token, feat_token = x[:, 0], x[:, 1:]
-        cnn_feat = feat_token.transpose(1, 2).view(B, C, H, W)
-        x = self.proj(cnn_feat) + cnn_feat + self.proj1(cnn_feat) + self.proj2(cnn_feat)
-        x = x.flatten(2).transpose(1, 2)
-        return torch.cat((cls_token.unsqueeze(1), x), dim=1)
+        """x [B, 1 + H W, C]: cls token + the H x W grid (H == W: TransMIL wrap-pads the bag to a square).  The three
+        depthwise convolutions and the identity are one 7x7 stencil kernel (weights summed here: exact up to fp32
+        reassociation); autograd splits the stencil's weight gradient back onto proj / proj1 / proj2."""
+        assert H == W, "PPEG runs on the square grid TransMIL builds (mil.py:232-235)"
+        C = x.shape[-1]
+        wsum = (self.proj.weight.reshape(C, 7, 7) + F.pad(self.proj1.weight.reshape(C, 5, 5), (1, 1, 1, 1))
+                + F.pad(self.proj2.weight.reshape(C, 3, 3), (2, 2, 2, 2))).reshape(C, 49)
+        bsum = self.proj.bias + self.proj1.bias + self.proj2.bias
+        return PPEGFn.apply(x, wsum, bsum, H)
 
 
 class TransMIL(nn.Module):
@@ -54,7 +58,7 @@ class TransMIL(nn.Module):
 
     def forward(self, x):
         fc1 = self._fc1[0]
-        h = F.relu(ops.mm_tc(x.float(), fc1.weight.t()) + fc1.bias)
+        h = ops.linear_pg(x, fc1.weight, fc1.bias, relu=True)            # mil.py:229 (bf16 bags enter as they are)
         N = h.shape[1]
         side = int(np.ceil(np.sqrt(N)))
         add_length = side * side - N

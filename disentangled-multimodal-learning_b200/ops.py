@@ -451,9 +451,65 @@ class LinearBf16BagFn(torch.autograd.Function):
         return dx, dW, colsum(dy)
 
 
+class LinearPgFn(torch.autograd.Function):
+    """y = [relu](x @ W^T + b) on the bf16-pair tcgen05 GEMM (csrc/pgemm.cu).  x [rows, K] fp32 (split into a pair) or bf16
+    (exact: one plane, no rounding added); W [N, K], b [N] fp32.  Bias and ReLU are the GEMM's epilogue; the weight
+    gradient is a split-K GEMM over the rows, the bias gradient a column-sum kernel."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        from .pairs import Pair, pgemm
+        rows, K = x.shape
+        N = W.shape[0]
+        xp = Pair.exact(x.contiguous()) if x.dtype == BF16 else Pair.from_f32(x)
+        Wp = Pair.from_f32(W)
+        y, _ = pgemm(xp, Wp, M=rows, N=N, K=K, bias=b.contiguous().float() if b is not None else None, relu=relu)
+        ctx.relu, ctx.has_bias, ctx.xdtype = relu, b is not None, x.dtype
+        ctx.pairs = (xp, Wp)
+        ctx.save_for_backward(y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .pairs import Pair, pgemm
+        xp, Wp = ctx.pairs
+        (y,) = ctx.saved_tensors
+        rows, K = xp.shape
+        N = Wp.shape[0]
+        dy = dy.contiguous().float()
+        if ctx.relu:
+            dy = torch.where(y > 0, dy, torch.zeros((), device=dy.device, dtype=dy.dtype))
+        dyp = Pair.from_f32(dy)
+        dW = torch.zeros(N, K, device=dy.device, dtype=F32)
+        tiles = ((N + 127) // 128) * ((K + 127) // 128)
+        splits = max(1, min(((rows + 63) // 64) // 8, (148 + tiles - 1) // tiles))
+        if splits > 1:
+            pgemm(dyp, xp, M=N, N=K, K=rows, a_trans=True, b_trans=True, out=dW, splits=splits)
+        else:
+            pgemm(dyp, xp, M=N, N=K, K=rows, a_trans=True, b_trans=True, out=dW)
+        db = None
+        if ctx.has_bias:
+            db = torch.empty(N, device=dy.device, dtype=F32)
+            call("dml_colsum", ptr(dy), rows, N, N, ptr(db), stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = pgemm(dyp, Wp, M=rows, N=K, K=N, b_trans=True)
+            dx = dx.to(ctx.xdtype)
+        return dx, dW, db, None
+
+
+def linear_pg(x: torch.Tensor, W: torch.Tensor, b, relu: bool = False) -> torch.Tensor:
+    """[relu](x @ W^T + b) over the last dimension of x [..., K] (fp32 or bf16) -> fp32 [..., N]."""
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype not in (BF16, F32):
+        x2 = x2.float()
+    return LinearPgFn.apply(x2, W, b, relu).reshape(*lead, W.shape[0])
+
+
 def fc1_bf16_bag(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """relu(x @ W^T + b) for a bf16 bag x [M, K] (DeformCrossTransMIL.py:100 on `path.float()`), fp32 output."""
-    return torch.relu(LinearBf16BagFn.apply(x, W, b))
+    return LinearPgFn.apply(x, W, b, True)
 
 
 class LayerNormFn(torch.autograd.Function):

@@ -59,6 +59,15 @@ class Pair:
     def float(self) -> torch.Tensor:
         return self.planes.float().sum(0)
 
+    def b1(self) -> "Pair":
+        """[P, R, C] -> [P, 1, R, C]: a 2-D operand shared by every entry of a one-dimensional batch."""
+        return Pair(self.planes.unsqueeze(1))
+
+    def head_slices(self, which: int, n_groups: int, H: int, d: int) -> "Pair":
+        """planes [P, B, n, n_groups * H * d] -> view [P, B, H, n, d] of column group `which` (q / k / v of a fused buffer)."""
+        P_, B, n, _ = self.planes.shape
+        return Pair(self.planes.view(P_, B, n, n_groups, H, d)[:, :, :, which].permute(0, 1, 3, 2, 4))
+
     def view(self, *shape) -> "Pair":
         return Pair(self.planes.view(self.nplanes, *shape))
 
@@ -95,7 +104,7 @@ def _operand(t: Pair, trans: bool, K: int, rows: int, batch_dims: int, row_offse
 
 def pgemm(A: Pair, B: Pair, *, M: int, N: int, K: int, a_trans=False, b_trans=False, batch=(), a_row_offset=0, a_k_offset=0,
           b_row_offset=0, b_k_offset=0, alpha=1.0, alpha_dev=None, ncol_split=0, alpha2=1.0, bias=None, relu=False,
-          diag=None, resid=None, accumulate=False, out: Optional[torch.Tensor] = None, want_f32=True, want_pair=False,
+          diag=None, resid=None, resid_scale=1.0, accumulate=False, out: Optional[torch.Tensor] = None, want_f32=True, want_pair=False,
           pair_out: Optional[Pair] = None, half_out: Optional[torch.Tensor] = None, half_scale_dev=None, absmax=None,
           softmax=0, aux: Optional[Pair] = None, splits=1):
     """value[b][m, n] = alpha * sum_k A_b(m, k) B_b(n, k) with the epilogue of `dml_pgemm_args`.
@@ -136,19 +145,23 @@ def pgemm(A: Pair, B: Pair, *, M: int, N: int, K: int, a_trans=False, b_trans=Fa
         a.use_diag, a.diag = 1, float(diag)
     if resid is not None:
         assert resid.dtype == F32 and resid.stride(-1) == 1 and resid.dim() == nb + 2
-        a.resid, a.ldr = ptr(resid), resid.stride(-2)
+        a.resid, a.ldr, a.resid_scale = ptr(resid), resid.stride(-2), float(resid_scale)
         a.r_bs_inner, a.r_bs_outer = bstrides(resid, nb)
         keep.append(resid)
     a.accumulate = int(bool(accumulate))
     shape = tuple(batch) + (M, N)
+    reduce_batch = out is not None and out.dim() == 2 and nb > 0      # every batch entry reduces into ONE [M, N] output
+    if reduce_batch:
+        splits = max(2, int(splits))                                   # the reducing (atomic) epilogue
+        a.splits = splits
     if splits > 1:
         assert out is not None, "split-K reduces into a caller-zeroed output"
     if out is None and (want_f32 or accumulate):
         out = torch.empty(shape, device=dev, dtype=F32)
     if out is not None:
-        assert out.dtype == F32 and out.stride(-1) == 1 and out.dim() == nb + 2
+        assert out.dtype == F32 and out.stride(-1) == 1 and (out.dim() == nb + 2 or reduce_batch)
         a.c, a.ldc = ptr(out), out.stride(-2)
-        a.c_bs_inner, a.c_bs_outer = bstrides(out, nb)
+        a.c_bs_inner, a.c_bs_outer = (0, 0) if reduce_batch else bstrides(out, nb)
     if pair_out is None and want_pair:
         assert N % 8 == 0
         pair_out = Pair.empty(shape, dev)

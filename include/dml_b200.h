@@ -161,7 +161,7 @@ typedef struct dml_pg_operand {
 } dml_pg_operand;
 
 /* value(m, n) = alpha [* *alpha_dev] [* alpha2 if n < ncol_split] * sum_k A[m, k] B[n, k]
- *               [+ bias[n]] [+ resid[m, n]] [+ c[m, n] if accumulate] -> [ReLU] -> [diag * (m == n) - value if use_diag]
+ *               [+ bias[n]] [+ resid_scale * resid[m, n]] [+ c[m, n] if accumulate] -> [ReLU] -> [diag * (m == n) - value if use_diag]
  * softmax = 1: value := softmax over n (N <= 256);  softmax = 2: value := aux * (value - sum_n value * aux), aux = bf16 pair
  * (the backward of that softmax).  Outputs (any subset): c float [M, ldc]; pair bf16 planes [M, ldp] (p_plane apart);
  * half_out fp16 [M, ldh] (times *half_scale_dev if given); absmax: device uint32 atomicMax of the bit pattern of |value|.
@@ -179,6 +179,7 @@ typedef struct dml_pgemm_args {
   const float* resid;
   int ldr;
   long long r_bs_inner, r_bs_outer;
+  float resid_scale;
   int accumulate;
   float* c;
   int ldc;
@@ -202,6 +203,41 @@ int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mu
                       long long plane_stride, void* stream);
 /* out[c] = sum_r x[r, c] (bias gradients over the tokens); out float [cols] is overwritten.                              */
 int dml_colsum(const float* x, long long rows, int cols, int ld, float* out, void* stream);
+
+/* Row LayerNorm that also (or only) writes the normalised rows as a bf16 pair [rows, D] (the operand of the projection GEMM
+ * that follows: TransLayer.norm -> to_qkv, mil.py:186 -> NystromAttention.py:89).  y or pair may be NULL, not both.        */
+int dml_layernorm_fwd_pair(const float* x, const float* w, const float* b, long long rows, int D, float eps, float* y,
+                           void* pair, long long plane_stride, float* mean, float* rstd, void* stream);
+
+/* ---- NystromAttention HBM kernels on bf16-pair storage (csrc/nystrom_pair.cu) ------------------------------------------
+ * qkv: pair [B, n_pad, ld] with q at column 0, k at column H d, v at column 2 H d (rows 0 .. pad-1 are the zero front
+ * padding, NystromAttention.py:79-85).                                                                                  */
+/* out pair [2 (q_l, k_l)][B, H, n_pad / l, d] = mult * sum over l consecutive padded tokens (NystromAttention.py:102-118). */
+int dml_ny_landmark_pool(const void* qkv, long long plane_stride, int ld, int B, int n_pad, int l, int H, int d, float mult_q,
+                         float mult_k, void* out, long long out_plane_stride, void* stream);
+/* y pair [rows, cols] = softmax over the columns of x float [rows, cols] (NystromAttention.py:137, the long rows of sim3);
+ * backward: dx pair = y * (dy - sum_j dy_j y_j).                                                                        */
+int dml_ny_softmax_rows_fwd(const float* x, long long rows, int cols, void* y, long long plane_stride, void* stream);
+int dml_ny_softmax_rows_bwd(const void* y, long long y_plane_stride, const float* dy, long long rows, int cols, void* dx,
+                            long long dx_plane_stride, void* stream);
+/* y pair [B, n_pad, H d] = a + depthwise conv_K(v) along the tokens (NystromAttention.py:144-145), a float [B, n_pad, H d]
+ * (heads merged in the columns), v = columns col0.. of the qkv pair (row stride ldv), w float [H, K].  Backward: dv (float,
+ * row stride lddv, columns dcol0..) is OVERWRITTEN with the input gradient of the convolution, dw float [H, K] likewise.  */
+int dml_ny_res_conv_fwd(const float* a, const void* v, long long v_plane_stride, int ldv, int col0, const float* w, int K, int B,
+                        int n_pad, int H, int d, void* y, long long y_plane_stride, void* stream);
+int dml_ny_res_conv_bwd(const float* dy, const void* v, long long v_plane_stride, int ldv, int col0, const float* w, int K, int B,
+                        int n_pad, int H, int d, float* dv, int lddv, int dcol0, float* dw, void* stream);
+/* d(qkv) pair [B, n_pad, 3 H d] from acc float [B, n_pad, 3 H d] (q columns: gradient of the scaled queries) and the landmark
+ * gradients dl float [2][B, H, n_pad / l, d]: dq = scale acc_q + scale/l dq_l, dk = acc_k + dk_l / l, dv = acc_v.         */
+int dml_ny_dqkv_finalize(const float* acc, const float* dl, int B, int n_pad, int l, int H, int d, float scale, void* out,
+                         long long plane_stride, void* stream);
+/* PPEG (models/mil.py:192-206) as one 7x7 depthwise stencil on the side x side token grid: x, y float [B, 1 + side^2, C],
+ * y = x + conv(x; wsum) + bsum on tokens 1.., token 0 copied; wsum float [C, 49] = the 7x7 + zero-padded 5x5 + 3x3 kernels,
+ * bsum float [C] the three biases.  flip = 1: the transposed stencil without bias (input gradient).  dml_ppeg_wgrad:
+ * dw float [C, 49], db float [C] of the summed stencil (overwritten).                                                    */
+int dml_ppeg_stencil(const float* x, const float* wsum, const float* bsum, int B, int side, int C, int flip, float* y,
+                     void* stream);
+int dml_ppeg_wgrad(const float* x, const float* dy, int B, int side, int C, float* dw, float* db, void* stream);
 
 /* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
  * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
