@@ -100,9 +100,10 @@ def colsum(x2d: torch.Tensor) -> torch.Tensor:
         # them can see it, so the fill is synchronised once here (never inside a graph capture: shapes are first seen in
         # the eager warm-up passes; a shape first met while capturing gets an uncached, capture-local vector)
         ones = torch.ones(rows, device=x2d.device, dtype=F32)
-        if torch.cuda.is_current_stream_capturing():
-            return torch.mv(x2d.t(), ones)
-        torch.cuda.current_stream(x2d.device).synchronize()
+        if x2d.is_cuda:
+            if torch.cuda.is_current_stream_capturing():
+                return torch.mv(x2d.t(), ones)
+            torch.cuda.current_stream(x2d.device).synchronize()
         _ONES[key] = ones
     return torch.mv(x2d.t(), ones)
 
