@@ -293,15 +293,19 @@ def bench_transmil(N, args, dev, rank, world, cpu=True):
     loss_fn = lambda out, b: torch.nn.functional.cross_entropy(out[1], b["label"], weight=w_ce)   # noqa: E731
     flat_adamw = lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=0.01, fused=True)         # noqa: E731
 
+    def eager_fwd_bwd():        # keeps no reference to the autograd graph: its AccumulateGrad nodes remember the stream they
+        loss_fn(net(dev_bags[0]["x"]), dev_bags[0]).backward()      # first ran on, which must not outlive this eager pass
+
     launches0 = _lib.launch_count
-    out = net(dev_bags[0]["x"])
-    loss_fn(out, dev_bags[0]).backward()
+    eager_fwd_bwd()
     launches_per_step = _lib.launch_count - launches0
     net.zero_grad(set_to_none=True)
     graph_error = None
     try:
         gstep = GraphedTrainStep(net, loss_fn, dev_bags[0], flat_optimizer=flat_adamw, model_keys=("x",), warmup=2)
     except Exception as ex:                                    # not capturable: time the eager step and say so
+        import traceback
+        traceback.print_exc(file=sys.stderr)
         graph_error = repr(ex)[:300]
         torch.cuda.synchronize()
         opt_e = torch.optim.AdamW([p_ for p_ in net.parameters() if p_.requires_grad], lr=2e-4, weight_decay=0.01, fused=True)
@@ -371,8 +375,7 @@ def bench_transmil(N, args, dev, rank, world, cpu=True):
     if gstep.reducer is not None:
         gstep.reducer.attach_views()
     _lib._timing_hook = hook
-    out = net(dev_bags[0]["x"])
-    loss_fn(out, dev_bags[0]).backward()
+    eager_fwd_bwd()
     torch.cuda.synchronize()
     _lib._timing_hook = None
     ktime = {}

@@ -134,6 +134,9 @@ KERNELS_PER_CALL = {
     "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
     "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
     "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1, "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1, "dml_split_f16": 2, "dml_gemm_nt_split": 1,
+    "dml_pgemm": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
+    "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
+    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events
