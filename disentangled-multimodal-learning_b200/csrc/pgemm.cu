@@ -21,7 +21,8 @@
 //   * split-K (fp32 reductions into a zeroed C) for the token-reduction products (weight gradients, attn3 @ v).
 //
 // CTA = one 128 x BN tile (BN = 64 / 128 / 256); warp 4 = TMA producer (ring of {A planes, B planes} 64-wide k-blocks,
-// 128-byte swizzle), warp 5 = MMA issuer + TMEM owner, warps 0-3 = epilogue.
+// 128-byte swizzle), warp 9 = MMA issuer + TMEM owner, warps 0-7 = epilogue (a row's columns are split between two threads,
+// 32-column groups, vector loads / stores; one CTA per SM, so the epilogue's own parallelism is what hides its latencies).
 #include <math.h>
 
 #include "../../include/dml_b200.h"
@@ -31,7 +32,7 @@ namespace dml {
 namespace tc {
 namespace pg {
 
-constexpr int kBM = 128, kBK = 64, kThreads = 32 * 6;
+constexpr int kBM = 128, kBK = 64, kThreads = 32 * 10;   // 8 epilogue warps, TMA producer, MMA issuer
 constexpr uint32_t kTileA = kBM * kBK * 2;   // 16 KB
 
 template <int BN>
@@ -42,7 +43,8 @@ struct Cfg {
   static constexpr uint32_t kOffBar = kStages * kStageBytes;
   static constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAcc = 2 * kStages, kNumBars = 2 * kStages + 1;
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
-  static constexpr uint32_t kSmemBytes = kOffTmemPtr + 16 + 1024;
+  static constexpr uint32_t kOffXch = kOffTmemPtr + 16;          // float[2][128]
+  static constexpr uint32_t kSmemBytes = kOffXch + 1024 + 1024;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -67,6 +69,7 @@ struct Params {
   uint32_t* absmax;
   int softmax;
   const bf16* aux; int ldx; long long x_bi, x_bo, x_plane;
+  int vec_ok;      // every output / side tensor allows 16-byte accesses at 4- (fp32) / 8- (16-bit) element column granularity
 };
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
@@ -107,7 +110,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     mbar_init(bar(C::kBarAcc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -116,7 +119,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---- TMA producer ----
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)p.a_planes * kTileA + (uint32_t)p.b_planes * C::kTileB;
@@ -149,7 +152,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ---- MMA issuer (uniform datapath, one elected lane) ----
     const bool leader = elect_one();
     const uint32_t idesc = idesc_bf16(128, BN, p.a_layout != 0, p.b_layout != 0);
@@ -173,8 +176,9 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     }
     tc_commit(bar(C::kBarAcc), leader);
   } else {
-    // ---- epilogue: TMEM lane = output row ----
-    const int row = m0 + warp * 32 + lane;
+    // ---- epilogue: 8 warps; TMEM lane = output row, the row's columns split between two threads (warps w and w + 4) ----
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = m0 + quarter * 32 + lane;
     const bool rv = row < p.M;
     float alpha = p.alpha;
     if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
@@ -187,26 +191,79 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     h16* hp = p.half_out ? p.half_out + (size_t)bo * p.h_bo + (size_t)bi * p.h_bi + rowl * p.ldh : nullptr;
     const bf16* xp = p.aux ? p.aux + (size_t)bo * p.x_bo + (size_t)bi * p.x_bi + rowl * p.ldx : nullptr;
     const float hscale = (p.half_out && p.half_scale_dev) ? __ldg(p.half_scale_dev) : 1.0f;
-    const uint32_t tb = tmem + (((uint32_t)warp * 32u) << 16);
+    const uint32_t tb = tmem + (((uint32_t)quarter * 32u) << 16);
+    float* xch = reinterpret_cast<float*>(sgen + C::kOffXch);          // [2 halves][128 rows] exchange of row statistics
     if (nk > 0) {
       mbar_wait(bar(C::kBarAcc), 0);
       tc_fence_after();
     }
-    // value of output element (row, col0 + e) before the softmax stage
-    auto load_chunk = [&](int c, float (&v)[16]) {
-      uint32_t a[16];
+    // this thread's column groups (32 wide): [g0, g1) of the tile
+    constexpr int kGroups = BN / 32;
+    const int g0 = half * (kGroups / 2), g1 = g0 + kGroups / 2;
+    // accumulator group -> alpha * acc (no other stage)
+    auto load_acc = [&](int g, float (&v)[32], float a_lo, float a_hi) {
+      uint32_t r0[16], r1[16];
       if (nk > 0) {
-        tmem_ld16(tb + c * 16, a);
-        tmem_ld_wait(a);
+        tmem_ld16(tb + g * 32, r0);
+        tmem_ld16(tb + g * 32 + 16, r1);
+        tmem_ld_wait2(r0, r1);
       } else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) a[e] = 0u;
+        for (int e = 0; e < 16; ++e) r0[e] = r1[e] = 0u;
       }
-      const int col0 = n0 + c * 16;
+      const int col0 = n0 + g * 32;
+      if (col0 + 32 <= p.ncol_split) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 16; ++e) { v[e] = __uint_as_float(r0[e]) * a_lo; v[16 + e] = __uint_as_float(r1[e]) * a_lo; }
+      } else if (col0 >= p.ncol_split) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { v[e] = __uint_as_float(r0[e]) * a_hi; v[16 + e] = __uint_as_float(r1[e]) * a_hi; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          v[e] = __uint_as_float(r0[e]) * (col0 + e < p.ncol_split ? a_lo : a_hi);
+          v[16 + e] = __uint_as_float(r1[e]) * (col0 + 16 + e < p.ncol_split ? a_lo : a_hi);
+        }
+      }
+    };
+    // the additive / pointwise stages on a group whose 32 columns all exist (vector accesses; host checked the alignment)
+    auto stages_full = [&](int col0, float (&v)[32]) {
+      if (biasp) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(biasp + col0 + e));
+          v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+        }
+      }
+      if (resp && rv) {
+        const float rs = p.resid_scale;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(resp + col0 + e));
+          v[e] = fmaf(rs, t.x, v[e]); v[e + 1] = fmaf(rs, t.y, v[e + 1]); v[e + 2] = fmaf(rs, t.z, v[e + 2]); v[e + 3] = fmaf(rs, t.w, v[e + 3]);
+        }
+      }
+      if (p.accumulate && rv) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(cp + col0 + e);
+          v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+      if (p.use_diag) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = (row == col0 + e ? p.diag : 0.f) - v[e];
+      }
+    };
+    auto stages_edge = [&](int col0, float (&v)[32]) {       // per-element version for a ragged last group / unaligned tensors
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
         const int col = col0 + e;
-        float x = __uint_as_float(a[e]) * (col < p.ncol_split ? alpha_q : alpha);
+        float x = v[e];
         if (rv && col < p.N) {
           if (biasp) x += __ldg(biasp + col);
           if (resp) x = fmaf(p.resid_scale, __ldg(resp + col), x);
@@ -217,141 +274,175 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
         v[e] = x;
       }
     };
-    auto store_chunk = [&](int c, const float (&v)[16]) {
-      if (!rv) return;
-      const int col0 = n0 + c * 16;
-      if (col0 >= p.N) return;
-      const bool full = col0 + 16 <= p.N;
+    auto store_full = [&](int col0, const float (&v)[32]) {
       if (cp) {
-        if (full && ((p.ldc & 3) == 0) && ((((uintptr_t)(cp + col0)) & 15) == 0)) {
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(cp + col0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (col0 + e < p.N) cp[col0 + e] = v[e];
-        }
+        for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(cp + col0 + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
       }
       if (pp) {
-        uint32_t hi[8], lo[8];
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        for (int e = 0; e < 16; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
         bf16* ph = pp + col0;
-        bf16* pl = pp + p.p_plane + col0;
-        if (full && ((((uintptr_t)ph) | ((uintptr_t)pl)) & 15) == 0) {
-          *reinterpret_cast<uint4*>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(ph + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<uint4*>(pl) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(pl + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        } else {
+        bf16* pl = ph + p.p_plane;
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (col0 + e < p.N) {
-              const uint32_t wh = hi[e >> 1], wl = lo[e >> 1];
-              reinterpret_cast<uint16_t*>(ph)[e] = (uint16_t)((e & 1) ? (wh >> 16) : (wh & 0xffffu));
-              reinterpret_cast<uint16_t*>(pl)[e] = (uint16_t)((e & 1) ? (wl >> 16) : (wl & 0xffffu));
-            }
+        for (int e = 0; e < 16; e += 4) {
+          *reinterpret_cast<uint4*>(ph + 2 * e) = make_uint4(hi[e], hi[e + 1], hi[e + 2], hi[e + 3]);
+          *reinterpret_cast<uint4*>(pl + 2 * e) = make_uint4(lo[e], lo[e + 1], lo[e + 2], lo[e + 3]);
         }
       }
       if (hp) {
-        uint32_t w[8];
+        uint32_t w[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) w[e] = pack_f16(v[2 * e] * hscale, v[2 * e + 1] * hscale);
-        h16* ph = hp + col0;
-        if (full && (((uintptr_t)ph) & 15) == 0) {
-          *reinterpret_cast<uint4*>(ph) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(ph + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-        } else {
+        for (int e = 0; e < 16; ++e) w[e] = pack_f16(v[2 * e] * hscale, v[2 * e + 1] * hscale);
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (col0 + e < p.N) reinterpret_cast<uint16_t*>(ph)[e] = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(hp + col0 + 2 * e) = make_uint4(w[e], w[e + 1], w[e + 2], w[e + 3]);
+      }
+    };
+    auto store_edge = [&](int col0, const float (&v)[32]) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int col = col0 + e;
+        if (col < p.N) {
+          if (cp) cp[col] = v[e];
+          if (pp) {
+            const bf16 h = __float2bfloat16_rn(v[e]);
+            pp[col] = h;
+            pp[p.p_plane + col] = __float2bfloat16_rn(v[e] - __bfloat162float(h));
+          }
+          if (hp) hp[col] = __float2half_rn(v[e] * hscale);
         }
       }
     };
+    auto load_aux = [&](int col0, bool full, float (&a)[32]) {
+      if (full && rv) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          const uint4 h = *reinterpret_cast<const uint4*>(xp + col0 + e), l = *reinterpret_cast<const uint4*>(xp + p.x_plane + col0 + e);
+          a[e] = bf16_lo_f(h.x) + bf16_lo_f(l.x); a[e + 1] = bf16_hi_f(h.x) + bf16_hi_f(l.x);
+          a[e + 2] = bf16_lo_f(h.y) + bf16_lo_f(l.y); a[e + 3] = bf16_hi_f(h.y) + bf16_hi_f(l.y);
+          a[e + 4] = bf16_lo_f(h.z) + bf16_lo_f(l.z); a[e + 5] = bf16_hi_f(h.z) + bf16_hi_f(l.z);
+          a[e + 6] = bf16_lo_f(h.w) + bf16_lo_f(l.w); a[e + 7] = bf16_hi_f(h.w) + bf16_hi_f(l.w);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          a[e] = (rv && col0 + e < p.N) ? __bfloat162float(xp[col0 + e]) + __bfloat162float(xp[p.x_plane + col0 + e]) : 0.f;
+      }
+    };
+    // combine a per-half row statistic across the two threads of a row (all 8 epilogue warps take part)
+    auto exchange = [&](float mine, bool is_max) -> float {
+      const int rl = quarter * 32 + lane;
+      xch[half * 128 + rl] = mine;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float other = xch[(half ^ 1) * 128 + rl];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      return is_max ? fmaxf(mine, other) : mine + other;
+    };
+    const bool vec = p.vec_ok != 0;
     float amax = 0.f;
     if (p.splits > 1) {
       // split-K: reduce alpha * partial into the zeroed C
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        if (n0 + c * 16 >= p.N) break;
-        float v[16];
-        load_chunk(c, v);
+      for (int g = g0; g < g1; ++g) {
+        const int col0 = n0 + g * 32;
+        if (col0 >= p.N) break;
+        float v[32];
+        load_acc(g, v, alpha_q, alpha);
         if (rv && nk > 0) {
+          if (vec && col0 + 32 <= p.N) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (n0 + c * 16 + e < p.N) atomicAdd(cp + n0 + c * 16 + e, v[e]);
+            for (int e = 0; e < 32; e += 4) atomicAdd(reinterpret_cast<float4*>(cp + col0 + e), make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (col0 + e < p.N) atomicAdd(cp + col0 + e, v[e]);
+          }
         }
       }
     } else if (p.softmax == 0) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        if (n0 + c * 16 >= p.N) break;
-        float v[16];
-        load_chunk(c, v);
+      for (int g = g0; g < g1; ++g) {
+        const int col0 = n0 + g * 32;
+        if (col0 >= p.N) break;
+        const bool full = vec && col0 + 32 <= p.N;
+        float v[32];
+        load_acc(g, v, alpha_q, alpha);
+        if (full) stages_full(col0, v); else stages_edge(col0, v);
         if (p.absmax) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (rv && n0 + c * 16 + e < p.N) amax = fmaxf(amax, fabsf(v[e]));
+          for (int e = 0; e < 32; ++e)
+            if (rv && col0 + e < p.N) amax = fmaxf(amax, fabsf(v[e]));
         }
-        store_chunk(c, v);
+        if (rv) {
+          if (full) store_full(col0, v); else store_edge(col0, v);
+        }
       }
     } else if (p.softmax == 1) {
-      // row softmax over the N columns of this tile (host guarantees one column tile)
-      const int nch = cdiv(p.N, 16);
+      // row softmax over the N columns of this tile (one column tile; value = alpha * acc): exponent in the log2 domain
+      const float al2 = alpha * kLog2e;
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        float v[16];
-        load_chunk(c, v);
+      for (int g = g0; g < g1; ++g) {
+        if (g * 32 >= p.N) break;
+        float v[32];
+        load_acc(g, v, al2, al2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (c * 16 + e < p.N) mx = fmaxf(mx, v[e]);
+        for (int e = 0; e < 32; ++e)
+          if (g * 32 + e < p.N) mx = fmaxf(mx, v[e]);
       }
+      mx = exchange(mx, true);
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        float v[16];
-        load_chunk(c, v);
+      for (int g = g0; g < g1; ++g) {
+        if (g * 32 >= p.N) break;
+        float v[32];
+        load_acc(g, v, al2, al2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (c * 16 + e < p.N) sum += __expf(v[e] - mx);
+        for (int e = 0; e < 32; ++e)
+          if (g * 32 + e < p.N) sum += ex2(v[e] - mx);
       }
+      sum = exchange(sum, false);
       const float inv = 1.0f / sum;
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        float v[16];
-        load_chunk(c, v);
+      for (int g = g0; g < g1; ++g) {
+        const int col0 = g * 32;
+        if (col0 >= p.N) break;
+        float v[32];
+        load_acc(g, v, al2, al2);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = __expf(v[e] - mx) * inv;
-        store_chunk(c, v);
+        for (int e = 0; e < 32; ++e) v[e] = ex2(v[e] - mx) * inv;
+        if (rv) {
+          if (vec && col0 + 32 <= p.N) store_full(col0, v); else store_edge(col0, v);
+        }
       }
     } else {
-      // softmax backward: C = dA (this product), aux = A (pair): dS = A * (dA - sum_j dA_j A_j)
-      const int nch = cdiv(p.N, 16);
+      // softmax backward: value = alpha * acc = dA, aux = A (pair): dS = A * (dA - sum_j dA_j A_j)
       float dot = 0.f;
-      auto load_aux = [&](int c, float (&a)[16]) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int col = c * 16 + e;
-          a[e] = (rv && col < p.N) ? __bfloat162float(xp[col]) + __bfloat162float(xp[p.x_plane + col]) : 0.f;
-        }
-      };
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        float v[16], a[16];
-        load_chunk(c, v);
-        load_aux(c, a);
+      for (int g = g0; g < g1; ++g) {
+        const int col0 = g * 32;
+        if (col0 >= p.N) break;
+        float v[32], a[32];
+        load_acc(g, v, alpha, alpha);
+        load_aux(col0, vec && col0 + 32 <= p.N, a);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dot = fmaf(v[e], a[e], dot);
+        for (int e = 0; e < 32; ++e) dot = fmaf(v[e], a[e], dot);      // aux is zero beyond N
       }
+      dot = exchange(dot, false);
 #pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        float v[16], a[16];
-        load_chunk(c, v);
-        load_aux(c, a);
+      for (int g = g0; g < g1; ++g) {
+        const int col0 = g * 32;
+        if (col0 >= p.N) break;
+        const bool full = vec && col0 + 32 <= p.N;
+        float v[32], a[32];
+        load_acc(g, v, alpha, alpha);
+        load_aux(col0, full, a);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = a[e] * (v[e] - dot);
-        store_chunk(c, v);
+        for (int e = 0; e < 32; ++e) v[e] = a[e] * (v[e] - dot);
+        if (rv) {
+          if (full) store_full(col0, v); else store_edge(col0, v);
+        }
       }
     }
     if (p.absmax) {
@@ -362,7 +453,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
   }
@@ -477,6 +568,7 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   if (a->accumulate && !a->c) return DML_EINVAL;
   if (softmax == 2 && !a->aux) return DML_EINVAL;
   if (softmax && a->N > 256) return DML_EUNSUPPORTED;
+  if (softmax && (a->bias || a->resid || a->accumulate || a->relu || a->use_diag || a->ncol_split > 0 || a->absmax)) return DML_EINVAL;
   if (a->pair && ((a->ldp % 8) || (a->p_plane % 8) || (((uintptr_t)a->pair) & 15))) return DML_EINVAL;
   const int BN = softmax ? (a->N > 128 ? 256 : (a->N > 64 ? 128 : 64)) : (a->N > 64 ? 128 : 64);
   CUtensorMap ma, mb;
@@ -500,6 +592,17 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   p.half_out = (h16*)a->half_out; p.ldh = a->ldh; p.h_bi = a->h_bs_inner; p.h_bo = a->h_bs_outer; p.half_scale_dev = a->half_scale_dev;
   p.absmax = (uint32_t*)a->absmax;
   p.softmax = softmax;
+  {
+    auto al16 = [](const void* q) { return (((uintptr_t)q) & 15) == 0; };
+    bool ok = true;
+    if (a->c) ok = ok && al16(a->c) && (a->ldc % 4) == 0 && (a->c_bs_inner % 4) == 0 && (a->c_bs_outer % 4) == 0;
+    if (a->resid) ok = ok && al16(a->resid) && (a->ldr % 4) == 0 && (a->r_bs_inner % 4) == 0 && (a->r_bs_outer % 4) == 0;
+    if (a->bias) ok = ok && al16(a->bias) && (a->bias_bs_inner % 4) == 0 && (a->bias_bs_outer % 4) == 0;
+    if (a->pair) ok = ok && (a->p_bs_inner % 8) == 0 && (a->p_bs_outer % 8) == 0;
+    if (a->half_out) ok = ok && al16(a->half_out) && (a->ldh % 8) == 0 && (a->h_bs_inner % 8) == 0 && (a->h_bs_outer % 8) == 0;
+    if (a->aux) ok = ok && al16(a->aux) && (a->ldx % 8) == 0 && (a->x_plane % 8) == 0 && (a->x_bs_inner % 8) == 0 && (a->x_bs_outer % 8) == 0;
+    p.vec_ok = ok ? 1 : 0;
+  }
   p.aux = (const bf16*)a->aux; p.ldx = a->ldx; p.x_bi = a->x_bs_inner; p.x_bo = a->x_bs_outer; p.x_plane = a->x_plane;
   const long long nz = (long long)a->nb_inner * a->nb_outer * splits;
   if (nz > 65535) return DML_EUNSUPPORTED;
