@@ -20,7 +20,8 @@
 //     and / or fp16 (the operand type of the fused attention kernels), plus an optional |C| maximum;
 //   * split-K (fp32 reductions into a zeroed C) for the token-reduction products (weight gradients, attn3 @ v).
 //
-// CTA = one 128 x BN tile (BN = 64 / 128 / 256); warp 4 = TMA producer (ring of {A planes, B planes} 64-wide k-blocks,
+// Persistent CTAs (one per SM) walk the 128 x BN output tiles (BN = 64 / 128 / 256) with two TMEM accumulator buffers, so the
+// epilogue of a tile overlaps the loads and MMAs of the next; warp 8 = TMA producer (ring of {A planes, B planes} 64-wide k-blocks,
 // 128-byte swizzle), warp 9 = MMA issuer + TMEM owner, warps 0-7 = epilogue (a row's columns are split between two threads,
 // 32-column groups, vector loads / stores; one CTA per SM, so the epilogue's own parallelism is what hides its latencies).
 #include <math.h>
@@ -41,7 +42,9 @@ struct Cfg {
   static constexpr uint32_t kTileB = BN * kBK * 2;
   static constexpr uint32_t kStageBytes = 2 * kTileA + 2 * kTileB;
   static constexpr uint32_t kOffBar = kStages * kStageBytes;
-  static constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAcc = 2 * kStages, kNumBars = 2 * kStages + 1;
+  static constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAccFull = 2 * kStages, kBarAccEmpty = 2 * kStages + 2,
+                       kNumBars = 2 * kStages + 4;
+  static constexpr uint32_t kTmemCols = 2 * BN;                  // two accumulator buffers
   static constexpr uint32_t kOffTmemPtr = kOffBar + kNumBars * 8;
   static constexpr uint32_t kOffXch = kOffTmemPtr + 16;          // float[2][128]
   static constexpr uint32_t kSmemBytes = kOffXch + 1024 + 1024;
@@ -69,6 +72,7 @@ struct Params {
   uint32_t* absmax;
   int softmax;
   const bf16* aux; int ldx; long long x_bi, x_bo, x_plane;
+  int tiles_m, tiles_n, total_tiles;
   int vec_ok;      // every output / side tensor allows 16-byte accesses at 4- (fp32) / 8- (16-bit) element column granularity
 };
 
@@ -95,23 +99,32 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
-  const int split = blockIdx.z % p.splits, batch = blockIdx.z / p.splits;
-  const int bi = batch % p.nb_inner, bo = batch / p.nb_inner;
   const int nk_all = cdiv(p.K, kBK);
   const int kb_per = cdiv(nk_all, p.splits);
-  const int kb0 = split * kb_per, kb1 = min(nk_all, kb0 + kb_per);
-  const int nk = max(kb1 - kb0, 0);
+  // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tile index = (z * tiles_n + n_tile) * tiles_m + m_tile, so
+  // the CTAs running at the same time share the B tile.  Two TMEM accumulator buffers: the MMAs of tile i + 1 run while the
+  // epilogue warps drain tile i.
+  struct Tile { int m0, n0, bi, bo, kb0, nk; };
+  auto decode = [&](int t) {
+    Tile T;
+    const int mt = t % p.tiles_m, r = t / p.tiles_m;
+    const int nt = r % p.tiles_n, z = r / p.tiles_n;
+    const int split = z % p.splits, batch = z / p.splits;
+    T.m0 = mt * kBM; T.n0 = nt * BN; T.bi = batch % p.nb_inner; T.bo = batch / p.nb_inner;
+    T.kb0 = split * kb_per;
+    T.nk = max(min(nk_all, T.kb0 + kb_per) - T.kb0, 0);
+    return T;
+  };
   auto bar = [&](int i) { return sbase + C::kOffBar + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + C::kOffTmemPtr);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(C::kBarFull + s), 1); mbar_init(bar(C::kBarEmpty + s), 1); }
-    mbar_init(bar(C::kBarAcc), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(C::kBarAccFull + b), 1); mbar_init(bar(C::kBarAccEmpty + b), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(C::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -123,31 +136,36 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     // ---- TMA producer ----
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)p.a_planes * kTileA + (uint32_t)p.b_planes * C::kTileB;
-      const int abi = p.a_bi ? bi : 0, abo = p.a_bo ? bo : 0, bbi = p.b_bi ? bi : 0, bbo = p.b_bo ? bo : 0;
-      for (int kb = 0; kb < nk; ++kb) {
-        const int st = kb % kStages;
-        mbar_wait(bar(C::kBarEmpty + st), ((kb / kStages) & 1) ^ 1);
-        const uint32_t dst = sbase + st * C::kStageBytes;
-        const uint32_t fb = bar(C::kBarFull + st);
-        mbar_expect_tx(fb, bytes);
-        const int k0 = (kb0 + kb) * kBK;
-        for (int pl = 0; pl < p.a_planes; ++pl) {
-          const uint32_t d = dst + pl * kTileA;
-          if (p.a_layout == 0) {
-            tma_load_5d(d, &ma, fb, k0 + p.a_k_off, m0 + p.a_row_off, abi, abo, pl);
-          } else {
-            tma_load_5d(d, &ma, fb, m0 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
-            tma_load_5d(d + 8192, &ma, fb, m0 + 64 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+      int it = 0;                                       // k-blocks issued so far (the ring runs across tiles)
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const Tile T = decode(t);
+        const int m0 = T.m0, n0 = T.n0;
+        const int abi = p.a_bi ? T.bi : 0, abo = p.a_bo ? T.bo : 0, bbi = p.b_bi ? T.bi : 0, bbo = p.b_bo ? T.bo : 0;
+        for (int kb = 0; kb < T.nk; ++kb, ++it) {
+          const int st = it % kStages;
+          mbar_wait(bar(C::kBarEmpty + st), ((it / kStages) & 1) ^ 1);
+          const uint32_t dst = sbase + st * C::kStageBytes;
+          const uint32_t fb = bar(C::kBarFull + st);
+          mbar_expect_tx(fb, bytes);
+          const int k0 = (T.kb0 + kb) * kBK;
+          for (int pl = 0; pl < p.a_planes; ++pl) {
+            const uint32_t d = dst + pl * kTileA;
+            if (p.a_layout == 0) {
+              tma_load_5d(d, &ma, fb, k0 + p.a_k_off, m0 + p.a_row_off, abi, abo, pl);
+            } else {
+              tma_load_5d(d, &ma, fb, m0 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+              tma_load_5d(d + 8192, &ma, fb, m0 + 64 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+            }
           }
-        }
-        for (int pl = 0; pl < p.b_planes; ++pl) {
-          const uint32_t d = dst + 2 * kTileA + pl * C::kTileB;
-          if (p.b_layout == 0) {
-            tma_load_5d(d, &mb, fb, k0 + p.b_k_off, n0 + p.b_row_off, bbi, bbo, pl);
-          } else {
+          for (int pl = 0; pl < p.b_planes; ++pl) {
+            const uint32_t d = dst + 2 * kTileA + pl * C::kTileB;
+            if (p.b_layout == 0) {
+              tma_load_5d(d, &mb, fb, k0 + p.b_k_off, n0 + p.b_row_off, bbi, bbo, pl);
+            } else {
 #pragma unroll
-            for (int s = 0; s < BN / 64; ++s)
-              tma_load_5d(d + s * 8192, &mb, fb, n0 + 64 * s + p.b_row_off, k0 + p.b_k_off, bbi, bbo, pl);
+              for (int s = 0; s < BN / 64; ++s)
+                tma_load_5d(d + s * 8192, &mb, fb, n0 + 64 * s + p.b_row_off, k0 + p.b_k_off, bbi, bbo, pl);
+            }
           }
         }
       }
@@ -157,27 +175,40 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     const bool leader = elect_one();
     const uint32_t idesc = idesc_bf16(128, BN, p.a_layout != 0, p.b_layout != 0);
     const uint32_t ka = p.a_layout ? 128u : 2u, kbs = p.b_layout ? 128u : 2u;   // descriptor advance per 16 k (16-byte units)
-    for (int kb = 0; kb < nk; ++kb) {
-      const int st = kb % kStages;
-      mbar_wait(bar(C::kBarFull + st), (kb / kStages) & 1);
+    int it = 0, ti = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+      const Tile T = decode(t);
+      const int buf = ti & 1;
+      mbar_wait(bar(C::kBarAccEmpty + buf), ((ti >> 1) & 1) ^ 1);        // the epilogue has drained this buffer
       tc_fence_after();
-      const uint32_t base = sbase + st * C::kStageBytes;
-      const uint64_t a0 = p.a_layout ? desc_mn(base) : smem_desc(base);
-      const uint64_t a1 = p.a_layout ? desc_mn(base + kTileA) : smem_desc(base + kTileA);
-      const uint64_t b0 = p.b_layout ? desc_mn(base + 2 * kTileA) : smem_desc(base + 2 * kTileA);
-      const uint64_t b1 = p.b_layout ? desc_mn(base + 2 * kTileA + C::kTileB) : smem_desc(base + 2 * kTileA + C::kTileB);
+      const uint32_t acc = tmem + buf * BN;
+      for (int kb = 0; kb < T.nk; ++kb, ++it) {
+        const int st = it % kStages;
+        mbar_wait(bar(C::kBarFull + st), (it / kStages) & 1);
+        tc_fence_after();
+        const uint32_t base = sbase + st * C::kStageBytes;
+        const uint64_t a0 = p.a_layout ? desc_mn(base) : smem_desc(base);
+        const uint64_t a1 = p.a_layout ? desc_mn(base + kTileA) : smem_desc(base + kTileA);
+        const uint64_t b0 = p.b_layout ? desc_mn(base + 2 * kTileA) : smem_desc(base + 2 * kTileA);
+        const uint64_t b1 = p.b_layout ? desc_mn(base + 2 * kTileA + C::kTileB) : smem_desc(base + 2 * kTileA + C::kTileB);
 #pragma unroll
-      for (int k = 0; k < kBK / 16; ++k) {
-        mma_ss(tmem, a0 + ka * k, b0 + kbs * k, idesc, (kb > 0) || (k > 0), leader);
-        if (p.b_planes > 1) mma_ss(tmem, a0 + ka * k, b1 + kbs * k, idesc, 1, leader);
-        if (p.a_planes > 1) mma_ss(tmem, a1 + ka * k, b0 + kbs * k, idesc, 1, leader);
+        for (int k = 0; k < kBK / 16; ++k) {
+          mma_ss(acc, a0 + ka * k, b0 + kbs * k, idesc, (kb > 0) || (k > 0), leader);
+          if (p.b_planes > 1) mma_ss(acc, a0 + ka * k, b1 + kbs * k, idesc, 1, leader);
+          if (p.a_planes > 1) mma_ss(acc, a1 + ka * k, b0 + kbs * k, idesc, 1, leader);
+        }
+        tc_commit(bar(C::kBarEmpty + st), leader);
       }
-      tc_commit(bar(C::kBarEmpty + st), leader);
+      tc_commit(bar(C::kBarAccFull + buf), leader);
     }
-    tc_commit(bar(C::kBarAcc), leader);
   } else {
     // ---- epilogue: 8 warps; TMEM lane = output row, the row's columns split between two threads (warps w and w + 4) ----
     const int quarter = warp & 3, half = warp >> 2;
+    int ti = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+    const Tile T = decode(t);
+    const int m0 = T.m0, n0 = T.n0, bi = T.bi, bo = T.bo, nk = T.nk;
+    const int buf = ti & 1;
     const int row = m0 + quarter * 32 + lane;
     const bool rv = row < p.M;
     float alpha = p.alpha;
@@ -191,12 +222,10 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     h16* hp = p.half_out ? p.half_out + (size_t)bo * p.h_bo + (size_t)bi * p.h_bi + rowl * p.ldh : nullptr;
     const bf16* xp = p.aux ? p.aux + (size_t)bo * p.x_bo + (size_t)bi * p.x_bi + rowl * p.ldx : nullptr;
     const float hscale = (p.half_out && p.half_scale_dev) ? __ldg(p.half_scale_dev) : 1.0f;
-    const uint32_t tb = tmem + (((uint32_t)quarter * 32u) << 16);
+    const uint32_t tb = tmem + buf * BN + (((uint32_t)quarter * 32u) << 16);
     float* xch = reinterpret_cast<float*>(sgen + C::kOffXch);          // [2 halves][128 rows] exchange of row statistics
-    if (nk > 0) {
-      mbar_wait(bar(C::kBarAcc), 0);
-      tc_fence_after();
-    }
+    mbar_wait(bar(C::kBarAccFull + buf), (ti >> 1) & 1);
+    tc_fence_after();
     // this thread's column groups (32 wide): [g0, g1) of the tile
     constexpr int kGroups = BN / 32;
     const int g0 = half * (kGroups / 2), g1 = g0 + kGroups / 2;
@@ -449,13 +478,18 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
       amax = warp_max(amax);
       if (lane == 0 && amax > 0.f) atomicMax(p.absmax, __float_as_uint(amax));
     }
+    // this warp's TMEM reads of the tile are complete (every tcgen05.ld above was waited for): hand the buffer back
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(C::kBarAccEmpty + buf));
+    }   // tiles
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::kTmemCols));
   }
 }
 
@@ -605,9 +639,15 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   }
   p.aux = (const bf16*)a->aux; p.ldx = a->ldx; p.x_bi = a->x_bs_inner; p.x_bo = a->x_bs_outer; p.x_plane = a->x_plane;
   const long long nz = (long long)a->nb_inner * a->nb_outer * splits;
-  if (nz > 65535) return DML_EUNSUPPORTED;
-  dim3 grid(cdiv(a->M, kBM), cdiv(a->N, BN), (unsigned)nz);
-  if (grid.y > 65535) return DML_EUNSUPPORTED;
+  p.tiles_m = cdiv(a->M, kBM);
+  p.tiles_n = cdiv(a->N, BN);
+  const long long total = (long long)p.tiles_m * p.tiles_n * nz;
+  if (total > 0x7fffffffLL) return DML_EUNSUPPORTED;
+  p.total_tiles = (int)total;
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
+    nsm = 148;
+  dim3 grid((unsigned)min((long long)nsm, total));
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (BN == 64) {
