@@ -26,14 +26,11 @@ class FusionNet(nn.Module):
     def forward(self, gene_features, image_features):
         W, b = self.fusion_layer.weight, self.fusion_layer.bias
         fd = self.feature_dim
-        if image_features.dim() == gene_features.dim() - 1:      # per-bag vector [B, dim], broadcast over tokens
-            second = (F.linear(image_features, W[:, fd:]) + b)[:, None, :]
-        else:
-            second = F.linear(image_features, W[:, fd:]) + b
-        first = ops.mm_tf32(gene_features, W[:, :fd].t())
-        if second.dim() == first.dim() and second.shape[-2] == 1 and first.is_cuda:
-            return ops.AddRowBiasFn.apply(first, second)      # bias / omic gradient = one GEMV instead of a column reduction
-        return first + second
+        if image_features.dim() == gene_features.dim() - 1:
+            # per-bag vector [B, dim], broadcast over the tokens: the epilogue bias of the path-half GEMM
+            vec = F.linear(image_features, W[:, fd:]) + b
+            return ops.FusionFn.apply(gene_features.float(), W[:, :fd], vec)
+        return ops.linear_pg(torch.cat((gene_features, image_features), dim=-1), W, b)      # token-level second input
 
 
 class DeformCrossTransLayer(nn.Module):
@@ -46,12 +43,8 @@ class DeformCrossTransLayer(nn.Module):
 
     def forward(self, x1, x2, attn_dim, return_vgrid, rows=None):
         if attn_dim == 1:
-            # one LayerNorm shared by both streams (reference :44,66)
-            x = self.attn1d(ops.layer_norm(x1, self.norm).transpose(1, 2), ops.layer_norm(x2, self.norm).transpose(1, 2),
-                            rows=rows)
-            if rows:
-                return x1[:, :rows] + x.transpose(1, 2)
-            return x1 + x.transpose(1, 2)
+            # one LayerNorm shared by both streams (reference :44,66) and the residual (:67), both inside the fused function
+            return self.attn1d(x1.transpose(1, 2), x2.transpose(1, 2), rows=rows, _norm=self.norm).transpose(1, 2)
         raise NotImplementedError("attn_dim == 2 is broken in the reference as shipped (SURVEY.md Q6) and "
                                   "DeformCrossAttention2D is not built yet (row N1)")
 
@@ -86,11 +79,8 @@ class DeformCrossTransMIL(nn.Module):
         if getattr(self.args, "return_vgrid", False):
             raise NotImplementedError("return_vgrid with attn_dim == 1 raises in the reference (SURVEY.md Q6)")
         fc1 = self._fc1[0]
-        if path.dtype == torch.bfloat16:      # bf16 bags: fc1 on the bf16 tensor-core path (fp32 accumulate/output)
-            B_, N_, K_ = path.shape
-            path = ops.fc1_bf16_bag(path.reshape(B_ * N_, K_), fc1.weight, fc1.bias).reshape(B_, N_, -1)
-        else:
-            path = F.relu(ops.mm_tf32(path.float(), fc1.weight.t()) + fc1.bias)
+        # fc1 + ReLU (:100) on the pair GEMM, bias and ReLU in its epilogue; a bf16 bag enters as it is (one exact plane)
+        path = ops.linear_pg(path, fc1.weight, fc1.bias, relu=True)
         ready = getattr(omic, "_dml_ready", None)      # omic vector produced on another stream (model._omic_ahead)
         if ready is not None:
             torch.cuda.current_stream().wait_event(ready)

@@ -104,11 +104,13 @@ class DeformCrossAttention1D(nn.Module):
             unsupported.append("more than 2 heads per offset group")
         self._unsupported = unsupported
 
-    def forward(self, x1, x2, return_vgrid=False, rows=None):
+    def forward(self, x1, x2, return_vgrid=False, rows=None, _norm=None):
         """x1, x2: [b, dim, n] channel-first (reference layout).  Returns [b, dim, n] (+ vgrid [(b g), n_kv]).
         rows (extension, default None = the reference contract): compute the attention output only for the first
         `rows` query tokens -> [b, dim, rows]; offsets, keys and values still see every token, so those rows and
-        every gradient are identical to the full call followed by a slice."""
+        every gradient are identical to the full call followed by a slice.
+        _norm (extension used by DeformCrossTransLayer): an nn.LayerNorm; x1 / x2 are then the layer's UN-normalised token
+        streams, the norm and the layer's residual x1 + attn are applied inside the fused function."""
         if self._unsupported:
             raise NotImplementedError("dml_b200 DeformCrossAttention1D: " + "; ".join(self._unsupported))
         if self.training and self.dropout.p > 0:
@@ -116,12 +118,13 @@ class DeformCrossAttention1D(nn.Module):
                                       "(the reference never sets it for the 1-D layer)")
         mlp = self.rel_pos_bias.mlp
         cfg = (self.heads, self.dim_head, self.offset_groups, self.downsample_factor, self.offset_kernel_size,
-               float(self.offset_scale), int(rows or 0))
+               float(self.offset_scale), int(rows or 0), float(_norm.eps) if _norm is not None else 0.0)
         out_t, vgrid = ops.DeformCrossAttn1DFn.apply(
             x1.transpose(1, 2), x2.transpose(1, 2),
             self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_out.weight, self.to_out.bias,
             self.to_offsets[0].weight, self.to_offsets[0].bias, self.to_offsets[2].weight,
-            mlp[0][0].weight, mlp[0][0].bias, mlp[1][0].weight, mlp[1][0].bias, mlp[2].weight, mlp[2].bias, cfg)
+            mlp[0][0].weight, mlp[0][0].bias, mlp[1][0].weight, mlp[1][0].bias, mlp[2].weight, mlp[2].bias,
+            _norm.weight if _norm is not None else None, _norm.bias if _norm is not None else None, cfg)
         out = out_t.transpose(1, 2)
         if return_vgrid:
             return out, vgrid

@@ -29,6 +29,7 @@ SIGNATURES = {
     "dml_offsets_kv_len": (_i, [_i, _i, _i]),
     "dml_offsets_fwd": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp]),
     "dml_offsets_bwd": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp, _vp]),
+    "dml_offsets_bwd_pair": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp, _vp, _ll, _vp]),
     "dml_kv_gather_fwd": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dml_kv_gather_bwd": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _vp]),
     "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
@@ -44,6 +45,7 @@ SIGNATURES = {
     "dml_pgemm": (_i, [C.c_void_p, _vp]),
     "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
     "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
+    "dml_relu_mask_pair": (_i, [_fp, _fp, _ll, _i, _i, _i, _vp, _i, _ll, _vp]),
     "dml_layernorm_fwd_pair": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _vp, _ll, _fp, _fp, _vp]),
     "dml_ny_landmark_pool": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _ll, _vp]),
     "dml_ny_softmax_rows_fwd": (_i, [_fp, _ll, _i, _vp, _ll, _vp]),
@@ -130,13 +132,14 @@ _ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace t
 
 # kernels launched per entry point (memsets not counted) - bench.py reports the total as gpu_launches
 KERNELS_PER_CALL = {
-    "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2,
+    "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2, "dml_offsets_bwd_pair": 2,
+    "dml_offsets_bwd_pair": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp, _vp, _ll, _vp]),
     "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
     "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
     "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1, "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1, "dml_split_f16": 2, "dml_gemm_nt_split": 1,
     "dml_pgemm": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
-    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1,
+    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events

@@ -253,82 +253,117 @@ dqkv_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ dl
 // PPEG (models/mil.py:192-206): y = x + conv7(x) + conv5(x) + conv3(x) on the side x side grid of tokens 1.., token 0 (cls)
 // passes through.  The three depthwise kernels are summed by the caller into one 7x7 weight wsum [C, 49] and one bias
 // bsum [C] (exact up to fp32 reassociation); flip = 1 applies the transposed stencil (the input gradient).
-// x, y: [B, 1 + side^2, C] token-major.  Thread = one channel of one pixel; a CTA covers an 4 x 8 pixel patch x 32 channels,
-// whose 10 x 14 neighbourhood stays in L1.
+// x, y: [B, 1 + side^2, C] token-major.  CTA = 32 channels x an 8 x 16 pixel tile; the (8 + 6) x (16 + 6) input halo is staged
+// in shared memory (a pixel's 32 channels = one coalesced 128-byte row, bank = channel: conflict free).  A thread owns one
+// channel and one 16-pixel output row: per input row it reads 22 values once and slides the 7 taps over them in registers
+// (9.6 shared loads per output instead of 49), weights in registers.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+constexpr int kPTH = 8, kPTW = 16, kPHW = kPTW + 6, kPHH = kPTH + 6;
+
+__device__ __forceinline__ void ppeg_stage_tile(const float* __restrict__ g, int side, int C, int c0, int y0, int x0, float* sm) {
+  // sm[(hy * kPHW + hx) * 32 + lane] = g[pixel (y0 - 3 + hy, x0 - 3 + hx), channel c0 + lane]  (zero outside the grid)
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int i = wp; i < kPHH * kPHW; i += 8) {
+    const int hy = i / kPHW, hx = i - hy * kPHW;
+    const int yy = y0 - 3 + hy, xx = x0 - 3 + hx;
+    float v = 0.f;
+    if (yy >= 0 && yy < side && xx >= 0 && xx < side && c0 + lane < C) v = g[((size_t)yy * side + xx) * C + c0 + lane];
+    sm[i * 32 + lane] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
 ppeg_stencil_kernel(const float* __restrict__ x, const float* __restrict__ wsum, const float* __restrict__ bsum, int side, int C,
                     int flip, float* __restrict__ y) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int pl = threadIdx.x >> 5;                      // 0..31: pixel inside the 4 x 8 patch
-  const int tiles_x = cdiv(side, 8);
+  __shared__ float sm[kPHH * kPHW * 32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, c = c0 + lane;
+  const int tiles_x = cdiv(side, kPTW);
   const int ty = blockIdx.y / tiles_x, tx = blockIdx.y % tiles_x;
-  const int py = ty * 4 + (pl >> 3), px = tx * 8 + (pl & 7);
+  const int y0 = ty * kPTH, x0 = tx * kPTW;
   const int b = blockIdx.z;
   const size_t base = (size_t)b * ((size_t)side * side + 1) * C;
-  if (blockIdx.y == 0 && pl == 0 && c < C) y[base + c] = x[base + c];          // cls token
-  if (c >= C || py >= side || px >= side) return;
-  const float* xg = x + base + C;                     // pixel grid
-  float acc = xg[((size_t)py * side + px) * C + c] + (flip ? 0.f : __ldg(bsum + c));
-  const float* wc = wsum + (size_t)c * 49;
+  if (blockIdx.y == 0 && wp == 0 && c < C) y[base + c] = x[base + c];          // cls token
+  ppeg_stage_tile(x + base + C, side, C, c0, y0, x0, sm);
+  float w[49];
 #pragma unroll
-  for (int dy = -3; dy <= 3; ++dy) {
-    const int yy = py + dy;
-    if (yy < 0 || yy >= side) continue;
+  for (int t = 0; t < 49; ++t) w[t] = c < C ? __ldg(wsum + (size_t)c * 49 + (flip ? 48 - t : t)) : 0.f;
+  const float bias = (c < C && !flip) ? __ldg(bsum + c) : 0.f;
+  __syncthreads();
+  const int oy = y0 + wp;                               // this warp's output row
+  float acc[kPTW];
 #pragma unroll
-    for (int dx = -3; dx <= 3; ++dx) {
-      const int xx = px + dx;
-      if (xx < 0 || xx >= side) continue;
-      const int tap = flip ? (3 - dy) * 7 + (3 - dx) : (dy + 3) * 7 + (dx + 3);
-      acc = fmaf(__ldg(wc + tap), xg[((size_t)yy * side + xx) * C + c], acc);
-    }
+  for (int j = 0; j < kPTW; ++j) acc[j] = sm[((wp + 3) * kPHW + j + 3) * 32 + lane] + bias;      // identity term
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    float in[kPHW];
+#pragma unroll
+    for (int j = 0; j < kPHW; ++j) in[j] = sm[((wp + dy) * kPHW + j) * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < kPTW; ++j)
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx) acc[j] = fmaf(w[dy * 7 + dx], in[j + dx], acc[j]);
   }
-  y[base + C + ((size_t)py * side + px) * C + c] = acc;
+  if (c < C && oy < side) {
+    float* yo = y + base + C + ((size_t)oy * side + x0) * C + c;
+#pragma unroll
+    for (int j = 0; j < kPTW; ++j)
+      if (x0 + j < side) yo[(size_t)j * C] = acc[j];
+  }
 }
 
 // weight / bias gradients of the summed stencil: dw[c, tap] = sum_p dy[p, c] x[p + off(tap), c], db[c] = sum_p dy[p, c].
-// grid (C / 32, pixel chunks, B); a thread owns one channel and walks the chunk's pixels with 50 register accumulators.
-__global__ void __launch_bounds__(128)
-ppeg_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int side, int C, int chunk, float* __restrict__ dw,
+// Same tiling; a CTA walks several pixel tiles (grid.y chunks) with its 49 + 1 sums in registers and flushes them once.
+__global__ void __launch_bounds__(256)
+ppeg_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int side, int C, int tiles_per_cta, float* __restrict__ dw,
                   float* __restrict__ db) {
-  __shared__ float red[4][32][51];
+  __shared__ float sm[kPHH * kPHW * 32];
+  __shared__ float red[50][33];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane, b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, c = c0 + lane;
+  const int tiles_x = cdiv(side, kPTW), ntiles = tiles_x * cdiv(side, kPTH);
+  const int b = blockIdx.z;
   const size_t base = (size_t)b * ((size_t)side * side + 1) * C + C;
-  const int npix = side * side;
-  const int p0 = blockIdx.y * chunk, p1 = min(npix, p0 + chunk);
   float acc[50];
 #pragma unroll
   for (int t = 0; t < 50; ++t) acc[t] = 0.f;
-  if (c < C) {
-    for (int p = p0 + wp; p < p1; p += 4) {
-      const int py = p / side, px = p - py * side;
-      const float g = dy[base + (size_t)p * C + c];
-      acc[49] += g;
+  const int t0 = blockIdx.y * tiles_per_cta, t1 = min(ntiles, t0 + tiles_per_cta);
+  for (int tile = t0; tile < t1; ++tile) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int y0 = ty * kPTH, x0 = tx * kPTW;
+    __syncthreads();
+    ppeg_stage_tile(x + base, side, C, c0, y0, x0, sm);
+    __syncthreads();
+    const int oy = y0 + wp;
+    float g[kPTW];
 #pragma unroll
-      for (int dyy = -3; dyy <= 3; ++dyy) {
-        const int yy = py + dyy;
+    for (int j = 0; j < kPTW; ++j) {
+      g[j] = (c < C && oy < side && x0 + j < side) ? dy[base + ((size_t)oy * side + x0 + j) * C + c] : 0.f;
+      acc[49] += g[j];
+    }
 #pragma unroll
-        for (int dxx = -3; dxx <= 3; ++dxx) {
-          const int xx = px + dxx;
-          if (yy >= 0 && yy < side && xx >= 0 && xx < side)
-            acc[(dyy + 3) * 7 + dxx + 3] = fmaf(g, x[base + ((size_t)yy * side + xx) * C + c], acc[(dyy + 3) * 7 + dxx + 3]);
-        }
-      }
+    for (int d = 0; d < 7; ++d) {
+      float in[kPHW];
+#pragma unroll
+      for (int j = 0; j < kPHW; ++j) in[j] = sm[((wp + d) * kPHW + j) * 32 + lane];
+#pragma unroll
+      for (int dx = 0; dx < 7; ++dx)
+#pragma unroll
+        for (int j = 0; j < kPTW; ++j) acc[d * 7 + dx] = fmaf(g[j], in[j + dx], acc[d * 7 + dx]);
     }
   }
-#pragma unroll
-  for (int t = 0; t < 50; ++t) red[wp][lane][t] = acc[t];
+  // reduce over the CTA's 8 warps (output rows), then one atomic per (channel, tap)
+  for (int t = threadIdx.x; t < 50 * 33; t += blockDim.x) (&red[0][0])[t] = 0.f;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * 50; idx += blockDim.x) {
-    const int ln = idx / 50, t = idx % 50;
-    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s += red[k][ln][t];
-    const int cc = blockIdx.x * 32 + ln;
+  for (int t = 0; t < 50; ++t) atomicAdd(&red[t][lane], acc[t]);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 50 * 32; idx += blockDim.x) {
+    const int t = idx >> 5, ln = idx & 31;
+    const int cc = c0 + ln;
     if (cc < C) {
-      if (t < 49) atomicAdd(dw + (size_t)cc * 49 + t, s);
-      else atomicAdd(db + cc, s);
+      if (t < 49) atomicAdd(dw + (size_t)cc * 49 + t, red[t][ln]);
+      else atomicAdd(db + cc, red[t][ln]);
     }
   }
 }
@@ -422,9 +457,9 @@ int dml_ppeg_stencil(const float* x, const float* wsum, const float* bsum, int B
                      void* stream) {
   using namespace dml;
   DML_CHECK_ARG(x && wsum && bsum && y && B > 0 && side > 0 && C > 0);
-  dim3 grid(cdiv(C, 32), cdiv(side, 4) * cdiv(side, 8), B);
+  dim3 grid(cdiv(C, 32), cdiv(side, nyp::kPTH) * cdiv(side, nyp::kPTW), B);
   if (grid.y > 65535 || B > 65535) return DML_EUNSUPPORTED;
-  nyp::ppeg_stencil_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(x, wsum, bsum, side, C, flip, y);
+  nyp::ppeg_stencil_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, wsum, bsum, side, C, flip, y);
   DML_RETURN_LAUNCH();
 }
 
@@ -435,11 +470,11 @@ int dml_ppeg_wgrad(const float* x, const float* dy, int B, int side, int C, floa
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 49, st);
   if (e != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)C, st)) != cudaSuccess) return (int)e;
-  const int npix = side * side;
-  const int chunks = max(1, min(cdiv(npix, 64), 148 * 4 / cdiv(C, 32)));
-  const int chunk = cdiv(npix, chunks);
   if (B > 65535) return DML_EUNSUPPORTED;
-  nyp::ppeg_wgrad_kernel<<<dim3(cdiv(C, 32), cdiv(npix, chunk), B), 128, 0, st>>>(x, dy, side, C, chunk, dw, db);
+  const int ntiles = cdiv(side, nyp::kPTH) * cdiv(side, nyp::kPTW);
+  const int ctas_y = max(1, min(ntiles, 148 * 4 / max(1, cdiv(C, 32) * B)));
+  const int per = cdiv(ntiles, ctas_y);
+  nyp::ppeg_wgrad_kernel<<<dim3(cdiv(C, 32), cdiv(ntiles, per), B), 256, 0, st>>>(x, dy, side, C, per, dw, db);
   DML_RETURN_LAUNCH();
 }
 

@@ -176,7 +176,7 @@ offsets_bwd_kernel(const h16* __restrict__ q, const float* __restrict__ w0, cons
 __global__ void __launch_bounds__(256)
 offsets_dq_combine_kernel(const float* __restrict__ dq_attn, const float* __restrict__ dy,
                           const float* __restrict__ w0, int B, int n, int C, int G, int ks, int stride, int pad,
-                          int n_kv, float scale, float* __restrict__ dq) {
+                          int n_kv, float scale, float* __restrict__ dq, dml::bf16* __restrict__ dq_pair, long long plane) {
   // C / 4 threads per token (host guarantees that C / 4 divides the block size): the channel of a thread never changes,
   // tokens advance by whole blocks - no per-element divisions (they made the first version compute-bound: 30 us for a
   // 67 MB pass)
@@ -201,7 +201,8 @@ offsets_dq_combine_kernel(const float* __restrict__ dq_attn, const float* __rest
       r[2] = fmaf(d.z, __ldg(w0 + (cc + 2) * ks + t), r[2]);
       r[3] = fmaf(d.w, __ldg(w0 + (cc + 3) * ks + t), r[3]);
     }
-    *reinterpret_cast<float4*>(dq + i) = make_float4(r[0], r[1], r[2], r[3]);
+    if (dq) *reinterpret_cast<float4*>(dq + i) = make_float4(r[0], r[1], r[2], r[3]);
+    if (dq_pair) dml::store_pair4(dq_pair + i, dq_pair + plane + i, r[0], r[1], r[2], r[3]);     // operand of the dWq / dx1 GEMMs
   }
 }
 
@@ -327,7 +328,16 @@ int dml_offsets_fwd(const void* q, const float* w0, const float* b0, const float
 int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float* w2, const float* d_off,
                     const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
                     float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* stream) {
-  DML_CHECK_ARG(q && w0 && b0 && w2 && d_off && dq_attn && dy_ws && wgrad && dq_out && B > 0 && n > 0 && G > 0);
+  return dml_offsets_bwd_pair(q, w0, b0, w2, d_off, dq_attn, attn_scale, B, n, C, G, ksize, stride, offset_scale, dy_ws, wgrad,
+                              dq_out, nullptr, 0, stream);
+}
+
+int dml_offsets_bwd_pair(const void* q, const float* w0, const float* b0, const float* w2, const float* d_off,
+                         const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
+                         float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* dq_pair, long long plane_stride,
+                         void* stream) {
+  DML_CHECK_ARG(q && w0 && b0 && w2 && d_off && dq_attn && dy_ws && wgrad && (dq_out || dq_pair) && B > 0 && n > 0 && G > 0);
+  if (dq_pair && ((((uintptr_t)dq_pair) & 7) || (plane_stride & 3))) return DML_EINVAL;
   if (C != G * 128 || ksize > dml::kMaxTaps || ksize < stride || ((ksize - stride) & 1)) return DML_EUNSUPPORTED;
   const int pad = (ksize - stride) / 2, n_kv = dml_offsets_kv_len(n, ksize, stride);
   const int Cg = C / G;
@@ -342,7 +352,7 @@ int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float
   const size_t total4 = (size_t)B * n * C / 4;
   const int blocks2 = (int)min((total4 + 255) / 256, (size_t)148 * 16);
   dml::offsets_dq_combine_kernel<<<blocks2, 256, 0, st>>>(dq_attn, dy_ws, w0, B, n, C, G, ksize, stride, pad, n_kv,
-                                                         attn_scale, (float*)dq_out);
+                                                         attn_scale, (float*)dq_out, (dml::bf16*)dq_pair, plane_stride);
   DML_RETURN_LAUNCH();
 }
 

@@ -528,6 +528,24 @@ pair_from_f32_kernel(const float* __restrict__ x, long long rows, int cols, int 
   }
 }
 
+// ReLU backward fused with the pair conversion: g[r, c] := act[r, c] > 0 ? g[r, c] : 0 (written back in place) and as a bf16 pair
+__global__ void __launch_bounds__(256)
+relu_mask_pair_kernel(float* __restrict__ g, const float* __restrict__ act, long long rows, int cols, int ldg, int lda,
+                      bf16* __restrict__ out, int ldp, long long plane) {
+  const int cols4 = cols >> 2;
+  const long long total = rows * cols4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(g + r * ldg + c);
+    const float4 a = *reinterpret_cast<const float4*>(act + r * lda + c);
+    v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
+    *reinterpret_cast<float4*>(g + r * ldg + c) = v;
+    bf16* oh = out + r * ldp + c;
+    store_pair4(oh, oh + plane, v.x, v.y, v.z, v.w);
+  }
+}
+
 // column sums of a [rows, cols] fp32 matrix (bias gradients): 32 x 8 threads per CTA over row chunks, atomics into zeroed out
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, long long rows, int cols, int ld, float* __restrict__ out) {
@@ -671,6 +689,17 @@ int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mu
   const long long total = rows * ((cols + 3) / 4);
   const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
   tc::pg::pair_from_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, mult, (bf16*)pair, ldp, plane_stride);
+  DML_RETURN_LAUNCH();
+}
+
+int dml_relu_mask_pair(float* g, const float* act, long long rows, int cols, int ldg, int lda, void* pair, int ldp,
+                       long long plane_stride, void* stream) {
+  using namespace dml;
+  DML_CHECK_ARG(g && act && pair && rows > 0 && cols > 0 && (cols % 4) == 0 && (ldg % 4) == 0 && (lda % 4) == 0 && (ldp % 4) == 0);
+  DML_CHECK_ARG(((((uintptr_t)g) | ((uintptr_t)act)) & 15) == 0 && (((uintptr_t)pair) & 7) == 0 && (plane_stride % 4) == 0);
+  const long long total = rows * (cols / 4);
+  const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
+  tc::pg::relu_mask_pair_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, act, rows, cols, ldg, lda, (bf16*)pair, ldp, plane_stride);
   DML_RETURN_LAUNCH();
 }
 

@@ -152,17 +152,34 @@ def _proj_nt(x, W, out_shape=None):
     return c.reshape(out_shape)
 
 
-class DeformCrossAttn1DFn(torch.autograd.Function):
-    """Forward + backward of DeformCrossAttention1D (DeformableAttention1D.py:156-240) on
-    token-major inputs x1t, x2t [B, n, dim] (fp32).  Returns (out [B, n, dim] fp32, vgrid [(B G), n_kv]).
+def loss_scale_from_amax(amax_bits: torch.Tensor) -> torch.Tensor:
+    """Device-side power-of-two loss scale from the bit pattern of max|t| (the `absmax` output of dml_pgemm): float[2] =
+    (s, 1/s) with 4 < s * max|t| <= 8 (s = 1 for an all-zero tensor); no host synchronisation."""
+    amax = amax_bits.view(F32).reshape(())
+    s = torch.exp2(torch.floor(torch.log2(8.0 / amax.clamp_min(1e-30))).clamp(-60.0, 60.0))
+    s = torch.where(amax > 0, s, torch.ones_like(s))
+    return torch.stack([s, 1.0 / s]).contiguous()
 
-    Precision policy: activations and every projection stay fp32 (TF32 tensor-core GEMMs, fp32
-    accumulate); the attention core takes fp16 q/k/v (11-bit significand like TF32) and keeps the softmax
-    statistics, the position bias, the output and all accumulators in fp32."""
+
+class DeformCrossAttn1DFn(torch.autograd.Function):
+    """Forward + backward of DeformCrossAttention1D (DeformableAttention1D.py:156-240) on token-major inputs x1t, x2t
+    [B, n, dim] (fp32).  Returns (out [B, n, dim] fp32, vgrid [(B G), n_kv]).
+
+    Every projection (to_q, to_k | to_v, to_out, the input gradients and all weight gradients) runs on the bf16-pair tcgen05
+    GEMM (csrc/pgemm.cu: fp32-class, 16-bit operand pairs, fp32 accumulate) whose epilogue writes what the next kernel
+    reads: q / k / v leave it as fp16 (the operand type of the fused attention kernels), to_out adds bias and residual, the
+    dO product also returns max|dO| for the device-side loss scale.  The attention core keeps softmax statistics, the
+    position bias, the output and all accumulators in fp32.
+
+    ln_w / ln_b (extension used by DeformCrossTransLayer, None for the plain module call): x1t, x2t are then the
+    UN-normalised streams of the layer (DeformCrossTransMIL.py:62-68); the shared LayerNorm is applied inside - to every
+    row of x1t (written only as the to_q operand pair) and to the one or two centre rows of x2t that the degenerate gather
+    reads - and the layer's residual x1t + attn is the to_out epilogue."""
 
     @staticmethod
-    def forward(ctx, x1t, x2t, Wq, Wk, Wv, Wo, bo, w0, b0, w2, m_w1, m_b1, m_W2, m_b2, m_W3, m_b3, cfg):
-        H, d, G, stride, ks, offset_scale, rows = cfg
+    def forward(ctx, x1t, x2t, Wq, Wk, Wv, Wo, bo, w0, b0, w2, m_w1, m_b1, m_W2, m_b2, m_W3, m_b3, ln_w, ln_b, cfg):
+        from .pairs import Pair, pgemm
+        H, d, G, stride, ks, offset_scale, rows, ln_eps = cfg
         B, n, dim = x1t.shape
         C = H * d
         Cg = C // G
@@ -170,6 +187,7 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         hid = m_w1.shape[0]
         scale = d ** -0.5
         dev = x1t.device
+        fused = ln_w is not None
         n_out = n if not rows else min(int(rows), n)      # leading query rows whose attention output is computed
         n_kv = kv_length(n, ks, stride)
         if n_kv < 1:
@@ -178,10 +196,11 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
 
         x1f = x1t.to(F32).contiguous()
         x2f = x2t.to(F32).contiguous()
-        Wq2, Wk2, Wv2 = (W.reshape(C, dim).float() for W in (Wq, Wk, Wv))
-        Wo2 = Wo.reshape(dim, C).float()
         w0f, b0f, w2f = w0.reshape(Cg, ks).contiguous().float(), b0.contiguous().float(), w2.reshape(Cg).contiguous().float()
         mlp = [t.contiguous().float() for t in (m_w1.reshape(-1), m_b1, m_W2, m_b2, m_W3, m_b3)]
+        Wq_p = Pair.from_f32(Wq.reshape(C, dim))
+        Wkv_p = Pair.from_f32(torch.cat((Wk.reshape(C, dim), Wv.reshape(C, dim)), 0))
+        Wo_p = Pair.from_f32(Wo.reshape(dim, C))
 
         # the bias table only depends on the MLP weights: build it on the side stream, next to the projections
         table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
@@ -191,59 +210,91 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         with torch.cuda.stream(side):
             call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), stream())
 
-        # q/k/v feed the softmax exponent: fp32-class projections (fp16 hi/lo pairs on tcgen05, 22-bit operands - the
-        # SIMT sgemm they replace was 94 us per call), one fp16 rounding at the end
-        q = _proj_nt(x1f, Wq2).to(F16)                                    # [B,n,C] (to_q, :175)
+        i0, i1, wy0, wy1 = centre_taps(n)
+        if fused:
+            # shared LayerNorm: every row of x1 (as the to_q operand pair only), the centre rows of x2
+            lnw, lnb = ln_w.contiguous().float(), ln_b.contiguous().float()
+            x1p = Pair.empty((B, n, dim), dev)
+            mean1 = torch.empty(B * n, device=dev, dtype=F32)
+            rstd1 = torch.empty_like(mean1)
+            call("dml_layernorm_fwd_pair", ptr(x1f), ptr(lnw), ptr(lnb), B * n, dim, float(ln_eps), None, ptr(x1p.planes),
+                 x1p.planes.stride(0), ptr(mean1), ptr(rstd1), st)
+            crow = [i0] if wy1 == 0.0 else [i0, i1]
+            xc_in = x2f[:, crow].contiguous()                          # [B, k, dim]
+            kc = len(crow)
+            x2c = torch.empty_like(xc_in)
+            mean2 = torch.empty(B * kc, device=dev, dtype=F32)
+            rstd2 = torch.empty_like(mean2)
+            call("dml_layernorm_fwd", ptr(xc_in), ptr(lnw), ptr(lnb), B * kc, dim, float(ln_eps), ptr(x2c), ptr(mean2), ptr(rstd2), st)
+            gi0, gi1, gn = 0, kc - 1, kc
+        else:
+            lnw = mean1 = rstd1 = xc_in = mean2 = rstd2 = None
+            x1p = Pair.from_f32(x1f)
+            x2c, gi0, gi1, gn, crow = x2f, i0, i1, n, None
+
+        # to_q (:175): fp32-class product, one fp16 rounding in the epilogue (q feeds the softmax exponent)
+        q = torch.empty(B, n, C, device=dev, dtype=F16)
+        pgemm(x1p, Wq_p.b1(), M=n, N=C, K=dim, batch=(B,), want_f32=False, half_out=q)
         vgrid = torch.empty(B * G, n_kv, device=dev, dtype=F32)
         g = torch.empty_like(vgrid)
         call("dml_offsets_fwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), B, n, C, G, ks, stride, float(offset_scale),
              ptr(vgrid), ptr(g), st)
-        i0, i1, wy0, wy1 = centre_taps(n)
         kv = torch.empty(B, n_kv, dim, device=dev, dtype=F32)
-        call("dml_kv_gather_fwd", ptr(x2f), ptr(g), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(kv), st)
-        kv_split = SplitOperand(kv.reshape(1, B * n_kv, dim), True)
-        k = _proj_nt(kv_split, Wk2, (B, n_kv, C)).to(F16)                 # [B,n_kv,C] (:199)
-        v = _proj_nt(kv_split, Wv2, (B, n_kv, C)).to(F16)
+        call("dml_kv_gather_fwd", ptr(x2c), ptr(g), B, gn, dim, G, n_kv, gi0, gi1, wy0, wy1, ptr(kv), st)
+        kv_p = Pair.from_f32(kv)
+        kvh = torch.empty(B, n_kv, 2 * C, device=dev, dtype=F16)            # k | v (:199), one GEMM
+        pgemm(kv_p, Wkv_p.b1(), M=n_kv, N=2 * C, K=dim, batch=(B,), want_f32=False, half_out=kvh)
+        k, v = kvh[..., :C], kvh[..., C:]
         cur.wait_stream(side)                                             # bias table ready
         # offsets / keys / values always need every query position; the attention itself only the first n_out rows
         q_att = q if n_out == n else q[:, :n_out].contiguous()
         o = torch.empty(B, n_out, C, device=dev, dtype=F32)
         lse = torch.empty(B, H, n_out, device=dev, dtype=F32)
-        call("dml_deform_attn_fwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n_out, n_kv, n, C, C, C, C,
+        call("dml_deform_attn_fwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n_out, n_kv, n, C, 2 * C, 2 * C, C,
              nout, scale, ptr(o), ptr(lse), st)
-        with tf32_matmul():
-            out = torch.matmul(o, Wo2.t()) + bo                           # to_out (:233)
+        o_p = Pair.from_f32(o)
+        out, _ = pgemm(o_p, Wo_p.b1(), M=n_out, N=dim, K=C, batch=(B,), bias=bo.contiguous().float(),
+                       resid=x1f[:, :n_out] if fused else None)          # to_out (:233) [+ the layer's residual]
 
         ctx.cfg = cfg
-        ctx.taps = (i0, i1, wy0, wy1)
-        ctx.save_for_backward(x1f, x2f, q, q_att, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp)
+        ctx.taps = (i0, i1, wy0, wy1, gi0, gi1, gn, crow)
+        ctx.pairs = (x1p, kv_p, o_p, Wq_p, Wkv_p, Wo_p)
+        ctx.save_for_backward(x1f, x2c, q, q_att, kvh, g, table, o, lse, w0f, b0f, w2f, lnw, mean1, rstd1, xc_in, mean2, rstd2, *mlp)
+        ctx.x2_shape = tuple(x2f.shape)
         return out, vgrid
 
     @staticmethod
     def backward(ctx, dout, dvgrid):
-        (x1f, x2f, q, q_att, kv, k, v, g, table, o, lse, Wq2, Wk2, Wv2, Wo2, w0f, b0f, w2f, *mlp) = ctx.saved_tensors
-        H, d, G, stride, ks, offset_scale, _rows = ctx.cfg
+        from .pairs import Pair, pgemm
+        (x1f, x2c, q, q_att, kvh, g, table, o, lse, w0f, b0f, w2f, lnw, mean1, rstd1, xc_in, mean2, rstd2, *mlp) = ctx.saved_tensors
+        x1p, kv_p, o_p, Wq_p, Wkv_p, Wo_p = ctx.pairs
+        H, d, G, stride, ks, offset_scale, _rows, ln_eps = ctx.cfg
+        fused = lnw is not None
         n_out = o.shape[1]
-        i0, i1, wy0, wy1 = ctx.taps
+        i0, i1, wy0, wy1, gi0, gi1, gn, crow = ctx.taps
         B, n, dim = x1f.shape
         C, Cg, nout, hid = H * d, (H * d) // G, H // G, mlp[0].shape[0]
-        n_kv = kv.shape[1]
+        n_kv = kvh.shape[1]
+        k, v = kvh[..., :C], kvh[..., C:]
         scale = d ** -0.5
         dev = x1f.device
         st = stream()
 
         dout = dout.contiguous().float()
-        # dO feeds dS = P (dP - D) directly: fp32-class product, one fp16 rounding below
-        d_o = gemm_nt(SplitOperand(dout.reshape(1, -1, dim), True), SplitOperand(Wo2[None], False),
-                      (1, dout.shape[0] * dout.shape[1], C)).reshape(dout.shape[0], dout.shape[1], C)   # [B,n,C] fp32
+        dout_p = Pair.from_f32(dout)
+        # dO = dout Wo feeds dS = P (dP - D) directly: fp32-class product; its maximum (for the fp16 loss scale) is the epilogue's
+        amax = torch.zeros(1, device=dev, dtype=torch.int32)
+        d_o, _ = pgemm(dout_p, Wo_p.b1(), M=n_out, N=C, K=dim, batch=(B,), b_trans=True, absmax=amax)
         # weight gradients are leaves of this backward: they run on the auxiliary stream, next to the chain
         # dO -> attention backward -> offsets / gather backward -> input gradients, and join it at the end
         cur, side = torch.cuda.current_stream(), side_stream(dev)
         side.wait_stream(cur)
-        with torch.cuda.stream(side), tf32_matmul():
-            dWo = wgrad_mm(dout.reshape(-1, dim), o.reshape(-1, C))        # [dim, C]
-            dbo = colsum(dout.reshape(-1, dim))
-        dscale = grad_scale(d_o)
+        with torch.cuda.stream(side):
+            dWo = torch.empty(dim, C, device=dev, dtype=F32)
+            _wgrad_pg(dout_p, o_p, dWo, M=dim, N=C, K=n_out, B=B)
+            dbo = torch.empty(dim, device=dev, dtype=F32)
+            call("dml_colsum", ptr(dout), B * n_out, dim, dim, ptr(dbo), stream())
+        dscale = loss_scale_from_amax(amax)
         d_o16 = torch.empty(d_o.shape, device=dev, dtype=F16)
         torch.mul(d_o, dscale[0], out=d_o16)                               # scale and round in one pass
 
@@ -258,29 +309,43 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         ws_bytes = _lib.load().dml_deform_attn_bwd_ws_bytes(B, H, n_out, n_kv)
         ds_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if 0 < ws_bytes <= DS_WS_MAX_BYTES else None
         call("dml_deform_attn_bwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
-             n_out, n_kv, n, C, C, C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
+             n_out, n_kv, n, C, 2 * C, 2 * C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
              ptr(segsum), ptr(ds_ws) if ds_ws is not None else None, st)
         del ds_ws
         if n_out != n:                                 # the other query rows only receive the offset-path gradient
             full = torch.zeros(B, n, C, device=dev, dtype=F32)
             full[:, :n_out] = dq_attn
             dq_attn = full
+        dk_p, dv_p = Pair.from_f32(dk), Pair.from_f32(dv)
         side.wait_stream(cur)
-        with torch.cuda.stream(side), tf32_matmul():
+        with torch.cuda.stream(side):
             mlp_g = torch.empty(CPB_GRAD_FLOATS, device=dev, dtype=F32)
             call("dml_cpb_param_grad", *[ptr(t) for t in mlp], hid, nout, ptr(table), ptr(segsum), ptr(mlp_g), stream())
-            kvf = kv.reshape(-1, dim)
-            dWk = wgrad_mm(dk.reshape(-1, C), kvf)
-            dWv = wgrad_mm(dv.reshape(-1, C), kvf)
-        with tf32_matmul():
-            dkv = (dk @ Wk2 + dv @ Wv2).contiguous()                       # [B,n_kv,dim]
+            dWk = torch.empty(C, dim, device=dev, dtype=F32)
+            dWv = torch.empty(C, dim, device=dev, dtype=F32)
+            _wgrad_pg(dk_p, kv_p, dWk, M=C, N=dim, K=n_kv, B=B)
+            _wgrad_pg(dv_p, kv_p, dWv, M=C, N=dim, K=n_kv, B=B)
+        Wk_p, Wv_p = Pair(Wkv_p.planes[:, :C]), Pair(Wkv_p.planes[:, C:])
+        dkv, _ = pgemm(dk_p, Wk_p.b1(), M=n_kv, N=dim, K=C, batch=(B,), b_trans=True)           # [B, n_kv, dim]
+        pgemm(dv_p, Wv_p.b1(), M=n_kv, N=dim, K=C, batch=(B,), b_trans=True, out=dkv, accumulate=True)
         dcentre = torch.empty(B, dim, device=dev, dtype=F32)
-        call("dml_kv_gather_bwd", ptr(x2f), ptr(g), ptr(dkv), B, n, dim, G, n_kv, i0, i1, wy0, wy1, ptr(dcentre),
+        call("dml_kv_gather_bwd", ptr(x2c), ptr(g), ptr(dkv), B, gn, dim, G, n_kv, gi0, gi1, wy0, wy1, ptr(dcentre),
              ptr(dg), st)
-        dx2t = torch.zeros_like(x2f)
-        dx2t[:, i0] += wy0 * dcentre
-        if wy1 != 0.0:
-            dx2t[:, i1] += wy1 * dcentre
+        dx2t = torch.zeros(ctx.x2_shape, device=dev, dtype=F32)
+        dlw = dlb = None
+        if fused:
+            kc = len(crow)
+            dxc = torch.stack([wy0 * dcentre] + ([wy1 * dcentre] if kc == 2 else []), 1).contiguous()      # [B, k, dim]
+            dxc_in = torch.empty_like(dxc)
+            dlw2 = torch.empty(dim, device=dev, dtype=F32)
+            dlb2 = torch.empty_like(dlw2)
+            call("dml_layernorm_bwd", ptr(dxc), ptr(xc_in), ptr(lnw), ptr(mean2), ptr(rstd2), B * kc, dim, ptr(dxc_in), ptr(dlw2),
+                 ptr(dlb2), st)
+            dx2t[:, crow] = dxc_in
+        else:
+            dx2t[:, i0] += wy0 * dcentre
+            if wy1 != 0.0:
+                dx2t[:, i1] += wy1 * dcentre
 
         d_off = dg * (2.0 / max(n_kv - 1, 1))                              # g = 2 vgrid / max(n_kv-1,1) - 1
         if dvgrid is not None:
@@ -288,18 +353,26 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         d_off = d_off.contiguous()
         dy_ws = torch.empty(B * G, n_kv, Cg, device=dev, dtype=F32)
         wgrad = torch.empty(Cg * ks + 2 * Cg, device=dev, dtype=F32)
-        dq = torch.empty(B, n, C, device=dev, dtype=F32)
-        call("dml_offsets_bwd", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), ptr(dq_attn), scale, B, n, C, G, ks,
-             stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), ptr(dq), st)
+        dq_p = Pair.empty((B, n, C), dev)                                  # total query gradient, as the GEMM operand only
+        call("dml_offsets_bwd_pair", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), ptr(dq_attn), scale, B, n, C, G, ks,
+             stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), None, ptr(dq_p.planes), dq_p.planes.stride(0), st)
         side.wait_stream(cur)
-        with torch.cuda.stream(side), tf32_matmul():
-            dWq = wgrad_mm(dq.reshape(-1, C), x1f.reshape(-1, dim))        # [C, dim]
-        with tf32_matmul():
-            dx1t = torch.matmul(dq, Wq2)
+        with torch.cuda.stream(side):
+            dWq = torch.empty(C, dim, device=dev, dtype=F32)
+            _wgrad_pg(dq_p, x1p, dWq, M=C, N=dim, K=n, B=B)
+        dx1t, _ = pgemm(dq_p, Wq_p.b1(), M=n, N=dim, K=C, batch=(B,), b_trans=True)
+        if fused:
+            dh = torch.empty_like(x1f)
+            dlw = torch.empty(dim, device=dev, dtype=F32)
+            dlb = torch.empty_like(dlw)
+            call("dml_layernorm_bwd", ptr(dx1t), ptr(x1f), ptr(lnw), ptr(mean1), ptr(rstd1), B * n, dim, ptr(dh), ptr(dlw), ptr(dlb), st)
+            dh[:, :n_out] += dout                                          # the layer's residual
+            dx1t = dh
+            dlw, dlb = dlw + dlw2, dlb + dlb2
         cur.wait_stream(side)
         for t in (dWo, dbo, mlp_g, dWk, dWv, dWq):                         # allocated on the auxiliary stream, consumed on this one
             t.record_stream(cur)
-        for t in (dout, o, segsum, dk, dv, dq):                            # allocated here, read there
+        for t in (dout, segsum, dout_p.planes, dk_p.planes, dv_p.planes, dq_p.planes):      # allocated here, read there
             t.record_stream(side)
 
         dw0 = wgrad[: Cg * ks].reshape(Cg, 1, ks)
@@ -313,7 +386,18 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         g_b3 = mlp_g[1184:1184 + nout]
         return (dx1t, dx2t, dWq.reshape(C, dim, 1), dWk.reshape(C, dim, 1), dWv.reshape(C, dim, 1),
                 dWo.reshape(dim, C, 1), dbo, dw0, db0, dw2, g_w1, g_b1, g_W2.contiguous(), g_b2, g_W3.contiguous(),
-                g_b3, None)
+                g_b3, dlw, dlb, None)
+
+
+def _wgrad_pg(G_p, X_p, out, *, M, N, K, B):
+    """out [M, N] = sum_b G_b^T X_b for token-major pairs G [B, K, M], X [B, K, N] (a weight gradient: the reduction runs over
+    the tokens): split-K pair GEMM, every bag reducing into the one output."""
+    from .pairs import pgemm
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    splits = max(1, min(((K + 63) // 64) // 8, (148 + tiles * B - 1) // (tiles * B)))
+    out.zero_()
+    pgemm(G_p, X_p, M=M, N=N, K=K, batch=(B,), a_trans=True, b_trans=True, out=out, splits=max(2, splits))
+    return out
 
 
 class LandmarkPoolFn(torch.autograd.Function):
@@ -497,6 +581,38 @@ class LinearPgFn(torch.autograd.Function):
             dx, _ = pgemm(dyp, Wp, M=rows, N=K, K=N, b_trans=True)
             dx = dx.to(ctx.xdtype)
         return dx, dW, db, None
+
+
+class FusionFn(torch.autograd.Function):
+    """FusionNet (DeformCrossTransMIL.py:28-38,105,111) without the [B, N, 256] concat or the [B, N, 128] repeat of the omic
+    vector: y[b] = path[b] @ Wp^T + vec[b], vec = omic @ Wo^T + bias a per-bag vector that enters as the GEMM's epilogue
+    bias.  path [B, N, D] fp32, Wp [D_out, D], vec [B, D_out]."""
+
+    @staticmethod
+    def forward(ctx, path, Wp, vec):
+        from .pairs import Pair, pgemm
+        B, N, D = path.shape
+        Do = Wp.shape[0]
+        pp, Wpp = Pair.from_f32(path), Pair.from_f32(Wp)
+        y, _ = pgemm(pp, Wpp.b1(), M=N, N=Do, K=D, batch=(B,), bias=vec.contiguous().float())
+        ctx.pairs = (pp, Wpp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .pairs import Pair, pgemm
+        pp, Wpp = ctx.pairs
+        B, N, D = pp.shape
+        Do = Wpp.shape[0]
+        dy = dy.contiguous().float()
+        dyp = Pair.from_f32(dy)
+        dpath, _ = pgemm(dyp, Wpp.b1(), M=N, N=D, K=Do, batch=(B,), b_trans=True)
+        dWp = torch.empty(Do, D, device=dy.device, dtype=F32)
+        _wgrad_pg(dyp, pp, dWp, M=Do, N=D, K=N, B=B)
+        dvec = torch.empty(B, Do, device=dy.device, dtype=F32)
+        for b in range(B):
+            call("dml_colsum", ptr(dy[b]), N, Do, Do, ptr(dvec[b]), stream())
+        return dpath, dWp, dvec
 
 
 def linear_pg(x: torch.Tensor, W: torch.Tensor, b, relu: bool = False) -> torch.Tensor:

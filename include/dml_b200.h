@@ -66,6 +66,13 @@ int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float
                     const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
                     float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* stream);
 
+/* The same with the total query gradient ALSO (or only: dq_out may be NULL) written as a bf16 pair [B, n, C], the operand of
+ * the dW_q / dx1 GEMMs (csrc/pgemm.cu).                                                                               */
+int dml_offsets_bwd_pair(const void* q, const float* w0, const float* b0, const float* w2, const float* d_off,
+                         const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
+                         float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* dq_pair, long long plane_stride,
+                         void* stream);
+
 /* ---- key/value gather (grid_sample_1d :36-43, :190-195; shipped degenerate semantics) */
 /* x2: float [B, n, dim] token-major; (i0,wy0),(i1,wy1): the sequence taps of y = 0 (centre of the sequence);
  * kv: float [B, n_kv, dim] = (x2[i0]*wy0 + x2[i1]*wy1) * tent(gnorm).                                 */
@@ -201,6 +208,10 @@ int dml_pgemm(const dml_pgemm_args* args, void* stream);
 /* x float [rows, cols] (row stride ld) * mult -> bf16 pair planes [rows, ldp], plane_stride elements apart.              */
 int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mult, void* pair, int ldp,
                       long long plane_stride, void* stream);
+/* ReLU backward fused with the pair conversion (fc1 + ReLU, DeformCrossTransMIL.py:100 / mil.py:229): g[r, c] := act[r, c] > 0 ?
+ * g[r, c] : 0, written back in place (row stride ldg) and as a bf16 pair [rows, ldp]; act row stride lda.               */
+int dml_relu_mask_pair(float* g, const float* act, long long rows, int cols, int ldg, int lda, void* pair, int ldp,
+                       long long plane_stride, void* stream);
 /* out[c] = sum_r x[r, c] (bias gradients over the tokens); out float [cols] is overwritten.                              */
 int dml_colsum(const float* x, long long rows, int cols, int ld, float* out, void* stream);
 
