@@ -647,8 +647,7 @@ def main():
     top = max(kavg, key=lambda k: kavg[k] * kcalls[k])
     exec_fwd = fl["qk"] + 2.0 * fl["pv"]                             # S = QK^T, O += P_hi V, O += P_lo V  (tcgen05 MMAs issued)
     exec_bwd = 5.0 * fl["qk"]                                        # S^T,dP^T,dV,dK (4) + dQ = dS K over the dS^T workspace (1): GEMMs of n x n_kv x 64
-    exec_fl = {"dml_deform_attn_fwd": fl["qk"] + fl["pv"], "dml_deform_attn_bwd": exec_bwd,
-               "dml_deform_attn_fwd_tc": exec_fwd, "dml_deform_attn_bwd_tc": exec_bwd}.get(top)
+    exec_fl = {"dml_deform_attn_fwd_tc": exec_fwd, "dml_deform_attn_bwd_tc": exec_bwd}.get(top)
     roof = None
     if exec_fl:
         ach = exec_fl / (kavg[top] * 1e-3) / 1e12

@@ -32,16 +32,12 @@ SIGNATURES = {
     "dml_offsets_bwd_pair": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp, _vp, _ll, _vp]),
     "dml_kv_gather_fwd": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dml_kv_gather_bwd": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _vp]),
-    "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
     "dml_deform_attn_fwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 11 + [_f, _vp, _fp, _vp]),
-    "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
     "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp, _vp]),
     "dml_deform_attn_bwd_ws_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "dml_deform_attn_dq_from_ds": (_i, [_vp, _vp, _fp] + [_i] * 6 + [_fp, _vp]),
     "dml_layernorm_fwd": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _fp, _fp, _vp]),
     "dml_layernorm_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
-    "dml_split_f16": (_i, [_fp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _fp, _vp, _vp]),
-    "dml_gemm_nt_split": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _fp, _i, _ll, _vp]),
     "dml_pgemm": (_i, [C.c_void_p, _vp]),
     "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
     "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
@@ -55,15 +51,7 @@ SIGNATURES = {
     "dml_ny_dqkv_finalize": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
     "dml_ppeg_stencil": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _fp, _vp]),
     "dml_ppeg_wgrad": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
-    "dml_debug_set_trace": (_i, [_vp]),
-    "dml_debug_set_seg_limit": (_i, [_i]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
-    "dml_landmark_pool_fwd": (_i, [_fp, _i, _i, _i, _i, _i, _i, _i, _f, _fp, _vp]),
-    "dml_landmark_pool_bwd": (_i, [_fp, _i, _i, _i, _i, _i, _f, _fp, _vp]),
-    "dml_softmax_rows_fwd": (_i, [_fp, _fp, _ll, _i, _vp]),
-    "dml_softmax_rows_bwd": (_i, [_fp, _fp, _fp, _ll, _i, _vp]),
-    "dml_res_conv_merge_fwd": (_i, [_fp, _fp, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _vp]),
-    "dml_res_conv_merge_bwd": (_i, [_fp, _fp, _i, _i, _fp, _i, _i, _i, _i, _i, _fp, _fp, _fp, _vp]),
 }
 
 
@@ -92,6 +80,16 @@ class PgemmArgs(C.Structure):
                 ("aux", C.c_void_p), ("ldx", C.c_int), ("x_bs_inner", C.c_longlong), ("x_bs_outer", C.c_longlong),
                 ("x_plane", C.c_longlong)]
 
+
+# libdml_b200_test.so (include/dml_b200_test.h): TEST-ONLY, loaded by tests / scripts through load_test(), never by the product
+# path.  It also exports its own dml_deform_attn_bwd_tc / dml_deform_attn_dq_from_ds (the knob build of the same source).
+TEST_LIB_PATH = os.path.join(_HERE, "lib", "libdml_b200_test.so")
+TEST_SIGNATURES = {
+    "dml_deform_attn_fwd": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 10 + [_f, _vp, _fp, _vp]),
+    "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
+    "dml_debug_set_trace": (_i, [_vp]),
+    "dml_debug_set_seg_limit": (_i, [_i]),
+}
 
 _lock = threading.Lock()
 _lib = None
@@ -128,15 +126,44 @@ def load(check_device: bool = False):
     return _lib
 
 
+_test_lib = None
+
+
+def load_test():
+    """dlopen the test-only library (tests and profiling scripts only)."""
+    global _test_lib
+    if _test_lib is None:
+        with _lock:
+            if _test_lib is None:
+                if not os.path.exists(TEST_LIB_PATH):
+                    raise DmlError(f"{TEST_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+                lib = C.CDLL(TEST_LIB_PATH)
+                both = dict(TEST_SIGNATURES)
+                both["dml_deform_attn_bwd_tc"] = SIGNATURES["dml_deform_attn_bwd_tc"]
+                for name, (res, args) in both.items():
+                    fn = getattr(lib, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _test_lib = lib
+    return _test_lib
+
+
+def call_test(name: str, *args):
+    """Invoke an int-returning entry point of the TEST-ONLY library; raise on failure."""
+    load(check_device=True)
+    rc = getattr(load_test(), name)(*args)
+    if rc != 0:
+        what = _ERR.get(rc) or (f"CUDA error {rc}" if rc > 0 else f"error {rc}")
+        raise DmlError(f"{name} (test library) failed: {what}")
+
+
 _ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace too small"}
 
 # kernels launched per entry point (memsets not counted) - bench.py reports the total as gpu_launches
 KERNELS_PER_CALL = {
     "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2, "dml_offsets_bwd_pair": 2,
-    "dml_offsets_bwd_pair": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _f, _i, _i, _i, _i, _i, _i, _f, _fp, _fp, _vp, _vp, _ll, _vp]),
-    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd": 3, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
-    "dml_landmark_pool_fwd": 1, "dml_landmark_pool_bwd": 1, "dml_softmax_rows_fwd": 1, "dml_softmax_rows_bwd": 1,
-    "dml_res_conv_merge_fwd": 1, "dml_res_conv_merge_bwd": 1, "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1, "dml_split_f16": 2, "dml_gemm_nt_split": 1,
+    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
+    "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1,
     "dml_pgemm": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
     "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1,

@@ -61,8 +61,10 @@ struct DkvWorkList {
   int n;
   DkvWork e[kDkvWorkMax];
 };
+#ifdef DML_TEST_KNOBS      // test-only build (libdml_b200_test.so): the product library has no mutable global state
 static long long* g_trace = nullptr;
 static int g_seg_limit = kSegSmem;
+#endif
 
 // D[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (O fp32 as written by the forward, dO the fp16 tensor the MMAs consume)
 __global__ void __launch_bounds__(256) bwd_prep_kernel(const float* __restrict__ o, const h16* __restrict__ d_o, int B, int n,
@@ -957,11 +959,13 @@ static int plan_dkv_worklist(int B, int G, int n, int n_kv, int nsm, dml::tc::Dk
 
 extern "C" {
 
+#ifdef DML_TEST_KNOBS
 /* debug: device buffer of long long[4 * 2 * ntiles] that the next dQ launches fill with clock64() stamps (NULL = off) */
 int dml_debug_set_trace(void* buf) {
   dml::tc::g_trace = (long long*)buf;
   return 0;
 }
+#endif
 
 /* bytes of the optional dS^T workspace of dml_deform_attn_bwd_tc: fp16 [(B H), ceil128(n_kv), ceil32(n)] */
 size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv) {
@@ -985,12 +989,14 @@ int dml_debug_dkv_worklist(int B, int H, int n, int n_kv, int nsm, int* out, int
   return np;
 }
 
-/* debug / test knob: tables with at least limit - 2 segments are treated as too large for the shared-memory segment
- * arrays of the dK/dV kernel (its general per-position path); limit <= 0 restores the default */
+#ifdef DML_TEST_KNOBS
+/* test knob: tables with at least limit - 2 segments are treated as too large for the shared-memory segment arrays of the
+ * dK/dV kernel (its general per-position path); limit <= 0 restores the default */
 int dml_debug_set_seg_limit(int limit) {
   dml::tc::g_seg_limit = limit > 0 ? limit : dml::tc::kSegSmem;
   return 0;
 }
+#endif
 
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
@@ -1033,8 +1039,13 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
   p.g = g; p.table = (const uint32_t*)table; p.lse = lse; p.dsum = dsum_ws; p.dscale = dscale;
   p.dq = dq; p.dk = dk; p.dv = dv; p.dg = dg; p.segsum = segsum;
   p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.n_seq = n_seq; p.scale = scale;
+#ifdef DML_TEST_KNOBS
   p.trace = dml::tc::g_trace;
   p.seg_limit = dml::tc::g_seg_limit;
+#else
+  p.trace = nullptr;
+  p.seg_limit = dml::tc::kSegSmem;
+#endif
   p.ds_ws = (h16*)ds_ws; p.n_pad = cdiv(n, 32) * 32; p.n_kv_pad = cdiv(n_kv, 128) * 128;
   CUtensorMap mds, mk64;
   if (ds_ws) {

@@ -14,9 +14,10 @@
 // replaces these kernels behind the same C entry points.
 #include <math.h>
 
-#include "../../include/dml_b200.h"
-#include "common.cuh"
-#include "cpb_table.cuh"
+#include "../../../include/dml_b200.h"
+#include "../../../include/dml_b200_test.h"
+#include "../common.cuh"
+#include "../cpb_table.cuh"
 
 namespace dml {
 

@@ -1,14 +1,13 @@
 """torch.autograd.Function wrappers around the C ABI (include/dml_b200.h).
 
-Host code here only allocates buffers, orders the launches on torch's current stream and
-calls plain library GEMMs (torch.matmul -> cuBLAS) for the unfused projections; every
-fused / hot operator is a hand-written sm_100a kernel reached through ``_lib.call``.
+Host code here only allocates buffers and orders the launches on torch's current stream; every operator of the path,
+the projections and weight gradients included (bf16-pair tcgen05 GEMM, ``pairs.pgemm``), is a hand-written sm_100a
+kernel reached through ``_lib.call``.
 """
 from __future__ import annotations
 
 import math
 import os
-from contextlib import contextmanager
 
 import torch
 
@@ -19,33 +18,6 @@ BF16 = torch.bfloat16
 F16 = torch.float16
 F32 = torch.float32
 CPB_GRAD_FLOATS = 1192  # DML_CPB_GRAD_FLOATS in include/dml_b200.h
-
-
-@contextmanager
-def tf32_matmul():
-    """fp32 GEMMs of this path run on the tensor cores in TF32 (fp32 accumulate)."""
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        yield
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
-@contextmanager
-def fp32_matmul():
-    """Exact fp32 GEMMs (no TF32) for the few small products whose rounding is amplified downstream."""
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        yield
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
-def mm_f32out(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """bf16 x bf16 -> fp32 2-D GEMM (weight gradients: no bf16 rounding of the long-K sums)."""
-    return torch.mm(a, b, out_dtype=F32)
 
 
 def centre_taps(n: int):
@@ -76,80 +48,8 @@ def side_stream(dev) -> torch.cuda.Stream:
     return _SIDE_STREAMS[key]
 
 
-def grad_scale(t: torch.Tensor) -> torch.Tensor:
-    """Device-side power-of-two loss scale for an fp16 operand: float[2] = (s, 1/s) with
-    4 < s * max|t| <= 8 (no host sync; s = 1 for an all-zero tensor)."""
-    lo, hi = torch.aminmax(t.detach())          # one pass, no |t| temporary
-    amax = torch.maximum(hi, -lo).float()
-    s = torch.exp2(torch.floor(torch.log2(8.0 / amax.clamp_min(1e-30))).clamp(-60.0, 60.0))
-    s = torch.where(amax > 0, s, torch.ones_like(s))
-    return torch.stack([s, 1.0 / s]).contiguous()
-
-
-_ONES = {}
-
-
-def colsum(x2d: torch.Tensor) -> torch.Tensor:
-    """Column sums of a tall [rows, C] matrix (bias gradients over 16 k tokens) as one GEMV with a cached ones vector:
-    torch's column reduction takes 13-25 us on these shapes, the GEMV 4-5."""
-    rows = x2d.shape[0]
-    key = (x2d.device, rows)
-    ones = _ONES.get(key)
-    if ones is None:
-        # the cached vector is read from several streams (towers, auxiliary streams): it must be complete before any of
-        # them can see it, so the fill is synchronised once here (never inside a graph capture: shapes are first seen in
-        # the eager warm-up passes; a shape first met while capturing gets an uncached, capture-local vector)
-        ones = torch.ones(rows, device=x2d.device, dtype=F32)
-        if x2d.is_cuda:
-            if torch.cuda.is_current_stream_capturing():
-                return torch.mv(x2d.t(), ones)
-            torch.cuda.current_stream(x2d.device).synchronize()
-        _ONES[key] = ones
-    return torch.mv(x2d.t(), ones)
-
-
-def wgrad_mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a^T b for tall a [rows, M], b [rows, N] (weight gradients: the reduction runs over the tokens).  cuBLAS maps the
-    single skinny GEMM to M N / (128 * 64) CTAs - 8 for a 512 x 128 gradient over 16 k tokens, 40-50 us; cut into 512-row
-    chunks it is a batched GEMM over all SMs plus a small sum."""
-    rows = a.shape[0]
-    chunk = 512
-    c = rows // chunk
-    if c < 4:
-        return a.t() @ b
-    n0 = c * chunk
-    out = torch.bmm(a[:n0].view(c, chunk, -1).transpose(1, 2), b[:n0].view(c, chunk, -1)).sum(0)
-    if n0 < rows:
-        out = out + a[n0:].t() @ b[n0:]
-    return out
-
-
-class AddRowBiasFn(torch.autograd.Function):
-    """x [..., rows, C] + v [..., 1, C] (a per-bag vector broadcast over the tokens); the gradient of v is a column sum."""
-
-    @staticmethod
-    def forward(ctx, x, v):
-        return x + v
-
-    @staticmethod
-    def backward(ctx, g):
-        g = g.contiguous()
-        B = g.shape[0] if g.dim() == 3 else 1
-        gv = torch.stack([colsum(g.reshape(B, -1, g.shape[-1])[i]) for i in range(B)])[:, None, :] if g.dim() == 3 else colsum(g)[None]
-        return g, gv
-
-
 # largest dS^T scratch the backward may allocate per call (bytes); DML_B200_DS_WS_MAX_GB overrides, 0 disables it
 DS_WS_MAX_BYTES = int(float(os.environ.get("DML_B200_DS_WS_MAX_GB", "6")) * (1 << 30))
-
-
-def _proj_nt(x, W, out_shape=None):
-    """x [B, rows, K] (tensor or an already split [1, B*rows, K] operand) times W[N, K]^T on the tcgen05 split GEMM."""
-    if not isinstance(x, SplitOperand):
-        out_shape = x.shape[:-1] + (W.shape[0],)
-        x = SplitOperand(x.reshape(1, -1, x.shape[-1]), True)
-    c = gemm_nt(x, SplitOperand(W[None], True), (1, x.rows, W.shape[0]))
-    return c.reshape(out_shape)
 
 
 def loss_scale_from_amax(amax_bits: torch.Tensor) -> torch.Tensor:
@@ -400,142 +300,6 @@ def _wgrad_pg(G_p, X_p, out, *, M, N, K, B):
     return out
 
 
-class LandmarkPoolFn(torch.autograd.Function):
-    """mean over l consecutive (front-padded) tokens: x [B, n_pad, H*d] (may be a column slice of the
-    fused qkv buffer) -> [B, H, n_pad/l, d] * mult  (NystromAttention.py:102-118)."""
-
-    @staticmethod
-    def forward(ctx, x, l, H, d, mult):
-        B, n_pad, W = x.shape
-        assert W == H * d and x.stride(2) == 1 and x.stride(0) == n_pad * x.stride(1)
-        out = torch.empty(B, H, n_pad // l, d, device=x.device, dtype=F32)
-        call("dml_landmark_pool_fwd", ptr(x), x.stride(1), 0, B, n_pad, l, H, d, float(mult), ptr(out), stream())
-        ctx.meta = (B, n_pad, l, H, d, float(mult))
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        B, n_pad, l, H, d, mult = ctx.meta
-        dout = dout.contiguous()
-        dx = torch.empty(B, n_pad, H * d, device=dout.device, dtype=F32)
-        call("dml_landmark_pool_bwd", ptr(dout), B, n_pad, l, H, d, mult, ptr(dx), stream())
-        return dx, None, None, None, None
-
-
-class SoftmaxRowsFn(torch.autograd.Function):
-    """softmax over the last dim of a contiguous fp32 tensor (NystromAttention.py:137)."""
-
-    @staticmethod
-    def forward(ctx, x):
-        x = x.contiguous()
-        y = torch.empty_like(x)
-        cols = x.shape[-1]
-        call("dml_softmax_rows_fwd", ptr(x), ptr(y), x.numel() // cols, cols, stream())
-        ctx.save_for_backward(y)
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        (y,) = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx = torch.empty_like(y)
-        cols = y.shape[-1]
-        call("dml_softmax_rows_bwd", ptr(y), ptr(dy), ptr(dx), y.numel() // cols, cols, stream())
-        return dx
-
-
-class ResConvMergeFn(torch.autograd.Function):
-    """y[b,i,(h d)] = a[b,h,i,d] + depthwise conv_K(v)[b,i,(h d)]  (NystromAttention.py:144-149).
-    v [B, n_pad, H*d] may be a column slice of the fused qkv buffer; w [H,1,K,1]."""
-
-    @staticmethod
-    def forward(ctx, a, v, w):
-        B, H, n_pad, d = a.shape
-        assert v.stride(2) == 1 and v.stride(0) == n_pad * v.stride(1)
-        a = a.contiguous()
-        wf = w.reshape(H, -1).contiguous().float()
-        K = wf.shape[1]
-        y = torch.empty(B, n_pad, H * d, device=a.device, dtype=F32)
-        call("dml_res_conv_merge_fwd", ptr(a), ptr(v), v.stride(1), 0, ptr(wf), K, B, n_pad, H, d, ptr(y), stream())
-        ctx.save_for_backward(v, wf)
-        ctx.meta = (B, H, n_pad, d, K, tuple(w.shape))
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        v, wf = ctx.saved_tensors
-        B, H, n_pad, d, K, wshape = ctx.meta
-        dy = dy.contiguous()
-        da = torch.empty(B, H, n_pad, d, device=dy.device, dtype=F32)
-        dv = torch.empty(B, n_pad, H * d, device=dy.device, dtype=F32)
-        dw = torch.empty(H, K, device=dy.device, dtype=F32)
-        call("dml_res_conv_merge_bwd", ptr(dy), ptr(v), v.stride(1), 0, ptr(wf), K, B, n_pad, H, d, ptr(da), ptr(dv),
-             ptr(dw), stream())
-        return da, dv, dw.reshape(wshape)
-
-
-class MatmulFn(torch.autograd.Function):
-    """a @ b for fp32 operands, forward and backward (same batch dims); tf32=True takes the TF32
-    tensor-core path (fp32 accumulate), tf32=False exact fp32."""
-
-    @staticmethod
-    def forward(ctx, a, b, tf32):
-        ctx.save_for_backward(a, b)
-        ctx.tf32 = tf32
-        with (tf32_matmul() if tf32 else fp32_matmul()):
-            return torch.matmul(a, b)
-
-    @staticmethod
-    def backward(ctx, g):
-        a, b = ctx.saved_tensors
-        with (tf32_matmul() if ctx.tf32 else fp32_matmul()):
-            da = torch.matmul(g, b.transpose(-1, -2)) if ctx.needs_input_grad[0] else None
-            db = torch.matmul(a.transpose(-1, -2), g) if ctx.needs_input_grad[1] else None
-        if db is not None and db.dim() > b.dim():
-            db = db.reshape(-1, *b.shape).sum(0)
-        return da, db, None
-
-
-def mm_tf32(a, b):
-    return MatmulFn.apply(a, b, True)
-
-
-def mm_fp32(a, b):
-    return MatmulFn.apply(a, b, False)
-
-
-def split_bf16(t: torch.Tensor):
-    """fp32 -> (hi, lo) bf16 pair with hi + lo == t to 16 significant bits."""
-    hi = t.to(BF16)
-    return hi, (t - hi.float()).to(BF16)
-
-
-class LinearBf16BagFn(torch.autograd.Function):
-    """y = x @ W^T + b for a bf16 bag x [M, K] (the bag is GIVEN in bf16: no rounding is added to it) and fp32
-    W [N, K]: the weight enters as a (hi, lo) bf16 pair and the incoming gradient likewise, so the product and
-    the weight gradient carry fp32-class accuracy on the bf16 tensor-core path (fp32 accumulate / output)."""
-
-    @staticmethod
-    def forward(ctx, x, W, b):
-        Wh, Wl = split_bf16(W)
-        y = torch.mm(x, Wh.t(), out_dtype=F32)
-        y += torch.mm(x, Wl.t(), out_dtype=F32)
-        ctx.save_for_backward(x, W)
-        return y + b
-
-    @staticmethod
-    def backward(ctx, dy):
-        x, W = ctx.saved_tensors
-        dyh, dyl = split_bf16(dy)
-        dW = torch.mm(dyh.t(), x, out_dtype=F32)
-        dW += torch.mm(dyl.t(), x, out_dtype=F32)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            with tf32_matmul():
-                dx = (dy @ W).to(x.dtype)
-        return dx, dW, colsum(dy)
-
-
 class LinearPgFn(torch.autograd.Function):
     """y = [relu](x @ W^T + b) on the bf16-pair tcgen05 GEMM (csrc/pgemm.cu).  x [rows, K] fp32 (split into a pair) or bf16
     (exact: one plane, no rounding added); W [N, K], b [N] fp32.  Bias and ReLU are the GEMM's epilogue; the weight
@@ -662,104 +426,3 @@ class LayerNormFn(torch.autograd.Function):
 def layer_norm(x, norm: torch.nn.LayerNorm):
     """norm(x) through the row-LayerNorm kernel; `norm` only holds the parameters (reference state_dict keys)."""
     return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# fp32-class batched GEMM on tcgen05 (csrc/gemm_tc.cu): used by NystromAttention
-# ---------------------------------------------------------------------------------------------------------------
-def _as_batched(t: torch.Tensor):
-    """[..., R, C] -> (tensor whose (R, C) block is row-major with one uniform batch stride, batch, R, C, ld, batch_stride,
-    transposed_view).  A transposed view of a row-major block is accepted as is (transposed_view = True: the memory
-    holds [C, R]); anything else is made contiguous."""
-    R, C = t.shape[-2], t.shape[-1]
-    lead = t.shape[:-2]
-    batch = 1
-    for d in lead:
-        batch *= d
-
-    def uniform(tt):
-        # the leading dims must collapse to one stride
-        st, sh = list(tt.stride()[:-2]), list(tt.shape[:-2])
-        dims = [(s_, n_) for s_, n_ in zip(st, sh) if n_ > 1]
-        if not dims:
-            return 0
-        bs = dims[-1][0]
-        expect = bs
-        for s_, n_ in reversed(dims):
-            if s_ != expect:
-                return None
-            expect = s_ * n_
-        return bs
-
-    if t.stride(-1) == 1 and t.stride(-2) >= C:
-        bs = uniform(t)
-        if bs is not None:
-            return t, batch, R, C, t.stride(-2), bs, False
-    if t.stride(-2) == 1 and t.stride(-1) >= R:
-        bs = uniform(t)
-        if bs is not None:
-            return t, batch, C, R, t.stride(-1), bs, True       # memory is [C, R] row-major
-    t = t.contiguous()
-    return t, batch, R, C, C, R * C, False
-
-
-class SplitOperand:
-    """fp32 [..., R, C] -> (hi, lo) fp16 [batch, rows, ldo] with the K axis contiguous, plus its device-side scale.
-    k_last=True: K is the last axis of `t` (rows = R); k_last=False: K is the second-to-last axis (rows = C, transposed
-    while splitting)."""
-
-    def __init__(self, t: torch.Tensor, k_last: bool):
-        t = t.float()
-        base, batch, R, C, ld, bs, tview = _as_batched(t)
-        # memory block [R, C] (after undoing a transposed view); logical K-last?  XOR with the view flag
-        transpose = (not k_last) != tview
-        rows, K = (C, R) if transpose else (R, C)
-        ldo = (K + 7) // 8 * 8
-        dev = t.device
-        self.hi = torch.empty(batch, rows, ldo, device=dev, dtype=F16)
-        self.lo = torch.empty_like(self.hi)
-        self.scale = torch.empty(2, device=dev, dtype=F32)
-        ws = torch.empty(1, device=dev, dtype=torch.int32)
-        call("dml_split_f16", ptr(base), bs, batch, R, C, ld, int(transpose), ldo, ptr(self.hi), ptr(self.lo),
-             ptr(self.scale), ptr(ws), stream())
-        self.batch, self.rows, self.K, self.ld = batch, rows, K, ldo
-
-
-def gemm_nt(A: SplitOperand, Bm: SplitOperand, out_shape, alpha: float = 1.0) -> torch.Tensor:
-    """C[b] = alpha * A[b] @ B[b]^T (fp32, contiguous `out_shape` = [..., M, N]); B may have batch 1 (shared)."""
-    assert A.K == Bm.K and (Bm.batch == A.batch)
-    c = torch.empty(out_shape, device=A.hi.device, dtype=F32)
-    M, N = A.rows, Bm.rows
-    call("dml_gemm_nt_split", ptr(A.hi), ptr(A.lo), ptr(Bm.hi), ptr(Bm.lo), ptr(A.scale), ptr(Bm.scale), float(alpha),
-         A.batch, M, N, A.K, A.ld, Bm.ld, ptr(c), N, M * N, stream())
-    return c
-
-
-class MatmulTcFn(torch.autograd.Function):
-    """a [..., M, K] @ b [..., K, N] (same leading dims, or b 2-D) on the tcgen05 split-fp16 GEMM, forward and backward."""
-
-    @staticmethod
-    def forward(ctx, a, b):
-        ctx.save_for_backward(a, b)
-        ctx.b2d = b.dim() == 2 and a.dim() > 2
-        a3 = a.reshape(-1, a.shape[-1])[None] if ctx.b2d else a
-        b3 = b[None] if ctx.b2d else b
-        out = gemm_nt(SplitOperand(a3, True), SplitOperand(b3, False), a3.shape[:-1] + (b.shape[-1],))
-        return out.reshape(a.shape[:-1] + (b.shape[-1],))
-
-    @staticmethod
-    def backward(ctx, g):
-        a, b = ctx.saved_tensors
-        g3 = g.reshape(-1, g.shape[-1])[None] if ctx.b2d else g
-        a3 = a.reshape(-1, a.shape[-1])[None] if ctx.b2d else a
-        b3 = b[None] if ctx.b2d else b
-        da = db = None
-        if ctx.needs_input_grad[0]:      # dA [M, K] = dC [M, N] . (B [K, N])^T
-            da = gemm_nt(SplitOperand(g3, True), SplitOperand(b3, True), a3.shape).reshape(a.shape)
-        if ctx.needs_input_grad[1]:      # dB [K, N] = A^T [K, M] . (dC^T [N, M])^T
-            db = gemm_nt(SplitOperand(a3, False), SplitOperand(g3, False), b3.shape).reshape(b.shape)
-        return da, db
-
-
-def mm_tc(a, b):
-    return MatmulTcFn.apply(a, b)

@@ -45,7 +45,7 @@ int dml_cpb_table_build(const float* w1, const float* b1, const float* W2, const
 /* Diagnostics: evaluate the table at count values of t: out float[count][2] = (bias0, bias1), seg int[count]
  * (may be NULL) = segment index.  Used by the tests to pin the table against the dense MLP.                 */
 int dml_cpb_eval(const void* table, const float* t, int count, float* out, int* seg, void* stream);
-/* Gradients of the six MLP parameters from the per-segment sums written by dml_deform_attn_bwd.
+/* Gradients of the six MLP parameters from the per-segment sums written by dml_deform_attn_bwd_tc.
  * segsum: float[dml_cpb_seg_max()][4] = (sum d0, sum d0*t, sum d1, sum d1*t); grads: float[DML_CPB_GRAD_FLOATS]
  * laid out dw1[32] db1[32] dW2[32][32] db2[32] dW3[2][32] db3[2] (rows/cols beyond hid/nout are zero). */
 int dml_cpb_param_grad(const float* w1, const float* b1, const float* W2, const float* b2, const float* W3,
@@ -79,7 +79,7 @@ int dml_offsets_bwd_pair(const void* q, const float* w0, const float* b0, const 
 int dml_kv_gather_fwd(const float* x2, const float* gnorm, int B, int n, int dim, int G, int n_kv, int i0, int i1,
                       float wy0, float wy1, void* kv, void* stream);
 /* dkv: float [B, n_kv, dim].  dcentre: float [B, dim] (overwritten) = sum_j dkv*tent;  dg: float [(B*G), n_kv],
- * ACCUMULATED into (call after dml_deform_attn_bwd, which initialises it).                           */
+ * ACCUMULATED into (call after dml_deform_attn_bwd_tc, which initialises it).                           */
 int dml_kv_gather_bwd(const float* x2, const float* gnorm, const float* dkv, int B, int n, int dim, int G, int n_kv,
                       int i0, int i1, float wy0, float wy1, float* dcentre, float* dg, void* stream);
 
@@ -87,10 +87,7 @@ int dml_kv_gather_bwd(const float* x2, const float* gnorm, const float* dkv, int
 /* q fp16 [B,n,ldq], k/v fp16 [B,n_kv,ldk/ldv] (the 16-bit operand type of the attention MMAs is IEEE half:
  * 11-bit significand, fp32 accumulate), head h in columns h*dim_head..; gnorm float [(B*G), n_kv],
  * G = H/heads_per_group; out FLOAT [B,n,ldo]; lse float [B,H,n] (log2 domain, saved for backward).     */
-int dml_deform_attn_fwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
-                        int H, int dim_head, int n, int n_kv, int ldq, int ldk, int ldv, int ldo,
-                        int heads_per_group, float scale, void* out, float* lse, void* stream);
-/* Same contract on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, TMA-fed 128-byte-swizzled
+/* On the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, TMA-fed 128-byte-swizzled
  * operand tiles, both heads of an offset group per CTA (heads_per_group must be 2).  n_seq >= n is the sequence
  * length used to normalise the query positions (rows 0..n-1 of a sequence of n_seq tokens are computed; n_seq == n
  * for the whole module, n_seq > n for a leading slice such as the cls row only).  q/k/v/out 16-byte aligned.       */
@@ -102,13 +99,7 @@ int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const fl
  * = (s, 1/s), read by the kernels (no host sync) to un-scale every output.  dsum_ws float [B,H,n] workspace.  Outputs (fp32, dense
  * [.., H*dim_head]): dq = dS.K (NOT yet multiplied by scale), dk, dv; dg float [(B*G), n_kv] and
  * segsum float [dml_cpb_seg_max()][4] are zeroed here and then accumulated.                          */
-int dml_deform_attn_bwd(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
-                        const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,
-                        int n_kv, int ldq, int ldk, int ldv, int ldo, int heads_per_group, float scale,
-                        const float* dscale, float* dsum_ws, float* dq, float* dk, float* dv, float* dg,
-                        float* segsum, void* stream);
-
-/* The same backward on tcgen05 / TMEM / TMA (two kernels: key-stationary dK/dV/dg/segment sums, query-stationary dQ;
+/* The backward on tcgen05 / TMEM / TMA (two kernels: key-stationary dK/dV/dg/segment sums, query-stationary dQ;
  * heads_per_group must be 2; n_seq as in dml_deform_attn_fwd_tc; every tensor pointer 16-byte aligned).
  * ds_ws: NULL, or a caller-owned scratch buffer of dml_deform_attn_bwd_ws_bytes(B, H, n, n_kv) bytes (contents
  * undefined afterwards).  With it the dK/dV kernel also stores dS^T in fp16 and dQ = dS.K runs as a streaming GEMM
@@ -133,20 +124,6 @@ int dml_layernorm_fwd(const float* x, const float* w, const float* b, long long 
                       float* mean, float* rstd, void* stream);
 int dml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                       long long rows, int D, float* dx, float* dw, float* db, void* stream);
-
-/* ---- fp32-class batched GEMM on tcgen05 (NystromAttention contractions, models/NystromAttention.py:89,122-125,138-140,150) */
-/* x float [batch, R, C] (row stride ld, batch stride batch_stride elements) -> hi, lo fp16 with hi + lo = x * s, laid out
- * [batch, R, ldo] (transpose = 0) or [batch, C, ldo] (transpose = 1), ldo a multiple of 8 >= the logical width, padding
- * zero-filled; s = power of two with 2^9 <= s max|x| < 2^10; scale (device float[2]) receives (s, 1/s); amax_ws: 4-byte
- * device workspace.                                                                                                  */
-int dml_split_f16(const float* x, long long batch_stride, int batch, int R, int C, int ld, int transpose, int ldo,
-                  void* hi, void* lo, float* scale, void* amax_ws, void* stream);
-/* C[b] (float [M, ldc], batch stride c_batch_stride elements) = alpha / (s_A s_B) * A[b] . B[b]^T with A = a_hi + a_lo
- * [batch, M, lda], B = b_hi + b_lo [batch, N, ldb] as produced by dml_split_f16 (fp16, K-contiguous); accumulated as
- * hi.hi + hi.lo + lo.hi in fp32 in TMEM.                                                                              */
-int dml_gemm_nt_split(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* scale_a,
-                      const float* scale_b, float alpha, int batch, int M, int N, int K, int lda, int ldb, float* c,
-                      int ldc, long long c_batch_stride, void* stream);
 
 /* ---- fp32-class batched GEMM from bf16 operand pairs (csrc/pgemm.cu) ----------------------------------------------
  * Replaces every plain contraction of the path: NystromAttention (models/NystromAttention.py:89 to_qkv, :122-125 the
@@ -250,33 +227,10 @@ int dml_ppeg_stencil(const float* x, const float* wsum, const float* bsum, int B
                      void* stream);
 int dml_ppeg_wgrad(const float* x, const float* dy, int B, int side, int C, float* dw, float* db, void* stream);
 
-/* Debug aid: device buffer long long[8 * ceil(n_kv / 32)] that the following dQ-kernel launches fill with clock64()
- * stamps of CTA (0,0,0) (per key tile and query group: S ready, sweep done, P seen by the MMA warp, MMAs issued).  NULL = off. */
-int dml_debug_set_trace(void* buf);
-/* Test knob: bias tables with at least limit - 2 segments take the dK/dV kernel's general per-position path (as tables too
- * large for its shared-memory segment arrays do); limit <= 0 restores the default.                                       */
-int dml_debug_set_seg_limit(int limit);
 /* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
  * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
  * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */
 int dml_debug_dkv_worklist(int B, int H, int n, int n_kv, int nsm, int* out, int cap);
-
-/* ---- Nystrom attention pieces (models/NystromAttention.py:74-157) ----------------------------- */
-/* landmark mean-pool (:102-118): x float [B,n_pad,ld], columns col0 + h*d + c -> out float [B,H,n_pad/l,d]
- * = mult * sum over l consecutive (padded) rows.                                                      */
-int dml_landmark_pool_fwd(const float* x, int ld, int col0, int B, int n_pad, int l, int H, int d, float mult,
-                          float* out, void* stream);
-int dml_landmark_pool_bwd(const float* dout, int B, int n_pad, int l, int H, int d, float mult, float* dx,
-                          void* stream); /* dx float [B,n_pad,H*d] (overwritten) */
-/* row softmax of the similarity matrices (:137) and its backward; rows are independent segments.     */
-int dml_softmax_rows_fwd(const float* x, float* y, long long rows, int cols, void* stream);
-int dml_softmax_rows_bwd(const float* y, const float* dy, float* dx, long long rows, int cols, void* stream);
-/* y[b,i,h*d+c] = a[b,h,i,c] + depthwise K-tap conv along i of v (:144-149), v float [B,n_pad,ldv] at col0. */
-int dml_res_conv_merge_fwd(const float* a, const float* v, int ldv, int col0, const float* w, int K, int B, int n_pad,
-                           int H, int d, float* y, void* stream);
-/* da float [B,H,n_pad,d], dv float [B,n_pad,H*d], dw float [H,K] (all overwritten).                   */
-int dml_res_conv_merge_bwd(const float* dy, const float* v, int ldv, int col0, const float* w, int K, int B, int n_pad,
-                           int H, int d, float* da, float* dv, float* dw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(autouse=True)
 def _exact_fp32_reference_maths():
     """torch's own GPU convolutions / matmuls default to TF32; the comparison maths in the tests must be
-    exact fp32 (the product path opts into TF32 explicitly where it wants it, ops.tf32_matmul)."""
+    exact fp32 (the product path runs its contractions on its own pair GEMM, not on torch's)."""
     import torch
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False

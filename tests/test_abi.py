@@ -35,6 +35,20 @@ def test_ctypes_table_matches_header():
     assert set(_lib.SIGNATURES) == header_symbols()
 
 
+def test_test_only_library_is_separate_from_the_product_library():
+    """The legacy mma.sync cross-check kernels and the debug knobs live in libdml_b200_test.so (include/dml_b200_test.h):
+    the product library neither declares nor exports them (no process-global mutable state behind the product ABI)."""
+    src = open(os.path.join(ROOT, "include", "dml_b200_test.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    tsyms = set(re.findall(r"\b(dml_[a-z0-9_]+)\s*\(", src))
+    assert tsyms == set(_lib.TEST_SIGNATURES)
+    assert not (tsyms & header_symbols())
+    prod, test = _lib.load(), _lib.load_test()
+    for s in tsyms:
+        assert hasattr(test, s), s
+        assert not hasattr(prod, s), f"{s} must not be exported by the product library"
+
+
 def test_header_arity_matches_ctypes():
     src = open(os.path.join(ROOT, "include", "dml_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)

@@ -190,7 +190,7 @@ def test_attention_rows_are_a_convex_combination_of_values_at_16k():
          math.log1p(2.0 + 4.0 / (n_kv - 1)) * 1.001 + 1e-3, ptr(table), stream())
     o = torch.empty(B, n, C, device=DEV, dtype=torch.float32)
     lse = torch.empty(B, Hh, n, device=DEV)
-    call("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, C, C, C, C, 2, d ** -0.5,
+    call("dml_deform_attn_fwd_tc", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, n, C, C, C, C, 2, d ** -0.5,
          ptr(o), ptr(lse), stream())
     vmin, vmax = v.float().amin(1, keepdim=True), v.float().amax(1, keepdim=True)
     assert bool(torch.isfinite(o.float()).all()) and bool(torch.isfinite(lse).all())
