@@ -100,8 +100,11 @@ class FlatGradAllReducer:
         world = dist.get_world_size(group)
         flat = self.flat
         if getattr(self, "attached", False):
-            dist.all_reduce(flat[: self.total], op=dist.ReduceOp.SUM, group=group)
-            flat[: self.total].div_(world)
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(flat[: self.total], op=dist.ReduceOp.AVG, group=group)      # one collective, no second pass
+            else:                                                                            # gloo has no AVG
+                dist.all_reduce(flat[: self.total], op=dist.ReduceOp.SUM, group=group)
+                flat[: self.total].div_(world)
             return
         flat.zero_()
         views = self._views(flat)
