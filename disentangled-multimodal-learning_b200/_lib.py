@@ -39,6 +39,8 @@ SIGNATURES = {
     "dml_layernorm_fwd": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _fp, _fp, _vp]),
     "dml_layernorm_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
     "dml_pgemm": (_i, [C.c_void_p, _vp]),
+    "dml_pgemm_chain_max": (_i, []),
+    "dml_pgemm_chain": (_i, [C.c_void_p, _i, _vp]),
     "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
     "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
     "dml_relu_mask_pair": (_i, [_fp, _fp, _ll, _i, _i, _i, _vp, _i, _ll, _vp]),
@@ -164,7 +166,7 @@ KERNELS_PER_CALL = {
     "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2, "dml_offsets_bwd_pair": 2,
     "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
     "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1,
-    "dml_pgemm": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
+    "dml_pgemm": 1, "dml_pgemm_chain": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
     "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1,
 }

@@ -24,6 +24,7 @@
 // epilogue of a tile overlaps the loads and MMAs of the next; warp 8 = TMA producer (ring of {A planes, B planes} 64-wide k-blocks,
 // 128-byte swizzle), warp 9 = MMA issuer + TMEM owner, warps 0-7 = epilogue (a row's columns are split between two threads,
 // 32-column groups, vector loads / stores; one CTA per SM, so the epilogue's own parallelism is what hides its latencies).
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "../../include/dml_b200.h"
@@ -90,15 +91,14 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool 
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// One GEMM problem on this CTA: every role walks the problem's tiles (blockIdx.x, + gridDim.x, ...).  `it` (k-blocks through
+// the shared-memory ring) and `ti` (tiles through the two TMEM accumulator buffers) are the calling thread's running
+// counters: they continue across problems when a kernel chains several of them.
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
-pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb, const Params p) {
+__device__ __forceinline__ void run_problem(const CUtensorMap* ma, const CUtensorMap* mb, const Params& p, uint32_t sbase,
+                                            uint8_t* sgen, uint32_t tmem, int warp, int lane, int& it, int& ti) {
   using C = Cfg<BN>;
   constexpr int kStages = C::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   const int nk_all = cdiv(p.K, kBK);
   const int kb_per = cdiv(nk_all, p.splits);
   // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tile index = (z * tiles_n + n_tile) * tiles_m + m_tile, so
@@ -116,27 +116,10 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     return T;
   };
   auto bar = [&](int i) { return sbase + C::kOffBar + 8u * i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + C::kOffTmemPtr);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(C::kBarFull + s), 1); mbar_init(bar(C::kBarEmpty + s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(C::kBarAccFull + b), 1); mbar_init(bar(C::kBarAccEmpty + b), 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(C::kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
   if (warp == 8) {
     // ---- TMA producer ----
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)p.a_planes * kTileA + (uint32_t)p.b_planes * C::kTileB;
-      int it = 0;                                       // k-blocks issued so far (the ring runs across tiles)
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const Tile T = decode(t);
         const int m0 = T.m0, n0 = T.n0;
@@ -151,20 +134,20 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
           for (int pl = 0; pl < p.a_planes; ++pl) {
             const uint32_t d = dst + pl * kTileA;
             if (p.a_layout == 0) {
-              tma_load_5d(d, &ma, fb, k0 + p.a_k_off, m0 + p.a_row_off, abi, abo, pl);
+              tma_load_5d(d, ma, fb, k0 + p.a_k_off, m0 + p.a_row_off, abi, abo, pl);
             } else {
-              tma_load_5d(d, &ma, fb, m0 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
-              tma_load_5d(d + 8192, &ma, fb, m0 + 64 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+              tma_load_5d(d, ma, fb, m0 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
+              tma_load_5d(d + 8192, ma, fb, m0 + 64 + p.a_row_off, k0 + p.a_k_off, abi, abo, pl);
             }
           }
           for (int pl = 0; pl < p.b_planes; ++pl) {
             const uint32_t d = dst + 2 * kTileA + pl * C::kTileB;
             if (p.b_layout == 0) {
-              tma_load_5d(d, &mb, fb, k0 + p.b_k_off, n0 + p.b_row_off, bbi, bbo, pl);
+              tma_load_5d(d, mb, fb, k0 + p.b_k_off, n0 + p.b_row_off, bbi, bbo, pl);
             } else {
 #pragma unroll
               for (int s = 0; s < BN / 64; ++s)
-                tma_load_5d(d + s * 8192, &mb, fb, n0 + 64 * s + p.b_row_off, k0 + p.b_k_off, bbi, bbo, pl);
+                tma_load_5d(d + s * 8192, mb, fb, n0 + 64 * s + p.b_row_off, k0 + p.b_k_off, bbi, bbo, pl);
             }
           }
         }
@@ -175,7 +158,6 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     const bool leader = elect_one();
     const uint32_t idesc = idesc_bf16(128, BN, p.a_layout != 0, p.b_layout != 0);
     const uint32_t ka = p.a_layout ? 128u : 2u, kbs = p.b_layout ? 128u : 2u;   // descriptor advance per 16 k (16-byte units)
-    int it = 0, ti = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
       const Tile T = decode(t);
       const int buf = ti & 1;
@@ -204,7 +186,6 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
   } else {
     // ---- epilogue: 8 warps; TMEM lane = output row, the row's columns split between two threads (warps w and w + 4) ----
     const int quarter = warp & 3, half = warp >> 2;
-    int ti = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
     const Tile T = decode(t);
     const int m0 = T.m0, n0 = T.n0, bi = T.bi, bo = T.bo, nk = T.nk;
@@ -485,6 +466,91 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
     }   // tiles
   }
 
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUtensorMap mb, const Params p) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + C::kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + C::kOffTmemPtr);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(C::kBarFull + s), 1); mbar_init(bar(C::kBarEmpty + s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(C::kBarAccFull + b), 1); mbar_init(bar(C::kBarAccEmpty + b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(C::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  int it = 0, ti = 0;
+  run_problem<BN>(&ma, &mb, p, sbase, sgen, tmem, warp, lane, it, ti);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::kTmemCols));
+  }
+}
+
+// Several dependent GEMM problems in ONE cooperative launch (the products of the pseudo-inverse recurrence,
+// models/NystromAttention.py:31-33, and of its adjoint): problem i + 1 reads what problem i wrote, so the CTAs meet at a grid
+// barrier between problems.  Global writes of the epilogue (generic proxy) are made visible to the TMA loads (async proxy) of
+// the other CTAs by a proxy fence on both sides of the barrier.  Every problem has at most gridDim.x tiles.
+constexpr int kMaxChain = 24;
+struct ChainParams {
+  int count;
+  CUtensorMap maps[2 * kMaxChain];
+  Params p[kMaxChain];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+pgemm_chain_kernel(const __grid_constant__ ChainParams cp) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
+  auto bar = [&](int i) { return sbase + C::kOffBar + 8u * i; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + C::kOffTmemPtr);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(C::kBarFull + s), 1); mbar_init(bar(C::kBarEmpty + s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(C::kBarAccFull + b), 1); mbar_init(bar(C::kBarAccEmpty + b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::kOffTmemPtr), "r"(C::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  int it = 0, ti = 0;
+  for (int i = 0; i < cp.count; ++i) {
+    run_problem<BN>(&cp.maps[2 * i], &cp.maps[2 * i + 1], cp.p[i], sbase, sgen, tmem, warp, lane, it, ti);
+    if (i + 1 < cp.count) {
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      grid.sync();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 9) {
@@ -602,7 +668,8 @@ static bool operand_ok(const dml_pg_operand& o) {
 
 extern "C" {
 
-int dml_pgemm(const dml_pgemm_args* a, void* stream) {
+// validate one problem, encode its tensor maps and fill the kernel parameters; *bn_out = the tile width the problem needs
+static int prepare_problem(const dml_pgemm_args* a, dml::tc::pg::Params& p, CUtensorMap* ma, CUtensorMap* mb, int* bn_out) {
   using namespace dml;
   using namespace dml::tc;
   using namespace dml::tc::pg;
@@ -623,11 +690,10 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   if (softmax && (a->bias || a->resid || a->accumulate || a->relu || a->use_diag || a->ncol_split > 0 || a->absmax)) return DML_EINVAL;
   if (a->pair && ((a->ldp % 8) || (a->p_plane % 8) || (((uintptr_t)a->pair) & 15))) return DML_EINVAL;
   const int BN = softmax ? (a->N > 128 ? 256 : (a->N > 64 ? 128 : 64)) : (a->N > 64 ? 128 : 64);
-  CUtensorMap ma, mb;
   int rc;
-  if ((rc = make_map5(&ma, a->A, a->K, a->nb_inner, a->nb_outer, kBM)) || (rc = make_map5(&mb, a->B, a->K, a->nb_inner, a->nb_outer, BN)))
+  if ((rc = make_map5(ma, a->A, a->K, a->nb_inner, a->nb_outer, kBM)) || (rc = make_map5(mb, a->B, a->K, a->nb_inner, a->nb_outer, BN)))
     return rc;
-  Params p{};
+  p = Params{};
   p.M = a->M; p.N = a->N; p.K = a->K; p.nb_inner = a->nb_inner; p.splits = splits;
   p.a_layout = a->A.layout; p.b_layout = a->B.layout;
   p.a_planes = a->A.plane_stride ? 2 : 1; p.b_planes = a->B.plane_stride ? 2 : 1;
@@ -662,10 +728,27 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   const long long total = (long long)p.tiles_m * p.tiles_n * nz;
   if (total > 0x7fffffffLL) return DML_EUNSUPPORTED;
   p.total_tiles = (int)total;
+  *bn_out = BN;
+  return DML_OK;
+}
+
+static int device_sm_count() {
   int dev = 0, nsm = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
     nsm = 148;
-  dim3 grid((unsigned)min((long long)nsm, total));
+  return nsm;
+}
+
+int dml_pgemm(const dml_pgemm_args* a, void* stream) {
+  using namespace dml;
+  using namespace dml::tc;
+  using namespace dml::tc::pg;
+  CUtensorMap ma, mb;
+  Params p;
+  int BN = 0;
+  int rc = prepare_problem(a, p, &ma, &mb, &BN);
+  if (rc) return rc;
+  dim3 grid((unsigned)min(device_sm_count(), p.total_tiles));
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (BN == 64) {
@@ -679,6 +762,35 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
     pgemm_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(ma, mb, p);
   }
   DML_RETURN_LAUNCH();
+}
+
+int dml_pgemm_chain_max(void) { return dml::tc::pg::kMaxChain; }
+
+/* count <= dml_pgemm_chain_max() DEPENDENT problems in one cooperative launch: problem i + 1 may read what problem i wrote
+ * (grid barrier between problems).  Every problem must need the 128-wide tile (64 < N, no fused softmax over more than 128
+ * columns), have at most one tile per SM (tiles_m * tiles_n * batch <= SM count) and no split-K.                         */
+int dml_pgemm_chain(const dml_pgemm_args* args, int count, void* stream) {
+  using namespace dml;
+  using namespace dml::tc;
+  using namespace dml::tc::pg;
+  DML_CHECK_ARG(args && count > 0 && count <= kMaxChain);
+  static thread_local ChainParams cp;      // 14 KB: assembled here, copied into the launch (a kernel parameter) before returning
+  cp.count = count;
+  const int nsm = device_sm_count();
+  int grid = 1;
+  for (int i = 0; i < count; ++i) {
+    int BN = 0;
+    int rc = prepare_problem(&args[i], cp.p[i], &cp.maps[2 * i], &cp.maps[2 * i + 1], &BN);
+    if (rc) return rc;
+    if (BN != 128 || cp.p[i].splits != 1 || cp.p[i].total_tiles > nsm) return DML_EUNSUPPORTED;
+    grid = max(grid, cp.p[i].total_tiles);
+  }
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(pgemm_chain_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmemBytes)) != cudaSuccess)
+    return (int)e;
+  void* kargs[1] = {(void*)&cp};
+  e = cudaLaunchCooperativeKernel((void*)pgemm_chain_kernel<128>, dim3(grid), dim3(kThreads), kargs, Cfg<128>::kSmemBytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? DML_OK : (int)e;
 }
 
 int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mult, void* pair, int ldp, long long plane_stride,

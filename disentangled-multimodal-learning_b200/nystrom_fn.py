@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream
-from .pairs import Pair, pgemm
+from .pairs import Pair, chain, pgemm
 
 F32 = torch.float32
 
@@ -56,16 +56,17 @@ def pinv_forward(x_pair: Pair, x_f32: torch.Tensor, iters: int, B: int, H: int, 
     denom = ax.sum(-1).max() * ax.sum(-2).max()                      # GLOBAL over batch and heads (quirk T3)
     z = Pair.from_f32((x_f32.transpose(-1, -2) / denom).contiguous())
     saved = []
-    for _ in range(iters):
-        xz_f, xz = pgemm(x_pair, z, M=m, N=m, K=m, b_trans=True, batch=bt, want_pair=True)
-        # t3 = 15 I - xz (7 I - xz) = 15 I - (7 xz - xz xz)
-        _, t3 = pgemm(xz, xz, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=-1.0, resid=xz_f, resid_scale=7.0, diag=15.0,
-                      want_f32=False, want_pair=True)
-        _, t5 = pgemm(xz, t3, M=m, N=m, K=m, b_trans=True, batch=bt, diag=13.0, want_f32=False, want_pair=True)
-        _, z_new = pgemm(z, t5, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=0.25, want_f32=False, want_pair=True)
-        if save:
-            saved.append((z, xz, t3, t5))
-        z = z_new
+    with chain():        # the 4 x iters dependent products leave as chained cooperative launches (grid barrier between products)
+        for _ in range(iters):
+            xz_f, xz = pgemm(x_pair, z, M=m, N=m, K=m, b_trans=True, batch=bt, want_pair=True)
+            # t3 = 15 I - xz (7 I - xz) = 15 I - (7 xz - xz xz)
+            _, t3 = pgemm(xz, xz, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=-1.0, resid=xz_f, resid_scale=7.0, diag=15.0,
+                          want_f32=False, want_pair=True)
+            _, t5 = pgemm(xz, t3, M=m, N=m, K=m, b_trans=True, batch=bt, diag=13.0, want_f32=False, want_pair=True)
+            _, z_new = pgemm(z, t5, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=0.25, want_f32=False, want_pair=True)
+            if save:
+                saved.append((z, xz, t3, t5))
+            z = z_new
     return z, saved
 
 
@@ -73,23 +74,24 @@ def pinv_backward(x_pair: Pair, x_f32: torch.Tensor, saved, G_f: torch.Tensor, G
     """Adjoint of pinv_forward: G = d z_final (fp32 + pair) -> d x (fp32 [B, H, m, m])."""
     bt = (B, H)
     dx = None
-    for (z, P, t3, t5) in reversed(saved):
-        # z' = 1/4 z t5
-        dz_f, _ = pgemm(G, t5, M=m, N=m, K=m, batch=bt, alpha=0.25)                                    # 1/4 G t5^T
-        _, du4 = pgemm(z, G, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-0.25, want_f32=False, want_pair=True)
-        # t5 = 13 I - P t3
-        dP, _ = pgemm(du4, t3, M=m, N=m, K=m, batch=bt)                                                # du4 t3^T
-        du2_f, du2 = pgemm(P, du4, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, want_pair=True)   # -P^T du4
-        # t3 = 15 I - (7 P - P P)  =>  dP += 7 du2 - du2 P^T - P^T du2
-        pgemm(du2, P, M=m, N=m, K=m, batch=bt, alpha=-1.0, resid=du2_f, resid_scale=7.0, out=dP, accumulate=True)
-        _, dPp = pgemm(P, du2, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, out=dP, accumulate=True,
-                       want_pair=True)
-        # P = x z
-        if dx is None:
-            dx, _ = pgemm(dPp, z, M=m, N=m, K=m, batch=bt)                                             # dP z^T
-        else:
-            pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=True)
-        G_f, G = pgemm(x_pair, dPp, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dz_f, accumulate=True, want_pair=True)
+    with chain():
+        for (z, P, t3, t5) in reversed(saved):
+            # z' = 1/4 z t5
+            dz_f, _ = pgemm(G, t5, M=m, N=m, K=m, batch=bt, alpha=0.25)                                    # 1/4 G t5^T
+            _, du4 = pgemm(z, G, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-0.25, want_f32=False, want_pair=True)
+            # t5 = 13 I - P t3
+            dP, _ = pgemm(du4, t3, M=m, N=m, K=m, batch=bt)                                                # du4 t3^T
+            du2_f, du2 = pgemm(P, du4, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, want_pair=True)   # -P^T du4
+            # t3 = 15 I - (7 P - P P)  =>  dP += 7 du2 - du2 P^T - P^T du2
+            pgemm(du2, P, M=m, N=m, K=m, batch=bt, alpha=-1.0, resid=du2_f, resid_scale=7.0, out=dP, accumulate=True)
+            _, dPp = pgemm(P, du2, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, out=dP, accumulate=True,
+                           want_pair=True)
+            # P = x z
+            if dx is None:
+                dx, _ = pgemm(dPp, z, M=m, N=m, K=m, batch=bt)                                             # dP z^T
+            else:
+                pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=True)
+            G_f, G = pgemm(x_pair, dPp, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dz_f, accumulate=True, want_pair=True)
     # z0 = x^T / (max row-sum * max column-sum): small torch graph (the scalar couples all bags and heads)
     with torch.enable_grad():
         xr = x_f32.detach().requires_grad_(True)

@@ -7,6 +7,8 @@ storage and fuses the epilogue stages the path needs (include/dml_b200.h, `dml_p
 from __future__ import annotations
 
 import ctypes as C
+import threading
+from contextlib import contextmanager
 from typing import Optional
 
 import torch
@@ -17,6 +19,66 @@ from ._lib import PgemmArgs, PgOperand, call, ptr, stream
 BF16 = torch.bfloat16
 F32 = torch.float32
 F16 = torch.float16
+
+
+_tls = threading.local()
+
+
+class _Chain:
+    """Problems recorded inside `chain()`: launched together by dml_pgemm_chain (one cooperative kernel per group of
+    dml_pgemm_chain_max() dependent problems, a grid barrier between problems), or one by one where the chained form does not
+    apply (tile width other than 128, more tiles than SMs)."""
+
+    def __init__(self):
+        self.args, self.keep = [], []
+
+    def flush(self):
+        if not self.args:
+            return
+        lib = _lib.load(check_device=True)
+        cap = lib.dml_pgemm_chain_max()
+        st = stream()
+        i = 0
+        while i < len(self.args):
+            grp = self.args[i:i + cap]
+            arr = (PgemmArgs * len(grp))(*grp)
+            if _lib._timing_hook is not None:
+                _lib._timing_hook("dml_pgemm_chain", 0)
+            rc = lib.dml_pgemm_chain(C.addressof(arr), len(grp), st) if len(grp) > 1 else -2
+            if _lib._timing_hook is not None:
+                _lib._timing_hook("dml_pgemm_chain", 1)
+            if rc == 0:
+                _lib.launch_count += 1
+            elif rc == -2:                       # DML_E_UNSUPPORTED: the same problems as separate launches, in order
+                for a in grp:
+                    call("dml_pgemm", C.addressof(a), st)
+            else:
+                raise _lib.DmlError(f"dml_pgemm_chain failed: {rc}")
+            i += cap
+        self.args, self.keep = [], []
+
+
+import os as _os
+
+CHAIN_DEFAULT = _os.environ.get("DML_B200_PGEMM_CHAIN", "0") != "0"
+
+
+@contextmanager
+def chain(enabled: Optional[bool] = None):
+    """Record the pgemm() calls of the block and launch them as chained cooperative kernels at its end.  Only pgemm() calls
+    may touch the recorded operands inside the block (their results do not exist until it closes)."""
+    if enabled is None:
+        enabled = CHAIN_DEFAULT
+    if not enabled or getattr(_tls, "chain", None) is not None:
+        yield None
+        return
+    c = _Chain()
+    _tls.chain = c
+    try:
+        yield c
+    finally:
+        _tls.chain = None
+    c.flush()
 
 
 class Pair:
@@ -184,5 +246,10 @@ def pgemm(A: Pair, B: Pair, *, M: int, N: int, K: int, a_trans=False, b_trans=Fa
         a.aux, a.ldx, a.x_plane = xp.data_ptr(), xp.stride(-2), xp.stride(0)
         a.x_bs_inner, a.x_bs_outer = bstrides(xp[0], nb)
         keep.append(aux)
-    call("dml_pgemm", C.addressof(a), stream())
+    rec = getattr(_tls, "chain", None)
+    if rec is not None:
+        rec.args.append(a)
+        rec.keep.append((A, B, bias, resid, out, pair_out, half_out, aux, alpha_dev, half_scale_dev, absmax))
+    else:
+        call("dml_pgemm", C.addressof(a), stream())
     return out, pair_out

@@ -182,6 +182,12 @@ typedef struct dml_pgemm_args {
   long long x_bs_inner, x_bs_outer, x_plane;
 } dml_pgemm_args;
 int dml_pgemm(const dml_pgemm_args* args, void* stream);
+/* `count` (<= dml_pgemm_chain_max()) DEPENDENT problems in one cooperative launch - the products of the pseudo-inverse
+ * recurrence (models/NystromAttention.py:31-33) and of its adjoint: problem i + 1 may read what problem i wrote (a grid
+ * barrier separates them).  Each problem must use the 128-wide tile (N > 64, no fused softmax over more than 128 columns),
+ * have at most one output tile per SM and no split-K; otherwise DML_E_UNSUPPORTED (call dml_pgemm per problem instead).  */
+int dml_pgemm_chain_max(void);
+int dml_pgemm_chain(const dml_pgemm_args* args, int count, void* stream);
 /* x float [rows, cols] (row stride ld) * mult -> bf16 pair planes [rows, ldp], plane_stride elements apart.              */
 int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mult, void* pair, int ldp,
                       long long plane_stride, void* stream);
