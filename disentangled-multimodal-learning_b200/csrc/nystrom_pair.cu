@@ -118,27 +118,33 @@ res_conv_fwd_kernel(const float* __restrict__ a, const bf16* __restrict__ v, lon
     *reinterpret_cast<float4*>(sm + r * kCols + c4) = val;
   }
   __syncthreads();
-  const int c = threadIdx.x % kCols, rg = threadIdx.x / kCols;
+  // a thread owns two adjacent columns (same head: d is even) and 16 rows in two 8-row strips: 4-byte pair stores
+  const int c = (threadIdx.x % (kCols / 2)) * 2, rg = threadIdx.x / (kCols / 2);      // rg in 0..3
   const int col = cb + c, h = col / d;
   float wk[kKMax];
 #pragma unroll
   for (int t = 0; t < kKMax; ++t) wk[t] = t < K ? w[h * K + t] : 0.f;
-  for (int chunk = 0; chunk < 4; ++chunk) {
-    const int r0 = rg * 32 + chunk * 8;
-    float win[8 + kKMax - 1];
+  for (int chunk = 0; chunk < 2; ++chunk) {
+    const int r0 = rg * 16 + chunk * 8;
+    float win0[8 + kKMax - 1], win1[8 + kKMax - 1];
 #pragma unroll
-    for (int t = 0; t < 8 + kKMax - 1; ++t) win[t] = (t < 8 + K - 1) ? sm[(r0 + t) * kCols + c] : 0.f;
+    for (int t = 0; t < 8 + kKMax - 1; ++t) {
+      const float2 v2 = (t < 8 + K - 1) ? *reinterpret_cast<const float2*>(sm + (r0 + t) * kCols + c) : make_float2(0.f, 0.f);
+      win0[t] = v2.x; win1[t] = v2.y;
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int gi = i0 + r0 + r;
       if (gi < n_pad) {
         const size_t o = ((size_t)b * n_pad + gi) * W + col;
-        float acc = a[o];
+        const float2 a2 = *reinterpret_cast<const float2*>(a + o);
+        float acc0 = a2.x, acc1 = a2.y;
 #pragma unroll
-        for (int t = 0; t < kKMax; ++t) acc = fmaf(wk[t], win[r + t], acc);
-        const bf16 hi = __float2bfloat16_rn(acc);
-        y[o] = hi;
-        y[yplane + o] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+        for (int t = 0; t < kKMax; ++t) { acc0 = fmaf(wk[t], win0[r + t], acc0); acc1 = fmaf(wk[t], win1[r + t], acc1); }
+        uint32_t hi, lo;
+        split_bf16x2(acc0, acc1, hi, lo);
+        *reinterpret_cast<uint32_t*>(y + o) = hi;
+        *reinterpret_cast<uint32_t*>(y + yplane + o) = lo;
       }
     }
   }
@@ -174,9 +180,9 @@ res_conv_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ v, lo
   const int c = threadIdx.x % kCols, rg = threadIdx.x / kCols;
   const int col = cb + c, h = col / d;
   const int hl = (cb + c) / d - cb / d;
-  float wk[kKMax], gw[kKMax];
+  float wkf[kKMax], gw[kKMax];      // wkf = the taps flipped: dv[i] = sum_t wkf[t] dy[i - half + t]
 #pragma unroll
-  for (int t = 0; t < kKMax; ++t) { wk[t] = t < K ? w[h * K + t] : 0.f; gw[t] = 0.f; }
+  for (int t = 0; t < kKMax; ++t) { wkf[t] = t < K ? w[h * K + (K - 1 - t)] : 0.f; gw[t] = 0.f; }
   for (int chunk = 0; chunk < 4; ++chunk) {
     const int r0 = rg * 32 + chunk * 8;
     float wdy[8 + kKMax - 1], wv[8 + kKMax - 1];
@@ -189,11 +195,11 @@ res_conv_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ v, lo
     for (int r = 0; r < 8; ++r) {
       const int gi = i0 + r0 + r;
       if (gi < n_pad) {
-        const float g = wdy[r + half];
+        const float g = tdy[(r0 + r + half) * kCols + c];      // dy at row gi (a shared-memory read: `half` is not a compile-time index)
         float acc = 0.f;
 #pragma unroll
         for (int t = 0; t < kKMax; ++t) {
-          if (t < K) acc = fmaf(wk[t], wdy[r + K - 1 - t], acc);
+          acc = fmaf(wkf[t], wdy[r + t], acc);
           gw[t] = fmaf(g, wv[r + t], gw[t]);
         }
         dv[((size_t)b * n_pad + gi) * lddv + dcol0 + col] = acc;
