@@ -115,6 +115,70 @@ def test_world2_sharding_allreduce_gather():
         assert torch.equal(tgrad, wslice)
 
 
+def _bn_net():
+    torch.manual_seed(5)
+    return torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.Linear(8, 3))
+
+
+def _bn_worker(rank, port, q):
+    from dml_b200.sync_bn import convert_sync_batchnorm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        net = convert_sync_batchnorm(_bn_net()).train()
+        torch.manual_seed(200)
+        x, y = torch.randn(10, 6), torch.randn(10, 3)
+        sl = slice(0, 3) if rank == 0 else slice(3, 10)              # UNEQUAL shards: the counts must ride along
+        xs = x[sl].clone().requires_grad_()
+        out = net(xs)
+        # the single-process loss is a mean over all 10 rows: weight each rank's mean by its share
+        loss = ((out - y[sl]) ** 2).sum() / (10 * 3)
+        loss.backward()
+        for p in net.parameters():                                   # SUM (the loss above is already globally normalised)
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+        q.put((rank, out.detach().numpy().copy(), xs.grad.numpy().copy(),
+               {k: p.grad.numpy().copy() for k, p in net.named_parameters()},
+               {k: v.numpy().copy() for k, v in net.state_dict().items() if "running" in k or "num_batches" in k}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_sync_batchnorm_statistics_match_the_global_batch():
+    """SyncBatchNorm1d over 2 gloo ranks with 3 + 7 rows == nn.BatchNorm1d over the 10-row batch: outputs, input gradients,
+    parameter gradients, running statistics (reference: SyncBatchNorm conversion at main.py:189,400)."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bn_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(WORLD):
+        r = q.get(timeout=180)
+        res[r[0]] = r[1:]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    net = _bn_net().train()
+    torch.manual_seed(200)
+    x, y = torch.randn(10, 6), torch.randn(10, 3)
+    xr = x.clone().requires_grad_()
+    out = net(xr)
+    ((out - y) ** 2).mean().backward()
+    got_out = torch.cat([torch.from_numpy(res[0][0]), torch.from_numpy(res[1][0])])
+    got_gx = torch.cat([torch.from_numpy(res[0][1]), torch.from_numpy(res[1][1])])
+    assert torch.allclose(got_out, out.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got_gx, xr.grad, rtol=1e-4, atol=1e-6)
+    for k, p in net.named_parameters():
+        for rank in range(WORLD):
+            assert torch.allclose(torch.from_numpy(res[rank][2][k]), p.grad, rtol=1e-4, atol=1e-6), k
+    for k, v in net.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            for rank in range(WORLD):
+                assert torch.allclose(torch.from_numpy(res[rank][3][k]).float(), v.float(), rtol=1e-5, atol=1e-6), k
+
+
 def test_lpt_balancing_of_variable_length_bags():
     lengths = [16384, 4096, 8192, 12000, 6000, 15000, 5000, 9000]
     parts = parallel.balance_bags_by_cost(lengths, 4)
