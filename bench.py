@@ -455,6 +455,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from dml_b200.parallel import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None      # before any pinned host buffer is allocated
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -728,7 +730,8 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
                 "kernel_ms_per_step": {k: round(kavg[k] * kcalls[k], 4) for k in sorted(kavg, key=lambda k: -kavg[k] * kcalls[k])},
-                "roofline": roof, "cpu_baseline": cpu, "cls_row_only": cls_only, "sustained": sustained, "transmil": transmil}
+                "roofline": roof, "cpu_baseline": cpu, "cls_row_only": cls_only, "sustained": sustained, "transmil": transmil,
+                "host_binding": numa}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

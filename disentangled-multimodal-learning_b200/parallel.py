@@ -13,6 +13,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process (and with it the first-touch placement of the pinned host buffers it allocates next) to the CPUs of
+    the NUMA node the GPU hangs off.  With 8 ranks each copying a 33.5 MB bag per step, host buffers on the wrong socket
+    put every copy on the inter-socket link (round 1: end-to-end scaling 0.90 against 0.98 device-timed).  Best effort:
+    returns what it did; never raises."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception as ex:      # containers without /sys access, single-socket hosts, ...
+        info["error"] = repr(ex)[:120]
+    return info
+
+
 def shard_bags(num_bags: int, rank: int, world: int, *, epoch: int = 0, seed: int = 0, shuffle: bool = True,
                drop_last: bool = True) -> List[int]:
     """Indices of the bags this rank processes in `epoch`: the same partition as
