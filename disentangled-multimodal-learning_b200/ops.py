@@ -119,9 +119,9 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
             rstd1 = torch.empty_like(mean1)
             call("dml_layernorm_fwd_pair", ptr(x1f), ptr(lnw), ptr(lnb), B * n, dim, float(ln_eps), None, ptr(x1p.planes),
                  x1p.planes.stride(0), ptr(mean1), ptr(rstd1), st)
-            crow = [i0] if wy1 == 0.0 else [i0, i1]
-            xc_in = x2f[:, crow].contiguous()                          # [B, k, dim]
-            kc = len(crow)
+            kc = 1 if wy1 == 0.0 else 2                                # the centre rows i0 (, i0 + 1) are adjacent
+            crow = (i0, i0 + kc)
+            xc_in = x2f[:, crow[0]:crow[1]].contiguous()               # [B, k, dim]
             x2c = torch.empty_like(xc_in)
             mean2 = torch.empty(B * kc, device=dev, dtype=F32)
             rstd2 = torch.empty_like(mean2)
@@ -234,14 +234,14 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dx2t = torch.zeros(ctx.x2_shape, device=dev, dtype=F32)
         dlw = dlb = None
         if fused:
-            kc = len(crow)
+            kc = crow[1] - crow[0]
             dxc = torch.stack([wy0 * dcentre] + ([wy1 * dcentre] if kc == 2 else []), 1).contiguous()      # [B, k, dim]
             dxc_in = torch.empty_like(dxc)
             dlw2 = torch.empty(dim, device=dev, dtype=F32)
             dlb2 = torch.empty_like(dlw2)
             call("dml_layernorm_bwd", ptr(dxc), ptr(xc_in), ptr(lnw), ptr(mean2), ptr(rstd2), B * kc, dim, ptr(dxc_in), ptr(dlw2),
                  ptr(dlb2), st)
-            dx2t[:, crow] = dxc_in
+            dx2t[:, crow[0]:crow[1]] = dxc_in
         else:
             dx2t[:, i0] += wy0 * dcentre
             if wy1 != 0.0:

@@ -324,12 +324,17 @@ def test_fc1_on_a_bf16_bag_matches_fp32_linear(rows, N):
     r = synth.normal((rows, 128), 3, "r").to(DEV)
     y = ops.fc1_bf16_bag(x, W, b)
     gW, gb = torch.autograd.grad((y * r).sum(), (W, b))
-    xd, Wd, bd = x.double(), W.detach().double().requires_grad_(), b.detach().double().requires_grad_()
-    yd = torch.relu(xd @ Wd.t() + bd)
-    gWd, gbd = torch.autograd.grad((yd * r.double()).sum(), (Wd, bd))
-    H.assert_close(y, yd, 1e-4, "fc1(bf16 bag)")
-    H.assert_close(gW, gWd, 1e-4, "dW fc1")
-    H.assert_close(gb, gbd, 1e-4, "db fc1")
+    xd, Wd, bd = x.double(), W.detach().double(), b.detach().double()
+    pre = xd @ Wd.t() + bd
+    H.assert_close(y, torch.relu(pre), 1e-4, "fc1(bf16 bag)")
+    # ReLU boundary: a pre-activation within fp32 rounding of zero may land on either side; such rows move dW by a whole
+    # r_ij x_i vector (1e-2 of max|dW| each), which says nothing about the GEMMs.  The gradients are therefore checked for
+    # OUR activation pattern, and the pattern itself against fp64 everywhere outside a 1e-5 band around zero.
+    mask = (y > 0)
+    assert bool((mask == (pre > 0))[pre.abs() > 1e-5].all())
+    g = r.double() * mask
+    H.assert_close(gW, g.t() @ xd, 1e-4, "dW fc1")
+    H.assert_close(gb, g.sum(0), 1e-4, "db fc1")
 
 
 @pytest.mark.parametrize("task", ["diag2021", "survival"])
