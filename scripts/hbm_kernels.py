@@ -51,16 +51,31 @@ y = torch.empty_like(x); mean = torch.empty(n, device=dev); rstd = torch.empty(n
 report("layernorm_fwd [16385,128]", timeit(lambda: call("dml_layernorm_fwd", ptr(x), ptr(ln.weight), ptr(ln.bias), n, 128, 1e-5, ptr(y), ptr(mean), ptr(rstd), stream())), x.numel() * 8)
 dyv = synth.normal((n, 128), 4, "dy").to(dev); dx = torch.empty_like(x); dw = torch.empty(128, device=dev); db = torch.empty(128, device=dev)
 report("layernorm_bwd [16385,128]", timeit(lambda: call("dml_layernorm_bwd", ptr(dyv), ptr(x), ptr(ln.weight), ptr(mean), ptr(rstd), n, 128, ptr(dx), ptr(dw), ptr(db), stream())), x.numel() * 12)
-# ---- Nystrom layer @16k: n_pad = 16640, H = 8, d = 64, l = 65 ----
-n_pad, Hh, d, l = 16640, 8, 64, 65
-qkv = synth.normal((1, n_pad, 3 * Hh * d), 5, "qkv").to(dev)
-out = torch.empty(1, Hh, n_pad // l, d, device=dev)
-report("landmark_pool_fwd (q columns of the fused qkv buffer)", timeit(lambda: call("dml_landmark_pool_fwd", ptr(qkv), 3 * Hh * d, 0, 1, n_pad, l, Hh, d, 1.0 / l, ptr(out), stream())), n_pad * Hh * d * 4)
-a = synth.normal((1, Hh, n_pad, d), 6, "a").to(dev); wc = synth.uniform((Hh, 33), 6, "w", 0.2).to(dev); yv = torch.empty(1, n_pad, Hh * d, device=dev)
-vs = qkv[..., 2 * Hh * d:]
-report("res_conv_merge_fwd (a + conv33(v))", timeit(lambda: call("dml_res_conv_merge_fwd", ptr(a), ptr(vs), 3 * Hh * d, 0, ptr(wc), 33, 1, n_pad, Hh, d, ptr(yv), stream())), n_pad * Hh * d * 4 * 3)
-s1 = synth.normal((Hh, n_pad, 256), 7, "s").to(dev); y1 = torch.empty_like(s1)
-report("softmax_rows_fwd [8*16640, 256]", timeit(lambda: call("dml_softmax_rows_fwd", ptr(s1), ptr(y1), Hh * n_pad, 256, stream())), s1.numel() * 8)
-s3 = synth.normal((Hh, 256, n_pad), 8, "s3").to(dev); y3 = torch.empty_like(s3)
-report("softmax_rows_fwd [8*256, 16640]", timeit(lambda: call("dml_softmax_rows_fwd", ptr(s3), ptr(y3), Hh * 256, n_pad, stream())), s3.numel() * 8)
+# ---- Nystrom layer @16k on pair storage: n_pad = 16640, H = 8, d = 64, l = 65, m = 256 ----
+from dml_b200.pairs import Pair
+n_pad, Hh, d, l, m = 16640, 8, 64, 65, 256
+W = Hh * d
+xin = synth.normal((16385, 512), 4, "xin").to(dev); lnw = torch.ones(512, device=dev); lnb = torch.zeros(512, device=dev)
+xnp = Pair.empty((16385, 512), dev); mean5 = torch.empty(16385, device=dev); rstd5 = torch.empty_like(mean5)
+report("layernorm_fwd_pair [16385,512] (fp32 in, operand pair out)", timeit(lambda: call("dml_layernorm_fwd_pair", ptr(xin), ptr(lnw), ptr(lnb), 16385, 512, 1e-5, None, ptr(xnp.planes), xnp.planes.stride(0), ptr(mean5), ptr(rstd5), stream())), xin.numel() * 8)
+qkv = Pair.from_f32(synth.normal((1, n_pad, 3 * W), 5, "qkv").to(dev))
+lm = Pair.empty((2, 1, Hh, m, d), dev)
+report("ny_landmark_pool (q and k of the qkv pair)", timeit(lambda: call("dml_ny_landmark_pool", ptr(qkv.planes), qkv.planes.stride(0), 3 * W, 1, n_pad, l, Hh, d, 1.0 / l, 1.0 / l, ptr(lm.planes), lm.planes.stride(0), stream())), 2 * n_pad * W * 4)
+a = synth.normal((1, n_pad, W), 6, "a").to(dev); wc = synth.uniform((Hh, 33), 6, "w", 0.2).to(dev); om = Pair.empty((1, n_pad, W), dev)
+report("ny_res_conv_fwd (a + conv33(v) -> to_out operand pair)", timeit(lambda: call("dml_ny_res_conv_fwd", ptr(a), ptr(qkv.planes), qkv.planes.stride(0), 3 * W, 2 * W, ptr(wc), 33, 1, n_pad, Hh, d, ptr(om.planes), om.planes.stride(0), stream())), n_pad * W * 4 * 3)
+acc = torch.empty(1, n_pad, 3 * W, device=dev); dwc = torch.empty(Hh, 33, device=dev)
+report("ny_res_conv_bwd (dy fp32, v pair -> dv fp32, dw)", timeit(lambda: call("dml_ny_res_conv_bwd", ptr(a), ptr(qkv.planes), qkv.planes.stride(0), 3 * W, 2 * W, ptr(wc), 33, 1, n_pad, Hh, d, ptr(acc), 3 * W, 2 * W, ptr(dwc), stream())), n_pad * W * 4 * 3)
+s3 = synth.normal((Hh * m, n_pad), 8, "s3").to(dev); y3 = Pair.empty((Hh * m, n_pad), dev); d3 = Pair.empty((Hh * m, n_pad), dev)
+report("ny_softmax_rows_fwd [8*256, 16640] (fp32 in, pair out)", timeit(lambda: call("dml_ny_softmax_rows_fwd", ptr(s3), Hh * m, n_pad, ptr(y3.planes), y3.planes.stride(0), stream())), s3.numel() * 8)
+report("ny_softmax_rows_bwd [8*256, 16640] (pair + fp32 in, pair out)", timeit(lambda: call("dml_ny_softmax_rows_bwd", ptr(y3.planes), y3.planes.stride(0), ptr(s3), Hh * m, n_pad, ptr(d3.planes), d3.planes.stride(0), stream())), s3.numel() * 12)
+dl = synth.normal((2, 1, Hh, m, d), 9, "dl").to(dev); dq = Pair.empty((1, n_pad, 3 * W), dev)
+report("ny_dqkv_finalize (fp32 in, pair out)", timeit(lambda: call("dml_ny_dqkv_finalize", ptr(acc), ptr(dl), 1, n_pad, l, Hh, d, 0.125, ptr(dq.planes), dq.planes.stride(0), stream())), acc.numel() * 8)
+xp = synth.normal((1, 1 + 128 * 128, 512), 10, "xp").to(dev); yp = torch.empty_like(xp)
+ws = synth.uniform((512, 49), 10, "ws", 0.1).to(dev); bs = torch.zeros(512, device=dev); dws = torch.empty(512, 49, device=dev); dbs = torch.empty(512, device=dev)
+report("ppeg_stencil [128x128 grid, 512 ch] (7x7 depthwise, fp32)", timeit(lambda: call("dml_ppeg_stencil", ptr(xp), ptr(ws), ptr(bs), 1, 128, 512, 0, ptr(yp), stream())), xp.numel() * 8)
+report("ppeg_wgrad [128x128 grid, 512 ch]", timeit(lambda: call("dml_ppeg_wgrad", ptr(xp), ptr(yp), 1, 128, 512, ptr(dws), ptr(dbs), stream())), xp.numel() * 8)
+big = synth.normal((16385, 512), 11, "big").to(dev); bp = Pair.empty((16385, 512), dev)
+report("pair_from_f32 [16385,512]", timeit(lambda: call("dml_pair_from_f32", ptr(big), 16385, 512, 512, 1.0, ptr(bp.planes), 512, bp.planes.stride(0), stream())), big.numel() * 8)
+cs = torch.empty(512, device=dev)
+report("colsum [16385,512]", timeit(lambda: call("dml_colsum", ptr(big), 16385, 512, 512, ptr(cs), stream())), big.numel() * 4)
 print(json.dumps({"hbm_peak_gbs_measured": PEAK, "kernels": res}, indent=1))
