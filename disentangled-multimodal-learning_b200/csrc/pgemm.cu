@@ -26,6 +26,7 @@
 // 32-column groups, vector loads / stores; one CTA per SM, so the epilogue's own parallelism is what hides its latencies).
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/dml_b200.h"
 #include "tc_common.cuh"
@@ -479,6 +480,11 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
   const int warp = warp_index_uniform(), lane = threadIdx.x & 31;
   auto bar = [&](int i) { return sbase + C::kOffBar + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + C::kOffTmemPtr);
+  // Programmatic dependent launch: the next kernel of the stream may start its own prologue (barrier init, TMEM allocation,
+  // descriptor fetch) on idle SMs while this grid is still running - chains of small dependent products (the pseudo-inverse
+  // recurrence: 32 CTAs each) are bound by exactly that per-launch latency.  Nothing below touches global memory before
+  // griddepcontrol.wait, which returns once the preceding grid has completed and its writes are visible.
+  if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(C::kBarFull + s), 1); mbar_init(bar(C::kBarEmpty + s), 1); }
@@ -493,6 +499,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap ma, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   int it = 0, ti = 0;
   run_problem<BN>(&ma, &mb, p, sbase, sgen, tmem, warp, lane, it, ti);
@@ -748,20 +755,31 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   int BN = 0;
   int rc = prepare_problem(a, p, &ma, &mb, &BN);
   if (rc) return rc;
-  dim3 grid((unsigned)min(device_sm_count(), p.total_tiles));
-  cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)min(device_sm_count(), p.total_tiles));
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see the kernel: griddepcontrol.wait guards every global access
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = []() { const char* v = getenv("DML_B200_PDL"); return !(v && v[0] == '0'); }();
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   if (BN == 64) {
     if ((e = cudaFuncSetAttribute(pgemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmemBytes)) != cudaSuccess) return (int)e;
-    pgemm_kernel<64><<<grid, kThreads, Cfg<64>::kSmemBytes, st>>>(ma, mb, p);
+    cfg.dynamicSmemBytes = Cfg<64>::kSmemBytes;
+    e = cudaLaunchKernelEx(&cfg, pgemm_kernel<64>, ma, mb, p);
   } else if (BN == 128) {
     if ((e = cudaFuncSetAttribute(pgemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmemBytes)) != cudaSuccess) return (int)e;
-    pgemm_kernel<128><<<grid, kThreads, Cfg<128>::kSmemBytes, st>>>(ma, mb, p);
+    cfg.dynamicSmemBytes = Cfg<128>::kSmemBytes;
+    e = cudaLaunchKernelEx(&cfg, pgemm_kernel<128>, ma, mb, p);
   } else {
     if ((e = cudaFuncSetAttribute(pgemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmemBytes)) != cudaSuccess) return (int)e;
-    pgemm_kernel<256><<<grid, kThreads, Cfg<256>::kSmemBytes, st>>>(ma, mb, p);
+    cfg.dynamicSmemBytes = Cfg<256>::kSmemBytes;
+    e = cudaLaunchKernelEx(&cfg, pgemm_kernel<256>, ma, mb, p);
   }
-  DML_RETURN_LAUNCH();
+  return e == cudaSuccess ? DML_OK : (int)e;
 }
 
 int dml_pgemm_chain_max(void) { return dml::tc::pg::kMaxChain; }
