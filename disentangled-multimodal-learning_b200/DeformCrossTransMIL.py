@@ -78,6 +78,8 @@ class DeformCrossTransMIL(nn.Module):
             raise NotImplementedError("only attn_dim == 1 is supported (SURVEY.md Q6)")
         if getattr(self.args, "return_vgrid", False):
             raise NotImplementedError("return_vgrid with attn_dim == 1 raises in the reference (SURVEY.md Q6)")
+        if path.is_cuda:      # the bias table depends on the CPB weights only: start it before fc1, off the critical chain
+            self.layer3.attn1d.prefetch_bias_table(path.shape[1] + 1, path.device)
         fc1 = self._fc1[0]
         # fc1 + ReLU (:100) on the pair GEMM, bias and ReLU in its epilogue; a bf16 bag enters as it is (one exact plane)
         path = ops.linear_pg(path, fc1.weight, fc1.bias, relu=True)

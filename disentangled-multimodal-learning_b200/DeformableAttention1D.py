@@ -104,6 +104,18 @@ class DeformCrossAttention1D(nn.Module):
             unsupported.append("more than 2 heads per offset group")
         self._unsupported = unsupported
 
+    def prefetch_bias_table(self, n: int, device):
+        """Start building the position-bias table for a sequence of n tokens now (it only depends on the CPB parameters): the
+        next forward() on the same stream picks it up instead of building it right before the attention kernel."""
+        mlp = self.rel_pos_bias.mlp
+        ws = [t.detach().contiguous().float() for t in (mlp[0][0].weight.reshape(-1), mlp[0][0].bias, mlp[1][0].weight,
+                                                        mlp[1][0].bias, mlp[2].weight, mlp[2].bias)]
+        n_kv = ops.kv_length(n, self.offset_kernel_size, self.downsample_factor)
+        if n_kv < 1:
+            return
+        self._prefetched = (n, ops.build_bias_table(ws, ws[0].shape[0], self.heads // self.offset_groups, n_kv,
+                                                    float(self.offset_scale), device))
+
     def forward(self, x1, x2, return_vgrid=False, rows=None, _norm=None):
         """x1, x2: [b, dim, n] channel-first (reference layout).  Returns [b, dim, n] (+ vgrid [(b g), n_kv]).
         rows (extension, default None = the reference contract): compute the attention output only for the first
@@ -117,8 +129,11 @@ class DeformCrossAttention1D(nn.Module):
             raise NotImplementedError("attention dropout > 0 is not implemented in the fused kernel "
                                       "(the reference never sets it for the 1-D layer)")
         mlp = self.rel_pos_bias.mlp
+        pre = getattr(self, "_prefetched", None)
+        self._prefetched = None
         cfg = (self.heads, self.dim_head, self.offset_groups, self.downsample_factor, self.offset_kernel_size,
-               float(self.offset_scale), int(rows or 0), float(_norm.eps) if _norm is not None else 0.0)
+               float(self.offset_scale), int(rows or 0), float(_norm.eps) if _norm is not None else 0.0,
+               pre[1] if pre is not None and pre[0] == x1.shape[-1] else None)
         out_t, vgrid = ops.DeformCrossAttn1DFn.apply(
             x1.transpose(1, 2), x2.transpose(1, 2),
             self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_out.weight, self.to_out.bias,

@@ -43,7 +43,8 @@ SIGNATURES = {
     "dml_pgemm_chain": (_i, [C.c_void_p, _i, _vp]),
     "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
     "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
-    "dml_relu_mask_pair": (_i, [_fp, _fp, _ll, _i, _i, _i, _vp, _i, _ll, _vp]),
+    "dml_scale_to_half": (_i, [_fp, _fp, _ll, _vp, _vp]),
+    "dml_relu_mask_pair": (_i, [_fp, _fp, _fp, _ll, _i, _i, _i, _vp, _i, _ll, _vp]),
     "dml_layernorm_fwd_pair": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _vp, _ll, _fp, _fp, _vp]),
     "dml_ny_landmark_pool": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _ll, _vp]),
     "dml_ny_softmax_rows_fwd": (_i, [_fp, _ll, _i, _vp, _ll, _vp]),
@@ -168,7 +169,7 @@ KERNELS_PER_CALL = {
     "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1,
     "dml_pgemm": 1, "dml_pgemm_chain": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
-    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1,
+    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1, "dml_scale_to_half": 1,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events

@@ -107,6 +107,7 @@ res_conv_fwd_kernel(const float* __restrict__ a, const bf16* __restrict__ v, lon
   const int half = K / 2;
   const int i0 = blockIdx.x * kRows, cb = blockIdx.y * kCols, b = blockIdx.z;
   const int trow = kRows + K - 1;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < trow * (kCols / 4); idx += blockDim.x) {
     const int r = idx / (kCols / 4), c4 = (idx % (kCols / 4)) * 4;
     const int gi = i0 + r - half;
@@ -163,6 +164,7 @@ res_conv_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ v, lo
   float* tdy = sm;
   float* tv = sm + trow * kCols;
   float* wred = tv + trow * kCols;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < trow * (kCols / 4); idx += blockDim.x) {
     const int r = idx / (kCols / 4), c4 = (idx % (kCols / 4)) * 4;
     const int gi = i0 + r - half;
@@ -267,15 +269,18 @@ dqkv_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ dl
 constexpr int kPTH = 8, kPTW = 16, kPHW = kPTW + 6, kPHH = kPTH + 6;
 
 __device__ __forceinline__ void ppeg_stage_tile(const float* __restrict__ g, int side, int C, int c0, int y0, int x0, float* sm) {
-  // sm[(hy * kPHW + hx) * 32 + lane] = g[pixel (y0 - 3 + hy, x0 - 3 + hx), channel c0 + lane]  (zero outside the grid)
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  for (int i = wp; i < kPHH * kPHW; i += 8) {
+  // sm[(hy * kPHW + hx) * 32 + ch] = g[pixel (y0 - 3 + hy, x0 - 3 + hx), channel c0 + ch]  (zero outside the grid): 16-byte
+  // cp.async copies with zero fill, all in flight at once (a register-staged loop paid one L2 latency per halo pixel)
+  for (int idx = threadIdx.x; idx < kPHH * kPHW * 8; idx += blockDim.x) {
+    const int i = idx >> 3, ch = (idx & 7) * 4;
     const int hy = i / kPHW, hx = i - hy * kPHW;
     const int yy = y0 - 3 + hy, xx = x0 - 3 + hx;
-    float v = 0.f;
-    if (yy >= 0 && yy < side && xx >= 0 && xx < side && c0 + lane < C) v = g[((size_t)yy * side + xx) * C + c0 + lane];
-    sm[i * 32 + lane] = v;
+    const bool ok = yy >= 0 && yy < side && xx >= 0 && xx < side && c0 + ch < C;
+    const float* src = ok ? g + ((size_t)yy * side + xx) * C + c0 + ch : g;
+    cp_async16(smem_u32(sm + i * 32 + ch), src, ok);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(256)
@@ -463,6 +468,7 @@ int dml_ppeg_stencil(const float* x, const float* wsum, const float* bsum, int B
                      void* stream) {
   using namespace dml;
   DML_CHECK_ARG(x && wsum && bsum && y && B > 0 && side > 0 && C > 0);
+  if ((C % 4) || ((((uintptr_t)x) | ((uintptr_t)y)) & 15)) return DML_EUNSUPPORTED;
   dim3 grid(cdiv(C, 32), cdiv(side, nyp::kPTH) * cdiv(side, nyp::kPTW), B);
   if (grid.y > 65535 || B > 65535) return DML_EUNSUPPORTED;
   nyp::ppeg_stencil_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, wsum, bsum, side, C, flip, y);
@@ -472,6 +478,7 @@ int dml_ppeg_stencil(const float* x, const float* wsum, const float* bsum, int B
 int dml_ppeg_wgrad(const float* x, const float* dy, int B, int side, int C, float* dw, float* db, void* stream) {
   using namespace dml;
   DML_CHECK_ARG(x && dy && dw && db && B > 0 && side > 0 && C > 0);
+  if ((C % 4) || (((uintptr_t)x) & 15)) return DML_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C * 49, st);
   if (e != cudaSuccess) return (int)e;

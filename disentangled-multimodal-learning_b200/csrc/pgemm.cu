@@ -601,10 +601,10 @@ pair_from_f32_kernel(const float* __restrict__ x, long long rows, int cols, int 
   }
 }
 
-// ReLU backward fused with the pair conversion: g[r, c] := act[r, c] > 0 ? g[r, c] : 0 (written back in place) and as a bf16 pair
+// ReLU backward fused with the pair conversion: gm[r, c] = act[r, c] > 0 ? g[r, c] : 0, as fp32 (gm may alias g) and as a bf16 pair
 __global__ void __launch_bounds__(256)
-relu_mask_pair_kernel(float* __restrict__ g, const float* __restrict__ act, long long rows, int cols, int ldg, int lda,
-                      bf16* __restrict__ out, int ldp, long long plane) {
+relu_mask_pair_kernel(const float* __restrict__ g, float* __restrict__ gm, const float* __restrict__ act, long long rows, int cols,
+                      int ldg, int lda, bf16* __restrict__ out, int ldp, long long plane) {
   const int cols4 = cols >> 2;
   const long long total = rows * cols4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -613,9 +613,20 @@ relu_mask_pair_kernel(float* __restrict__ g, const float* __restrict__ act, long
     float4 v = *reinterpret_cast<const float4*>(g + r * ldg + c);
     const float4 a = *reinterpret_cast<const float4*>(act + r * lda + c);
     v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f; v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
-    *reinterpret_cast<float4*>(g + r * ldg + c) = v;
+    *reinterpret_cast<float4*>(gm + r * ldg + c) = v;
     bf16* oh = out + r * ldp + c;
     store_pair4(oh, oh + plane, v.x, v.y, v.z, v.w);
+  }
+}
+
+// x * (*scale) -> fp16, 8 elements per thread (the loss-scaled dO operand of the attention backward)
+__global__ void __launch_bounds__(256)
+scale_to_half_kernel(const float* __restrict__ x, const float* __restrict__ scale, long long n8, h16* __restrict__ out) {
+  const float s = __ldg(scale);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i * 8), b = *reinterpret_cast<const float4*>(x + i * 8 + 4);
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_f16(a.x * s, a.y * s), pack_f16(a.z * s, a.w * s), pack_f16(b.x * s, b.y * s),
+                                                        pack_f16(b.z * s, b.w * s));
   }
 }
 
@@ -822,14 +833,23 @@ int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mu
   DML_RETURN_LAUNCH();
 }
 
-int dml_relu_mask_pair(float* g, const float* act, long long rows, int cols, int ldg, int lda, void* pair, int ldp,
+int dml_relu_mask_pair(const float* g, float* gm, const float* act, long long rows, int cols, int ldg, int lda, void* pair, int ldp,
                        long long plane_stride, void* stream) {
   using namespace dml;
-  DML_CHECK_ARG(g && act && pair && rows > 0 && cols > 0 && (cols % 4) == 0 && (ldg % 4) == 0 && (lda % 4) == 0 && (ldp % 4) == 0);
+  DML_CHECK_ARG(g && gm && ((((uintptr_t)gm) & 15) == 0) && act && pair && rows > 0 && cols > 0 && (cols % 4) == 0 && (ldg % 4) == 0 && (lda % 4) == 0 && (ldp % 4) == 0);
   DML_CHECK_ARG(((((uintptr_t)g) | ((uintptr_t)act)) & 15) == 0 && (((uintptr_t)pair) & 7) == 0 && (plane_stride % 4) == 0);
   const long long total = rows * (cols / 4);
   const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
-  tc::pg::relu_mask_pair_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, act, rows, cols, ldg, lda, (bf16*)pair, ldp, plane_stride);
+  tc::pg::relu_mask_pair_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, gm, act, rows, cols, ldg, lda, (bf16*)pair, ldp, plane_stride);
+  DML_RETURN_LAUNCH();
+}
+
+int dml_scale_to_half(const float* x, const float* scale_dev, long long n, void* out, void* stream) {
+  using namespace dml;
+  DML_CHECK_ARG(x && scale_dev && out && n > 0 && (n % 8) == 0 && ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0);
+  const long long n8 = n / 8;
+  const int blocks = (int)min((n8 + 255) / 256, (long long)148 * 16);
+  tc::pg::scale_to_half_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, scale_dev, n8, (h16*)out);
   DML_RETURN_LAUNCH();
 }
 

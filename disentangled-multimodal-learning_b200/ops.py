@@ -52,6 +52,19 @@ def side_stream(dev) -> torch.cuda.Stream:
 DS_WS_MAX_BYTES = int(float(os.environ.get("DML_B200_DS_WS_MAX_GB", "6")) * (1 << 30))
 
 
+def build_bias_table(mlp, hid: int, nout: int, n_kv: int, offset_scale: float, dev):
+    """Launch dml_cpb_table_build for the CPB MLP parameters `mlp` (contiguous fp32: w1, b1, W2, b2, W3, b3) on the auxiliary
+    stream of the current stream; returns (table, event recorded after the build)."""
+    table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
+    t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
+    cur, side = torch.cuda.current_stream(), side_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), stream())
+        ev = side.record_event()
+    return table, ev
+
+
 def loss_scale_from_amax(amax_bits: torch.Tensor) -> torch.Tensor:
     """Device-side power-of-two loss scale from the bit pattern of max|t| (the `absmax` output of dml_pgemm): float[2] =
     (s, 1/s) with 4 < s * max|t| <= 8 (s = 1 for an all-zero tensor); no host synchronisation."""
@@ -79,7 +92,8 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x1t, x2t, Wq, Wk, Wv, Wo, bo, w0, b0, w2, m_w1, m_b1, m_W2, m_b2, m_W3, m_b3, ln_w, ln_b, cfg):
         from .pairs import Pair, pgemm
-        H, d, G, stride, ks, offset_scale, rows, ln_eps = cfg
+        H, d, G, stride, ks, offset_scale, rows, ln_eps = cfg[:8]
+        prefetched = cfg[8] if len(cfg) > 8 else None
         B, n, dim = x1t.shape
         C = H * d
         Cg = C // G
@@ -102,14 +116,13 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         Wkv_p = Pair.from_f32(torch.cat((Wk.reshape(C, dim), Wv.reshape(C, dim)), 0))
         Wo_p = Pair.from_f32(Wo.reshape(dim, C))
 
-        # the bias table only depends on the MLP weights: build it on the side stream, next to the projections
-        table = torch.empty(_lib.load().dml_cpb_table_bytes(), device=dev, dtype=torch.uint8)
-        t_max = math.log1p(2.0 + 2.0 * float(offset_scale) / max(n_kv - 1, 1)) * 1.001 + 1e-3
+        # the bias table only depends on the MLP weights: it is built on the side stream, next to the projections - or was
+        # started even earlier by the caller (prefetch_bias_table, at the top of DeformCrossTransMIL.forward)
         cur, side = torch.cuda.current_stream(), side_stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), stream())
-
+        if prefetched is not None:
+            table, table_ready = prefetched
+        else:
+            table, table_ready = build_bias_table(mlp, hid, nout, n_kv, offset_scale, dev)
         i0, i1, wy0, wy1 = centre_taps(n)
         if fused:
             # shared LayerNorm: every row of x1 (as the to_q operand pair only), the centre rows of x2
@@ -145,7 +158,8 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         kvh = torch.empty(B, n_kv, 2 * C, device=dev, dtype=F16)            # k | v (:199), one GEMM
         pgemm(kv_p, Wkv_p.b1(), M=n_kv, N=2 * C, K=dim, batch=(B,), want_f32=False, half_out=kvh)
         k, v = kvh[..., :C], kvh[..., C:]
-        cur.wait_stream(side)                                             # bias table ready
+        cur.wait_event(table_ready)                                       # bias table ready
+        table.record_stream(cur)
         # offsets / keys / values always need every query position; the attention itself only the first n_out rows
         q_att = q if n_out == n else q[:, :n_out].contiguous()
         o = torch.empty(B, n_out, C, device=dev, dtype=F32)
@@ -156,7 +170,7 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         out, _ = pgemm(o_p, Wo_p.b1(), M=n_out, N=dim, K=C, batch=(B,), bias=bo.contiguous().float(),
                        resid=x1f[:, :n_out] if fused else None)          # to_out (:233) [+ the layer's residual]
 
-        ctx.cfg = cfg
+        ctx.cfg = cfg[:8]
         ctx.taps = (i0, i1, wy0, wy1, gi0, gi1, gn, crow)
         ctx.pairs = (x1p, kv_p, o_p, Wq_p, Wkv_p, Wo_p)
         ctx.save_for_backward(x1f, x2c, q, q_att, kvh, g, table, o, lse, w0f, b0f, w2f, lnw, mean1, rstd1, xc_in, mean2, rstd2, *mlp)
@@ -196,7 +210,10 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
             call("dml_colsum", ptr(dout), B * n_out, dim, dim, ptr(dbo), stream())
         dscale = loss_scale_from_amax(amax)
         d_o16 = torch.empty(d_o.shape, device=dev, dtype=F16)
-        torch.mul(d_o, dscale[0], out=d_o16)                               # scale and round in one pass
+        if d_o.numel() % 8 == 0:
+            call("dml_scale_to_half", ptr(d_o), ptr(dscale), d_o.numel(), ptr(d_o16), st)      # scale and round in one pass
+        else:
+            torch.mul(d_o, dscale[0], out=d_o16)
 
         dq_attn = torch.empty(B, n_out, C, device=dev, dtype=F32)
         dk = torch.empty(B, n_kv, C, device=dev, dtype=F32)
@@ -326,9 +343,15 @@ class LinearPgFn(torch.autograd.Function):
         rows, K = xp.shape
         N = Wp.shape[0]
         dy = dy.contiguous().float()
-        if ctx.relu:
-            dy = torch.where(y > 0, dy, torch.zeros((), device=dy.device, dtype=dy.dtype))
-        dyp = Pair.from_f32(dy)
+        if ctx.relu and N % 8 == 0:
+            dym = torch.empty_like(dy)                  # the incoming gradient belongs to autograd: the masked copy is ours
+            dyp = Pair.empty((rows, N), dy.device)
+            call("dml_relu_mask_pair", ptr(dy), ptr(dym), ptr(y), rows, N, N, N, ptr(dyp.planes), N, dyp.planes.stride(0), stream())
+            dy = dym
+        else:
+            if ctx.relu:
+                dy = torch.where(y > 0, dy, torch.zeros((), device=dy.device, dtype=dy.dtype))
+            dyp = Pair.from_f32(dy)
         dW = torch.zeros(N, K, device=dy.device, dtype=F32)
         tiles = ((N + 127) // 128) * ((K + 127) // 128)
         splits = max(1, min(((rows + 63) // 64) // 8, (148 + tiles - 1) // tiles))

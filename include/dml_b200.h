@@ -191,10 +191,13 @@ int dml_pgemm_chain(const dml_pgemm_args* args, int count, void* stream);
 /* x float [rows, cols] (row stride ld) * mult -> bf16 pair planes [rows, ldp], plane_stride elements apart.              */
 int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mult, void* pair, int ldp,
                       long long plane_stride, void* stream);
-/* ReLU backward fused with the pair conversion (fc1 + ReLU, DeformCrossTransMIL.py:100 / mil.py:229): g[r, c] := act[r, c] > 0 ?
- * g[r, c] : 0, written back in place (row stride ldg) and as a bf16 pair [rows, ldp]; act row stride lda.               */
-int dml_relu_mask_pair(float* g, const float* act, long long rows, int cols, int ldg, int lda, void* pair, int ldp,
-                       long long plane_stride, void* stream);
+/* ReLU backward fused with the pair conversion (fc1 + ReLU, DeformCrossTransMIL.py:100 / mil.py:229): gm[r, c] = act[r, c] > 0 ?
+ * g[r, c] : 0 as fp32 (row stride ldg for g and gm; gm may alias g) and as a bf16 pair [rows, ldp]; act row stride lda.  */
+int dml_relu_mask_pair(const float* g, float* gm, const float* act, long long rows, int cols, int ldg, int lda, void* pair,
+                       int ldp, long long plane_stride, void* stream);
+/* out (fp16) = x * (*scale_dev) over n contiguous floats (n a multiple of 8): the loss-scaled dO operand of the attention
+ * backward, scale from the device-side loss scale (no host synchronisation).                                            */
+int dml_scale_to_half(const float* x, const float* scale_dev, long long n, void* out, void* stream);
 /* out[c] = sum_r x[r, c] (bias gradients over the tokens); out float [cols] is overwritten.                              */
 int dml_colsum(const float* x, long long rows, int cols, int ld, float* out, void* stream);
 
