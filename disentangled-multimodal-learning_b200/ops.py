@@ -416,6 +416,58 @@ def fc1_bf16_bag(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor) -> torch.Ten
     return LinearPgFn.apply(x, W, b, True)
 
 
+class MaxNetFn(torch.autograd.Function):
+    """The omic MLP of MaxNet (models/model.py:173-218): 4 x (Linear -> ELU -> AlphaDropout) -> ReLU as one kernel per
+    direction (csrc/maxnet.cu).  x [B, in]; params = W0, b0, ..., W3, b3; p = AlphaDropout probability (0 in eval mode)."""
+
+    @staticmethod
+    def forward(ctx, x, p, *params):
+        import ctypes as C
+        x = x.contiguous().float()
+        B = x.shape[0]
+        Ws = [w.contiguous().float() for w in params[0::2]]
+        bs = [b.contiguous().float() for b in params[1::2]]
+        dims = [x.shape[1]] + [w.shape[0] for w in Ws]
+        dev = x.device
+        na, nh = sum(dims[1:]), sum(dims[:-1])
+        u = torch.rand(B, na, device=dev, dtype=F32) if p > 0.0 else None
+        act = torch.empty(B, na, device=dev, dtype=F32)
+        hsave = torch.empty(B, nh, device=dev, dtype=F32)
+        feat = torch.empty(B, dims[-1], device=dev, dtype=F32)
+        Wp = (C.c_void_p * 4)(*[w.data_ptr() for w in Ws])
+        bp = (C.c_void_p * 4)(*[b.data_ptr() for b in bs])
+        dm = (C.c_int * 5)(*dims)
+        call("dml_maxnet_fwd", ptr(x), Wp, bp, dm, B, ptr(u) if u is not None else None, float(p), ptr(act), ptr(hsave),
+             ptr(feat), stream())
+        ctx.p, ctx.dims = float(p), dims
+        ctx.save_for_backward(u, act, hsave, feat, *Ws, *bs)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        import ctypes as C
+        u, act, hsave, feat, *wb = ctx.saved_tensors
+        Ws, bs = wb[:4], wb[4:]
+        dims = ctx.dims
+        B = feat.shape[0]
+        dfeat = dfeat.contiguous().float()
+        sizes = [dims[l + 1] * dims[l] + dims[l + 1] for l in range(4)]
+        dparams = torch.empty(sum(sizes), device=feat.device, dtype=F32)
+        dx = torch.empty(B, dims[0], device=feat.device, dtype=F32) if ctx.needs_input_grad[0] else None
+        Wp = (C.c_void_p * 4)(*[w.data_ptr() for w in Ws])
+        bp = (C.c_void_p * 4)(*[b.data_ptr() for b in bs])
+        dm = (C.c_int * 5)(*dims)
+        call("dml_maxnet_bwd", ptr(dfeat), Wp, bp, dm, B, ptr(u) if u is not None else None, ctx.p, ptr(act), ptr(hsave), ptr(feat),
+             ptr(dparams), ptr(dx) if dx is not None else None, stream())
+        grads, off = [], 0
+        for l in range(4):
+            nw = dims[l + 1] * dims[l]
+            grads.append(dparams[off: off + nw].view(dims[l + 1], dims[l]))
+            grads.append(dparams[off + nw: off + nw + dims[l + 1]])
+            off += sizes[l]
+        return (dx, None, *grads)
+
+
 class LayerNormFn(torch.autograd.Function):
     """LayerNorm over the last dim (128 / 256 / 512) of a contiguous fp32 tensor: one warp per row, statistics saved
     for the backward, weight / bias gradients reduced per CTA (DeformCrossTransLayer.norm, TransLayer.norm)."""

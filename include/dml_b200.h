@@ -236,6 +236,18 @@ int dml_ppeg_stencil(const float* x, const float* wsum, const float* bsum, int B
                      void* stream);
 int dml_ppeg_wgrad(const float* x, const float* dy, int B, int side, int C, float* dw, float* db, void* stream);
 
+/* ---- MaxNet: the omic MLP in front of each tower (models/model.py:173-218) as one kernel per direction ------------------
+ * Four Linear -> ELU -> AlphaDropout blocks and the final ReLU.  dims int[5] = {input, 64, 48, 32, omic_dim} (each <= 512);
+ * W, b: HOST arrays of 4 device pointers (nn.Linear layouts).  u: uniform numbers float [B][dim1+dim2+dim3+dim4] for the
+ * AlphaDropout of training (torch's formula with drop probability p), NULL in eval mode.  Saved for the backward: act (same
+ * shape as u: the ELU outputs), hsave float [B][dim0+dim1+dim2+dim3] (the input of every layer), feat float [B][dim4] (the
+ * output).  dml_maxnet_bwd: dparams float [sum_l (dim[l+1] dim[l] + dim[l+1])] = dW_0, db_0, dW_1, ... (overwritten; summed over
+ * the B rows), dx float [B][dim0] or NULL.                                                                              */
+int dml_maxnet_fwd(const float* x, const float* const* W, const float* const* b, const int* dims, int B, const float* u, float p,
+                   float* act, float* hsave, float* feat, void* stream);
+int dml_maxnet_bwd(const float* dfeat, const float* const* W, const float* const* b, const int* dims, int B, const float* u, float p,
+                   const float* act, const float* hsave, const float* feat, float* dparams, float* dx, void* stream);
+
 /* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
  * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
  * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */

@@ -307,3 +307,46 @@ def test_layernorm_rows(rows, D):
     H.assert_close(g[0], gr[0], 1e-5, "d x")
     H.assert_close(g[1], gr[1], 2e-5, "d weight")
     H.assert_close(g[2], gr[2], 2e-5, "d bias")
+
+
+@pytest.mark.parametrize("B,din", [(1, 59), (3, 361), (2, 431)])
+def test_maxnet_fused_kernels_match_torch(B, din):
+    """MaxNet (models/model.py:173-218) as one kernel per direction: eval mode against the torch modules (fp64), training mode
+    against the same formula evaluated in torch with the kernel's own uniform numbers (AlphaDropout, torch's constants)."""
+    from dml_b200.model import MaxNet
+    torch.manual_seed(0)
+    net = MaxNet(input_dim=din, omic_dim=128, dropout_rate=0.25, label_dim=4).to(DEV)
+    x = synth.normal((B, din), 13, "xo").to(DEV).requires_grad_()
+    r = synth.normal((B, 128), 13, "ro").to(DEV)
+    net.eval()
+    feat = net(x_omic=x)[0]
+    g = torch.autograd.grad((feat * r).sum(), [x] + [p for p in net.encoder.parameters()])
+    ref_net = MaxNet(input_dim=din, omic_dim=128, dropout_rate=0.25, label_dim=4).double().to(DEV)
+    ref_net.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    ref_net.eval()
+    xd = x.detach().double().requires_grad_()
+    ref = ref_net.relu(ref_net.encoder(xd))
+    gr = torch.autograd.grad((ref * r.double()).sum(), [xd] + [p for p in ref_net.encoder.parameters()])
+    H.assert_close(feat, ref, 1e-5, "MaxNet features")
+    for a, b in zip(g, gr):
+        H.assert_close(a, b, 2e-5, "MaxNet gradient")
+    # training mode: reproduce the kernel's AlphaDropout from its saved uniform numbers
+    net.train()
+    torch.manual_seed(7)
+    feat = net(x_omic=x)[0]
+    g = torch.autograd.grad((feat * r).sum(), [x] + [p for p in net.encoder.parameters()])
+    torch.manual_seed(7)
+    u = torch.rand(B, 64 + 48 + 32 + 128, device=DEV).double()
+    p, alpha = 0.25, 1.7580993408473766
+    a_ = 1.0 / math.sqrt((alpha * alpha * p + 1) * (1 - p))
+    h, off = xd, 0
+    for blk in ref_net.encoder:
+        y = F.elu(blk[0](h))
+        uu = u[:, off: off + y.shape[1]]
+        h = torch.where(uu < p, torch.full_like(y, alpha * a_ * (p - 1)), a_ * y + alpha * a_ * p)
+        off += y.shape[1]
+    ref = F.relu(h)
+    gr = torch.autograd.grad((ref * r.double()).sum(), [xd] + [p_ for p_ in ref_net.encoder.parameters()])
+    H.assert_close(feat, ref, 1e-5, "MaxNet features (training)")
+    for a, b in zip(g, gr):
+        H.assert_close(a, b, 2e-5, "MaxNet gradient (training)")
