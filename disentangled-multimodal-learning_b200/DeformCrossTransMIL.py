@@ -97,7 +97,14 @@ class DeformCrossTransMIL(nn.Module):
         # (the offsets, keys and values still see every token), the n x n_kv attention work drops to 1 x n_kv.
         rows = 1 if getattr(self.args, "cls_row_only", False) else None
         h = self.layer3(h, path, 1, False, rows=rows)
-        h = self.norm(h[:, 0])                 # LayerNorm is per token: norm(h)[:, 0] == norm(h[:, 0])
-        logits = self._fc2(h)
-        encoded = self.multimodal_projection(h)
+        # norm(h)[:, 0] -> _fc2, multimodal_projection (:128-151): LayerNorm is per token, so only the cls row is normalised;
+        # the row's norm and both heads are one kernel per direction
+        if h.is_cuda and self.norm.elementwise_affine:
+            encoded, logits = ops.TowerHeadFn.apply(h, self.norm.weight, self.norm.bias, self._fc2.weight, self._fc2.bias,
+                                                    self.multimodal_projection.weight, self.multimodal_projection.bias,
+                                                    self.norm.eps)
+        else:
+            h = self.norm(h[:, 0])
+            logits = self._fc2(h)
+            encoded = self.multimodal_projection(h)
         return encoded, logits, None

@@ -56,6 +56,10 @@ SIGNATURES = {
     "dml_ppeg_wgrad": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
     "dml_maxnet_fwd": (_i, [_fp, _vp, _vp, _vp, _i, _fp, _f, _fp, _fp, _fp, _vp]),
     "dml_maxnet_bwd": (_i, [_fp, _vp, _vp, _vp, _i, _fp, _f, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "dml_tower_head_fwd": (_i, [_fp, _ll, _i, _i, _fp, _fp, _f, _fp, _fp, _i, _fp, _fp, _i, _fp, _fp, _fp, _fp, _vp]),
+    "dml_tower_head_bwd": (_i, [_fp, _ll, _i, _i, _fp, _fp, _i, _fp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _ll, _vp]),
+    "dml_linear3_fwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
+    "dml_linear3_bwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
 }
 
@@ -171,7 +175,8 @@ KERNELS_PER_CALL = {
     "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1,
     "dml_pgemm": 1, "dml_pgemm_chain": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
-    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1, "dml_scale_to_half": 1, "dml_maxnet_fwd": 1, "dml_maxnet_bwd": 1,
+    "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1, "dml_scale_to_half": 1, "dml_maxnet_fwd": 1, "dml_maxnet_bwd": 1, "dml_tower_head_fwd": 1, "dml_tower_head_bwd": 1,
+    "dml_linear3_fwd": 1, "dml_linear3_bwd": 1,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events

@@ -129,13 +129,22 @@ class DeformPathomicNet(nn.Module):
             omic_vec_immune, _, _ = self.omic_net_immune(x_omic=kwargs['x_omic_immune'])
             vec_immune, _, grads_immune = self.pathomic_net_immune(path=x_path, omic=omic_vec_immune)
         features = torch.cat((vec_tumor, vec_immune), 1)
-        hazard = self.classifier(features)
-        hazard_tumor = self.classifier_tumor(vec_tumor)
-        hazard_immune = self.classifier_immune(vec_immune)
-        if self.args.task_type == "survival":
-            hazard = torch.sigmoid(hazard)
-            hazard_tumor = torch.sigmoid(hazard_tumor)
-            hazard_immune = torch.sigmoid(hazard_immune)
+        if features.is_cuda:
+            # classifier(features), classifier_tumor(vec_tumor), classifier_immune(vec_immune) (+ sigmoid for survival,
+            # model.py:555-558) as one kernel per direction: nothing else can run between the forward and the backward of a bag
+            from . import ops
+            hazard, hazard_tumor, hazard_immune = ops.Linear3Fn.apply(
+                vec_tumor, vec_immune, self.classifier.weight, self.classifier.bias, self.classifier_tumor[0].weight,
+                self.classifier_tumor[0].bias, self.classifier_immune[0].weight, self.classifier_immune[0].bias,
+                self.args.task_type == "survival")
+        else:
+            hazard = self.classifier(features)
+            hazard_tumor = self.classifier_tumor(vec_tumor)
+            hazard_immune = self.classifier_immune(vec_immune)
+            if self.args.task_type == "survival":
+                hazard = torch.sigmoid(hazard)
+                hazard_tumor = torch.sigmoid(hazard_tumor)
+                hazard_immune = torch.sigmoid(hazard_immune)
         logits = [hazard_tumor, hazard_immune, hazard]
         return features, vec_tumor, vec_immune, logits, None, grads_tumor, grads_immune
 

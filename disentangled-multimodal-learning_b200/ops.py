@@ -468,6 +468,85 @@ class MaxNetFn(torch.autograd.Function):
         return (dx, None, *grads)
 
 
+class TowerHeadFn(torch.autograd.Function):
+    """(encoded, logits) = heads on the cls row of the layer output (DeformCrossTransMIL.py:128-151): h = LayerNorm(x[:, 0]),
+    logits = _fc2(h), encoded = multimodal_projection(h) - one kernel per direction (csrc/heads.cu).  x [B, n, D]."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, W2, b2, Wp, bp, eps):
+        B, n, D = x.shape
+        dev = x.device
+        x0 = x[:, 0].contiguous().float()
+        ws = [t.contiguous().float() for t in (ln_w, ln_b, W2, b2, Wp, bp)]
+        nc, De = W2.shape[0], Wp.shape[0]
+        hn = torch.empty(B, D, device=dev, dtype=F32)
+        stats = torch.empty(B, 2, device=dev, dtype=F32)
+        logits = torch.empty(B, nc, device=dev, dtype=F32)
+        enc = torch.empty(B, De, device=dev, dtype=F32)
+        call("dml_tower_head_fwd", ptr(x0), D, B, D, ptr(ws[0]), ptr(ws[1]), float(eps), ptr(ws[2]), ptr(ws[3]), nc, ptr(ws[4]),
+             ptr(ws[5]), De, ptr(hn), ptr(stats), ptr(logits), ptr(enc), stream())
+        ctx.shape = (B, n, D, nc, De)
+        ctx.save_for_backward(x0, hn, stats, ws[0], ws[2], ws[4])
+        return enc, logits
+
+    @staticmethod
+    def backward(ctx, denc, dlogits):
+        x0, hn, stats, lw, W2, Wp = ctx.saved_tensors
+        B, n, D, nc, De = ctx.shape
+        dev = x0.device
+        dx = torch.zeros(B, n, D, device=dev, dtype=F32)           # only the cls row receives a gradient
+        dparams = torch.empty(2 * D + nc * D + nc + De * D + De, device=dev, dtype=F32)
+        denc = denc.contiguous().float() if denc is not None else None
+        dlogits = dlogits.contiguous().float() if dlogits is not None else None
+        call("dml_tower_head_bwd", ptr(x0), D, B, D, ptr(lw), ptr(W2), nc, ptr(Wp), De, ptr(hn), ptr(stats),
+             ptr(dlogits) if dlogits is not None else None, ptr(denc) if denc is not None else None, ptr(dparams), ptr(dx),
+             n * D, stream())
+        o = 0
+        dlw, o = dparams[o: o + D], o + D
+        dlb, o = dparams[o: o + D], o + D
+        dW2, o = dparams[o: o + nc * D].view(nc, D), o + nc * D
+        db2, o = dparams[o: o + nc], o + nc
+        dWp, o = dparams[o: o + De * D].view(De, D), o + De * D
+        dbp = dparams[o: o + De]
+        return dx, dlw, dlb, dW2, db2, dWp, dbp, None
+
+
+class Linear3Fn(torch.autograd.Function):
+    """The three classifiers of DeformPathomicNet (models/model.py:535-558) as one kernel per direction: yc = act(Wc cat(a, b) +
+    bc), ya = act(Wa a + ba), yb = act(Wb b + bb); act = sigmoid for the survival task."""
+
+    @staticmethod
+    def forward(ctx, a, b, Wc, bc, Wa, ba, Wb, bb, sigmoid):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        ws = [t.contiguous().float() for t in (Wc, bc, Wa, ba, Wb, bb)]
+        B, Da, Db, nc = a.shape[0], a.shape[1], b.shape[1], Wc.shape[0]
+        ys = [torch.empty(B, nc, device=a.device, dtype=F32) for _ in range(3)]
+        call("dml_linear3_fwd", ptr(a), ptr(b), B, Da, Db, *[ptr(t) for t in ws], nc, int(bool(sigmoid)), *[ptr(y) for y in ys], stream())
+        ctx.meta = (B, Da, Db, nc, int(bool(sigmoid)))
+        ctx.save_for_backward(a, b, ws[0], ws[2], ws[4], *ys)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, gyc, gya, gyb):
+        a, b, Wc, Wa, Wb, yc, ya, yb = ctx.saved_tensors
+        B, Da, Db, nc, sig = ctx.meta
+        dev = a.device
+        gs = [g.contiguous().float() if g is not None else None for g in (gyc, gya, gyb)]
+        dparams = torch.empty(nc * (Da + Db) + nc + nc * Da + nc + nc * Db + nc, device=dev, dtype=F32)
+        da = torch.empty(B, Da, device=dev, dtype=F32)
+        db = torch.empty(B, Db, device=dev, dtype=F32)
+        call("dml_linear3_bwd", ptr(a), ptr(b), B, Da, Db, ptr(Wc), ptr(Wa), ptr(Wb), nc, sig, ptr(yc), ptr(ya), ptr(yb),
+             *[ptr(g) if g is not None else None for g in gs], ptr(dparams), ptr(da), ptr(db), stream())
+        o = 0
+        dWc, o = dparams[o: o + nc * (Da + Db)].view(nc, Da + Db), o + nc * (Da + Db)
+        dbc, o = dparams[o: o + nc], o + nc
+        dWa, o = dparams[o: o + nc * Da].view(nc, Da), o + nc * Da
+        dba, o = dparams[o: o + nc], o + nc
+        dWb, o = dparams[o: o + nc * Db].view(nc, Db), o + nc * Db
+        dbb = dparams[o: o + nc]
+        return da, db, dWc, dbc, dWa, dba, dWb, dbb, None
+
+
 class LayerNormFn(torch.autograd.Function):
     """LayerNorm over the last dim (128 / 256 / 512) of a contiguous fp32 tensor: one warp per row, statistics saved
     for the backward, weight / bias gradients reduced per CTA (DeformCrossTransLayer.norm, TransLayer.norm)."""

@@ -248,6 +248,27 @@ int dml_maxnet_fwd(const float* x, const float* const* W, const float* const* b,
 int dml_maxnet_bwd(const float* dfeat, const float* const* W, const float* const* b, const int* dims, int B, const float* u, float p,
                    const float* act, const float* hsave, const float* feat, float* dparams, float* dx, void* stream);
 
+/* ---- small dense heads, one kernel per direction (csrc/heads.cu) ---------------------------------------------------------
+ * Tower head (models/DeformCrossTransMIL.py:128-151): h = LayerNorm(x[:, 0]); logits = W2 h + b2 (nc units); enc = Wp h + bp (De
+ * units).  x points at row 0 of bag 0, bags bag_stride floats apart, D <= 512 features.  Saved: hn float [B, D], stats float
+ * [B, 2] (mean, rstd).  Backward: dlogits / denc may be NULL (no gradient); dparams float [2 D + nc D + nc + De D + De] = d ln_w,
+ * d ln_b, dW2, db2, dWp, dbp (overwritten, summed over the bags); dx: row 0 of bag 0 of the (caller-zeroed) input gradient.  */
+int dml_tower_head_fwd(const float* x, long long bag_stride, int B, int D, const float* ln_w, const float* ln_b, float eps,
+                       const float* W2, const float* b2, int nc, const float* Wp, const float* bp, int De, float* hn, float* stats,
+                       float* logits, float* enc, void* stream);
+int dml_tower_head_bwd(const float* x, long long bag_stride, int B, int D, const float* ln_w, const float* W2, int nc, const float* Wp,
+                       int De, const float* hn, const float* stats, const float* dlogits, const float* denc, float* dparams,
+                       float* dx, long long dx_bag_stride, void* stream);
+/* The three classifiers of DeformPathomicNet (models/model.py:535-558): yc = act(Wc cat(a, b) + bc), ya = act(Wa a + ba), yb =
+ * act(Wb b + bb), act = sigmoid (survival) or identity; a [B, Da], b [B, Db], nc <= 64 outputs each.  Backward: gy* may be NULL;
+ * dparams float = dWc [nc, Da + Db], dbc, dWa, dba, dWb, dbb (overwritten); da [B, Da], db [B, Db].                           */
+int dml_linear3_fwd(const float* a, const float* b, int B, int Da, int Db, const float* Wc, const float* bc, const float* Wa,
+                    const float* ba, const float* Wb, const float* bb, int nc, int sigmoid, float* yc, float* ya, float* yb,
+                    void* stream);
+int dml_linear3_bwd(const float* a, const float* b, int B, int Da, int Db, const float* Wc, const float* Wa, const float* Wb, int nc,
+                    int sigmoid, const float* yc, const float* ya, const float* yb, const float* gyc, const float* gya,
+                    const float* gyb, float* dparams, float* da, float* db, void* stream);
+
 /* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
  * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
  * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */

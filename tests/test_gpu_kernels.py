@@ -350,3 +350,52 @@ def test_maxnet_fused_kernels_match_torch(B, din):
     H.assert_close(feat, ref, 1e-5, "MaxNet features (training)")
     for a, b in zip(g, gr):
         H.assert_close(a, b, 2e-5, "MaxNet gradient (training)")
+
+
+@pytest.mark.parametrize("B,n", [(1, 37), (3, 5)])
+def test_tower_head_kernels_match_torch(B, n):
+    """norm(h)[:, 0] -> _fc2, multimodal_projection (DeformCrossTransMIL.py:128-151) as one kernel per direction."""
+    D, nc, De = 128, 4, 128
+    h = synth.normal((B, n, D), 17, "h").to(DEV).requires_grad_()
+    P = {k: v.to(DEV).requires_grad_() for k, v in synth.fill_like(
+        {"norm.weight": (D,), "norm.bias": (D,), "fc2.weight": (nc, D), "fc2.bias": (nc,), "proj.weight": (De, D), "proj.bias": (De,)}, 17).items()}
+    enc, logits = ops.TowerHeadFn.apply(h, P["norm.weight"], P["norm.bias"], P["fc2.weight"], P["fc2.bias"], P["proj.weight"],
+                                        P["proj.bias"], 1e-5)
+    r1, r2 = synth.normal((B, De), 17, "r1").to(DEV), synth.normal((B, nc), 17, "r2").to(DEV)
+    names = list(P)
+    g = torch.autograd.grad((enc * r1).sum() + (logits * r2).sum(), [h] + [P[k] for k in names])
+    hd = h.detach().double().requires_grad_()
+    Pd = {k: v.detach().double().requires_grad_() for k, v in P.items()}
+    hn = F.layer_norm(hd, (D,), Pd["norm.weight"], Pd["norm.bias"], 1e-5)[:, 0]
+    enc_r, log_r = F.linear(hn, Pd["proj.weight"], Pd["proj.bias"]), F.linear(hn, Pd["fc2.weight"], Pd["fc2.bias"])
+    gr = torch.autograd.grad((enc_r * r1.double()).sum() + (log_r * r2.double()).sum(), [hd] + [Pd[k] for k in names])
+    H.assert_close(enc, enc_r, 1e-5, "encoded")
+    H.assert_close(logits, log_r, 1e-5, "logits")
+    for nm, a, b in zip(["h"] + names, g, gr):
+        H.assert_close(a, b, 2e-5, "tower head grad " + nm)
+
+
+@pytest.mark.parametrize("sigmoid", [False, True])
+def test_three_classifier_head_matches_torch(sigmoid):
+    B, Da, Db, nc = 3, 128, 128, 4
+    a = synth.normal((B, Da), 19, "a").to(DEV).requires_grad_()
+    b = synth.normal((B, Db), 19, "b").to(DEV).requires_grad_()
+    P = {k: v.to(DEV).requires_grad_() for k, v in synth.fill_like(
+        {"c.weight": (nc, Da + Db), "c.bias": (nc,), "a.weight": (nc, Da), "a.bias": (nc,), "b.weight": (nc, Db), "b.bias": (nc,)}, 19).items()}
+    ys = ops.Linear3Fn.apply(a, b, P["c.weight"], P["c.bias"], P["a.weight"], P["a.bias"], P["b.weight"], P["b.bias"], sigmoid)
+    rs = [synth.normal((B, nc), 19, f"r{i}").to(DEV) for i in range(3)]
+    names = list(P)
+    g = torch.autograd.grad(sum((y * r).sum() for y, r in zip(ys, rs)), [a, b] + [P[k] for k in names])
+    ad, bd = a.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    Pd = {k: v.detach().double().requires_grad_() for k, v in P.items()}
+    act = torch.sigmoid if sigmoid else (lambda t: t)
+    yr = [act(F.linear(torch.cat((ad, bd), 1), Pd["c.weight"], Pd["c.bias"])), act(F.linear(ad, Pd["a.weight"], Pd["a.bias"])),
+          act(F.linear(bd, Pd["b.weight"], Pd["b.bias"]))]
+    gr = torch.autograd.grad(sum((y * r.double()).sum() for y, r in zip(yr, rs)), [ad, bd] + [Pd[k] for k in names])
+    for y, r_ in zip(ys, yr):
+        H.assert_close(y, r_, 1e-5, "classifier outputs")
+    for nm, x, y in zip(["a", "b"] + names, g, gr):
+        H.assert_close(x, y, 2e-5, "classifier grad " + nm)
+    # only the fused head's output drives the loss in training (train_test.py:833-853): the other two gradients are None
+    (ga,) = torch.autograd.grad(ys[0].sum(), [a], allow_unused=True)
+    assert ga is not None
