@@ -419,6 +419,8 @@ __device__ __forceinline__ void seg_flush_warp(const SegSink& ssum, bool need, i
 //   kMode 0  the 16 positions lie in at most two adjacent segments [seg_first, seg_first + 1] split at xb: the two
 //            segments' coefficients (clo, chi) sit in registers, a position costs one compare and two selects - no table
 //            access at all - and the sums go to two register buckets (the common case);
+//   kMode 3  no lane of the warp meets a boundary in its 16 positions (most tiles away from the diagonal): one pair of
+//            coefficients, no compare / select, one bucket, and the slope leaves the dg sum;
 //   kMode 1  some lane of the warp crosses two or three boundaries: segment = seg_first + number of boundaries passed,
 //            coefficients from the shared-memory segment array, four register buckets;
 //   kMode 2  anything else (table with more than kSegSmem segments, > 3 boundaries in 16 positions): per-position
@@ -432,6 +434,7 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
   const uint32_t hoff = head ? 8u : 0u;
   const float xb = bnd.x;
   float ba[4] = {0.f, 0.f, 0.f, 0.f}, bb[4] = {0.f, 0.f, 0.f, 0.f};   // kMode 0: [0] whole tile, [1] at or above xb; kMode 1: per segment
+  float dgflat = 0.f;                                                  // kMode 3: sum of dS / (|p| + 1)
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {                           // two sub-chunks of 8 queries
     uint32_t a[8], pa[8];
@@ -462,7 +465,9 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
         int cell, seg = 0;
         const bool above = x >= xb;
         float2 t;                                          // this head's (slope, intercept)
-        if (kMode == 0) {
+        if (kMode == 3) {
+          t = clo;
+        } else if (kMode == 0) {
           t = above ? chi : clo;
         } else if (kMode == 1) {
           seg = (above ? 1 : 0) + (x >= bnd.y ? 1 : 0) + (x >= bnd.z ? 1 : 0);      // relative to seg_first
@@ -476,6 +481,11 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
         if (kKeyMasked && !key_valid) { p0 = 0.f; s0 = 0.f; }
         pp[u] = p0; dd[u] = s0;
         // d bias / d g_j = -a / (|p| + 1)
+        if (kMode == 3) {                                   // one slope for the whole sweep: it multiplies the sum afterwards
+          dgflat = fmaf(s0, rcp_approx(qa), dgflat);
+          ba[0] += s0; bb[0] = fmaf(s0, x, bb[0]);
+          continue;
+        }
         dgacc = fmaf(s0 * slope, -rcp_approx(qa), dgacc);
         if (kMode == 2) {
           if (seg != run.seg) { seg_flush(ssum, run, head); run.seg = seg; }
@@ -499,13 +509,14 @@ __device__ __forceinline__ void dkv_sweep(const Lookup& L, const SegLookup& SL, 
     if (dsp) *reinterpret_cast<uint4*>(dsp + c * 8) = make_uint4(ws[0], ws[1], ws[2], ws[3]);   // dS^T row of this key, 8 queries
   }
   if (kMode == 0) { ba[0] -= ba[1]; bb[0] -= bb[1]; }      // [0] below the boundary, [1] at or above it
+  if (kMode == 3) dgacc = fmaf(-clo.x, dgflat, dgacc);
   if (trc) *trc = clock64();
   if (kMode != 2) {
     // hand the buckets to the running sums.  Completed segments of this lane, in order: the old run when it is not
     // seg_first (else it merges into bucket 0), then buckets 0 .. span-1; bucket `span` becomes the new run.  Round j
     // flushes every lane's j-th completed segment warp-cooperatively, so a tile costs as many rounds as the worst lane
     // has completed segments (one in the usual boundary-crossing tile).
-    constexpr int kB = kMode == 1 ? 4 : 2;
+    constexpr int kB = kMode == 1 ? 4 : kMode == 3 ? 1 : 2;
     const int span = seg_last - seg_first;
     const bool old = seg_first != run.seg;
     if (!old) { ba[0] += run.a; bb[0] += run.b; }
@@ -721,7 +732,7 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
           seg_last = sf + (x_last >= bnd.x ? 1 : 0);
           clo = lds_f32x2(SL.coef + (uint32_t)sf * 16u + (head ? 8u : 0u));
           chi = lds_f32x2(SL.coef + (uint32_t)sf * 16u + 16u + (head ? 8u : 0u));
-          mode = 0;
+          mode = __any_sync(0xffffffffu, x_last >= bnd.x) ? 0 : 3;
         } else {
           bnd.z = lds_f32(SL.bp + (uint32_t)sf * 4u + 8u);
           int sl = sf;
@@ -738,11 +749,13 @@ deform_attn_dkv_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       h16* const dsp = ds_row ? ds_row + t * kBI : nullptr;      // ds_row already points at this CTA's first tile
 #define DML_DKV_SWEEP(M, E) dkv_sweep<M, E>(L, SL, tS, rowa, head, g_j, kvld, sc2, seg_first, seg_last, bnd, clo, chi, dgacc, run, ssum, dsp, tr0 ? p.trace + t * 8 + 0 : nullptr)
       if (!key_masked) {
-        if (mode == 0) DML_DKV_SWEEP(false, 0);
+        if (mode == 3) DML_DKV_SWEEP(false, 3);
+        else if (mode == 0) DML_DKV_SWEEP(false, 0);
         else if (mode == 1) DML_DKV_SWEEP(false, 1);
         else DML_DKV_SWEEP(false, 2);
       } else {
-        if (mode == 0) DML_DKV_SWEEP(true, 0);
+        if (mode == 3) DML_DKV_SWEEP(true, 3);
+        else if (mode == 0) DML_DKV_SWEEP(true, 0);
         else if (mode == 1) DML_DKV_SWEEP(true, 1);
         else DML_DKV_SWEEP(true, 2);
       }

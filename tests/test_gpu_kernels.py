@@ -385,7 +385,7 @@ def test_three_classifier_head_matches_torch(sigmoid):
     ys = ops.Linear3Fn.apply(a, b, P["c.weight"], P["c.bias"], P["a.weight"], P["a.bias"], P["b.weight"], P["b.bias"], sigmoid)
     rs = [synth.normal((B, nc), 19, f"r{i}").to(DEV) for i in range(3)]
     names = list(P)
-    g = torch.autograd.grad(sum((y * r).sum() for y, r in zip(ys, rs)), [a, b] + [P[k] for k in names])
+    g = torch.autograd.grad(sum((y * r).sum() for y, r in zip(ys, rs)), [a, b] + [P[k] for k in names], retain_graph=True)
     ad, bd = a.detach().double().requires_grad_(), b.detach().double().requires_grad_()
     Pd = {k: v.detach().double().requires_grad_() for k, v in P.items()}
     act = torch.sigmoid if sigmoid else (lambda t: t)
