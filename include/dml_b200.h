@@ -269,6 +269,38 @@ int dml_linear3_bwd(const float* a, const float* b, int B, int Da, int Db, const
                     int sigmoid, const float* yc, const float* ya, const float* yb, const float* gyc, const float* gya,
                     const float* gyb, float* dparams, float* da, float* db, void* stream);
 
+/* ---- genomic-guided co-attention with one head and a few tokens on one side (csrc/coattn.cu) -------------------------------
+ * Replaces the long-side work of multi_head_attention_forward (models/MultiheadAttention.py:7-321; the copy in
+ * models/cmta_utils.py:667-) as MCAT / CMTA call it (models/model.py:1007,1047: 4 genomic queries over the patch keys;
+ * model.py:1168-1170,1229-1238: patches over genomic keys and back), num_heads = 1, no masks, no attention dropout.  The long
+ * side x is float [B, S, E] addressed with element strides (xs_b between bags, xs_r between rows; the reference's [S, B, E]
+ * tensors are xs_b = E, xs_r = B E), E = 256, F <= 8 tokens on the short side; other shapes return DML_E_UNSUPPORTED.  The
+ * projections of the long side are folded into the short side by the caller (exact re-association, see coattn.cu):
+ * few queries:  qt[b, f] = W_k^T q_f, c[b, f] = q_f . b_k with q = scaling (W_q query + b_q)
+ *               -> raw float [B, F, S] pre-softmax scores (the tensor need_raw=True returns, :300-303), px float [B, F, E] =
+ *                  sum_s softmax_s(raw)[f, s] x_s (attention output before W_v / out_proj), lse float [B, F]
+ * few keys:     kt[b, f] = scaling W_q^T k_f, c[b, f] = scaling b_q . k_f, vt[b, f] = W_o v_f, bo = out_proj bias
+ *               -> raw float [B, S, F], out float [B, S, E] = softmax_f(raw) vt + bo (the finished attn_output)
+ * Workspaces (floats, caller-owned): *_ws_floats.  Backward partial sums come back per 128-row chunk (dml_coattn_chunks(S) per
+ * bag) for the caller to add: fq: ws float [B, chunks, F, E + 1] = (d qt, d c); fk: ws float [B, chunks, (2 F + 1) E + F] =
+ * (d kt [F, E], d vt [F, E], d bo [E], d c [F]).  draw (gradient reaching the raw scores) may be NULL.  No atomics.           */
+int dml_coattn_chunks(int S);
+size_t dml_coattn_fq_fwd_ws_floats(int B, int F, int S, int E);
+size_t dml_coattn_fq_bwd_ws_floats(int B, int F, int S, int E);
+size_t dml_coattn_fk_bwd_ws_floats(int B, int F, int S, int E);
+int dml_coattn_fq_fwd(const float* x, long long xs_b, long long xs_r, const float* qt, const float* c, int B, int F, int S, int E,
+                      float* raw, float* px, float* lse, float* ws, void* stream);
+/* dpx float [B, F, E] = gradient of px, dsum float [B, F] = dpx . px; dx float [B, S, E] (contiguous, overwritten).          */
+int dml_coattn_fq_bwd(const float* x, long long xs_b, long long xs_r, const float* qt, const float* raw, const float* lse,
+                      const float* dpx, const float* dsum, const float* draw, int B, int F, int S, int E, float* dx, float* ws,
+                      void* stream);
+int dml_coattn_fk_fwd(const float* x, long long xs_b, long long xs_r, const float* kt, const float* c, const float* vt, const float* bo,
+                      int B, int F, int S, int E, float* raw, float* out, void* stream);
+/* dout float [B, S, E] addressed with strides (gs_b, gs_r); dx float [B, S, E] (contiguous, overwritten).                    */
+int dml_coattn_fk_bwd(const float* x, long long xs_b, long long xs_r, const float* dout, long long gs_b, long long gs_r, const float* kt,
+                      const float* vt, const float* raw, const float* draw, int B, int F, int S, int E, float* dx, float* ws,
+                      void* stream);
+
 /* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
  * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
  * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */

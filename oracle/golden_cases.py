@@ -28,6 +28,12 @@ PATHOMIC_CASES = [
     dict(name="pathomic_diag_n260_b2", B=2, N=260, seed=51, task="diag2021"),
     dict(name="pathomic_surv_n132_b1", B=1, N=132, seed=52, task="survival"),
 ]
+# raw-score co-attention (models/MultiheadAttention.py) as MCAT / CMTA call it: 1 head, E = 256.  L queries over S keys.
+COATTN_CASES = [
+    dict(name="coattn_mcat_l4_s300_b2", B=2, L=4, S=300, seed=61),          # model.py:1047 (4 genomic queries over the patches)
+    dict(name="coattn_cmta_l333_s6_b1", B=1, L=333, S=6, seed=62),          # model.py:1229-1233 (patches ask, genomic keys)
+    dict(name="coattn_cmta_l6_s333_b1", B=1, L=6, S=333, seed=63),          # model.py:1234-1238 (and back)
+]
 
 MAX_KEEP = 8192
 

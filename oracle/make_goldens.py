@@ -79,7 +79,7 @@ def pack(d):
     return out
 
 
-from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, thin)
+from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, thin)
 
 
 def gen_deform():
@@ -125,6 +125,32 @@ def gen_nystrom():
             d["grad." + k] = thin(v)
         np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
         print(c["name"], float(out.abs().mean()), float(gx.abs().mean()))
+
+
+def gen_coattn():
+    """models/MultiheadAttention.py (and its copy in cmta_utils.py, which must agree bit for bit)."""
+    from dml_b200 import synth
+    from models.MultiheadAttention import MultiheadAttention
+    from models.cmta_utils import MultiheadAttention as MhaCMTA
+    for c in COATTN_CASES:
+        mod = MultiheadAttention(embed_dim=256, num_heads=1)
+        load_synth(mod, c["seed"], gain=2.0)
+        q = synth.normal((c["L"], c["B"], 256), c["seed"], "query").requires_grad_()
+        kv = synth.normal((c["S"], c["B"], 256), c["seed"], "key").requires_grad_()
+        r = synth.normal((c["L"], c["B"], 256), c["seed"], "r")
+        r2 = synth.normal((c["B"], 1, c["L"], c["S"]), c["seed"], "r2", scale=0.1)
+        out, raw = mod(q, kv, kv)
+        mod2 = MhaCMTA(embed_dim=256, num_heads=1)
+        mod2.load_state_dict(mod.state_dict())
+        o2, r2_ = mod2(q, kv, kv)
+        assert torch.equal(o2, out) and torch.equal(r2_, raw)
+        loss = (out * r).sum() + (raw * r2).sum()          # a gradient reaches the raw scores too
+        gq, gkv = torch.autograd.grad(loss, (q, kv), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(out=thin(out), raw=thin(raw), gq=thin(gq), gkv=thin(gkv))
+        d.update({"grad." + k: thin(v) for k, v in g.items()})
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], float(out.abs().mean()), float(gkv.abs().mean()))
 
 
 class _Args:
@@ -195,7 +221,7 @@ def main():
     """python -m oracle.make_goldens [--missing]   (--missing: only write fixtures that do not exist yet)"""
     os.makedirs(OUT, exist_ok=True)
     if "--missing" in sys.argv:
-        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES):
+        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES):
             cases[:] = [c for c in cases if not os.path.exists(os.path.join(OUT, c["name"] + ".npz"))]
     sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
     install_reference_shims()
@@ -208,6 +234,7 @@ def main():
         gen_deform()
         gen_nystrom()
         gen_towers()
+        gen_coattn()
 
 
 if __name__ == "__main__":

@@ -113,5 +113,10 @@ def pathomic_shapes(label_dim=4):
     return s
 
 
+def mha_shapes(E=256):
+    """state_dict of models/MultiheadAttention.py:MultiheadAttention(embed_dim=E) (packed in-projection)."""
+    return {"in_proj_weight": (3 * E, E), "in_proj_bias": (3 * E,), "out_proj.weight": (E, E), "out_proj.bias": (E,)}
+
+
 def leafify(P):
     return {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}

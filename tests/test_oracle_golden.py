@@ -4,8 +4,8 @@ import pytest
 import torch
 
 from dml_b200 import synth
-from oracle import deform1d, nystrom, towers
-from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, PATHOMIC_CASES, TOWER_CASES, TRANSMIL_CASES, thin)
+from oracle import coattn, deform1d, nystrom, towers
+from oracle.golden_cases import (COATTN_CASES, DEFORM_CASES, NYSTROM_CASES, PATHOMIC_CASES, TOWER_CASES, TRANSMIL_CASES, thin)
 from tests import helpers as H
 
 TOL = 2e-5
@@ -140,4 +140,23 @@ def test_deform_pathomic_net_matches_reference(c):
     label = bag["label_diag"] if c["task"] == "diag2021" else bag["label_surv"]
     loss = towers.bag_loss(logits, label, c["task"], bag["censor"])
     H.assert_close(loss, G["loss"], TOL, "loss")
+    _check_param_grads(P, loss, G)
+
+
+@pytest.mark.parametrize("c", COATTN_CASES, ids=lambda c: c["name"])
+def test_raw_score_multihead_attention_matches_reference(c):
+    """models/MultiheadAttention.py as MCAT / CMTA call it (1 head, E = 256), both directions; a gradient reaches the raw scores."""
+    G = H.golden(c["name"])
+    P = H.leafify(synth.fill_like(H.mha_shapes(256), c["seed"], gain=2.0))
+    q = synth.normal((c["L"], c["B"], 256), c["seed"], "query").requires_grad_()
+    kv = synth.normal((c["S"], c["B"], 256), c["seed"], "key").requires_grad_()
+    r = synth.normal((c["L"], c["B"], 256), c["seed"], "r")
+    r2 = synth.normal((c["B"], 1, c["L"], c["S"]), c["seed"], "r2", scale=0.1)
+    out, raw = coattn.multihead_attention_raw(q, kv, P)
+    H.assert_close(thin(out), G["out"], TOL, "out")
+    H.assert_close(thin(raw), G["raw"], TOL, "raw scores")
+    loss = (out * r).sum() + (raw * r2).sum()
+    gq, gkv = torch.autograd.grad(loss, (q, kv), retain_graph=True)
+    H.assert_close(thin(gq), G["gq"], TOL, "d query")
+    H.assert_close(thin(gkv), G["gkv"], TOL, "d key/value")
     _check_param_grads(P, loss, G)
