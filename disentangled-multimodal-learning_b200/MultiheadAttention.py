@@ -62,7 +62,7 @@ class _FewQueriesFn(torch.autograd.Function):
         lib = _lib.load(check_device=True)
         dpx = dpx.contiguous().float()
         dsum = (dpx * px).sum(-1).contiguous()
-        nchunk = lib.dml_coattn_chunks(S)
+        nchunk = lib.dml_coattn_chunks(B, S, 0)
         ws = torch.empty(B, nchunk, Fq, E + 1, device=x.device, dtype=torch.float32)
         dx = torch.empty(B, S, E, device=x.device, dtype=torch.float32)
         draw_p = None
@@ -99,7 +99,7 @@ class _FewKeysFn(torch.autograd.Function):
         Fk = kt.shape[1]
         lib = _lib.load(check_device=True)
         dout = _rows_view(dout)
-        nchunk = lib.dml_coattn_chunks(S)
+        nchunk = lib.dml_coattn_chunks(B, S, 0)
         per = (2 * Fk + 1) * E + Fk
         ws = torch.empty(B, nchunk, per, device=x.device, dtype=torch.float32)
         dx = torch.empty(B, S, E, device=x.device, dtype=torch.float32)

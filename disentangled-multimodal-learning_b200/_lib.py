@@ -61,7 +61,7 @@ SIGNATURES = {
     "dml_linear3_fwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
     "dml_linear3_bwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
-    "dml_coattn_chunks": (_i, [_i]),
+    "dml_coattn_chunks": (_i, [_i, _i, _i]),
     "dml_coattn_fq_fwd_ws_floats": (C.c_size_t, [_i, _i, _i, _i]),
     "dml_coattn_fq_bwd_ws_floats": (C.c_size_t, [_i, _i, _i, _i]),
     "dml_coattn_fk_bwd_ws_floats": (C.c_size_t, [_i, _i, _i, _i]),

@@ -281,10 +281,10 @@ int dml_linear3_bwd(const float* a, const float* b, int B, int Da, int Db, const
  *                  sum_s softmax_s(raw)[f, s] x_s (attention output before W_v / out_proj), lse float [B, F]
  * few keys:     kt[b, f] = scaling W_q^T k_f, c[b, f] = scaling b_q . k_f, vt[b, f] = W_o v_f, bo = out_proj bias
  *               -> raw float [B, S, F], out float [B, S, E] = softmax_f(raw) vt + bo (the finished attn_output)
- * Workspaces (floats, caller-owned): *_ws_floats.  Backward partial sums come back per 128-row chunk (dml_coattn_chunks(S) per
- * bag) for the caller to add: fq: ws float [B, chunks, F, E + 1] = (d qt, d c); fk: ws float [B, chunks, (2 F + 1) E + F] =
+ * Workspaces (floats, caller-owned): *_ws_floats.  Backward partial sums come back per CTA (dml_coattn_chunks(B, S, 0) row chunks per
+ * bag, about one CTA per SM) for the caller to add: fq: ws float [B, chunks, F, E + 1] = (d qt, d c); fk: ws float [B, chunks, (2 F + 1) E + F] =
  * (d kt [F, E], d vt [F, E], d bo [E], d c [F]).  draw (gradient reaching the raw scores) may be NULL.  No atomics.           */
-int dml_coattn_chunks(int S);
+int dml_coattn_chunks(int B, int S, int nsm);      /* nsm <= 0: the current device's SM count */
 size_t dml_coattn_fq_fwd_ws_floats(int B, int F, int S, int E);
 size_t dml_coattn_fq_bwd_ws_floats(int B, int F, int S, int E);
 size_t dml_coattn_fk_bwd_ws_floats(int B, int F, int S, int E);
