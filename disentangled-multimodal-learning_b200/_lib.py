@@ -61,6 +61,9 @@ SIGNATURES = {
     "dml_linear3_fwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
     "dml_linear3_bwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
+    "dml_gram_splits": (_i, [_i, _ll, _i]),
+    "dml_gram_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _ll, _fp, _vp]),
+    "dml_rows_mix": (_i, [_fp, _vp, _ll, _i, _i, _i, _ll, _fp, _ll, _ll, _vp]),
     "dml_coattn_chunks": (_i, [_i, _i, _i]),
     "dml_coattn_fq_fwd_ws_floats": (C.c_size_t, [_i, _i, _i, _i]),
     "dml_coattn_fq_bwd_ws_floats": (C.c_size_t, [_i, _i, _i, _i]),

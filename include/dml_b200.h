@@ -301,6 +301,21 @@ int dml_coattn_fk_bwd(const float* x, long long xs_b, long long xs_r, const floa
                       const float* vt, const float* raw, const float* draw, int B, int F, int S, int E, float* dx, float* ws,
                       void* stream);
 
+/* ---- similarity matrices of the batch losses (csrc/gram.cu) ---------------------------------------------------------------
+ * utils/loss.py:25-64 (PathBatchLoss), :90-143 (OmicDomainScaleLoss): sim[g] = A[g] B[g]^T over N = batch_size x world_size
+ * <= 64 rows of K floats (K = L1 L2 up to 2.9 M: an HBM-bound stream over the gathered attention maps).  Rows come through a
+ * DEVICE table of N row base pointers (a_rows[i] = row i of group 0) plus a group stride in floats, so the gathered per-rank
+ * tensors and the `view(N, 8, -1).transpose(0, 1)` of loss.py:42-43 are read in place.  K and the strides are multiples of 4,
+ * rows 16-byte aligned.  part float [G, dml_gram_splits(G, K, 0), N, N]: per-CTA partial matrices, the caller adds them
+ * (deterministic).  a_rows == b_rows (same table, same stride) reads the rows once.                                          */
+int dml_gram_splits(int G, long long K, int nsm);      /* nsm <= 0: the current device's SM count */
+int dml_gram_fwd(const float* const* a_rows, long long a_gs, const float* const* b_rows, long long b_gs, int G, int N, long long K,
+                 float* part, void* stream);
+/* The adjoint for the LOCAL rows (utils/gather.py:16-20 keeps only the local slice of the gradient): out[g][i, :] = sum_j
+ * W[g][i, j] x[g][j, :], i < nrows <= 16, j < N <= 64; W float [G, nrows, N]; out rows out_rs floats apart, groups out_gs.    */
+int dml_rows_mix(const float* W, const float* const* x_rows, long long x_gs, int G, int nrows, int N, long long K, float* out,
+                 long long out_gs, long long out_rs, void* stream);
+
 /* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
  * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
  * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */

@@ -34,6 +34,11 @@ COATTN_CASES = [
     dict(name="coattn_cmta_l333_s6_b1", B=1, L=333, S=6, seed=62),          # model.py:1229-1233 (patches ask, genomic keys)
     dict(name="coattn_cmta_l6_s333_b1", B=1, L=6, S=333, seed=63),          # model.py:1234-1238 (and back)
 ]
+# utils/loss.py batch losses at world_size 1 (N = batch): attention maps [N, 8, L1, L2], omic [N, 128], vgrid [8 N, 2, 12, 12]
+LOSS_CASES = [
+    dict(name="losses_n4_l50x12", N=4, L1=50, L2=12, seed=81),
+    dict(name="losses_n8_l37x20", N=8, L1=37, L2=20, seed=82),
+]
 
 MAX_KEEP = 8192
 
@@ -56,3 +61,13 @@ def thin(v):
     while cdiv(r, sr) * cdiv(c, sc) > MAX_KEEP:
         sr += 2
     return v2[::sr, ::sc]
+
+
+def loss_inputs(c):
+    """Positive, row-normalised maps (what softmax attention produces) and the small BatchLoss inputs; shared with the tests."""
+    from dml_b200 import synth
+    shp = (c["N"], 8, c["L1"], c["L2"])
+    att = {k: torch.softmax(synth.normal(shp, c["seed"], k) * 2.0, dim=-1) for k in ("a1_10", "a1_20", "a2_10", "a2_20")}
+    att["omic"] = synth.normal((c["N"], 128), c["seed"], "omic")
+    att["vgrid"] = synth.normal((8 * c["N"], 2, 12, 12), c["seed"], "vgrid")
+    return att

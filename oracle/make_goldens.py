@@ -79,7 +79,7 @@ def pack(d):
     return out
 
 
-from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, thin)
+from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES, loss_inputs, thin)
 
 
 def gen_deform():
@@ -153,6 +153,26 @@ def gen_coattn():
         print(c["name"], float(out.abs().mean()), float(gkv.abs().mean()))
 
 
+def gen_losses():
+    """utils/loss.py at world_size = 1 (the gather is the identity): values and input gradients."""
+    from utils.loss import BatchLoss, OmicDomainScaleLoss, PathBatchLoss
+    for c in LOSS_CASES:
+        x = {k: v.requires_grad_() for k, v in loss_inputs(c).items()}
+        pb = PathBatchLoss(c["N"], 1)(x["a1_10"], x["a1_20"])
+        od = OmicDomainScaleLoss(c["N"], 1)(x["a1_10"], x["a1_20"], x["a2_10"], x["a2_20"])
+        bl = BatchLoss(c["N"], 1)(x["omic"], x["vgrid"])
+        d = dict(path_batch=pb, omic_domain=od, batch=bl)
+        g = torch.autograd.grad(pb.sum(), (x["a1_10"], x["a1_20"]), retain_graph=True)
+        d["pb.g10"], d["pb.g20"] = thin(g[0]), thin(g[1])
+        g = torch.autograd.grad(od, (x["a1_10"], x["a1_20"], x["a2_10"], x["a2_20"]), retain_graph=True)
+        for k, v in zip(("a1_10", "a1_20", "a2_10", "a2_20"), g):
+            d["od.g_" + k] = thin(v)
+        g = torch.autograd.grad(bl.sum(), (x["omic"], x["vgrid"]))
+        d["bl.g_omic"], d["bl.g_vgrid"] = thin(g[0]), thin(g[1])
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], float(pb.sum()), float(od), float(bl.sum()))
+
+
 class _Args:
     def __init__(self, **kw):
         self.__dict__.update(kw)
@@ -221,7 +241,7 @@ def main():
     """python -m oracle.make_goldens [--missing]   (--missing: only write fixtures that do not exist yet)"""
     os.makedirs(OUT, exist_ok=True)
     if "--missing" in sys.argv:
-        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES):
+        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES):
             cases[:] = [c for c in cases if not os.path.exists(os.path.join(OUT, c["name"] + ".npz"))]
     sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
     install_reference_shims()
@@ -235,6 +255,7 @@ def main():
         gen_nystrom()
         gen_towers()
         gen_coattn()
+        gen_losses()
 
 
 if __name__ == "__main__":

@@ -4,8 +4,9 @@ import pytest
 import torch
 
 from dml_b200 import synth
-from oracle import coattn, deform1d, nystrom, towers
-from oracle.golden_cases import (COATTN_CASES, DEFORM_CASES, NYSTROM_CASES, PATHOMIC_CASES, TOWER_CASES, TRANSMIL_CASES, thin)
+from oracle import coattn, deform1d, losses, nystrom, towers
+from oracle.golden_cases import (COATTN_CASES, DEFORM_CASES, LOSS_CASES, NYSTROM_CASES, PATHOMIC_CASES, TOWER_CASES, TRANSMIL_CASES,
+                                 loss_inputs, thin)
 from tests import helpers as H
 
 TOL = 2e-5
@@ -160,3 +161,25 @@ def test_raw_score_multihead_attention_matches_reference(c):
     H.assert_close(thin(gq), G["gq"], TOL, "d query")
     H.assert_close(thin(gkv), G["gkv"], TOL, "d key/value")
     _check_param_grads(P, loss, G)
+
+
+@pytest.mark.parametrize("c", LOSS_CASES, ids=lambda c: c["name"])
+def test_batch_losses_match_reference(c):
+    """utils/loss.py PathBatchLoss / OmicDomainScaleLoss / BatchLoss at world_size 1: values and input gradients."""
+    G = H.golden(c["name"])
+    x = {k: v.requires_grad_() for k, v in loss_inputs(c).items()}
+    pb = losses.path_batch_loss(x["a1_10"], x["a1_20"])
+    od = losses.omic_domain_scale_loss(x["a1_10"], x["a1_20"], x["a2_10"], x["a2_20"])
+    bl = losses.batch_loss(x["omic"], x["vgrid"])
+    H.assert_close(pb, G["path_batch"], TOL, "PathBatchLoss")
+    H.assert_close(od, G["omic_domain"], TOL, "OmicDomainScaleLoss")
+    H.assert_close(bl, G["batch"], TOL, "BatchLoss")
+    g = torch.autograd.grad(pb.sum(), (x["a1_10"], x["a1_20"]), retain_graph=True)
+    H.assert_close(thin(g[0]), G["pb.g10"], TOL, "d PathBatchLoss / d att10")
+    H.assert_close(thin(g[1]), G["pb.g20"], TOL, "d PathBatchLoss / d att20")
+    g = torch.autograd.grad(od, (x["a1_10"], x["a1_20"], x["a2_10"], x["a2_20"]), retain_graph=True)
+    for k, v in zip(("a1_10", "a1_20", "a2_10", "a2_20"), g):
+        H.assert_close(thin(v), G["od.g_" + k], 5 * TOL, "d OmicDomainScaleLoss / d " + k)
+    g = torch.autograd.grad(bl.sum(), (x["omic"], x["vgrid"]))
+    H.assert_close(thin(g[0]), G["bl.g_omic"], TOL, "d BatchLoss / d omic")
+    H.assert_close(thin(g[1]), G["bl.g_vgrid"], TOL, "d BatchLoss / d vgrid")
