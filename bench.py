@@ -415,6 +415,97 @@ def bench_transmil(N, args, dev, rank, world, cpu=True):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def bench_coattn(dev, cpu=True, B=8, S=16384, F=4, steps=20, warmup=3):
+    """BASELINE configs[4] (MCAT / CMTA co-attention, config_others.yaml:60: B = 8): fwd + bwd of the raw-score MultiheadAttention
+    (models/MultiheadAttention.py) through the public module, both directions (F genomic tokens x S patches and back), bags
+    device-resident and rotated (> L2).  HBM-bound: roofline = algorithmic bytes of the four streaming kernels / time."""
+    from dml_b200 import synth
+    from dml_b200.MultiheadAttention import MultiheadAttention
+    E = 256
+    shapes = {"in_proj_weight": (3 * E, E), "in_proj_bias": (3 * E,), "out_proj.weight": (E, E), "out_proj.bias": (E,)}
+    mods = []
+    for seed in (1, 2):
+        m = MultiheadAttention(E, 1)
+        m.load_state_dict(synth.fill_like(shapes, seed), strict=True)
+        mods.append(m.to(dev))
+    nset = max(2, int(300e6 // (B * S * E * 4)) + 1)
+    g = torch.Generator(device=dev).manual_seed(3)
+    bags = [torch.randn(B, S, E, device=dev, generator=g).requires_grad_() for _ in range(nset)]
+    few = torch.randn(F, B, E, device=dev, generator=g).requires_grad_()
+
+    def step(i):
+        bag = bags[i % nset]
+        bag.grad = None
+        long_side = bag.transpose(0, 1)                               # [S, B, E] view, as model.py:1041 builds it
+        o1, r1 = mods[0](few, long_side, long_side)                   # genomic queries over the patches
+        o2, r2 = mods[1](long_side, few, few)                         # patches over the genomic keys
+        (o1.sum() + o2.sum()).backward()
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    # one captured CUDA graph per resident bag set (the step is ~60 small launches around four streaming kernels)
+    launch, mode = step, "eager"
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(nset):
+                step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs = []
+        for i in range(nset):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                step(i)
+            graphs.append(gr)
+        launch, mode = (lambda i: graphs[i % nset].replay()), "CUDA-graph replay"
+        for i in range(nset):
+            launch(i)
+        torch.cuda.synchronize()
+    except Exception as ex:      # capture is an optimisation of the measurement harness only
+        mode = f"eager (graph capture failed: {type(ex).__name__})"
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        launch(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pk, pk_kind = peaks()
+    row = B * S * E * 4
+    alg = (row + B * F * S * 4) + (2 * row + B * F * S * 4) + (2 * row + B * S * F * 4) + (3 * row + B * S * F * 4) + row   # 4 kernels + the dx add
+    rec = {"metric": f"bags/sec, co-attention fwd+bwd both directions (B={B} bags x {S} patches x {E}, {F} genomic tokens)",
+           "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup, "data": "synthetic",
+           "config": {"workload": "MCAT / CMTA raw-score MultiheadAttention (model.py:1007,1168-1170), 1 head, E = 256",
+                      "step": mode, "l2": f"{nset} bag sets rotated ({nset * row / 1e6:.0f} MB)"},
+           "roofline": {"kernel": "coattn fq_fwd + fq_bwd + fk_fwd + fk_bwd (whole step, eager launches included)", "bound": "hbm",
+                        "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind,
+                        "note": "per-kernel figures: profiles/r2_c_coattn_achieved_bandwidth.json"}}
+    if cpu:
+        from oracle import coattn as OC
+        P = {k: v.detach().cpu() for k, v in mods[0].state_dict().items()}
+        bag_c = bags[0].detach().cpu().requires_grad_()
+        few_c = few.detach().cpu().requires_grad_()
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def one():
+            t0 = time.perf_counter()
+            ls = bag_c.transpose(0, 1)
+            o1, _ = OC.multihead_attention_raw(few_c, ls, P)
+            o2, _ = OC.multihead_attention_raw(ls, few_c, P)
+            (o1.sum() + o2.sum()).backward()
+            return time.perf_counter() - t0
+        one()
+        best = min(one() for _ in range(3))
+        rec["cpu_baseline"] = {"value": B / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"oracle port (torch fp32), the same {B} x {S} step, best of 3: {best:.2f} s"}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -657,7 +748,7 @@ def main():
         roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the entry point's kernels at N = 16 384 from
-                # ncu (profiles/r1_c_launches_prof_attn_n16385.csv).  Backward: 50 MB (D = dO.O) + 214 MB + 1058 MB (dK/dV
+                # ncu (profiles/r1_c_launches_prof_attn_n16385.csv, re-captured in profiles/r2_a_ncu_full_attn_summary.csv).  Backward: 50 MB (D = dO.O) + 214 MB + 1058 MB (dK/dV
                 # kernel, writes the fp16 dS^T workspace: 8 heads x 4096 x 16416 x 2 B = 1.08 GB) + 1086 MB + 29 MB (dQ
                 # GEMM, reads it back); algorithmic without the workspace: q,k,v,dO fp16 + O, dQ, dK, dV fp32 = 97 MB
                 "traffic": ({"dml_deform_attn_fwd_tc": 25.4e6, "dml_deform_attn_bwd_tc": 2438e6}.get(top)
@@ -719,6 +810,14 @@ def main():
             except Exception as ex:      # never lose the headline line to the side measurement
                 transmil[f"n{n_t}"] = {"error": repr(ex)}
 
+    # ---- MCAT / CMTA co-attention (BASELINE configs[4]'s cross-attention path): its own sub-record ----
+    coattn = None
+    if rank == 0 and world == 1 and not args.no_transmil:
+        try:
+            coattn = bench_coattn(dev, cpu=not args.no_cpu_baseline)
+        except Exception as ex:
+            coattn = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -731,7 +830,7 @@ def main():
                 "gpu_launches": launches,
                 "kernel_ms_per_step": {k: round(kavg[k] * kcalls[k], 4) for k in sorted(kavg, key=lambda k: -kavg[k] * kcalls[k])},
                 "roofline": roof, "cpu_baseline": cpu, "cls_row_only": cls_only, "sustained": sustained, "transmil": transmil,
-                "host_binding": numa}
+                "coattn": coattn, "host_binding": numa}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

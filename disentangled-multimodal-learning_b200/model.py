@@ -180,6 +180,19 @@ def _ce_weight(values, device):
     return _CE_WEIGHT_CACHE[key]
 
 
+def _cumprod_bins(x):
+    """torch.cumprod(x, dim=1) for the handful of survival bins as running products: the same values, but its backward is
+    plain multiplications - torch's cumprod backward tests the input for zeros on the host, which a CUDA-graph capture of
+    the step cannot contain."""
+    cols, out = x.unbind(1), []
+    run = cols[0]
+    out.append(run)
+    for c in cols[1:]:
+        run = run * c
+        out.append(run)
+    return torch.stack(out, dim=1)
+
+
 def bag_loss(logits, label, task_type, censor=None):
     """The loss trainDeformPathomicModel back-propagates (train_test.py:826-853): fused head only."""
     hz = logits[2]
@@ -188,8 +201,7 @@ def bag_loss(logits, label, task_type, censor=None):
     if task_type == "grade":
         return F.cross_entropy(hz, label, weight=_ce_weight(GRADE_CE_WEIGHTS, hz.device))
     if task_type == "survival":
-        S = torch.cumprod(1 - hz, dim=1)
-        return nll_loss(hz, S, label, censor, alpha=0)
+        return nll_loss(hz, _cumprod_bins(1 - hz), label, censor, alpha=0)
     raise ValueError(task_type)
 
 
