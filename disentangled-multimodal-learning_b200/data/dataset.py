@@ -23,9 +23,11 @@ LABEL_COLUMNS = 12
 
 class SyntheticBagDataset(Dataset):
     def __init__(self, num_bags: int, n_patches: Union[int, Tuple[int, int]] = 2500, seed: int = 42,
-                 bag_dtype: torch.dtype = torch.float32, two_scales: bool = False):
-        """n_patches: a fixed bag length (the reference's 2 500) or a (lo, hi) range drawn per bag, rounded to even."""
+                 bag_dtype: torch.dtype = torch.float32, two_scales: bool = False, cache: bool = True):
+        """n_patches: a fixed bag length (the reference's 2 500) or a (lo, hi) range drawn per bag, rounded to even.
+        cache: keep generated items in host memory (drawing 16 384 x 1 024 normals costs ~0.1 s per bag on the CPU)."""
         self.num_bags, self.seed, self.bag_dtype, self.two_scales = int(num_bags), int(seed), bag_dtype, two_scales
+        self._cache = {} if cache else None
         if isinstance(n_patches, int):
             self.lengths = [n_patches] * self.num_bags
         else:
@@ -37,6 +39,14 @@ class SyntheticBagDataset(Dataset):
         return self.num_bags
 
     def __getitem__(self, i):
+        if self._cache is not None and i in self._cache:
+            return self._cache[i]
+        item = self._make(i)
+        if self._cache is not None:
+            self._cache[i] = item
+        return item
+
+    def _make(self, i):
         n = self.lengths[i]
         s = self.seed * 100003 + i
         b = synth.synthetic_bag(n, seed=s, B=1)

@@ -73,6 +73,36 @@ def balance_bags_by_cost(lengths: Sequence[int], world: int) -> List[List[int]]:
     return out
 
 
+class LengthBucketedSampler(torch.utils.data.Sampler):
+    """DistributedSampler for variable-length bags: every step hands the `world` ranks bags of NEIGHBOURING lengths (bags sorted
+    by length, consecutive groups of `world` = one step, the steps shuffled per epoch), so no rank waits at the gradient
+    all-reduce for a neighbour that drew a 16k bag against its 4k one (cost ~ N^2).  Same contract as
+    DistributedSampler(drop_last=True): every rank the same number of bags, each bag at most once per epoch."""
+
+    def __init__(self, lengths: Sequence[int], world: int, rank: int, seed: int = 0, shuffle: bool = True):
+        self.lengths, self.world, self.rank, self.seed, self.shuffle, self.epoch = list(lengths), world, rank, seed, shuffle, 0
+        order = sorted(range(len(self.lengths)), key=lambda i: (-self.lengths[i], i))
+        usable = (len(order) // world) * world
+        self.steps = [order[i:i + world] for i in range(0, usable, world)]
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+
+    def __len__(self):
+        return len(self.steps)
+
+    def __iter__(self):
+        idx = list(range(len(self.steps)))
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(self.seed + self.epoch)
+            idx = torch.randperm(len(self.steps), generator=g).tolist()
+        # within a step the longest bag rotates over the ranks from step to step
+        for n, k in enumerate(idx):
+            step = self.steps[k]
+            yield step[(self.rank + n) % self.world]
+
+
 class FlatGradAllReducer:
     """Averages the gradients of `params` across ranks with a single collective on one flat fp32 buffer.
     Parameters without a gradient on this rank (the never-used attn2d.* / pooler.* weights, quirk Q7) contribute

@@ -104,7 +104,7 @@ def trainDeformPathomicModel(model, dataloader, optimizer, scheduler, logger, ar
     history = []
     for epoch in range(args.epochs):
         sampler = getattr(train_loader, "sampler", None)
-        if isinstance(sampler, torch.utils.data.distributed.DistributedSampler):
+        if hasattr(sampler, "set_epoch"):
             sampler.set_epoch(epoch)
         t0, losses = time.time(), []
         for batch in train_loader:
@@ -112,7 +112,7 @@ def trainDeformPathomicModel(model, dataloader, optimizer, scheduler, logger, ar
             if scheduler is not None:
                 scheduler.step()
         rec = {"epoch": epoch, "loss": float(torch.stack(losses).mean()) if losses else float("nan"),
-               "bags_per_s": len(losses) * train_loader.batch_size / max(time.time() - t0, 1e-9)}
+               "bags_per_s": len(losses) * train_loader.batch_size * int(getattr(args, "world_size", 1)) / max(time.time() - t0, 1e-9)}
         if rank == 0 and test_loader is not None and (epoch + 1) % int(getattr(args, "eval_every", 1)) == 0:
             rec.update(evaluate(model, test_loader, args))
         if rank == 0 and logger is not None:
@@ -131,6 +131,7 @@ def main(argv: Optional[List[str]] = None):
     ap.add_argument("--epochs", type=int, default=1)
     ap.add_argument("--lr", type=float, default=2e-4)
     ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--bucketed", action="store_true", help="length-bucketed sampler: the ranks of a step get bags of neighbouring lengths")
     a = ap.parse_args(argv)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -144,7 +145,11 @@ def main(argv: Optional[List[str]] = None):
     n_p = a.patches[0] if len(a.patches) == 1 else (a.patches[0], a.patches[1])
     train = SyntheticBagDataset(a.bags, n_p, seed=42, bag_dtype=torch.bfloat16)
     test = SyntheticBagDataset(max(8, a.bags // 4), n_p, seed=43, bag_dtype=torch.bfloat16)
-    sampler = torch.utils.data.distributed.DistributedSampler(train, world, rank, shuffle=True, seed=42, drop_last=True) if world > 1 else None
+    sampler = None
+    if a.bucketed:
+        sampler = parallel.LengthBucketedSampler(train.lengths, world, rank, seed=42)
+    elif world > 1:
+        sampler = torch.utils.data.distributed.DistributedSampler(train, world, rank, shuffle=True, seed=42, drop_last=True)
     tl = torch.utils.data.DataLoader(train, batch_size=1, shuffle=sampler is None, sampler=sampler, num_workers=0, pin_memory=True, drop_last=True)
     vl = torch.utils.data.DataLoader(test, batch_size=1, shuffle=False) if rank == 0 else None
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=a.lr, weight_decay=0.01)

@@ -17,3 +17,27 @@ def test_centre_taps_and_key_count():
     assert ops.centre_taps(16385) == (8192, 8193, 1.0, 0.0)
     assert ops.centre_taps(128)[2:] == (0.5, 0.5)
     assert ops.kv_length(16385, 6, 4) == 4096 and ops.kv_length(2049, 6, 4) == 512
+
+
+def test_length_bucketed_sampler_partitions_like_a_distributed_sampler():
+    import random
+    from dml_b200.parallel import LengthBucketedSampler
+    rnd = random.Random(3)
+    lengths = [rnd.randrange(4000, 16385, 2) for _ in range(37)]
+    world = 4
+    per_rank = []
+    for rank in range(world):
+        s = LengthBucketedSampler(lengths, world, rank, seed=11)
+        s.set_epoch(2)
+        per_rank.append(list(s))
+        assert len(per_rank[-1]) == len(s) == 37 // world
+    flat = [i for r in per_rank for i in r]
+    assert len(set(flat)) == len(flat) == (37 // world) * world                  # each bag at most once, every rank the same count
+    order = sorted(lengths, reverse=True)
+    for step in zip(*per_rank):                                                  # the bags of one step are neighbours in length
+        ls = sorted((lengths[i] for i in step), reverse=True)
+        k = order.index(ls[0])
+        assert ls == order[k:k + world] or len(set(ls)) < world
+    s0 = LengthBucketedSampler(lengths, world, 0, seed=11)
+    a = list(s0); s0.set_epoch(1); b = list(s0)
+    assert a != b and sorted(a) != [] 
