@@ -687,7 +687,15 @@ static bool operand_ok(const dml_pg_operand& o) {
 extern "C" {
 
 // validate one problem, encode its tensor maps and fill the kernel parameters; *bn_out = the tile width the problem needs
-static int prepare_problem(const dml_pgemm_args* a, dml::tc::pg::Params& p, CUtensorMap* ma, CUtensorMap* mb, int* bn_out) {
+static int sm_count_cached() {      // per call, from the current device (no process-global state)
+  int dev = 0, nsm = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || nsm <= 0)
+    nsm = 148;
+  return nsm;
+}
+
+static int prepare_problem(const dml_pgemm_args* a, dml::tc::pg::Params& p, CUtensorMap* ma, CUtensorMap* mb, int* bn_out,
+                           bool narrow_small) {
   using namespace dml;
   using namespace dml::tc;
   using namespace dml::tc::pg;
@@ -707,7 +715,12 @@ static int prepare_problem(const dml_pgemm_args* a, dml::tc::pg::Params& p, CUte
   if (softmax && a->N > 256) return DML_EUNSUPPORTED;
   if (softmax && (a->bias || a->resid || a->accumulate || a->relu || a->use_diag || a->ncol_split > 0 || a->absmax)) return DML_EINVAL;
   if (a->pair && ((a->ldp % 8) || (a->p_plane % 8) || (((uintptr_t)a->pair) & 15))) return DML_EINVAL;
-  const int BN = softmax ? (a->N > 128 ? 256 : (a->N > 64 ? 128 : 64)) : (a->N > 64 ? 128 : 64);
+  int BN = softmax ? (a->N > 128 ? 256 : (a->N > 64 ? 128 : 64)) : (a->N > 64 ? 128 : 64);
+  // a small problem (the 8 x 256^3 products of the pseudo-inverse: 32 tiles of 128 x 128) is latency-bound per CTA: half-width
+  // tiles put it on twice the SMs with half the operand bytes, MMAs and epilogue columns each
+  if (narrow_small && !softmax && BN == 128 &&
+      2LL * cdiv(a->M, kBM) * cdiv(a->N, 128) * a->nb_inner * a->nb_outer * splits <= (long long)sm_count_cached())
+    BN = 64;
   int rc;
   if ((rc = make_map5(ma, a->A, a->K, a->nb_inner, a->nb_outer, kBM)) || (rc = make_map5(mb, a->B, a->K, a->nb_inner, a->nb_outer, BN)))
     return rc;
@@ -764,7 +777,8 @@ int dml_pgemm(const dml_pgemm_args* a, void* stream) {
   CUtensorMap ma, mb;
   Params p;
   int BN = 0;
-  int rc = prepare_problem(a, p, &ma, &mb, &BN);
+  static const bool narrow = []() { const char* v = getenv("DML_B200_PGEMM_NARROW"); return !(v && v[0] == '0'); }();
+  int rc = prepare_problem(a, p, &ma, &mb, &BN, narrow);
   if (rc) return rc;
   cudaError_t e;
   cudaLaunchConfig_t cfg{};
@@ -809,7 +823,7 @@ int dml_pgemm_chain(const dml_pgemm_args* args, int count, void* stream) {
   int grid = 1;
   for (int i = 0; i < count; ++i) {
     int BN = 0;
-    int rc = prepare_problem(&args[i], cp.p[i], &cp.maps[2 * i], &cp.maps[2 * i + 1], &BN);
+    int rc = prepare_problem(&args[i], cp.p[i], &cp.maps[2 * i], &cp.maps[2 * i + 1], &BN, false);
     if (rc) return rc;
     if (BN != 128 || cp.p[i].splits != 1 || cp.p[i].total_tiles > nsm) return DML_EUNSUPPORTED;
     grid = max(grid, cp.p[i].total_tiles);

@@ -1,3 +1,7 @@
-for mode in "" "--bucketed"; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 -m dml_b200.train_test --task survival --bags 48 --patches 4096 16384 --epochs 4 $mode > gpurun_out/r2_trainer_surv_varlen_2gpu$mode.log 2>&1; echo "trainer$mode exit $?"; tail -4 gpurun_out/r2_trainer_surv_varlen_2gpu$mode.log
-done
+python -m pytest tests/test_gpu_pgemm.py tests/test_gpu_nystrom.py -m gpu -q -x 2>&1 | tail -2
+python bench.py --workload transmil --no-cpu-baseline > gpurun_out/r2_bench_transmil_narrow.json 2>/dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_transmil_narrow.json').read().strip().splitlines()[-1]); print('narrow', d['ms_per_step'], d['kernel_ms_per_step']['dml_pgemm'])"
+DML_B200_PGEMM_NARROW=0 python bench.py --workload transmil --no-cpu-baseline > gpurun_out/r2_bench_transmil_wide.json 2>/dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_transmil_wide.json').read().strip().splitlines()[-1]); print('wide', d['ms_per_step'], d['kernel_ms_per_step']['dml_pgemm'])"
+python bench.py --workload transmil --n-patches 6000 --no-cpu-baseline > gpurun_out/r2_bench_transmil_narrow_6000.json 2>/dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_transmil_narrow_6000.json').read().strip().splitlines()[-1]); print('narrow 6000', d['ms_per_step'], d['kernel_ms_per_step']['dml_pgemm'])"
