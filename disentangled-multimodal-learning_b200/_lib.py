@@ -61,6 +61,10 @@ SIGNATURES = {
     "dml_linear3_fwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _vp]),
     "dml_linear3_bwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _fp, _i, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "dml_debug_dkv_worklist": (_i, [_i, _i, _i, _i, _i, C.POINTER(C.c_int), _i]),
+    "dml_ny_pinv_init_sums_floats": (C.c_size_t, [_i, _i]),
+    "dml_ny_pinv_init_part_floats": (C.c_size_t, [_i, _i]),
+    "dml_ny_pinv_init_fwd": (_i, [_fp, _i, _i, _fp, _vp, _ll, _vp]),
+    "dml_ny_pinv_init_bwd": (_i, [_fp, _fp, _fp, _fp, _i, _i, _fp, _fp, _vp]),
     "dml_gram_splits": (_i, [_i, _ll, _i]),
     "dml_gram_fwd": (_i, [_vp, _ll, _vp, _ll, _i, _i, _ll, _fp, _vp]),
     "dml_rows_mix": (_i, [_fp, _vp, _ll, _i, _i, _i, _ll, _fp, _ll, _ll, _vp]),
@@ -188,6 +192,7 @@ KERNELS_PER_CALL = {
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,
     "dml_ny_dqkv_finalize": 1, "dml_ppeg_stencil": 1, "dml_ppeg_wgrad": 1, "dml_relu_mask_pair": 1, "dml_scale_to_half": 1, "dml_maxnet_fwd": 1, "dml_maxnet_bwd": 1, "dml_tower_head_fwd": 1, "dml_tower_head_bwd": 1,
     "dml_linear3_fwd": 1, "dml_linear3_bwd": 1,
+    "dml_ny_pinv_init_fwd": 2, "dml_ny_pinv_init_bwd": 2, "dml_gram_fwd": 1, "dml_rows_mix": 1,
     "dml_coattn_fq_fwd": 2, "dml_coattn_fq_bwd": 1, "dml_coattn_fk_fwd": 1, "dml_coattn_fk_bwd": 1,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process

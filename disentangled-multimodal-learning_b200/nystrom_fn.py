@@ -52,10 +52,13 @@ def _mm_tokens(A, Bm, out, *, M, N, K, batch, reduce_into_2d=False, **kw):
 def pinv_forward(x_pair: Pair, x_f32: torch.Tensor, iters: int, B: int, H: int, m: int, save: bool):
     """moore_penrose_iter_pinv (NystromAttention.py:20-35).  Returns (z pair, saved iterates)."""
     bt = (B, H)
-    ax = x_f32.abs()
-    denom = ax.sum(-1).max() * ax.sum(-2).max()                      # GLOBAL over batch and heads (quirk T3)
-    z = Pair.from_f32((x_f32.transpose(-1, -2) / denom).contiguous())
-    saved = []
+    lib = _lib.load(check_device=True)
+    x_f32 = x_f32.contiguous()
+    sums = torch.empty(lib.dml_ny_pinv_init_sums_floats(B * H, m), device=x_f32.device, dtype=F32)
+    z = Pair.empty((B, H, m, m), x_f32.device)
+    # z0 = x^T / (max row abs-sum * max column abs-sum), both maxima GLOBAL over batch and heads (quirk T3): two launches
+    call("dml_ny_pinv_init_fwd", ptr(x_f32), B * H, m, ptr(sums), ptr(z.planes), z.planes.stride(0), stream())
+    saved = [sums]
     with chain():        # the 4 x iters dependent products leave as chained cooperative launches (grid barrier between products)
         for _ in range(iters):
             xz_f, xz = pgemm(x_pair, z, M=m, N=m, K=m, b_trans=True, batch=bt, want_pair=True)
@@ -74,6 +77,7 @@ def pinv_backward(x_pair: Pair, x_f32: torch.Tensor, saved, G_f: torch.Tensor, G
     """Adjoint of pinv_forward: G = d z_final (fp32 + pair) -> d x (fp32 [B, H, m, m])."""
     bt = (B, H)
     dx = None
+    sums, saved = saved[0], saved[1:]
     with chain():
         for (z, P, t3, t5) in reversed(saved):
             # z' = 1/4 z t5
@@ -92,13 +96,15 @@ def pinv_backward(x_pair: Pair, x_f32: torch.Tensor, saved, G_f: torch.Tensor, G
             else:
                 pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=True)
             G_f, G = pgemm(x_pair, dPp, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dz_f, accumulate=True, want_pair=True)
-    # z0 = x^T / (max row-sum * max column-sum): small torch graph (the scalar couples all bags and heads)
-    with torch.enable_grad():
-        xr = x_f32.detach().requires_grad_(True)
-        ax = xr.abs()
-        z0 = xr.transpose(-1, -2) / (ax.sum(-1).max() * ax.sum(-2).max())
-        (g0,) = torch.autograd.grad(z0, xr, G_f)
-    return g0 if dx is None else dx + g0
+    # z0 = x^T / (max row-sum * max column-sum): the scalar couples all bags and heads; two launches, the chain's dx added in
+    lib = _lib.load(check_device=True)
+    x_f32 = x_f32.contiguous()
+    G_f = G_f.contiguous()
+    part = torch.empty(lib.dml_ny_pinv_init_part_floats(B * H, m), device=x_f32.device, dtype=F32)
+    out = torch.empty_like(x_f32)
+    call("dml_ny_pinv_init_bwd", ptr(G_f), ptr(x_f32), ptr(sums), None if dx is None else ptr(dx.contiguous()), B * H, m, ptr(part),
+         ptr(out), stream())
+    return out
 
 
 class NystromAttnFn(torch.autograd.Function):

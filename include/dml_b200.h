@@ -269,6 +269,17 @@ int dml_linear3_bwd(const float* a, const float* b, int B, int Da, int Db, const
                     int sigmoid, const float* yc, const float* ya, const float* yb, const float* gyc, const float* gya,
                     const float* gyb, float* dparams, float* da, float* db, void* stream);
 
+/* ---- initial iterate of the pseudo-inverse and its adjoint (csrc/pinv_init.cu) ---------------------------------------------
+ * moore_penrose_iter_pinv, models/NystromAttention.py:20-27: z0 = x^T / (max row abs-sum * max column abs-sum), both maxima taken
+ * over ALL NB = batch x heads matrices (quirk T3).  x float [NB, m, m]; sums float [2, NB, m] (row sums, column sums: written by
+ * the forward, read by the backward); z0 as a bf16 pair [NB, m, m].  Backward: g = d z0 float [NB, m, m] -> dx = the full gradient
+ * (through the transpose, the scale and both maxima) + addend (may be NULL); part: dml_ny_pinv_init_part_floats workspace.       */
+size_t dml_ny_pinv_init_sums_floats(int NB, int m);
+size_t dml_ny_pinv_init_part_floats(int NB, int m);
+int dml_ny_pinv_init_fwd(const float* x, int NB, int m, float* sums, void* z_pair, long long plane_stride, void* stream);
+int dml_ny_pinv_init_bwd(const float* g, const float* x, const float* sums, const float* addend, int NB, int m, float* part, float* dx,
+                         void* stream);
+
 /* ---- genomic-guided co-attention with one head and a few tokens on one side (csrc/coattn.cu) -------------------------------
  * Replaces the long-side work of multi_head_attention_forward (models/MultiheadAttention.py:7-321; the copy in
  * models/cmta_utils.py:667-) as MCAT / CMTA call it (models/model.py:1007,1047: 4 genomic queries over the patch keys;

@@ -1,1 +1,3 @@
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"res_conv" -c 2 -o gpurun_out/r2_res_conv_full -f python scripts/prof_transmil.py 16384 3 > gpurun_out/ncu_res_conv.log 2>&1; echo "exit $?"; tail -2 gpurun_out/ncu_res_conv.log
+python -m pytest tests/test_gpu_nystrom.py tests/test_gpu_modules.py -m gpu -q -x -k "nystrom or transmil or pinv or Nystrom or TransMIL" 2>&1 | tail -4
+for n in 16384 6000; do python bench.py --workload transmil --n-patches $n --no-cpu-baseline > gpurun_out/r2_bench_transmil_pv_$n.json 2>/dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/r2_bench_transmil_pv_$n.json').read().strip().splitlines()[-1]); print('pv $n', d['ms_per_step'], d['launches_per_step'], {k:round(v,3) for k,v in list(d['kernel_ms_per_step'].items())[:6]})"; done

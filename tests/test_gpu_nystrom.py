@@ -132,3 +132,27 @@ def test_transmil_training_step_is_graph_capturable_and_matches_eager():
     net.train()
     step = GraphedTrainStep(net, loss_fn, inp, optimizer=None, model_keys=("x",), warmup=2)
     assert torch.isfinite(step(inp)).all()
+
+
+@pytest.mark.parametrize("NB,m", [(8, 256), (16, 64), (3, 40)])
+def test_pinv_initial_iterate_and_its_adjoint(NB, m):
+    """z0 = x^T / (max row abs-sum * max column abs-sum) with GLOBAL maxima (NystromAttention.py:20-27, quirk T3), and the full
+    gradient through the transpose, the scale and both arg-max rows / columns, against torch autograd in fp64."""
+    lib = __import__("dml_b200")._lib.load(check_device=True)
+    x = synth.normal((NB, m, m), 17, "x").to(DEV)
+    G = synth.normal((NB, m, m), 17, "g").to(DEV)
+    add = synth.normal((NB, m, m), 17, "add").to(DEV)
+    sums = torch.empty(lib.dml_ny_pinv_init_sums_floats(NB, m), device=DEV)
+    z = Pair.empty((NB, m, m), DEV)
+    call("dml_ny_pinv_init_fwd", ptr(x), NB, m, ptr(sums), ptr(z.planes), z.planes.stride(0), stream())
+    xd = x.double().requires_grad_()
+    ax = xd.abs()
+    z_ref = xd.transpose(-1, -2) / (ax.sum(-1).max() * ax.sum(-2).max())
+    H.assert_close(z.float(), z_ref, 1e-5, "z0")
+    (g_ref,) = torch.autograd.grad(z_ref, xd, G.double())
+    part = torch.empty(lib.dml_ny_pinv_init_part_floats(NB, m), device=DEV)
+    dx = torch.empty_like(x)
+    for addend in (None, add):
+        call("dml_ny_pinv_init_bwd", ptr(G), ptr(x), ptr(sums), None if addend is None else ptr(addend), NB, m, ptr(part), ptr(dx),
+             stream())
+        H.assert_close(dx, g_ref + (0 if addend is None else addend.double()), 1e-5, "d x")
