@@ -100,23 +100,28 @@ softmax_rows_bwd_kernel(const bf16* __restrict__ y, long long yplane, const floa
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kRows = 64, kCols = 128, kKMax = 33, kHeadSlots = 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 res_conv_fwd_kernel(const float* __restrict__ a, const bf16* __restrict__ v, long long vplane, int ldv, int col0,
                     const float* __restrict__ w, int K, int n_pad, int W, int d, bf16* __restrict__ y, long long yplane) {
   extern __shared__ float sm[];
   const int half = K / 2;
   const int i0 = blockIdx.x * kRows, cb = blockIdx.y * kCols, b = blockIdx.z;
   const int trow = kRows + K - 1;
-#pragma unroll 4
-  for (int idx = threadIdx.x; idx < trow * (kCols / 4); idx += blockDim.x) {
-    const int r = idx / (kCols / 4), c4 = (idx % (kCols / 4)) * 4;
-    const int gi = i0 + r - half;
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gi >= 0 && gi < n_pad) {
-      const bf16* p = v + ((size_t)b * n_pad + gi) * ldv + col0 + cb + c4;
-      val = load_pair4(p, p + vplane);
+  // stage the tile + halo: six iterations' loads go out before the first one is unpacked (12 iterations at K = 33)
+  constexpr int kStageIters = ((kRows + kKMax - 1) * (kCols / 4) + 255) / 256;
+#pragma unroll 6
+  for (int it = 0; it < kStageIters; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    if (idx < trow * (kCols / 4)) {
+      const int r = idx / (kCols / 4), c4 = (idx % (kCols / 4)) * 4;
+      const int gi = i0 + r - half;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gi >= 0 && gi < n_pad) {
+        const bf16* p = v + ((size_t)b * n_pad + gi) * ldv + col0 + cb + c4;
+        val = load_pair4(p, p + vplane);
+      }
+      *reinterpret_cast<float4*>(sm + r * kCols + c4) = val;
     }
-    *reinterpret_cast<float4*>(sm + r * kCols + c4) = val;
   }
   __syncthreads();
   // a thread owns two adjacent columns (same head: d is even) and 16 rows in two 8-row strips: 4-byte pair stores
@@ -127,6 +132,12 @@ res_conv_fwd_kernel(const float* __restrict__ a, const bf16* __restrict__ v, lon
   for (int t = 0; t < kKMax; ++t) wk[t] = t < K ? w[h * K + t] : 0.f;
   for (int chunk = 0; chunk < 2; ++chunk) {
     const int r0 = rg * 16 + chunk * 8;
+    float2 av[8];                  // the addend of the 8 rows: requested before the window is read, consumed after the taps
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int gi = min(i0 + r0 + r, n_pad - 1);
+      av[r] = __ldg(reinterpret_cast<const float2*>(a + ((size_t)b * n_pad + gi) * W + col));
+    }
     float win0[8 + kKMax - 1], win1[8 + kKMax - 1];
 #pragma unroll
     for (int t = 0; t < 8 + kKMax - 1; ++t) {
@@ -138,10 +149,10 @@ res_conv_fwd_kernel(const float* __restrict__ a, const bf16* __restrict__ v, lon
       const int gi = i0 + r0 + r;
       if (gi < n_pad) {
         const size_t o = ((size_t)b * n_pad + gi) * W + col;
-        const float2 a2 = *reinterpret_cast<const float2*>(a + o);
-        float acc0 = a2.x, acc1 = a2.y;
+        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
         for (int t = 0; t < kKMax; ++t) { acc0 = fmaf(wk[t], win0[r + t], acc0); acc1 = fmaf(wk[t], win1[r + t], acc1); }
+        acc0 += av[r].x; acc1 += av[r].y;
         uint32_t hi, lo;
         split_bf16x2(acc0, acc1, hi, lo);
         *reinterpret_cast<uint32_t*>(y + o) = hi;
@@ -153,7 +164,7 @@ res_conv_fwd_kernel(const float* __restrict__ a, const bf16* __restrict__ v, lon
 
 // backward: dv[b, i, c] = sum_t w[h, t] dy[b, i - t + K/2, c]  (stored into the gradient buffer: ld, col0);
 //           dw[h, t] += sum_{b, i, c in head h} dy[b, i, c] v[b, i + t - K/2, c]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 res_conv_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ v, long long vplane, int ldv, int col0,
                     const float* __restrict__ w, int K, int n_pad, int W, int d, int H, float* __restrict__ dv, int lddv,
                     int dcol0, float* __restrict__ dw) {
@@ -164,18 +175,22 @@ res_conv_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ v, lo
   float* tdy = sm;
   float* tv = sm + trow * kCols;
   float* wred = tv + trow * kCols;
-#pragma unroll 4
-  for (int idx = threadIdx.x; idx < trow * (kCols / 4); idx += blockDim.x) {
-    const int r = idx / (kCols / 4), c4 = (idx % (kCols / 4)) * 4;
-    const int gi = i0 + r - half;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), vv = g;
-    if (gi >= 0 && gi < n_pad) {
-      g = *reinterpret_cast<const float4*>(dy + ((size_t)b * n_pad + gi) * W + cb + c4);
-      const bf16* p = v + ((size_t)b * n_pad + gi) * ldv + col0 + cb + c4;
-      vv = load_pair4(p, p + vplane);
+  constexpr int kStageIters = ((kRows + kKMax - 1) * (kCols / 4) + 255) / 256;
+#pragma unroll 6
+  for (int it = 0; it < kStageIters; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    if (idx < trow * (kCols / 4)) {
+      const int r = idx / (kCols / 4), c4 = (idx % (kCols / 4)) * 4;
+      const int gi = i0 + r - half;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f), vv = g;
+      if (gi >= 0 && gi < n_pad) {
+        g = __ldg(reinterpret_cast<const float4*>(dy + ((size_t)b * n_pad + gi) * W + cb + c4));
+        const bf16* p = v + ((size_t)b * n_pad + gi) * ldv + col0 + cb + c4;
+        vv = load_pair4(p, p + vplane);
+      }
+      *reinterpret_cast<float4*>(tdy + r * kCols + c4) = g;
+      *reinterpret_cast<float4*>(tv + r * kCols + c4) = vv;
     }
-    *reinterpret_cast<float4*>(tdy + r * kCols + c4) = g;
-    *reinterpret_cast<float4*>(tv + r * kCols + c4) = vv;
   }
   for (int idx = threadIdx.x; idx < kHeadSlots * kKMax; idx += blockDim.x) wred[idx] = 0.f;
   __syncthreads();
@@ -187,24 +202,30 @@ res_conv_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ v, lo
   for (int t = 0; t < kKMax; ++t) { wkf[t] = t < K ? w[h * K + (K - 1 - t)] : 0.f; gw[t] = 0.f; }
   for (int chunk = 0; chunk < 4; ++chunk) {
     const int r0 = rg * 32 + chunk * 8;
-    float wdy[8 + kKMax - 1], wv[8 + kKMax - 1];
+    {      // dv: one 40-row window of dy in registers
+      float wdy[8 + kKMax - 1];
 #pragma unroll
-    for (int t = 0; t < 8 + kKMax - 1; ++t) {
-      wdy[t] = (t < 8 + K - 1) ? tdy[(r0 + t) * kCols + c] : 0.f;
-      wv[t] = (t < 8 + K - 1) ? tv[(r0 + t) * kCols + c] : 0.f;
-    }
+      for (int t = 0; t < 8 + kKMax - 1; ++t) wdy[t] = (t < 8 + K - 1) ? tdy[(r0 + t) * kCols + c] : 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int gi = i0 + r0 + r;
-      if (gi < n_pad) {
-        const float g = tdy[(r0 + r + half) * kCols + c];      // dy at row gi (a shared-memory read: `half` is not a compile-time index)
+      for (int r = 0; r < 8; ++r) {
+        const int gi = i0 + r0 + r;
         float acc = 0.f;
 #pragma unroll
-        for (int t = 0; t < kKMax; ++t) {
-          acc = fmaf(wkf[t], wdy[r + t], acc);
-          gw[t] = fmaf(g, wv[r + t], gw[t]);
-        }
-        dv[((size_t)b * n_pad + gi) * lddv + dcol0 + col] = acc;
+        for (int t = 0; t < kKMax; ++t) acc = fmaf(wkf[t], wdy[r + t], acc);
+        if (gi < n_pad) dv[((size_t)b * n_pad + gi) * lddv + dcol0 + col] = acc;
+      }
+    }
+    asm volatile("" ::: "memory");      // keep the two windows from being live together (register budget: two CTAs per SM)
+    {      // dw: the window of v against dy of the 8 rows
+      float wv[8 + kKMax - 1];
+#pragma unroll
+      for (int t = 0; t < 8 + kKMax - 1; ++t) wv[t] = (t < 8 + K - 1) ? tv[(r0 + t) * kCols + c] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int gi = i0 + r0 + r;
+        const float g = gi < n_pad ? tdy[(r0 + r + half) * kCols + c] : 0.f;      // dy at row gi (`half` is not a compile-time index)
+#pragma unroll
+        for (int t = 0; t < kKMax; ++t) gw[t] = fmaf(g, wv[r + t], gw[t]);
       }
     }
   }
