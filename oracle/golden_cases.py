@@ -39,6 +39,18 @@ LOSS_CASES = [
     dict(name="losses_n4_l50x12", N=4, L1=50, L2=12, seed=81),
     dict(name="losses_n8_l37x20", N=8, L1=37, L2=20, seed=82),
 ]
+# DeformCrossAttention2D as the teacher / student encoders build it (models/Modules.py:107-126: dim 128, 8 heads = 8 offset
+# groups, dim_head 64, stride 4, offset_scale 4) on side x side grids; s50 is the reference's own bag (2 500 patches, 144 keys)
+DEFORM2D_CASES = [
+    dict(name="deform2d_s20_b2", b=2, side=20, seed=91),
+    dict(name="deform2d_s50_b1", b=1, side=50, seed=92),
+    dict(name="deform2d_s23_b1", b=1, side=23, seed=93),      # 25 keys: not a multiple of the 16-key tile
+]
+# ClusterMergeNet (models/ClusterMergeNet.py:183-207) at sample ratios that give 8 and 32 clusters (Modules.py:258-261)
+CLUSTER_CASES = [
+    dict(name="clustermerge_n400_b2", B=2, N=400, ratio=0.02, seed=95),
+    dict(name="clustermerge_n2500_b1", B=1, N=2500, ratio=0.0128, seed=96),
+]
 
 MAX_KEEP = 8192
 

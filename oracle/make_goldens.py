@@ -79,7 +79,8 @@ def pack(d):
     return out
 
 
-from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES, loss_inputs, thin)
+from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES, DEFORM2D_CASES, CLUSTER_CASES, loss_inputs,
+                                 thin)
 
 
 def gen_deform():
@@ -173,6 +174,58 @@ def gen_losses():
         print(c["name"], float(pb.sum()), float(od), float(bl.sum()))
 
 
+def gen_deform2d():
+    """models/DeformableAttention2D.py as models/Modules.py builds it (eval mode: the attention dropout is the identity)."""
+    from dml_b200 import synth
+    from models.DeformableAttention2D import DeformCrossAttention2D
+    for c in DEFORM2D_CASES:
+        mod = DeformCrossAttention2D(dim=128, dim_head=64, heads=8, dropout=0.1, downsample_factor=4, offset_scale=4,
+                                     offset_groups=8, offset_kernel_size=6).eval()
+        load_synth(mod, c["seed"], gain=2.0)
+        n = c["side"] ** 2
+        x1 = synth.normal((c["b"], 128, n), c["seed"], "x1").requires_grad_()
+        x2 = synth.normal((c["b"], 128, n), c["seed"], "x2").requires_grad_()
+        r = synth.normal((c["b"], 128, n), c["seed"], "r")
+        out, attn = mod(x1, x2)
+        _, vgrid = mod(x1, x2, return_vgrid=True)
+        r2 = synth.normal(tuple(attn.shape), c["seed"], "r2")
+        loss = (out * r).sum() + (attn * r2).sum()             # the teacher / student losses read the attention map too
+        gx1, gx2 = torch.autograd.grad(loss, (x1, x2), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(out=thin(out), attn=thin(attn), vgrid=vgrid, gx1=thin(gx1), gx2=thin(gx2))
+        d.update({"grad." + k: thin(v) for k, v in g.items()})
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], float(out.abs().mean()), float(gx1.abs().mean()), float(gx2.abs().mean()))
+
+
+def gen_cluster():
+    """models/ClusterMergeNet.py; the torch.rand of cluster_dpc_knn (:103) is replaced by the seeded noise the tests regenerate."""
+    from dml_b200 import synth
+    from models.ClusterMergeNet import ClusterMergeNet
+    real_rand = torch.rand
+    for c in CLUSTER_CASES:
+        mod = ClusterMergeNet(sample_ratio=c["ratio"], dim_out=128)
+        load_synth(mod, c["seed"])
+        x = synth.normal((c["B"], c["N"], 128), c["seed"], "x").requires_grad_()
+        noise = synth.uniform((c["B"], c["N"]), c["seed"], "noise", 0.5) + 0.5
+        torch.rand = lambda *a, **k: noise.clone()
+        try:
+            tok = dict(x=x, token_num=c["N"], idx_token=torch.arange(c["N"])[None].repeat(c["B"], 1),
+                       agg_weight=x.new_ones(c["B"], c["N"], 1))
+            down, _ = mod(tok)
+        finally:
+            torch.rand = real_rand
+        merged = down["x"]
+        r = synth.normal(tuple(merged.shape), c["seed"], "r")
+        loss = (merged * r).sum()
+        (gx,) = torch.autograd.grad(loss, (x,), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(merged=merged, idx_cluster=down["idx_token"], gx=thin(gx))
+        d.update({"grad." + k: v for k, v in g.items()})
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], tuple(merged.shape), float(merged.abs().mean()), np.bincount(down["idx_token"].reshape(-1).numpy())[:8])
+
+
 class _Args:
     def __init__(self, **kw):
         self.__dict__.update(kw)
@@ -241,7 +294,8 @@ def main():
     """python -m oracle.make_goldens [--missing]   (--missing: only write fixtures that do not exist yet)"""
     os.makedirs(OUT, exist_ok=True)
     if "--missing" in sys.argv:
-        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES):
+        for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES,
+                      DEFORM2D_CASES, CLUSTER_CASES):
             cases[:] = [c for c in cases if not os.path.exists(os.path.join(OUT, c["name"] + ".npz"))]
     sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
     install_reference_shims()
@@ -256,6 +310,8 @@ def main():
         gen_towers()
         gen_coattn()
         gen_losses()
+        gen_deform2d()
+        gen_cluster()
 
 
 if __name__ == "__main__":

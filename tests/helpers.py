@@ -120,3 +120,8 @@ def mha_shapes(E=256):
 
 def leafify(P):
     return {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in P.items()}
+
+
+def cluster_shapes(C=128):
+    """state_dict of models/ClusterMergeNet.py:ClusterMergeNet(dim_out=C)."""
+    return {"norm.weight": (C,), "norm.bias": (C,), "score.weight": (1, C), "score.bias": (1,)}
