@@ -76,6 +76,27 @@ SIGNATURES = {
     "dml_coattn_fq_bwd": (_i, [_fp, _ll, _ll, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "dml_coattn_fk_fwd": (_i, [_fp, _ll, _ll, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "dml_coattn_fk_bwd": (_i, [_fp, _ll, _ll, _fp, _ll, _ll, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "dml_da2_kv_side": (_i, [_i, _i, _i]),
+    "dml_da2_gproj_fwd": (_i, [_fp, _fp, _ll, _fp, _vp]),
+    "dml_da2_gproj_parts": (_i, [_ll]),
+    "dml_da2_gproj_bwd": (_i, [_fp, _fp, _fp, _ll, _i, _fp, _fp, _fp, _vp]),
+    "dml_da2_reduce_parts": (_i, [_fp, _i, _ll, _i, _fp, _vp]),
+    "dml_da2_offsets_fwd": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _fp, _fp, _vp]),
+    "dml_da2_offsets_parts": (_i, [_i, _i, _i, _i]),
+    "dml_da2_offsets_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _vp]),
+    "dml_da2_gather_fwd": (_i, [_fp, _fp, _i, _i, _i, _fp, _vp]),
+    "dml_da2_gather_bwd": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
+    "dml_da2_bias_fwd": (_i, [_fp] * 7 + [_i, _i, _i, _fp, _vp]),
+    "dml_da2_bias_bwd_parts": (_i, [_i, _i]),
+    "dml_da2_bias_bwd": (_i, [_fp] * 7 + [_i, _i, _i, _fp, _fp, _fp, _vp]),
+    "dml_da2_attn_fwd": (_i, [_fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _fp, _vp]),
+    "dml_da2_cols_chunks": (_i, [_i, _i, _i]),
+    "dml_da2_attn_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _vp]),
+    "dml_dpc_density": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
+    "dml_dpc_parent": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp, _vp]),
+    "dml_dpc_assign": (_i, [_fp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dml_merge_fwd": (_i, [_fp, _fp, _vp, _i, _i, _i, _i, _fp, _fp, _vp]),
+    "dml_merge_bwd": (_i, [_fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),
 }
 
 
@@ -194,6 +215,7 @@ KERNELS_PER_CALL = {
     "dml_linear3_fwd": 1, "dml_linear3_bwd": 1,
     "dml_ny_pinv_init_fwd": 2, "dml_ny_pinv_init_bwd": 2, "dml_gram_fwd": 1, "dml_rows_mix": 1,
     "dml_coattn_fq_fwd": 2, "dml_coattn_fq_bwd": 1, "dml_coattn_fk_fwd": 1, "dml_coattn_fk_bwd": 1,
+    "dml_da2_gproj_bwd": 3, "dml_da2_offsets_bwd": 3, "dml_da2_bias_bwd": 2, "dml_da2_attn_bwd": 3,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events

@@ -327,6 +327,67 @@ int dml_gram_fwd(const float* const* a_rows, long long a_gs, const float* const*
 int dml_rows_mix(const float* W, const float* const* x_rows, long long x_gs, int G, int nrows, int N, long long K, float* out,
                  long long out_gs, long long out_rs, void* stream);
 
+/* ---- DeformCrossAttention2D (csrc/deform2d.cu, deform2d_bias.cu) --------------------------------------------
+ * models/DeformableAttention2D.py:162-342 as models/Modules.py:107-126 and DeformCrossTransMIL.py:45-54 build it: dim 128,
+ * 8 heads = 8 offset groups, dim_head 64, grouped 1x1 projections (16 -> 64 channels per group), n = side^2 tokens, m = hk^2
+ * sampled keys.  All tensors token-major fp32: x1, x2 [B, n, 128], q [B, n, 512], kvf [B, m, 128], k, v [B, m, 512],
+ * vgrid [(B 8), 2, hk, hk], vs [(B 8), m, 2] (normalised sampling positions), attn / bias / dS [B, 8, n, m].                   */
+int dml_da2_kv_side(int side, int ksize, int stride);          /* hk = floor((side + 2 pad - ksize) / stride) + 1 (:209)        */
+/* grouped 1x1 convolution (to_q :248, to_k / to_v :285): y[r][64 g + c] = sum_k x[r][16 g + k] W[64 g + c][k]                    */
+int dml_da2_gproj_fwd(const float* x, const float* W, long long rows, float* y, void* stream);
+int dml_da2_gproj_parts(long long rows);                       /* parts: float [dml_da2_gproj_parts(rows)][8192]                 */
+/* dx [rows, 128] (NULL: skip; accumulate_dx: += ), dW [512, 16] (NULL: skip)                                                   */
+int dml_da2_gproj_bwd(const float* dy, const float* x, const float* W, long long rows, int accumulate_dx, float* dx, float* parts,
+                      float* dW, void* stream);
+/* out[i] (+)= sum_p parts[p][i], fixed order                                                                                    */
+int dml_da2_reduce_parts(const float* parts, int nparts, long long len, int accumulate, float* out, void* stream);
+/* to_offsets + vgrid + normalize_grid (:208-214, :257-270).  wdw [64, ks, ks], bdw [64], w2 [2, 64].                             */
+int dml_da2_offsets_fwd(const float* q, const float* wdw, const float* bdw, const float* w2, int B, int side, int ksize, int stride,
+                        float offset_scale, float* vgrid, float* vs, void* stream);
+int dml_da2_offsets_parts(int B, int side, int ksize, int stride);   /* parts: float [dml_da2_offsets_parts()][2496]              */
+/* dvs = d loss / d vs; dvgrid_ext (may be NULL) = gradient that reached the returned vgrid.  dconv: float [(B 8), m, 64] scratch.
+ * grads: float [2496] = dWdw [64][ks ks] | db [64] | dW2 [2][64]; dq [B, n, 512] += the gradient through the depthwise window.   */
+int dml_da2_offsets_bwd(const float* q, const float* wdw, const float* bdw, const float* w2, const float* dvs, const float* dvgrid_ext,
+                        int B, int side, int ksize, int stride, float offset_scale, float* dconv, float* parts, float* grads, float* dq,
+                        void* stream);
+/* bilinear gather of the grouped x2 at vs (F.grid_sample bilinear / zeros / align_corners = False, :274-277) and its adjoint:
+ * dx2 (zeroed by the caller) += the scatter (atomics), dvs += the gradient through the sampling position.                        */
+int dml_da2_gather_fwd(const float* x2, const float* vs, int B, int side, int m, float* kvf, void* stream);
+int dml_da2_gather_bwd(const float* dkvf, const float* x2, const float* vs, int B, int side, int m, float* dx2, float* dvs, void* stream);
+/* position bias MLP 2 -> 32 -> 32 -> 1 on the tensor cores (CPB, :121-158, :302-305): bias [B, 8, n, m]                          */
+int dml_da2_bias_fwd(const float* vs, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                     int B, int side, int m, float* bias, void* stream);
+#define DML_DA2_BIAS_GRAD_FLOATS 1192 /* dW1 [32][2] | db1 [32] | dW2 [32][32] | db2 [32] | dW3 [32] | db3 [1] (+ pad) */
+int dml_da2_bias_bwd_parts(int B, int side);                   /* parts: float [dml_da2_bias_bwd_parts()][1192]                  */
+/* ds = gradient at the bias (= dS); dvs [(B 8), m, 2] (zeroed by the caller) += (atomics)                                        */
+int dml_da2_bias_bwd(const float* vs, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* ds,
+                     int B, int side, int m, float* parts, float* grads, float* dvs, void* stream);
+/* attention rows (:290-321).  attn: in = the position bias, out = softmax(scale q k^T + bias).  keep (may be NULL): dropout
+ * keep-mask bytes [B, 8, n, m] applied (x keep_scale) to the aggregation only (:316).  o [B, n, 512].                            */
+int dml_da2_attn_fwd(const float* q, const float* k, const float* v, float* attn, const unsigned char* keep, float keep_scale, int B, int n,
+                     int m, float scale, float* o, void* stream);
+int dml_da2_cols_chunks(int B, int n, int m);                  /* parts: float [dml_da2_cols_chunks()][2][B, m, 512]             */
+/* dO [B, n, 512], dA (may be NULL) = gradient that reached the returned attention map.  ds [B, 8, n, m] out = dS (also the
+ * gradient of the bias); dq [B, n, 512] out; dkv [2][B, m, 512] out = dk, dv.                                                   */
+int dml_da2_attn_bwd(const float* q, const float* k, const float* v, const float* attn, const float* dO, const float* dA,
+                     const unsigned char* keep, float keep_scale, int B, int n, int m, float scale, float* ds, float* dq, float* parts,
+                     float* dkv, void* stream);
+
+/* ---- ClusterMergeNet (csrc/cluster.cu; models/ClusterMergeNet.py:68-207) ----------------------------------------------------
+ * DPC-KNN without the N x N distance matrix: x float [B, N, 128] (LayerNorm output), distances = sqrt(sum of squared
+ * differences) / sqrt(C), k = 5 neighbours.                                                                                    */
+/* density [B, N] = exp(-mean of the 5 smallest d^2) + 1e-6 noise (:98-104); rowmax2 [B, N] = max_j (d sqrt(C))^2                */
+int dml_dpc_density(const float* x, const float* noise, int B, int N, int C, float* density, float* rowmax2, void* stream);
+/* parent [B, N] = min(dist_max[b], min over tokens of higher density of d) (:111-114)                                          */
+int dml_dpc_parent(const float* x, const float* density, const float* dist_max, int B, int N, int C, float* parent, void* stream);
+/* idx [B, N] (int64) = index of the nearest of the K centre tokens centres [B, K] (int64) (:121-123)                            */
+int dml_dpc_assign(const float* x, const long long* centres, int B, int N, int C, int K, long long* idx, void* stream);
+/* merge_tokens (:133-166): merged [B, K, C] = sum_{i in c} x_i w_i / W_c, all_w [B, K] = W_c = sum w_i + 1e-6; and the adjoint   */
+int dml_merge_fwd(const float* x, const float* w, const long long* idx, int B, int N, int C, int K, float* merged, float* all_w,
+                  void* stream);
+int dml_merge_bwd(const float* dmerged, const float* x, const float* w, const long long* idx, const float* merged, const float* all_w,
+                  int B, int N, int C, int K, float* dx, float* dw, void* stream);
+
 /* Test aid (host only): the work list dml_deform_attn_bwd_tc gives its dK/dV kernel for this problem shape on a device
  * with nsm SMs, as (item, first tile, end tile) int triples in launch order (item = key block + ceil(n_kv/128) * (head
  * pair + H/2 * batch), 32-query tiles).  Returns the number of pieces, 0 when the launch is one CTA per item.          */
