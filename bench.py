@@ -506,6 +506,94 @@ def bench_coattn(dev, cpu=True, B=8, S=16384, F=4, steps=20, warmup=3):
     return rec
 
 
+def bench_deform2d(dev, cpu=True, B=4, side=50, steps=20, warmup=3):
+    """BASELINE configs[3] (DeformCrossAttention2D, the variant the shipped YAMLs select; teacher batch of config_mine_*.yaml:
+    batch_size 4 x 2 500 patches -> 144 sampled keys): fwd + bwd of the module through its public interface, gradients arriving
+    at out and at the returned attention map (the teacher / student losses read both).  Dense maths of the reference per pair
+    (query, key, head): position-bias MLP 2 x 1 120 FLOP + QK^T / PV 2 x 128 FLOP forward, twice that backward."""
+    from dml_b200 import _lib, synth
+    from dml_b200.DeformableAttention2D import DeformCrossAttention2D
+    shapes = {"to_offsets.0.weight": (64, 1, 6, 6), "to_offsets.0.bias": (64,), "to_offsets.2.weight": (2, 64, 1, 1),
+              "rel_pos_bias.mlp.0.0.weight": (32, 2), "rel_pos_bias.mlp.0.0.bias": (32,), "rel_pos_bias.mlp.1.0.weight": (32, 32),
+              "rel_pos_bias.mlp.1.0.bias": (32,), "rel_pos_bias.mlp.2.weight": (1, 32), "rel_pos_bias.mlp.2.bias": (1,),
+              "to_q.weight": (512, 16, 1, 1), "to_k.weight": (512, 16, 1, 1), "to_v.weight": (512, 16, 1, 1),
+              "to_out.weight": (128, 512, 1, 1), "to_out.bias": (128,)}
+    mod = DeformCrossAttention2D(dim=128, dim_head=64, heads=8, dropout=0.1, downsample_factor=4, offset_scale=4, offset_groups=8,
+                                 offset_kernel_size=6)
+    sd = synth.fill_like(shapes, 5, gain=2.0)
+    mod.load_state_dict(sd, strict=True)
+    mod = mod.to(dev).eval()
+    n = side * side
+    g = torch.Generator(device=dev).manual_seed(3)
+    nset = 3
+    xs = [(torch.randn(B, 128, n, device=dev, generator=g).requires_grad_(), torch.randn(B, 128, n, device=dev, generator=g).requires_grad_())
+          for _ in range(nset)]
+
+    def step(i):
+        x1, x2 = xs[i % nset]
+        x1.grad = x2.grad = None
+        mod.zero_grad(set_to_none=True)
+        out, attn = mod(x1, x2)
+        (out.sum() + (attn * attn).sum()).backward()
+        return attn.shape[-1]
+
+    for i in range(warmup):
+        m = step(i)
+    torch.cuda.synchronize()
+    events = []
+
+    def hook(name, phase):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        events.append((name, ev))
+
+    _lib._timing_hook = hook
+    step(0)
+    torch.cuda.synchronize()
+    _lib._timing_hook = None
+    kt = {}
+    for i in range(0, len(events), 2):
+        kt[events[i][0]] = kt.get(events[i][0], 0.0) + events[i][1].elapsed_time(events[i + 1][1])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pk, pk_kind = peaks()
+    pairs = 8 * B * n * m
+    dense = 3.0 * pairs * (2240 + 256)
+    mma_fwd, mma_bwd = pairs * 3 * 2048, pairs * 12 * 2048      # issued bf16 MMA FLOP: 3 per product forward; 6 + 3 + 3 backward
+    rec = {"metric": f"attention modules/sec, DeformCrossAttention2D fwd+bwd (B={B} bags x {n} patches, {m} keys, 8 heads)",
+           "value": 1.0 / (ms * 1e-3), "unit": "modules/sec", "ms_per_step": ms, "steps": steps, "warmup": warmup, "data": "synthetic",
+           "config": {"workload": "DeformCrossAttention2D (models/DeformableAttention2D.py:162-342) as models/Modules.py:107-126 builds it",
+                      "step": "eager launches", "l2": f"{nset} input sets rotated; the step itself streams {pairs * 4 * 5 / 1e6:.0f} MB of maps"},
+           "entry_points_ms": {k: round(v, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1])},
+           "roofline": {"kernel": "dml_da2_bias_bwd (position-bias MLP backward, mma.sync bf16 m16n8k16)", "bound": "tensor",
+                        "achieved": mma_bwd / (kt["dml_da2_bias_bwd"] * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": mma_bwd / (kt["dml_da2_bias_bwd"] * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": pk_kind + " (sustained; a tcgen05 figure - the kernel issues legacy mma.sync)",
+                        "forward_kernel_issued_tflops": mma_fwd / (kt["dml_da2_bias_fwd"] * 1e-3) / 1e12,
+                        "dense_math_tflop_per_step": dense / 1e12,
+                        "dense_math_roofline_ms": dense / (pk["bf16_tflops_sustained"] * 1e12) * 1e3}}
+    if cpu:
+        from oracle import deform2d as O2
+        P = {k: v.clone().requires_grad_() for k, v in sd.items()}
+        x1c, x2c = xs[0][0].detach().cpu().requires_grad_(), xs[0][1].detach().cpu().requires_grad_()
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def one():
+            t0 = time.perf_counter()
+            out, attn, _ = O2.deform_cross_attention_2d(x1c, x2c, P)
+            (out.sum() + (attn * attn).sum()).backward()
+            return time.perf_counter() - t0
+        best = min(one() for _ in range(2))
+        rec["cpu_baseline"] = {"value": 1.0 / best, "unit": "modules/sec", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"oracle port (torch fp32), the same B = {B} step, best of 2: {best:.2f} s"}
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -818,6 +906,14 @@ def main():
         except Exception as ex:
             coattn = {"error": repr(ex)}
 
+    # ---- DeformCrossAttention2D (BASELINE configs[3]'s operator) at the teacher's batch: its own sub-record ----
+    deform2d = None
+    if rank == 0 and world == 1 and not args.no_transmil:
+        try:
+            deform2d = bench_deform2d(dev, cpu=not args.no_cpu_baseline)
+        except Exception as ex:
+            deform2d = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -830,7 +926,7 @@ def main():
                 "gpu_launches": launches,
                 "kernel_ms_per_step": {k: round(kavg[k] * kcalls[k], 4) for k in sorted(kavg, key=lambda k: -kavg[k] * kcalls[k])},
                 "roofline": roof, "cpu_baseline": cpu, "cls_row_only": cls_only, "sustained": sustained, "transmil": transmil,
-                "coattn": coattn, "host_binding": numa}
+                "coattn": coattn, "deform2d": deform2d, "host_binding": numa}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

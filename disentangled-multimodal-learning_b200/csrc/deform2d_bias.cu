@@ -8,11 +8,12 @@
 //   arithmetic of pgemm.cu): 3 MMAs per product, fp32-class result.
 // Backward (same tiling, everything in registers).  The upstream gradient g_p = dS_p of a pair is a per-row scalar, and rows of dS
 // sum to zero (softmax): every parameter gradient is a cancellation-dominated sum, so rounding errors must either be tiny or cancel
-// like the signal does.  Hence: dH1 = g_p (U W2) with U = (Z2 > 0) * w3 - the MMA runs on the masked CONSTANT w3 (its pair split is
-// the same for every pair with that activation pattern, so its 2^-16 error is coherent and cancels with the signal) and g_p is
-// applied in fp32 afterwards (the accumulator layout of two n-tiles IS the A layout of one k-step: U is built straight into A
-// fragments); dW2 += U^T (g_p H1) takes both operands through movmatrix (8 x 8 transposes).  Every backward product runs on
-// THREE bf16 parts per operand (24 bits, 6 MMAs), the recompute of Z2 included (its ReLU masks are discontinuous).
+// like the signal does - every backward product is fp32-class (24-bit operands: three bf16 parts).  The structure keeps that cheap:
+// dH1 = g_p (M W2') with M = (Z2 > 0) a 0 / 1 mask (EXACT in one bf16 part; the accumulator layout of two n-tiles IS the A layout
+// of one k-step, so M is built straight into A fragments), W2' = diag(w3) W2 pre-multiplied in the shared-memory table (three
+// parts) and g_p applied in fp32 afterwards: 3 MMAs; dW2 = diag(w3) M^T (g_p H1) takes both operands through movmatrix (8 x 8
+// transposes), M exact, g_p H1 in three parts: 3 MMAs; only the recompute of Z2 = H1 W2^T (its masks are discontinuous in Z2)
+// needs both operands in three parts: 6 MMAs.
 // tcgen05 is not used here: the M = 16-key tiles are produced in registers, K = N = 32, and a TMEM round trip per tile would
 // cost more than the MMAs it feeds.
 #include "common.cuh"
@@ -41,10 +42,11 @@ __device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& h, u
 
 // fragment tables of W2 in shared memory, [which][component][ks][nt][reg][lane] packed bf16x2 (512 words per component):
 //   which = 0 (forward, Z2 = H1 W2^T):  B[kdim = m][n = k] = W2[k][m]:  word = {W2[8nt+g][16ks+2t+8reg], W2[8nt+g][16ks+2t+8reg+1]}
-//   which = 1 (backward, R = U W2):     B[kdim = k][n = m] = W2[k][m]:  word = {W2[16ks+2t+8reg][8nt+g], W2[16ks+2t+8reg+1][8nt+g]}
+//   which = 1 (backward, R = M W2'):    B[kdim = k][n = m] = W2'[k][m]: word = {W2'[16ks+2t+8reg][8nt+g], W2'[16ks+2t+8reg+1][8nt+g]}
 // kComp = 2: bf16 pair (hi, lo; 16 bits); kComp = 3: (hi, mid, lo; 24 bits)
+// row_scale (may be NULL): the backward table holds diag(row_scale) W2, i.e. w3[k] W2[k][m] (see bias_bwd_kernel)
 template <int kComp>
-__device__ __forceinline__ void build_w2_frags(const float* __restrict__ W2, uint32_t* tab, int nwhich) {
+__device__ __forceinline__ void build_w2_frags(const float* __restrict__ W2, uint32_t* tab, int nwhich, const float* row_scale = nullptr) {
   for (int i = threadIdx.x; i < 512 * nwhich; i += blockDim.x) {
     const int which = i >> 9, r = i & 511;
     const int lane = r & 31, reg = (r >> 5) & 1, nt = (r >> 6) & 3, ks = (r >> 8) & 1;
@@ -54,8 +56,13 @@ __device__ __forceinline__ void build_w2_frags(const float* __restrict__ W2, uin
       v0 = W2[(8 * nt + g) * kHid + 16 * ks + 2 * t + 8 * reg];
       v1 = W2[(8 * nt + g) * kHid + 16 * ks + 2 * t + 8 * reg + 1];
     } else {
-      v0 = W2[(16 * ks + 2 * t + 8 * reg) * kHid + 8 * nt + g];
-      v1 = W2[(16 * ks + 2 * t + 8 * reg + 1) * kHid + 8 * nt + g];
+      const int k0 = 16 * ks + 2 * t + 8 * reg;
+      v0 = W2[k0 * kHid + 8 * nt + g];
+      v1 = W2[(k0 + 1) * kHid + 8 * nt + g];
+      if (row_scale) {
+        v0 *= row_scale[k0];
+        v1 *= row_scale[k0 + 1];
+      }
     }
     uint32_t* dst = tab + which * kComp * 512 + r;
     if (kComp == 2) {
@@ -179,6 +186,26 @@ __device__ __forceinline__ void mma_32x32_x6(float (&acc)[4][4], const uint32_t 
   }
 }
 
+// acc[nt] += A (ONE exact part: a 0 / 1 mask) x table (three parts)
+__device__ __forceinline__ void mma_32x32_m3(float (&acc)[4][4], const uint32_t (&a)[2][4], const uint32_t* tab, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t b[3][4][2];
+#pragma unroll
+    for (int cp = 0; cp < 3; ++cp)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int base = cp * 512 + ((ks * 4 + nt) * 2) * 32 + lane;
+        b[cp][nt][0] = tab[base];
+        b[cp][nt][1] = tab[base + 32];
+      }
+#pragma unroll
+    for (int cp = 2; cp >= 0; --cp)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[ks], b[cp][nt][0], b[cp][nt][1]);
+  }
+}
+
 __device__ __forceinline__ void query_xy(int i, int side, float& qx, float& qy) {
   const int y = i / side, x = i - y * side;
   const float den = (float)max(side - 1, 1);
@@ -253,7 +280,7 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
   float* dvs_s = vs_s + 2 * m;                              // 2 m floats
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int bg = blockIdx.y, n = side * side;
-  build_w2_frags<3>(W2, tab, 2);
+  build_w2_frags<3>(W2, tab, 2, W3);
   for (int i = threadIdx.x; i < 2 * m; i += 256) {
     vs_s[i] = vs[(size_t)bg * 2 * m + i];
     dvs_s[i] = 0.f;
@@ -261,9 +288,6 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
   for (int i = threadIdx.x; i < 1200; i += 256) gsum[i] = 0.f;
   Consts c;
   load_consts(c, W1, b1, b2, W3, t);
-  uint32_t w3p[3][4];                      // packed (w3[2 nt], w3[2 nt + 1]) of the thread's neurons in three parts
-#pragma unroll
-  for (int nt = 0; nt < 4; ++nt) split3_bf16x2(c.w3[2 * nt], c.w3[2 * nt + 1], w3p[0][nt], w3p[1][nt], w3p[2][nt]);
   __syncthreads();
 
   float aW2[2][4][4];
@@ -306,9 +330,10 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
         }
         mma_32x32_x6(z, a3, tab, lane);
       }
-      // output layer; U = (Z2 > 0) * w3 as A fragments (same element -> register mapping as H1), three pre-split parts
+      // output layer; the ReLU mask M = (Z2 > 0) as A fragments (same element -> register mapping as H1): 0 / 1 is EXACT in one
+      // bf16 part, and w3 rides in the table (R = M (diag(w3) W2)) and in the final scaling of dW2 - no operand split needed
       if (t == 0) ab3 += g0 + g1;
-      uint32_t u3[3][2][4];
+      uint32_t mk[2][4];
       {
         bool m0[8], m1[8];
 #pragma unroll
@@ -317,22 +342,20 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
           m0[e] = z0 > 0.f;
           m1[e] = z1 > 0.f;
           aw3[e] += g0 * fmaxf(z0, 0.f) + g1 * fmaxf(z1, 0.f);
-          ab2[e] += (m0[e] ? g0 : 0.f) * c.w3[e] + (m1[e] ? g1 : 0.f) * c.w3[e];
+          ab2[e] += (m0[e] ? g0 : 0.f) + (m1[e] ? g1 : 0.f);             // x w3[e] at the end
         }
 #pragma unroll
-        for (int cp = 0; cp < 3; ++cp)
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            u3[cp][ks][0] = mask_pk(w3p[cp][2 * ks], m0[4 * ks], m0[4 * ks + 1]);
-            u3[cp][ks][1] = mask_pk(w3p[cp][2 * ks], m1[4 * ks], m1[4 * ks + 1]);
-            u3[cp][ks][2] = mask_pk(w3p[cp][2 * ks + 1], m0[4 * ks + 2], m0[4 * ks + 3]);
-            u3[cp][ks][3] = mask_pk(w3p[cp][2 * ks + 1], m1[4 * ks + 2], m1[4 * ks + 3]);
-          }
+        for (int ks = 0; ks < 2; ++ks) {
+          mk[ks][0] = mask_pk(0x3f803f80u, m0[4 * ks], m0[4 * ks + 1]);
+          mk[ks][1] = mask_pk(0x3f803f80u, m1[4 * ks], m1[4 * ks + 1]);
+          mk[ks][2] = mask_pk(0x3f803f80u, m0[4 * ks + 2], m0[4 * ks + 3]);
+          mk[ks][3] = mask_pk(0x3f803f80u, m1[4 * ks + 2], m1[4 * ks + 3]);
+        }
       }
-      // R = U W2, then dH1 = g_p R in fp32 (g_p is a per-row scalar: it never enters a 16-bit operand here)
+      // R = M W2', then dH1 = g_p R in fp32 (g_p is a per-row scalar: it never enters a 16-bit operand here)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) z[nt][0] = z[nt][1] = z[nt][2] = z[nt][3] = 0.f;
-      mma_32x32_x6(z, u3, tab + 1536, lane);
+      mma_32x32_m3(z, mk, tab + 1536, lane);
       float dtx0 = 0.f, dty0 = 0.f, dtx1 = 0.f, dty1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -361,18 +384,16 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
         const float dt = rr < 8 ? ((lane & 1) ? y0 : x0) : ((lane & 1) ? y1 : x1);
         if (j0 + rr < m) atomicAdd(&dvs_s[2 * j0 + lane], -dt / (fabsf(p) + 1.f));     // p = q - vs
       }
-      // dW2 += U^T (g H1): A' = transposed U blocks, B' = transposed blocks of g_p H1, three bf16 parts each
-      //   A'(mt) = { T(pk0[2mt]), T(pk0[2mt+1]), T(pk1[2mt]), T(pk1[2mt+1]) };  pk0[nt] = u[nt>>1][(nt&1)*2], pk1[nt] = u[nt>>1][(nt&1)*2+1]
-      uint32_t at[3][2][4];
+      // dW2 / w3 += M^T (g H1): A' = transposed mask blocks (exact), B' = transposed blocks of g_p H1 in three bf16 parts
+      //   A'(mt) = { T(pk0[2mt]), T(pk0[2mt+1]), T(pk1[2mt]), T(pk1[2mt+1]) };  pk0[nt] = mk[nt>>1][(nt&1)*2], pk1[nt] = mk[nt>>1][(nt&1)*2+1]
+      uint32_t at[2][4];
 #pragma unroll
-      for (int cp = 0; cp < 3; ++cp)
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          at[cp][mt][0] = movmatrix_t(u3[cp][mt][0]);
-          at[cp][mt][1] = movmatrix_t(u3[cp][mt][2]);
-          at[cp][mt][2] = movmatrix_t(u3[cp][mt][1]);
-          at[cp][mt][3] = movmatrix_t(u3[cp][mt][3]);
-        }
+      for (int mt = 0; mt < 2; ++mt) {
+        at[mt][0] = movmatrix_t(mk[mt][0]);
+        at[mt][1] = movmatrix_t(mk[mt][2]);
+        at[mt][2] = movmatrix_t(mk[mt][1]);
+        at[mt][3] = movmatrix_t(mk[mt][3]);
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         uint32_t q0[3], q1[3], b0[3], b1[3];
@@ -384,17 +405,9 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
           b1[cp] = movmatrix_t(q1[cp]);
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[2][mt], b0[0], b1[0]);
+        for (int cp = 2; cp >= 0; --cp)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[0][mt], b0[2], b1[2]);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[1][mt], b0[1], b1[1]);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[1][mt], b0[0], b1[0]);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[0][mt], b0[1], b1[1]);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[0][mt], b0[0], b1[0]);
+          for (int mt = 0; mt < 2; ++mt) mma_bf16_16816(aW2[mt][nt], at[mt], b0[cp], b1[cp]);
       }
     }
   }
@@ -420,10 +433,11 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           float* o = gsum + kGW2 + (16 * mt + g) * kHid + 8 * nt + 2 * t;
-          o[0] += aW2[mt][nt][0];
-          o[1] += aW2[mt][nt][1];
-          o[8 * kHid] += aW2[mt][nt][2];
-          o[8 * kHid + 1] += aW2[mt][nt][3];
+          const float wa = W3[16 * mt + g], wb = W3[16 * mt + 8 + g];           // the w3 factor taken out of the mask operand
+          o[0] += aW2[mt][nt][0] * wa;
+          o[1] += aW2[mt][nt][1] * wa;
+          o[8 * kHid] += aW2[mt][nt][2] * wb;
+          o[8 * kHid + 1] += aW2[mt][nt][3] * wb;
         }
       if (g == 0) {
 #pragma unroll
@@ -432,7 +446,7 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
           gsum[kGW1 + nb * 2] += aw1x[e];
           gsum[kGW1 + nb * 2 + 1] += aw1y[e];
           gsum[kGb1 + nb] += ab1[e];
-          gsum[kGb2 + nb] += ab2[e];
+          gsum[kGb2 + nb] += ab2[e] * c.w3[e];
           gsum[kGW3 + nb] += aw3[e];
         }
         if (t == 0) gsum[kGb3] += ab3;

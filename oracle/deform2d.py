@@ -58,10 +58,12 @@ def bias_mlp(pos: torch.Tensor, P: Params) -> torch.Tensor:
 
 def deform_cross_attention_2d(x1: torch.Tensor, x2: torch.Tensor, P: Params, *, heads: int = 8, groups: int = 8,
                               stride: int = 4, offset_scale: float = 4.0, drop_keep: Optional[torch.Tensor] = None,
-                              drop_p: float = 0.0):
+                              drop_p: float = 0.0, rows: Optional[torch.Tensor] = None):
     """DeformCrossAttention2D.forward (DeformableAttention2D.py:224-342).  x1, x2: [B, dim, n] with n a perfect square.
     Returns (out [B, dim, n], attn [B, heads, n, n_kv], vgrid [(B G), 2, hk, wk]).  ``drop_keep`` (bool [B, heads, n, n_kv]) is the
-    dropout keep-mask applied to attn before the aggregation (:316, training mode); None = eval."""
+    dropout keep-mask applied to attn before the aggregation (:316, training mode); None = eval.
+    ``rows`` (long [r], oracle-only): evaluate the attention for these query tokens only - out [B, dim, r], attn [B, heads, r,
+    n_kv] - so that 100k-token bags (whose full map is 20 GB per activation) can be spot-checked; same maths row for row."""
     B, dim, n = x1.shape
     side = int(math.isqrt(n))
     assert side * side == n, "the reference views the sequence as a square grid (:241-242)"
@@ -84,10 +86,12 @@ def deform_cross_attention_2d(x1: torch.Tensor, x2: torch.Tensor, P: Params, *, 
     q = q * d ** -0.5                                                                       # :290
     heads_of = lambda t: t.reshape(B, H, d, -1).transpose(2, 3)                             # :294  [B, H, tokens, d]
     qh, kh, vh = heads_of(q), heads_of(k), heads_of(v)
-    sim = qh @ kh.transpose(2, 3)                                                           # :298
     g = xy_grid(side, side).to(x1)
     gx, gy = normalize_xy(g[0], g[1], side, side)                                           # :302-303
     gq = torch.stack((gx, gy), -1).reshape(1, n, 1, 2)
+    if rows is not None:
+        qh, gq, n = qh[:, :, rows], gq[:, rows], int(rows.numel())
+    sim = qh @ kh.transpose(2, 3)                                                           # :298
     pos = gq - vs.reshape(B * G, 1, hk * wk, 2)                                             # :150
     bias = bias_mlp(pos, P)                                                                 # [(B G), n, n_kv, H/G]
     bias = bias.reshape(B, G, n, hk * wk, H // G).permute(0, 1, 4, 2, 3).reshape(B, H, n, hk * wk)   # :156
@@ -96,7 +100,7 @@ def deform_cross_attention_2d(x1: torch.Tensor, x2: torch.Tensor, P: Params, *, 
     attn = sim.softmax(dim=-1)                                                              # :313
     a = attn if drop_keep is None else attn * drop_keep.to(attn) / (1.0 - drop_p)           # :316
     out = a @ vh                                                                            # :320
-    out = out.transpose(2, 3).reshape(B, C, side, side)                                     # :321
+    out = out.transpose(2, 3).reshape(B, C, n, 1)                                           # :321 (a 1x1 conv follows: the grid shape is immaterial)
     out = F.conv2d(out, P["to_out.weight"], P["to_out.bias"])                               # :322
     return out.reshape(B, dim, n), attn, vgrid
 

@@ -101,3 +101,55 @@ def test_reference_mcat_and_cmta_build_on_the_shadowed_coattention():
     for mode, n in (("mcat", 92), ("cmta", 104)):
         r = res[mode]
         assert r["same"] and r["ours_used"] and r["ref_clean"] and r["n"] == n and r["loss_module"].startswith("dml_b200"), (mode, r)
+
+
+SCRIPT_TEACHER = textwrap.dedent('''
+    import sys, types, json
+    sys.path.insert(0, %(root)r); sys.path.insert(0, %(ref)r)
+    import torch
+    from oracle.make_goldens import install_reference_shims
+    install_reference_shims()
+    from types import SimpleNamespace
+    args = SimpleNamespace(path_dim=128, omic_dim=128, mmhid=128, attn_dim=2, return_vgrid=False, label_dim=4,
+                           input_size_omic_tumor=59, input_size_omic_immune=361, return_grad="False", dropout_rate=0.1,
+                           init_type="max", fusion_type="concat", task_type="survival", mode="teacher",
+                           input_size_omic=431, act_type="none", use_bilinear=1, skip=1, gpu_ids="0", use_sparsemax=0,
+                           init_gain=0.02, path_cluster_num=0.0008, omic_cluster_num=2, combination_type="max_confidence",
+                           combination_type_teas="max_confidence", combination_type_stus="max_confidence", path_scale=1, path_gate=1,
+                           omic_scale=1, omic_gate=1, cut_fuse_grad=False)
+    def build(shadow, mode):
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        if shadow:                                                  # INTEGRATION.md section 1
+            from dml_b200 import DeformableAttention2D as _d2, ClusterMergeNet as _cm
+            sys.modules["models.DeformableAttention2D"] = _d2
+            sys.modules["models.ClusterMergeNet"] = _cm
+        from models.model import define_net
+        args.mode = mode
+        net = define_net(args)
+        mods = {type(m).__module__ for m in net.modules()}
+        return {k: list(v.shape) for k, v in net.state_dict().items()}, sorted(mods)
+    res = {}
+    for mode in ("teacher", "student"):
+        ref_sd, ref_mods = build(False, mode)
+        our_sd, our_mods = build(True, mode)
+        res[mode] = {"same": ref_sd == our_sd, "n": len(our_sd), "ours": [m for m in our_mods if m.startswith("dml_b200")],
+                     "ref_clean": not any(m.startswith("dml_b200") for m in ref_mods)}
+    print(json.dumps(res))
+''')
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout exists only in the build container")
+def test_reference_teacher_and_student_build_on_the_shadowed_2d_attention():
+    """SURVEY 8f N1: the unmodified models/model.py + models/Modules.py build the teacher and student nets (the variant the
+    shipped YAMLs select: attn_dim 2) on dml_b200.DeformableAttention2D / ClusterMergeNet with identical state_dict keys and shapes."""
+    out = subprocess.run([sys.executable, "-c", SCRIPT_TEACHER % {"root": ROOT, "ref": REF}], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert "dml_b200.DeformableAttention2D" in res["teacher"]["ours"], res
+    assert "dml_b200.ClusterMergeNet" in res["student"]["ours"] and "dml_b200.DeformableAttention2D" in res["student"]["ours"], res
+    for mode in ("teacher", "student"):
+        r = res[mode]
+        assert r["same"] and r["ref_clean"] and r["n"] > 50, (mode, r)

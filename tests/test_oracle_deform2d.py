@@ -43,6 +43,19 @@ def test_deform2d_matches_reference(c):
         H.assert_close(thin(g), G["grad." + k], TOL, k, atol=1e-3 if k.endswith("mlp.2.bias") else 0.0)
 
 
+def test_row_subset_oracle_equals_full_rows():
+    """The rows= variant used for the 100k-token spot checks is the full computation restricted to those query rows."""
+    c = DEFORM2D_CASES[0]
+    P, x1, x2, _, _ = deform2d_inputs(c)
+    rows = torch.tensor([0, 7, 199, 200, 399])
+    with torch.no_grad():
+        out, attn, vg = deform2d.deform_cross_attention_2d(x1, x2, P)
+        o2, a2, v2 = deform2d.deform_cross_attention_2d(x1, x2, P, rows=rows)
+    assert torch.equal(vg, v2)
+    H.assert_close(o2, out[:, :, rows], 1e-6, "out rows")
+    H.assert_close(a2, attn[:, :, rows], 1e-6, "attn rows")
+
+
 def test_kv_side_integers():
     assert deform2d.kv_side(50) == 12 and deform2d.kv_side(316) == 79 and deform2d.kv_side(23) == 5 and deform2d.kv_side(6) == 1
 
