@@ -51,6 +51,12 @@ CLUSTER_CASES = [
     dict(name="clustermerge_n400_b2", B=2, N=400, ratio=0.02, seed=95),
     dict(name="clustermerge_n2500_b1", B=1, N=2500, ratio=0.0128, seed=96),
 ]
+# the teacher / student callers of the 2-D operator (models/Modules.py: TeacherNet :357-397, StudentNet :429-458), eval mode
+TEACHER_CASES = [
+    dict(name="teacher_s20_b2", kind="teacher", B=2, side=20, seed=101),
+    dict(name="teacher_s50_b1", kind="teacher", B=1, side=50, seed=102),
+    dict(name="student_s50_b2", kind="student", B=2, side=50, seed=103),       # 2 500 tokens -> ceil(0.0008 N) = 2 clusters
+]
 
 MAX_KEEP = 8192
 

@@ -79,7 +79,7 @@ def pack(d):
     return out
 
 
-from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES, DEFORM2D_CASES, CLUSTER_CASES, loss_inputs,
+from oracle.golden_cases import (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES, DEFORM2D_CASES, CLUSTER_CASES, TEACHER_CASES, loss_inputs,
                                  thin)
 
 
@@ -226,6 +226,50 @@ def gen_cluster():
         print(c["name"], tuple(merged.shape), float(merged.abs().mean()), np.bincount(down["idx_token"].reshape(-1).numpy())[:8])
 
 
+def teacher_inputs(c):
+    """Inputs shared with the tests: a bag of post-ReLU patch features, two 128-d omic embeddings, output weights."""
+    from dml_b200 import synth
+    n = c["side"] ** 2
+    bag = synth.synthetic_bag(n, c["seed"], c["B"])["x_path"]
+    omic = [synth.normal((c["B"], 128), c["seed"], "omic1"), synth.normal((c["B"], 128), c["seed"], "omic2")]
+    noise = synth.uniform((c["B"], n), c["seed"], "noise", 0.5) + 0.5
+    return bag, omic, noise
+
+
+def gen_teacher():
+    """models/Modules.py TeacherNet / StudentNet in eval mode (the attention dropouts are the identity); the student's
+    torch.rand (ClusterMergeNet.py:103) is replaced by seeded noise."""
+    from dml_b200 import synth
+    from models.Modules import StudentNet, TeacherNet
+    real_rand = torch.rand
+    for c in TEACHER_CASES:
+        args = _Args(path_dim=128, label_dim=4, attn_dim=2, path_cluster_num=0.0008)
+        mod = (TeacherNet if c["kind"] == "teacher" else StudentNet)(args).eval()
+        load_synth(mod, c["seed"])
+        bag, omic, noise = teacher_inputs(c)
+        bag = bag.requires_grad_()
+        torch.rand = lambda *a, **k: noise.clone()
+        try:
+            out = mod(bag, omic)
+        finally:
+            torch.rand = real_rand
+        logits = out[0]
+        atts = out[6:8] if c["kind"] == "teacher" else out[5:6]
+        loss = (logits * synth.normal(tuple(logits.shape), c["seed"], "r_log")).sum()
+        for i, a in enumerate(atts):
+            loss = loss + (a * synth.normal(tuple(a.shape), c["seed"], f"r_att{i}")).sum() * 0.01
+        (gbag,) = torch.autograd.grad(loss, (bag,), retain_graph=True)
+        g = grads_of(mod, loss)
+        d = dict(logits=logits, hazards=out[1], risk=out[3], gbag=thin(gbag[0]))
+        if c["kind"] == "teacher":
+            d.update(feature1=out[4], feature2=out[5], att1=thin(out[6]), att2=thin(out[7]))
+        else:
+            d.update(feature=out[4], att=thin(out[5]))
+        d.update({"grad." + k: thin(v) for k, v in g.items()})
+        np.savez(os.path.join(OUT, c["name"] + ".npz"), **pack(d))
+        print(c["name"], logits.detach().numpy().round(4)[0], float(gbag.abs().mean()))
+
+
 class _Args:
     def __init__(self, **kw):
         self.__dict__.update(kw)
@@ -295,7 +339,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if "--missing" in sys.argv:
         for cases in (DEFORM_CASES, NYSTROM_CASES, TOWER_CASES, TRANSMIL_CASES, PATHOMIC_CASES, COATTN_CASES, LOSS_CASES,
-                      DEFORM2D_CASES, CLUSTER_CASES):
+                      DEFORM2D_CASES, CLUSTER_CASES, TEACHER_CASES):
             cases[:] = [c for c in cases if not os.path.exists(os.path.join(OUT, c["name"] + ".npz"))]
     sys.path.insert(0, os.path.dirname(OUT.rstrip("/")).rsplit("/tests", 1)[0])
     install_reference_shims()
@@ -312,6 +356,7 @@ def main():
         gen_losses()
         gen_deform2d()
         gen_cluster()
+        gen_teacher()
 
 
 if __name__ == "__main__":
