@@ -134,6 +134,7 @@ TEST_SIGNATURES = {
     "dml_deform_attn_bwd": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 10 + [_f] + [_fp] * 7 + [_vp]),
     "dml_debug_set_trace": (_i, [_vp]),
     "dml_debug_set_seg_limit": (_i, [_i]),
+    "dml_test_mma_sync_peak": (_i, [_i, _i, _i, _fp, _vp]),
 }
 
 _lock = threading.Lock()

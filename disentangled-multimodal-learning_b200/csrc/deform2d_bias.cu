@@ -117,27 +117,18 @@ __device__ __forceinline__ void layer1(const Consts& c, float tx0, float ty0, fl
   }
 }
 
-// acc[nt] += A (16 x 32, two k-steps) x B-table `tab` (hi at tab, lo at tab + 512), pair arithmetic (3 MMAs per product)
-__device__ __forceinline__ void mma_32x32(float (&acc)[4][4], const uint32_t (&ahi)[2][4], const uint32_t (&alo)[2][4],
-                                          const uint32_t* tab, int lane) {
+// acc[nt] += A (16 x 32, two k-steps: hi / lo parts) x B fragments (hi / lo parts) held in registers (forward kernel: 32 words per
+// thread, loaded once per warp): pair arithmetic, 3 MMAs per product, term-major so that consecutive MMAs hit different accumulators
+__device__ __forceinline__ void mma_32x32_reg(float (&acc)[4][4], const uint32_t (&ahi)[2][4], const uint32_t (&alo)[2][4],
+                                              const uint32_t (&bh)[2][4][2], const uint32_t (&bl)[2][4][2]) {
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int base = ((ks * 4 + nt) * 2) * 32 + lane;
-      bh[nt][0] = tab[base];
-      bh[nt][1] = tab[base + 32];
-      bl[nt][0] = tab[512 + base];
-      bl[nt][1] = tab[512 + base + 32];
-    }
-    // term-major order: consecutive MMAs go to different accumulators (no back-to-back dependency)
+    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], alo[ks], bh[ks][nt][0], bh[ks][nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], alo[ks], bh[nt][0], bh[nt][1]);
+    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], ahi[ks], bl[ks][nt][0], bl[ks][nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], ahi[ks], bl[nt][0], bl[nt][1]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], ahi[ks], bh[nt][0], bh[nt][1]);
+    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], ahi[ks], bh[ks][nt][0], bh[ks][nt][1]);
   }
 }
 
@@ -228,6 +219,16 @@ __global__ void __launch_bounds__(256) bias_fwd_kernel(const float* __restrict__
   load_consts(c, W1, b1, b2, W3, t);
   const float bias3 = b3[0];
   __syncthreads();
+  uint32_t bh[2][4][2], bl[2][4][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int rg = 0; rg < 2; ++rg) {
+        bh[ks][nt][rg] = tab[((ks * 4 + nt) * 2 + rg) * 32 + lane];
+        bl[ks][nt][rg] = tab[512 + ((ks * 4 + nt) * 2 + rg) * 32 + lane];
+      }
   for (int qi = 0; qi < kFwdQ; ++qi) {
     const int i = (blockIdx.x * 8 + warp) * kFwdQ + qi;
     if (i >= n) break;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(256) bias_fwd_kernel(const float* __restrict__
         z[nt][0] = z[nt][2] = c.b2[2 * nt];
         z[nt][1] = z[nt][3] = c.b2[2 * nt + 1];
       }
-      mma_32x32(z, ahi, alo, tab, lane);
+      mma_32x32_reg(z, ahi, alo, bh, bl);
       float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {

@@ -30,6 +30,10 @@ int dml_debug_set_trace(void* buf);
  * large for its shared-memory segment arrays do); limit <= 0 restores the default.                                       */
 int dml_debug_set_seg_limit(int limit);
 
+/* Issue-rate microbenchmark of mma.sync.m16n8k16 (bf16, fp32 accumulate): `ctas` CTAs of 8 warps, `chains` (4 / 8 / 16)
+ * independent accumulators per warp, `iters` rounds: ctas * 8 * chains * iters MMAs of 4096 MACs each.                       */
+int dml_test_mma_sync_peak(int ctas, int chains, int iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
