@@ -92,8 +92,9 @@ SIGNATURES = {
     "dml_da2_attn_fwd": (_i, [_fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _fp, _vp]),
     "dml_da2_cols_chunks": (_i, [_i, _i, _i]),
     "dml_da2_attn_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _vp]),
-    "dml_dpc_density": (_i, [_fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
-    "dml_dpc_parent": (_i, [_fp, _fp, _fp, _i, _i, _i, _fp, _vp]),
+    "dml_dpc_split": (_i, [_fp, _ll, _i, _vp, _fp, _vp]),
+    "dml_dpc_density": (_i, [_vp, _fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
+    "dml_dpc_parent": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _fp, _vp]),
     "dml_dpc_assign": (_i, [_fp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "dml_merge_fwd": (_i, [_fp, _fp, _vp, _i, _i, _i, _i, _fp, _fp, _vp]),
     "dml_merge_bwd": (_i, [_fp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, _i, _fp, _fp, _vp]),

@@ -1,52 +1,57 @@
 // ClusterMergeNet (models/ClusterMergeNet.py:68-207): DPC-KNN clustering and the weighted token merge.
 // The reference materialises the N x N distance matrix three times (cdist, the masked copy, the gathered rows: 40 GB each at
 // N = 99 856); here the distances are recomputed tile by tile in shared memory and only O(N) results leave the SM:
+//   dpc_split   : x -> three bf16 parts per value (24 bits) + |x|^2
 //   dpc_density : per token the 5 smallest distances (self included) -> exp(-mean d^2) + noise, and the row maximum of d^2
 //   dpc_parent  : per token the distance to the nearest token of higher density (or dist_max)
 //   dpc_assign  : per token the nearest of the K selected centres
 //   merge_fwd / merge_bwd : weighted mean of the tokens of a cluster and its adjoint.
-// x: fp32 [B, N, 128] (the LayerNorm output); distances are sums of squared differences in fp32 divided by C.
+// x: fp32 [B, N, 128] (the LayerNorm output).
 #include "common.cuh"
 
 namespace dml {
 namespace {
 
 constexpr int kCc = 128;       // channels
-constexpr int kTR = 32;        // rows (tokens) per CTA
-constexpr int kTJ = 32;        // columns per tile
-constexpr int kLd = 132;       // shared row stride (floats): 16-byte aligned, rows 8 apart land in distinct banks
 
-struct Tile {
-  float xi[kTR * kLd];
-  float xj[kTJ * kLd];
-};
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiled N x N squared distances on the tensor cores: d2(i, j) = |x_i|^2 + |x_j|^2 - 2 x_i . x_j with the dot products as
+// mma.sync.m16n8k16 on THREE bf16 parts per operand (hi + mid + lo = 24 bits, 6 MMAs per product: the arithmetic class of the
+// fp32 matmul torch.cdist itself uses for N > 25, ClusterMergeNet.py:88).  CTA = 128 rows (warp = 16 rows whose A fragments
+// stay in registers for the whole sweep: 96 words) x column tiles of 64 tokens streamed through a double-buffered, XOR-swizzled
+// shared-memory ring with cp.async; B fragments by ldmatrix; the epilogue (top-5 insertion / masked minimum) runs on the
+// accumulator fragments, so only O(N) results leave the SM.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRowsCta = 128, kColsTile = 64;
+constexpr uint32_t kPlaneBytes = kColsTile * kCc * 2;          // 16 KB: one bf16 part of a column tile
+constexpr uint32_t kStageBytes = 3 * kPlaneBytes + 512;        // + |x_j|^2 [64] and density_j [64]
+constexpr uint32_t kDistSmem = 2 * kStageBytes;
 
-__device__ __forceinline__ void load_rows(float* dst, const float* __restrict__ x, int b, int N, int r0) {
-  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-    const int r = i >> 5, c4 = i & 31;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < N) v = *reinterpret_cast<const float4*>(x + ((size_t)b * N + r0 + r) * kCc + c4 * 4);
-    *reinterpret_cast<float4*>(dst + r * kLd + c4 * 4) = v;
-  }
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& h, uint32_t& m, uint32_t& l) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  const float r0 = x0 - bf16_lo_f(h), r1 = x1 - bf16_hi_f(h);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(m) : "f"(r1), "f"(r0));
+  const float s0 = r0 - bf16_lo_f(m), s1 = r1 - bf16_hi_f(m);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(s1), "f"(s0));
 }
 
-// squared distances of row r to columns cs, cs + 8, cs + 16, cs + 24 of the tile
-__device__ __forceinline__ void tile_d2(const Tile& T, int r, int cs, float (&d2)[4]) {
-  d2[0] = d2[1] = d2[2] = d2[3] = 0.f;
-  const float* xi = T.xi + r * kLd;
-#pragma unroll 4
-  for (int c = 0; c < kCc; c += 4) {
-    const float4 a = *reinterpret_cast<const float4*>(xi + c);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4 b = *reinterpret_cast<const float4*>(T.xj + (cs + 8 * u) * kLd + c);
-      const float e0 = a.x - b.x, e1 = a.y - b.y, e2 = a.z - b.z, e3 = a.w - b.w;
-      d2[u] = fmaf(e0, e0, d2[u]);
-      d2[u] = fmaf(e1, e1, d2[u]);
-      d2[u] = fmaf(e2, e2, d2[u]);
-      d2[u] = fmaf(e3, e3, d2[u]);
-    }
-  }
+// planes: bf16 [3][rows][128]; norms [rows] = |x|^2 in fp32.  One warp per row.
+__global__ void __launch_bounds__(256) dpc_split_kernel(const float* __restrict__ x, long long rows, uint32_t* __restrict__ planes,
+                                                        float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * kCc + lane * 4);
+  uint32_t h0, m0, l0, h1, m1, l1;
+  split3(v.x, v.y, h0, m0, l0);
+  split3(v.z, v.w, h1, m1, l1);
+  const size_t plane = (size_t)rows * (kCc / 2);             // in 32-bit words
+  uint32_t* o = planes + r * (kCc / 2) + lane * 2;
+  *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(o + plane) = make_uint2(m0, m1);
+  *reinterpret_cast<uint2*>(o + 2 * plane) = make_uint2(l0, l1);
+  const float n2 = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+  if (lane == 0) norms[r] = n2;
 }
 
 __device__ __forceinline__ void insert5(float (&best)[5], float v) {
@@ -62,83 +67,179 @@ __device__ __forceinline__ void insert5(float (&best)[5], float v) {
   }
 }
 
-// density[b, i] = exp(-mean_{5 nearest} d^2 / C) + 1e-6 noise[b, i];  rowmax2[b, i] = max_j d^2(i, j)
-__global__ void __launch_bounds__(256) dpc_density_kernel(const float* __restrict__ x, const float* __restrict__ noise, int N,
-                                                          float* __restrict__ density, float* __restrict__ rowmax2) {
-  __shared__ __align__(16) Tile T;
-  __shared__ float cand[kTR][8][6];
-  const int b = blockIdx.y, r0 = blockIdx.x * kTR;
-  const int r = threadIdx.x >> 3, cs = threadIdx.x & 7;
-  load_rows(T.xi, x, b, N, r0);
-  float best[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
-  float mx = 0.f;
-  for (int j0 = 0; j0 < N; j0 += kTJ) {
-    __syncthreads();
-    load_rows(T.xj, x, b, N, j0);
-    __syncthreads();
-    float d2[4];
-    tile_d2(T, r, cs, d2);
+// kParent = false: density[b, i] = exp(-mean of the 5 smallest d2 / C) + 1e-6 noise, aux_out = row maximum of d2   (:98-104)
+// kParent = true : aux_out = parent[b, i] = min(dist_max[b], min_{j: density_j > density_i} sqrt(d2 / C))          (:111-114)
+template <bool kParent>
+__global__ void __launch_bounds__(256, 1) dpc_dist_kernel(const uint32_t* __restrict__ planes, const float* __restrict__ norms,
+                                                           const float* __restrict__ noise, const float* __restrict__ dist_max, int N,
+                                                           float* __restrict__ density, float* __restrict__ aux_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.y;
+  const size_t rows_all = (size_t)gridDim.y * N, plane_w = rows_all * (kCc / 2);
+  const size_t brow = (size_t)b * N;
+  const int i0 = blockIdx.x * kRowsCta + warp * 16 + g, i1 = i0 + 8;                  // the thread's two rows
+  // A fragments of the warp's 16 rows: [part][k-step][reg]
+  uint32_t a[3][8][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (j0 + cs + 8 * u < N) {
-        insert5(best, d2[u]);
-        mx = fmaxf(mx, d2[u]);
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = (r & 1) ? i1 : i0;
+        const int colw = 8 * ks + t + ((r & 2) ? 4 : 0);                                // 32-bit word = 2 channels
+        a[p][ks][r] = row < N ? planes[p * plane_w + (brow + row) * (kCc / 2) + colw] : 0u;
       }
+  const float ni0 = i0 < N ? norms[brow + i0] : 0.f, ni1 = i1 < N ? norms[brow + i1] : 0.f;
+  float di0 = 0.f, di1 = 0.f;
+  if (kParent) {
+    di0 = i0 < N ? density[brow + i0] : INFINITY;
+    di1 = i1 < N ? density[brow + i1] : INFINITY;
   }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) cand[r][cs][k] = best[k];
-  cand[r][cs][5] = mx;
-  __syncthreads();
-  if (cs == 0 && r0 + r < N) {
-    float b5[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
-    float m2 = 0.f;
-    for (int s = 0; s < 8; ++s) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) insert5(b5, cand[r][s][k]);
-      m2 = fmaxf(m2, cand[r][s][5]);
-    }
-    // reference: dist = cdist / sqrt(C); density = exp(-mean(dist_nearest^2)) + rand * 1e-6   (ClusterMergeNet.py:88-104)
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      const float d = sqrtf(b5[k]) / sqrtf((float)kCc);
-      s += d * d;
-    }
-    const size_t at = (size_t)b * N + r0 + r;
-    density[at] = expf(-(s / 5.f)) + noise[at] * 1e-6f;
-    rowmax2[at] = m2;
-  }
-}
+  float best0[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY}, best1[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+  float ex0 = kParent ? INFINITY : 0.f, ex1 = ex0;                                      // running min (parent) / max (density)
 
-// parent[b, i] = min(dist_max[b], min_{j: density_j > density_i} d(i, j)),  d = sqrt(d2) / sqrt(C)   (:111-114)
-__global__ void __launch_bounds__(256) dpc_parent_kernel(const float* __restrict__ x, const float* __restrict__ density,
-                                                         const float* __restrict__ dist_max, int N, float* __restrict__ parent) {
-  __shared__ __align__(16) Tile T;
-  __shared__ float dj[kTJ];
-  __shared__ float cand[kTR][8];
-  const int b = blockIdx.y, r0 = blockIdx.x * kTR;
-  const int r = threadIdx.x >> 3, cs = threadIdx.x & 7;
-  load_rows(T.xi, x, b, N, r0);
-  const float di = (r0 + r < N) ? density[(size_t)b * N + r0 + r] : INFINITY;
-  float best = INFINITY;
-  for (int j0 = 0; j0 < N; j0 += kTJ) {
+  const int ntiles = cdiv(N, kColsTile);
+  auto load_tile = [&](int tile, int buf) {
+    const int j0 = tile * kColsTile;
+    unsigned char* base = smem + buf * kStageBytes;
+    for (int c = threadIdx.x; c < 3 * kColsTile * 16; c += 256) {
+      const int part = c >> 10, row = (c >> 4) & 63, ch = c & 15;
+      const bool ok = j0 + row < N;
+      const uint32_t* src = planes + part * plane_w + (brow + (ok ? j0 + row : 0)) * (kCc / 2) + ch * 4;
+      cp_async16(smem_u32(base + part * kPlaneBytes + row * 256 + ((ch ^ (row & 7)) << 4)), src, ok);
+    }
+    if (threadIdx.x < kColsTile) {
+      const int j = j0 + threadIdx.x;
+      float* f = reinterpret_cast<float*>(base + 3 * kPlaneBytes);
+      f[threadIdx.x] = j < N ? norms[brow + j] : 0.f;
+      if (kParent) f[64 + threadIdx.x] = j < N ? density[brow + j] : -INFINITY;
+    }
+  };
+  load_tile(0, 0);
+  cp_async_commit();
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) load_tile(tile + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    load_rows(T.xj, x, b, N, j0);
-    if (threadIdx.x < kTJ) dj[threadIdx.x] = (j0 + threadIdx.x < N) ? density[(size_t)b * N + j0 + threadIdx.x] : -INFINITY;
-    __syncthreads();
-    float d2[4];
-    tile_d2(T, r, cs, d2);
+    const unsigned char* base = smem + buf * kStageBytes;
+    const uint32_t sbase = smem_u32(base);
+    float acc[8][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (dj[cs + 8 * u] > di) best = fminf(best, d2[u]);
+    for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t bf[3][8][2];                                  // [part][n-tile][b0, b1]
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int ntp = 0; ntp < 4; ++ntp) {
+          const int mi = lane >> 3, row = 16 * ntp + (mi >> 1) * 8 + (lane & 7), ch = 2 * ks + (mi & 1);
+          uint32_t r4[4];
+          ldmatrix_x4(r4, sbase + p * kPlaneBytes + row * 256 + ((ch ^ (row & 7)) << 4));
+          bf[p][2 * ntp][0] = r4[0];
+          bf[p][2 * ntp][1] = r4[1];
+          bf[p][2 * ntp + 1][0] = r4[2];
+          bf[p][2 * ntp + 1][1] = r4[3];
+        }
+      // (a part, b part): smallest terms first; 8 independent accumulators between dependent MMAs
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a[2][ks], bf[0][nt][0], bf[0][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a[0][ks], bf[2][nt][0], bf[2][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a[1][ks], bf[1][nt][0], bf[1][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a[1][ks], bf[0][nt][0], bf[0][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a[0][ks], bf[1][nt][0], bf[1][nt][1]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_bf16_16816(acc[nt], a[0][ks], bf[0][nt][0], bf[0][nt][1]);
+    }
+    // epilogue on the accumulator fragments
+    const float* nj = reinterpret_cast<const float*>(base + 3 * kPlaneBytes);
+    const int j0 = tile * kColsTile;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = 8 * nt + 2 * t, j = j0 + c;
+      const float2 n2 = *reinterpret_cast<const float2*>(nj + c);
+      float d00 = fmaxf(ni0 + n2.x - 2.f * acc[nt][0], 0.f), d01 = fmaxf(ni0 + n2.y - 2.f * acc[nt][1], 0.f);
+      float d10 = fmaxf(ni1 + n2.x - 2.f * acc[nt][2], 0.f), d11 = fmaxf(ni1 + n2.y - 2.f * acc[nt][3], 0.f);
+      if (j == i0) d00 = 0.f;
+      if (j + 1 == i0) d01 = 0.f;
+      if (j == i1) d10 = 0.f;
+      if (j + 1 == i1) d11 = 0.f;
+      if (kParent) {
+        const float2 dj = *reinterpret_cast<const float2*>(nj + 64 + c);       // -inf beyond N: never "higher"
+        if (dj.x > di0) ex0 = fminf(ex0, d00);
+        if (dj.y > di0) ex0 = fminf(ex0, d01);
+        if (dj.x > di1) ex1 = fminf(ex1, d10);
+        if (dj.y > di1) ex1 = fminf(ex1, d11);
+      } else {
+        if (j < N) {
+          insert5(best0, d00);
+          insert5(best1, d10);
+          ex0 = fmaxf(ex0, d00);
+          ex1 = fmaxf(ex1, d10);
+        }
+        if (j + 1 < N) {
+          insert5(best0, d01);
+          insert5(best1, d11);
+          ex0 = fmaxf(ex0, d01);
+          ex1 = fmaxf(ex1, d11);
+        }
+      }
+    }
+    __syncthreads();
   }
-  cand[r][cs] = best;
-  __syncthreads();
-  if (cs == 0 && r0 + r < N) {
-    float m2 = INFINITY;
-    for (int s = 0; s < 8; ++s) m2 = fminf(m2, cand[r][s]);
-    const float dm = dist_max[b];
-    parent[(size_t)b * N + r0 + r] = (m2 == INFINITY) ? dm : fminf(dm, sqrtf(m2) / sqrtf((float)kCc));
+  // combine the four threads of a row (columns were split over the quad)
+  const float invc = 1.f / sqrtf((float)kCc);
+  if (kParent) {
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      ex0 = fminf(ex0, __shfl_xor_sync(0xffffffffu, ex0, o));
+      ex1 = fminf(ex1, __shfl_xor_sync(0xffffffffu, ex1, o));
+    }
+    if (t == 0) {
+      const float dm = dist_max[b];
+      if (i0 < N) aux_out[brow + i0] = ex0 == INFINITY ? dm : fminf(dm, sqrtf(ex0) * invc);
+      if (i1 < N) aux_out[brow + i1] = ex1 == INFINITY ? dm : fminf(dm, sqrtf(ex1) * invc);
+    }
+  } else {
+    float m0[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY}, m1[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll
+    for (int src = 0; src < 4; ++src)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        insert5(m0, __shfl_sync(0xffffffffu, best0[k], (lane & ~3) | src));
+        insert5(m1, __shfl_sync(0xffffffffu, best1[k], (lane & ~3) | src));
+      }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      ex0 = fmaxf(ex0, __shfl_xor_sync(0xffffffffu, ex0, o));
+      ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, o));
+    }
+    if (t == 0) {
+      // reference: dist = cdist / sqrt(C); density = exp(-mean(dist_nearest^2)) + rand * 1e-6   (ClusterMergeNet.py:88-104)
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float e0 = sqrtf(m0[k]) * invc, e1 = sqrtf(m1[k]) * invc;
+        s0 += e0 * e0;
+        s1 += e1 * e1;
+      }
+      if (i0 < N) {
+        density[brow + i0] = expf(-(s0 / 5.f)) + noise[brow + i0] * 1e-6f;
+        aux_out[brow + i0] = ex0;
+      }
+      if (i1 < N) {
+        density[brow + i1] = expf(-(s1 / 5.f)) + noise[brow + i1] * 1e-6f;
+        aux_out[brow + i1] = ex1;
+      }
+    }
   }
 }
 
@@ -210,17 +311,32 @@ using namespace dml;
 
 extern "C" {
 
-int dml_dpc_density(const float* x, const float* noise, int B, int N, int C, float* density, float* rowmax2, void* stream) {
-  DML_CHECK_ARG(x && noise && density && rowmax2 && B > 0 && N >= 5 && B <= 65535);
+int dml_dpc_split(const float* x, long long rows, int C, void* planes, float* norms, void* stream) {
+  DML_CHECK_ARG(x && planes && norms && rows > 0);
   if (C != kCc) return DML_EUNSUPPORTED;
-  dpc_density_kernel<<<dim3(cdiv(N, kTR), B), 256, 0, (cudaStream_t)stream>>>(x, noise, N, density, rowmax2);
+  dpc_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, reinterpret_cast<uint32_t*>(planes), norms);
   DML_RETURN_LAUNCH();
 }
 
-int dml_dpc_parent(const float* x, const float* density, const float* dist_max, int B, int N, int C, float* parent, void* stream) {
-  DML_CHECK_ARG(x && density && dist_max && parent && B > 0 && N > 0 && B <= 65535);
+int dml_dpc_density(const void* planes, const float* norms, const float* noise, int B, int N, int C, float* density, float* rowmax2,
+                    void* stream) {
+  DML_CHECK_ARG(planes && norms && noise && density && rowmax2 && B > 0 && N >= 5 && B <= 65535);
   if (C != kCc) return DML_EUNSUPPORTED;
-  dpc_parent_kernel<<<dim3(cdiv(N, kTR), B), 256, 0, (cudaStream_t)stream>>>(x, density, dist_max, N, parent);
+  cudaError_t e = cudaFuncSetAttribute(dpc_dist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistSmem);
+  if (e != cudaSuccess) return (int)e;
+  dpc_dist_kernel<false><<<dim3(cdiv(N, kRowsCta), B), 256, kDistSmem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint32_t*>(planes), norms, noise, nullptr, N, density, rowmax2);
+  DML_RETURN_LAUNCH();
+}
+
+int dml_dpc_parent(const void* planes, const float* norms, const float* density, const float* dist_max, int B, int N, int C, float* parent,
+                   void* stream) {
+  DML_CHECK_ARG(planes && norms && density && dist_max && parent && B > 0 && N > 0 && B <= 65535);
+  if (C != kCc) return DML_EUNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(dpc_dist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistSmem);
+  if (e != cudaSuccess) return (int)e;
+  dpc_dist_kernel<true><<<dim3(cdiv(N, kRowsCta), B), 256, kDistSmem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint32_t*>(planes), norms, nullptr, dist_max, N, const_cast<float*>(density), parent);
   DML_RETURN_LAUNCH();
 }
 

@@ -132,10 +132,13 @@ def dpc_knn(x: torch.Tensor, cluster_num: int, noise: torch.Tensor):
     st = stream()
     density = torch.empty(B, N, device=x.device, dtype=F32)
     rowmax2 = torch.empty_like(density)
-    call("dml_dpc_density", ptr(x), ptr(noise.contiguous().float()), B, N, C, ptr(density), ptr(rowmax2), st)
+    planes = torch.empty(3, B * N, C, device=x.device, dtype=torch.bfloat16)      # three bf16 parts per value (24 bits)
+    norms = torch.empty(B * N, device=x.device, dtype=F32)
+    call("dml_dpc_split", ptr(x), B * N, C, ptr(planes), ptr(norms), st)
+    call("dml_dpc_density", ptr(planes), ptr(norms), ptr(noise.contiguous().float()), B, N, C, ptr(density), ptr(rowmax2), st)
     dist_max = (rowmax2.max(dim=1)[0].sqrt() / (C ** 0.5)).contiguous()
     parent = torch.empty_like(density)
-    call("dml_dpc_parent", ptr(x), ptr(density), ptr(dist_max), B, N, C, ptr(parent), st)
+    call("dml_dpc_parent", ptr(planes), ptr(norms), ptr(density), ptr(dist_max), B, N, C, ptr(parent), st)
     score = parent * density                                                        # :117
     index_down = torch.topk(score, k=cluster_num, dim=-1)[1].contiguous()           # :118
     idx = torch.empty(B, N, device=x.device, dtype=torch.int64)

@@ -226,7 +226,7 @@ def test_module_matches_reference_goldens(c):
         H.assert_close(thin(p.grad.cpu()), G["grad." + k], tol_of(k), "grad " + k, atol=1e-3 if k.endswith("mlp.2.bias") else 0.0)
 
 
-@pytest.mark.parametrize("B,side,train", [(4, 50, False), (2, 50, True), (1, 64, False)])
+@pytest.mark.parametrize("B,side,train", [(4, 50, False), (2, 50, True), (1, 64, False), (8, 12, True), (3, 8, False), (1, 101, False)])
 def test_module_matches_oracle_at_bag_size(B, side, train):
     """The teacher's batch (config: batch_size 4, 2 500 patches, 144 keys), training mode with the attention dropout (same keep
     mask through the oracle), gradients arriving at out, attn and vgrid."""
