@@ -91,13 +91,17 @@ __device__ __forceinline__ void load_consts(Consts& c, const float* W1, const fl
   }
 }
 
-// signed log of the relative position of (row = lane >> 1, component = lane & 1) of the tile; p_out = the position itself
+// signed log of the relative position of (row = lane >> 1, component = lane & 1) of the tile; p_out = the position itself.
+// kAccurate (backward): logf instead of the lg2 approximation - the ReLU masks of layer 1 are discontinuous in t, and every mask
+// that differs from the reference's is a term of the cancellation-dominated gradient sums
+template <bool kAccurate>
 __device__ __forceinline__ float tile_t(const float* vs_s, int j0, int m, int lane, float qx, float qy, float& p_out) {
   const int j = j0 + (lane >> 1);
   const float kvc = (j < m) ? vs_s[2 * j0 + lane] : 0.f;
   const float p = ((lane & 1) ? qy : qx) - kvc;
   p_out = p;
-  return copysignf(__logf(fabsf(p) + 1.f), p) * (p != 0.f ? 1.f : 0.f);
+  const float a = fabsf(p) + 1.f;
+  return copysignf(kAccurate ? logf(a) : __logf(a), p) * (p != 0.f ? 1.f : 0.f);
 }
 
 // H1 of the thread's elements for rows g (h0) and g + 8 (h1), and the A fragments (hi / lo) of both k-steps
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256) bias_fwd_kernel(const float* __restrict__
     float* orow = bias + ((size_t)bg * n + i) * m;
     for (int j0 = 0; j0 < m; j0 += 16) {
       float p;
-      const float tt = tile_t(vs_s, j0, m, lane, qx, qy, p);
+      const float tt = tile_t<false>(vs_s, j0, m, lane, qx, qy, p);
       const float tx0 = __shfl_sync(0xffffffffu, tt, 2 * g), ty0 = __shfl_sync(0xffffffffu, tt, 2 * g + 1);
       const float tx1 = __shfl_sync(0xffffffffu, tt, 2 * g + 16), ty1 = __shfl_sync(0xffffffffu, tt, 2 * g + 17);
       float h0[8], h1[8];
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
     const float* grow = ds + ((size_t)bg * n + i) * m;
     for (int j0 = 0; j0 < m; j0 += 16) {
       float p;
-      const float tt = tile_t(vs_s, j0, m, lane, qx, qy, p);
+      const float tt = tile_t<true>(vs_s, j0, m, lane, qx, qy, p);
       const float tx0 = __shfl_sync(0xffffffffu, tt, 2 * g), ty0 = __shfl_sync(0xffffffffu, tt, 2 * g + 1);
       const float tx1 = __shfl_sync(0xffffffffu, tt, 2 * g + 16), ty1 = __shfl_sync(0xffffffffu, tt, 2 * g + 17);
       const float g0 = (j0 + g < m) ? grow[j0 + g] : 0.f, g1 = (j0 + 8 + g < m) ? grow[j0 + 8 + g] : 0.f;

