@@ -19,6 +19,8 @@ from __future__ import annotations
 
 from math import ceil
 
+import os
+
 import torch
 
 from . import _lib
@@ -73,29 +75,74 @@ def pinv_forward(x_pair: Pair, x_f32: torch.Tensor, iters: int, B: int, H: int, 
     return z, saved
 
 
+PINV_BWD_TWO_STREAMS = os.environ.get("DML_B200_PINV_TWO_STREAMS", "1") != "0"
+
+
+def _tls_chain():
+    from . import pairs
+    return pairs._tls
+
+
+def CHAIN_DEFAULT_ON():
+    from . import pairs
+    return pairs.CHAIN_DEFAULT
+
+
 def pinv_backward(x_pair: Pair, x_f32: torch.Tensor, saved, G_f: torch.Tensor, G: Pair, B: int, H: int, m: int):
     """Adjoint of pinv_forward: G = d z_final (fp32 + pair) -> d x (fp32 [B, H, m, m])."""
     bt = (B, H)
     dx = None
     sums, saved = saved[0], saved[1:]
+    # Each step is 8 products of dependency depth 5: {dz, du4} | {dP, du2} | dP += | dP += , dPp | {dx, G}.  The second member of
+    # every independent pair goes to the auxiliary stream (each product occupies 64 of the 148 SMs), so the latency-bound chain is
+    # 5 launches deep per step instead of 8.  Outputs of the auxiliary-stream products are allocated on the main stream first.
+    from .ops import side_stream
+    dev = x_f32.device
+    two_streams = PINV_BWD_TWO_STREAMS and getattr(_tls_chain(), "chain", None) is None and not CHAIN_DEFAULT_ON()
+    cur = torch.cuda.current_stream()
+    side = side_stream(dev) if two_streams else None
+
+    class _on_side:
+        def __enter__(self):
+            if side is not None:
+                side.wait_stream(cur)
+                self.ctx = torch.cuda.stream(side)
+                self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *a):
+            if side is not None:
+                self.ctx.__exit__(*a)
+            return False
+
+    shape = (B, H, m, m)
     with chain():
         for (z, P, t3, t5) in reversed(saved):
             # z' = 1/4 z t5
-            dz_f, _ = pgemm(G, t5, M=m, N=m, K=m, batch=bt, alpha=0.25)                                    # 1/4 G t5^T
+            dz_f = torch.empty(shape, device=dev, dtype=F32)
+            with _on_side():
+                pgemm(G, t5, M=m, N=m, K=m, batch=bt, alpha=0.25, out=dz_f)                                # 1/4 G t5^T
             _, du4 = pgemm(z, G, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-0.25, want_f32=False, want_pair=True)
             # t5 = 13 I - P t3
-            dP, _ = pgemm(du4, t3, M=m, N=m, K=m, batch=bt)                                                # du4 t3^T
+            dP = torch.empty(shape, device=dev, dtype=F32)
+            with _on_side():
+                pgemm(du4, t3, M=m, N=m, K=m, batch=bt, out=dP)                                            # du4 t3^T
             du2_f, du2 = pgemm(P, du4, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, want_pair=True)   # -P^T du4
+            if side is not None:
+                cur.wait_stream(side)
             # t3 = 15 I - (7 P - P P)  =>  dP += 7 du2 - du2 P^T - P^T du2
             pgemm(du2, P, M=m, N=m, K=m, batch=bt, alpha=-1.0, resid=du2_f, resid_scale=7.0, out=dP, accumulate=True)
             _, dPp = pgemm(P, du2, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, out=dP, accumulate=True,
                            want_pair=True)
             # P = x z
-            if dx is None:
-                dx, _ = pgemm(dPp, z, M=m, N=m, K=m, batch=bt)                                             # dP z^T
-            else:
-                pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=True)
+            first = dx is None
+            if first:
+                dx = torch.empty(shape, device=dev, dtype=F32)
+            with _on_side():
+                pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=not first)                       # dP z^T
             G_f, G = pgemm(x_pair, dPp, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dz_f, accumulate=True, want_pair=True)
+            if side is not None:
+                cur.wait_stream(side)          # the step's operands may be released / overwritten from here on
     # z0 = x^T / (max row-sum * max column-sum): the scalar couples all bags and heads; two launches, the chain's dx added in
     lib = _lib.load(check_device=True)
     x_f32 = x_f32.contiguous()
