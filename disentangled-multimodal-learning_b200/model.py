@@ -114,11 +114,13 @@ class DeformPathomicNet(nn.Module):
         if two_streams:
             cur = torch.cuda.current_stream()
             side = _tower_stream(x_path.device)
+            # issued in the reference's order - tumor, then immune (model.py:517-521) - so that the AlphaDropout draws of the
+            # two omic MLPs consume the generator in the same order
+            omic_vec_tumor = _omic_ahead(self.omic_net_tumor, kwargs['x_omic_tumor'], 3)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 omic_vec_immune = _omic_ahead(self.omic_net_immune, kwargs['x_omic_immune'], 2)
                 vec_immune, _, grads_immune = self.pathomic_net_immune(path=x_path, omic=omic_vec_immune)
-            omic_vec_tumor = _omic_ahead(self.omic_net_tumor, kwargs['x_omic_tumor'], 3)
         else:
             omic_vec_tumor, _, _ = self.omic_net_tumor(x_omic=kwargs['x_omic_tumor'])
         vec_tumor, _, grads_tumor = self.pathomic_net_tumor(path=x_path, omic=omic_vec_tumor)
