@@ -3,17 +3,24 @@
 // A 2 -> 32 -> 32 -> 1 MLP per (query, key, group): 1 120 MACs each, 91 % of them the 32 x 32 layer.  With a 2-D input the exact
 // piecewise-linear table of the 1-D module (cpb_table.cu) does not exist, so the layer runs as a GEMM on the tensor cores:
 //   one warp = one query i, tiles of 16 keys;  H1 [16 keys x 32] is produced by the threads DIRECTLY in the A-fragment layout of
-//   mma.m16n8k16 (each thread evaluates the 2 x 8 (key, neuron) elements it owns), Z2 = H1 W2^T is 8 MMAs, and the ReLU / W3
-//   reduction happens on the accumulator fragments (thread-local + two shuffles).  Operands are bf16 pairs (hi + lo, the
-//   arithmetic of pgemm.cu): 3 MMAs per product, fp32-class result.
+//   mma.m16n8k16 (each thread evaluates the 2 x 8 (key, neuron) elements it owns), Z2 = H1 W2^T is 8 MMAs per operand-part pair,
+//   and the ReLU / W3 reduction happens on the accumulator fragments (thread-local + two shuffles).
+// Operand arithmetic.  An mma.sync costs the scheduler ~8.5 issue cycles on this part (measured: the MMA pipe time ADDS to the
+// issue time of the other instructions), so the number of MMAs matters as much as the instruction count.  H1 and W2 are O(1)
+// quantities with a known bound, so they go in as fp16 PAIRS (hi + lo = 22 bits, 3 MMAs per product: hh, hl, lh) after an exact
+// power-of-two scaling that puts their maxima at 2^12 (the lo part of anything above 3e-5 of the maximum is then a normal fp16);
+// the scale is undone in fp32 on the accumulators.  Quantities of unknown magnitude (anything that carries the upstream gradient)
+// use bf16 parts (fp32 exponent range).
 // Backward (same tiling, everything in registers).  The upstream gradient g_p = dS_p of a pair is a per-row scalar, and rows of dS
-// sum to zero (softmax): every parameter gradient is a cancellation-dominated sum, so rounding errors must either be tiny or cancel
-// like the signal does - every backward product is fp32-class (24-bit operands: three bf16 parts).  The structure keeps that cheap:
-// dH1 = g_p (M W2') with M = (Z2 > 0) a 0 / 1 mask (EXACT in one bf16 part; the accumulator layout of two n-tiles IS the A layout
-// of one k-step, so M is built straight into A fragments), W2' = diag(w3) W2 pre-multiplied in the shared-memory table (three
-// parts) and g_p applied in fp32 afterwards: 3 MMAs; dW2 = diag(w3) M^T (g_p H1) takes both operands through movmatrix (8 x 8
-// transposes), M exact, g_p H1 in three parts: 3 MMAs; only the recompute of Z2 = H1 W2^T (its masks are discontinuous in Z2)
-// needs both operands in three parts: 6 MMAs.
+// sum to zero (softmax): every parameter gradient is a cancellation-dominated sum whose condition number with respect to ANY
+// operand perturbation is 10^2..10^3, and the ReLU masks are discontinuous - every backward product is fp32-class (>= 22 bits;
+// with 16-bit operands the gradients came out 2e-3..8e-3 off, measured).  The structure keeps that cheap:
+//   Z2 recompute  = H1 W2^T              fp16 pairs, 3 MMAs (masks need the accuracy, not the range);
+//   dH1 = g_p (M W2'), M = (Z2 > 0)      the 0 / 1 mask is EXACT in one fp16 part (the accumulator layout of two n-tiles IS the A
+//                                        layout of one k-step: M is built in place), W2' = diag(w3) W2 pre-multiplied in the table
+//                                        as an fp16 pair, g_p applied in fp32 afterwards: 2 MMAs;
+//   dW2 = diag(w3) M^T (g_p H1)          both operands through movmatrix (8 x 8 transposes), M exact (one bf16 part), g_p H1 in
+//                                        three bf16 parts: 3 MMAs.
 // tcgen05 is not used here: the M = 16-key tiles are produced in registers, K = N = 32, and a TMEM round trip per tile would
 // cost more than the MMAs it feeds.
 #include "common.cuh"
@@ -40,13 +47,12 @@ __device__ __forceinline__ void split3_bf16x2(float x0, float x1, uint32_t& h, u
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(s1), "f"(s0));
 }
 
-// fragment tables of W2 in shared memory, [which][component][ks][nt][reg][lane] packed bf16x2 (512 words per component):
+// fragment tables of W2 in shared memory, [which][part][ks][nt][reg][lane] packed fp16x2, hi then lo (512 words per part):
 //   which = 0 (forward, Z2 = H1 W2^T):  B[kdim = m][n = k] = W2[k][m]:  word = {W2[8nt+g][16ks+2t+8reg], W2[8nt+g][16ks+2t+8reg+1]}
 //   which = 1 (backward, R = M W2'):    B[kdim = k][n = m] = W2'[k][m]: word = {W2'[16ks+2t+8reg][8nt+g], W2'[16ks+2t+8reg+1][8nt+g]}
-// kComp = 2: bf16 pair (hi, lo; 16 bits); kComp = 3: (hi, mid, lo; 24 bits)
-// row_scale (may be NULL): the backward table holds diag(row_scale) W2, i.e. w3[k] W2[k][m] (see bias_bwd_kernel)
-template <int kComp>
-__device__ __forceinline__ void build_w2_frags(const float* __restrict__ W2, uint32_t* tab, int nwhich, const float* row_scale = nullptr) {
+// with W2' = diag(w3) W2.  scale[which]: the power of two that puts the table's maximum at 2^12 (applied here, exact).
+__device__ __forceinline__ void build_w2_frags(const float* __restrict__ W2, const float* __restrict__ w3, uint32_t* tab, int nwhich,
+                                               const float* scale) {
   for (int i = threadIdx.x; i < 512 * nwhich; i += blockDim.x) {
     const int which = i >> 9, r = i & 511;
     const int lane = r & 31, reg = (r >> 5) & 1, nt = (r >> 6) & 3, ks = (r >> 8) & 1;
@@ -57,20 +63,48 @@ __device__ __forceinline__ void build_w2_frags(const float* __restrict__ W2, uin
       v1 = W2[(8 * nt + g) * kHid + 16 * ks + 2 * t + 8 * reg + 1];
     } else {
       const int k0 = 16 * ks + 2 * t + 8 * reg;
-      v0 = W2[k0 * kHid + 8 * nt + g];
-      v1 = W2[(k0 + 1) * kHid + 8 * nt + g];
-      if (row_scale) {
-        v0 *= row_scale[k0];
-        v1 *= row_scale[k0 + 1];
-      }
+      v0 = W2[k0 * kHid + 8 * nt + g] * w3[k0];
+      v1 = W2[(k0 + 1) * kHid + 8 * nt + g] * w3[k0 + 1];
     }
-    uint32_t* dst = tab + which * kComp * 512 + r;
-    if (kComp == 2) {
-      split_bf16x2(v0, v1, dst[0], dst[512]);
-    } else {
-      split3_bf16x2(v0, v1, dst[0], dst[512], dst[1024]);
-    }
+    uint32_t* dst = tab + which * 1024 + r;
+    split_f16(v0 * scale[which], v1 * scale[which], dst[0], dst[512]);
   }
+}
+
+// power of two s with max * s in (2^11, 2^12] (1 for max = 0)
+__device__ __forceinline__ float pow2_scale(float mx) { return mx > 0.f ? exp2f(12.f - ceilf(log2f(mx))) : 1.f; }
+
+// scales[0] = s_w (W2), scales[1] = s_2 (W2' = diag(w3) W2), scales[2] = s_h (bound of H1); call with all threads, then sync
+__device__ __forceinline__ void compute_scales(const float* W1, const float* b1, const float* W2, const float* W3, float* scales,
+                                               float* red) {
+  float mw = 0.f, m2 = 0.f;
+  for (int i = threadIdx.x; i < kHid * kHid; i += blockDim.x) {
+    const float w = fabsf(W2[i]);
+    mw = fmaxf(mw, w);
+    m2 = fmaxf(m2, w * fabsf(W3[i >> 5]));
+  }
+  mw = warp_max(mw);
+  m2 = warp_max(m2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[warp] = mw;
+    red[8 + warp] = m2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, hb = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a = fmaxf(a, red[w]);
+      b = fmaxf(b, red[8 + w]);
+    }
+    // |t| <= log(3) < 1.0987 for normalised positions in [-1, 1] displaced by at most 1 (wider positions only cost headroom: the
+    // scaled maximum 2^12 is 16x below the fp16 limit)
+    for (int k = 0; k < kHid; ++k) hb = fmaxf(hb, (fabsf(W1[2 * k]) + fabsf(W1[2 * k + 1])) * 1.0987f + fabsf(b1[k]));
+    scales[0] = pow2_scale(a);
+    scales[1] = pow2_scale(b);
+    scales[2] = pow2_scale(hb);
+  }
+  __syncthreads();
 }
 
 // neurons owned by a thread (t = lane & 3): e = 0..7 -> 2t + (e & 1) + 8 (e >> 1)
@@ -79,14 +113,16 @@ __device__ __forceinline__ int neuron_of(int t, int e) { return 2 * t + (e & 1) 
 struct Consts {
   float w1x[8], w1y[8], b1[8], b2[8], w3[8];
 };
-__device__ __forceinline__ void load_consts(Consts& c, const float* W1, const float* b1, const float* b2, const float* W3, int t) {
+// layer 1 is scaled by s_h (H1 comes out pre-scaled), b2 by s_h s_w (the scale of the Z2 accumulators); w3 stays
+__device__ __forceinline__ void load_consts(Consts& c, const float* W1, const float* b1, const float* b2, const float* W3, int t, float s_h,
+                                            float s_z) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int nb = neuron_of(t, e);
-    c.w1x[e] = W1[nb * 2];
-    c.w1y[e] = W1[nb * 2 + 1];
-    c.b1[e] = b1[nb];
-    c.b2[e] = b2[nb];
+    c.w1x[e] = W1[nb * 2] * s_h;
+    c.w1y[e] = W1[nb * 2 + 1] * s_h;
+    c.b1[e] = b1[nb] * s_h;
+    c.b2[e] = b2[nb] * s_z;
     c.w3[e] = W3[nb];
   }
 }
@@ -104,7 +140,7 @@ __device__ __forceinline__ float tile_t(const float* vs_s, int j0, int m, int la
   return copysignf(kAccurate ? logf(a) : __logf(a), p) * (p != 0.f ? 1.f : 0.f);
 }
 
-// H1 of the thread's elements for rows g (h0) and g + 8 (h1), and the A fragments (hi / lo) of both k-steps
+// (scaled) H1 of the thread's elements for rows g (h0) and g + 8 (h1), and the fp16 A fragments (hi / lo) of both k-steps
 __device__ __forceinline__ void layer1(const Consts& c, float tx0, float ty0, float tx1, float ty1, float (&h0)[8], float (&h1)[8],
                                        uint32_t (&ahi)[2][4], uint32_t (&alo)[2][4]) {
 #pragma unroll
@@ -114,92 +150,56 @@ __device__ __forceinline__ void layer1(const Consts& c, float tx0, float ty0, fl
   }
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
-    split_bf16x2(h0[4 * ks], h0[4 * ks + 1], ahi[ks][0], alo[ks][0]);
-    split_bf16x2(h1[4 * ks], h1[4 * ks + 1], ahi[ks][1], alo[ks][1]);
-    split_bf16x2(h0[4 * ks + 2], h0[4 * ks + 3], ahi[ks][2], alo[ks][2]);
-    split_bf16x2(h1[4 * ks + 2], h1[4 * ks + 3], ahi[ks][3], alo[ks][3]);
+    split_f16(h0[4 * ks], h0[4 * ks + 1], ahi[ks][0], alo[ks][0]);
+    split_f16(h1[4 * ks], h1[4 * ks + 1], ahi[ks][1], alo[ks][1]);
+    split_f16(h0[4 * ks + 2], h0[4 * ks + 3], ahi[ks][2], alo[ks][2]);
+    split_f16(h1[4 * ks + 2], h1[4 * ks + 3], ahi[ks][3], alo[ks][3]);
   }
 }
 
-// acc[nt] += A (16 x 32, two k-steps: hi / lo parts) x B fragments (hi / lo parts) held in registers (forward kernel: 32 words per
-// thread, loaded once per warp): pair arithmetic, 3 MMAs per product, term-major so that consecutive MMAs hit different accumulators
+// acc[nt] += A (16 x 32, two k-steps: fp16 hi / lo) x B fragments (fp16 hi / lo) held in registers (forward kernel: 32 words per
+// thread, loaded once per warp): 3 MMAs per product (hh, hl, lh), term-major so that consecutive MMAs hit different accumulators
 __device__ __forceinline__ void mma_32x32_reg(float (&acc)[4][4], const uint32_t (&ahi)[2][4], const uint32_t (&alo)[2][4],
                                               const uint32_t (&bh)[2][4][2], const uint32_t (&bl)[2][4][2]) {
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], alo[ks], bh[ks][nt][0], bh[ks][nt][1]);
+    for (int nt = 0; nt < 4; ++nt) mma_f16_16816(acc[nt], alo[ks], bh[ks][nt][0], bh[ks][nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], ahi[ks], bl[ks][nt][0], bl[ks][nt][1]);
+    for (int nt = 0; nt < 4; ++nt) mma_f16_16816(acc[nt], ahi[ks], bl[ks][nt][0], bl[ks][nt][1]);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], ahi[ks], bh[ks][nt][0], bh[ks][nt][1]);
+    for (int nt = 0; nt < 4; ++nt) mma_f16_16816(acc[nt], ahi[ks], bh[ks][nt][0], bh[ks][nt][1]);
+  }
+}
+
+// the same with the B fragments read from the shared-memory table (hi at tab, lo at tab + 512); kParts = 2: A has hi / lo parts
+// (3 MMAs), kParts = 1: A is one exact part (a 0 / 1 mask; alo unused, 2 MMAs)
+template <int kParts>
+__device__ __forceinline__ void mma_32x32_tab(float (&acc)[4][4], const uint32_t (&ahi)[2][4], const uint32_t (&alo)[2][4],
+                                              const uint32_t* tab, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int base = ((ks * 4 + nt) * 2) * 32 + lane;
+      bh[nt][0] = tab[base];
+      bh[nt][1] = tab[base + 32];
+      bl[nt][0] = tab[512 + base];
+      bl[nt][1] = tab[512 + base + 32];
+    }
+    if (kParts == 2) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_f16_16816(acc[nt], alo[ks], bh[nt][0], bh[nt][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_f16_16816(acc[nt], ahi[ks], bl[nt][0], bl[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_f16_16816(acc[nt], ahi[ks], bh[nt][0], bh[nt][1]);
   }
 }
 
 __device__ __forceinline__ uint32_t mask_pk(uint32_t pk, bool a, bool b) { return pk & ((a ? 0x0000ffffu : 0u) | (b ? 0xffff0000u : 0u)); }
-
-// The backward runs every product at 24 bits: the parameter gradients are cancellation-dominated sums over ReLU-masked terms
-// (rows of dS sum to zero), their condition number with respect to ANY operand perturbation is ~10^2..10^3, and the masks
-// (Z2 > 0) are discontinuous in Z2 - with 16-bit operands the gradients came out 2e-3 .. 8e-3 off (measured); the reference's own
-// fp32 result is 1e-4 .. 9e-4 off fp64 on these tensors.  Operands in three bf16 parts, 6 MMAs per product
-// (hh, hm, mh, mm, hl, lh; the dropped terms are <= 2^-24).
-__device__ __forceinline__ void split_rows3(const float (&h0)[8], const float (&h1)[8], uint32_t (&a)[3][2][4]) {
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    split3_bf16x2(h0[4 * ks], h0[4 * ks + 1], a[0][ks][0], a[1][ks][0], a[2][ks][0]);
-    split3_bf16x2(h1[4 * ks], h1[4 * ks + 1], a[0][ks][1], a[1][ks][1], a[2][ks][1]);
-    split3_bf16x2(h0[4 * ks + 2], h0[4 * ks + 3], a[0][ks][2], a[1][ks][2], a[2][ks][2]);
-    split3_bf16x2(h1[4 * ks + 2], h1[4 * ks + 3], a[0][ks][3], a[1][ks][3], a[2][ks][3]);
-  }
-}
-// acc[nt] += A (three parts) x table (three parts at tab, tab + 512, tab + 1024)
-__device__ __forceinline__ void mma_32x32_x6(float (&acc)[4][4], const uint32_t (&a)[3][2][4], const uint32_t* tab, int lane) {
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    uint32_t b[3][4][2];
-#pragma unroll
-    for (int cp = 0; cp < 3; ++cp)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int base = cp * 512 + ((ks * 4 + nt) * 2) * 32 + lane;
-        b[cp][nt][0] = tab[base];
-        b[cp][nt][1] = tab[base + 32];
-      }
-    // smallest terms first; term-major order keeps consecutive MMAs on different accumulators
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[2][ks], b[0][nt][0], b[0][nt][1]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[0][ks], b[2][nt][0], b[2][nt][1]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[1][ks], b[1][nt][0], b[1][nt][1]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[1][ks], b[0][nt][0], b[0][nt][1]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[0][ks], b[1][nt][0], b[1][nt][1]);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[0][ks], b[0][nt][0], b[0][nt][1]);
-  }
-}
-
-// acc[nt] += A (ONE exact part: a 0 / 1 mask) x table (three parts)
-__device__ __forceinline__ void mma_32x32_m3(float (&acc)[4][4], const uint32_t (&a)[2][4], const uint32_t* tab, int lane) {
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    uint32_t b[3][4][2];
-#pragma unroll
-    for (int cp = 0; cp < 3; ++cp)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int base = cp * 512 + ((ks * 4 + nt) * 2) * 32 + lane;
-        b[cp][nt][0] = tab[base];
-        b[cp][nt][1] = tab[base + 32];
-      }
-#pragma unroll
-    for (int cp = 2; cp >= 0; --cp)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a[ks], b[cp][nt][0], b[cp][nt][1]);
-  }
-}
 
 __device__ __forceinline__ void query_xy(int i, int side, float& qx, float& qy) {
   const int y = i / side, x = i - y * side;
@@ -214,13 +214,18 @@ __global__ void __launch_bounds__(256) bias_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ b3, int side, int m, float* __restrict__ bias) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   uint32_t* tab = smem_u;                                   // 1024 words
-  float* vs_s = reinterpret_cast<float*>(smem_u + 1024);    // 2 m floats
+  float* scales = reinterpret_cast<float*>(smem_u + 1024);  // 32 floats: s_w, s_2, s_h + reduction scratch
+  float* vs_s = scales + 32;                                // 2 m floats
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int bg = blockIdx.y, n = side * side;
-  build_w2_frags<2>(W2, tab, 1);
+  compute_scales(W1, b1, W2, W3, scales, scales + 8);
+  build_w2_frags(W2, W3, tab, 1, scales);
   for (int i = threadIdx.x; i < 2 * m; i += 256) vs_s[i] = vs[(size_t)bg * 2 * m + i];
+  const float s_z = scales[2] * scales[0];                  // scale of the Z2 accumulators
   Consts c;
-  load_consts(c, W1, b1, b2, W3, t);
+  load_consts(c, W1, b1, b2, W3, t, scales[2], s_z);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) c.w3[e] *= 1.f / s_z;         // the epilogue un-scales (exact: powers of two)
   const float bias3 = b3[0];
   __syncthreads();
   uint32_t bh[2][4][2], bl[2][4][2];
@@ -279,20 +284,23 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ ds, int side, int m, float* __restrict__ parts,
                                                        float* __restrict__ dvs) {
   extern __shared__ __align__(16) uint32_t smem_u[];
-  uint32_t* tab = smem_u;                                   // 3072 words: forward + backward fragments, three parts each
-  float* gsum = reinterpret_cast<float*>(smem_u + 3072);    // kGradFloats (padded to 1200)
+  uint32_t* tab = smem_u;                                   // 2048 words: forward + backward fragments, fp16 hi / lo each
+  float* scales = reinterpret_cast<float*>(smem_u + 2048);  // 32 floats
+  float* gsum = scales + 32;                                // kGradFloats (padded to 1200)
   float* vs_s = gsum + 1200;                                // 2 m floats
   float* dvs_s = vs_s + 2 * m;                              // 2 m floats
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int bg = blockIdx.y, n = side * side;
-  build_w2_frags<3>(W2, tab, 2, W3);
+  compute_scales(W1, b1, W2, W3, scales, scales + 8);
+  build_w2_frags(W2, W3, tab, 2, scales);
   for (int i = threadIdx.x; i < 2 * m; i += 256) {
     vs_s[i] = vs[(size_t)bg * 2 * m + i];
     dvs_s[i] = 0.f;
   }
   for (int i = threadIdx.x; i < 1200; i += 256) gsum[i] = 0.f;
+  const float s_h = scales[2], s_z = scales[2] * scales[0], inv_s2 = 1.f / scales[1];
   Consts c;
-  load_consts(c, W1, b1, b2, W3, t);
+  load_consts(c, W1, b1, b2, W3, t, s_h, s_z);
   __syncthreads();
 
   float aW2[2][4][4];
@@ -318,27 +326,22 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
       const float tx0 = __shfl_sync(0xffffffffu, tt, 2 * g), ty0 = __shfl_sync(0xffffffffu, tt, 2 * g + 1);
       const float tx1 = __shfl_sync(0xffffffffu, tt, 2 * g + 16), ty1 = __shfl_sync(0xffffffffu, tt, 2 * g + 17);
       const float g0 = (j0 + g < m) ? grow[j0 + g] : 0.f, g1 = (j0 + 8 + g < m) ? grow[j0 + 8 + g] : 0.f;
-      float h0[8], h1[8];
-      float z[4][4];
+      float h0[8], h1[8];                      // H1 x s_h
+      float z[4][4];                           // Z2 x s_h s_w
       {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          h0[e] = fmaxf(fmaf(c.w1x[e], tx0, fmaf(c.w1y[e], ty0, c.b1[e])), 0.f);
-          h1[e] = fmaxf(fmaf(c.w1x[e], tx1, fmaf(c.w1y[e], ty1, c.b1[e])), 0.f);
-        }
-        uint32_t a3[3][2][4];
-        split_rows3(h0, h1, a3);
+        uint32_t ahi[2][4], alo[2][4];
+        layer1(c, tx0, ty0, tx1, ty1, h0, h1, ahi, alo);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           z[nt][0] = z[nt][2] = c.b2[2 * nt];
           z[nt][1] = z[nt][3] = c.b2[2 * nt + 1];
         }
-        mma_32x32_x6(z, a3, tab, lane);
+        mma_32x32_tab<2>(z, ahi, alo, tab, lane);
       }
       // output layer; the ReLU mask M = (Z2 > 0) as A fragments (same element -> register mapping as H1): 0 / 1 is EXACT in one
       // bf16 part, and w3 rides in the table (R = M (diag(w3) W2)) and in the final scaling of dW2 - no operand split needed
       if (t == 0) ab3 += g0 + g1;
-      uint32_t mk[2][4];
+      uint32_t mk[2][4], mkb[2][4];           // fp16 ones (R = M W2') and bf16 ones (dW2 = M^T (g H1))
       {
         bool m0[8], m1[8];
 #pragma unroll
@@ -351,21 +354,24 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
         }
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-          mk[ks][0] = mask_pk(0x3f803f80u, m0[4 * ks], m0[4 * ks + 1]);
-          mk[ks][1] = mask_pk(0x3f803f80u, m1[4 * ks], m1[4 * ks + 1]);
-          mk[ks][2] = mask_pk(0x3f803f80u, m0[4 * ks + 2], m0[4 * ks + 3]);
-          mk[ks][3] = mask_pk(0x3f803f80u, m1[4 * ks + 2], m1[4 * ks + 3]);
+          mkb[ks][0] = mask_pk(0x3f803f80u, m0[4 * ks], m0[4 * ks + 1]);
+          mkb[ks][1] = mask_pk(0x3f803f80u, m1[4 * ks], m1[4 * ks + 1]);
+          mkb[ks][2] = mask_pk(0x3f803f80u, m0[4 * ks + 2], m0[4 * ks + 3]);
+          mkb[ks][3] = mask_pk(0x3f803f80u, m1[4 * ks + 2], m1[4 * ks + 3]);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) mk[ks][r] = mkb[ks][r] & 0x3c003c00u;      // bf16 1.0 = 0x3f80 -> fp16 1.0 = 0x3c00
         }
       }
       // R = M W2', then dH1 = g_p R in fp32 (g_p is a per-row scalar: it never enters a 16-bit operand here)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) z[nt][0] = z[nt][1] = z[nt][2] = z[nt][3] = 0.f;
-      mma_32x32_m3(z, mk, tab + 1536, lane);
+      mma_32x32_tab<1>(z, mk, mk, tab + 1024, lane);
+      const float gs0 = g0 * inv_s2, gs1 = g1 * inv_s2;                                  // un-scale W2' here
       float dtx0 = 0.f, dty0 = 0.f, dtx1 = 0.f, dty1 = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float a0 = h0[e] > 0.f ? g0 * z[e >> 1][e & 1] : 0.f;
-        const float a1 = h1[e] > 0.f ? g1 * z[e >> 1][2 + (e & 1)] : 0.f;
+        const float a0 = h0[e] > 0.f ? gs0 * z[e >> 1][e & 1] : 0.f;
+        const float a1 = h1[e] > 0.f ? gs1 * z[e >> 1][2 + (e & 1)] : 0.f;
         ab1[e] += a0 + a1;
         aw1x[e] += a0 * tx0 + a1 * tx1;
         aw1y[e] += a0 * ty0 + a1 * ty1;
@@ -387,17 +393,17 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
         const float x0 = __shfl_sync(0xffffffffu, dtx0, src), y0 = __shfl_sync(0xffffffffu, dty0, src);
         const float x1 = __shfl_sync(0xffffffffu, dtx1, src), y1 = __shfl_sync(0xffffffffu, dty1, src);
         const float dt = rr < 8 ? ((lane & 1) ? y0 : x0) : ((lane & 1) ? y1 : x1);
-        if (j0 + rr < m) atomicAdd(&dvs_s[2 * j0 + lane], -dt / (fabsf(p) + 1.f));     // p = q - vs
+        if (j0 + rr < m) atomicAdd(&dvs_s[2 * j0 + lane], -dt * (1.f / s_h) / (fabsf(p) + 1.f));     // p = q - vs; w1 was scaled
       }
       // dW2 / w3 += M^T (g H1): A' = transposed mask blocks (exact), B' = transposed blocks of g_p H1 in three bf16 parts
       //   A'(mt) = { T(pk0[2mt]), T(pk0[2mt+1]), T(pk1[2mt]), T(pk1[2mt+1]) };  pk0[nt] = mk[nt>>1][(nt&1)*2], pk1[nt] = mk[nt>>1][(nt&1)*2+1]
       uint32_t at[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        at[mt][0] = movmatrix_t(mk[mt][0]);
-        at[mt][1] = movmatrix_t(mk[mt][2]);
-        at[mt][2] = movmatrix_t(mk[mt][1]);
-        at[mt][3] = movmatrix_t(mk[mt][3]);
+        at[mt][0] = movmatrix_t(mkb[mt][0]);
+        at[mt][1] = movmatrix_t(mkb[mt][2]);
+        at[mt][2] = movmatrix_t(mkb[mt][1]);
+        at[mt][3] = movmatrix_t(mkb[mt][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           float* o = gsum + kGW2 + (16 * mt + g) * kHid + 8 * nt + 2 * t;
-          const float wa = W3[16 * mt + g], wb = W3[16 * mt + 8 + g];           // the w3 factor taken out of the mask operand
+          const float wa = W3[16 * mt + g] * (1.f / s_h), wb = W3[16 * mt + 8 + g] * (1.f / s_h);   // w3 (taken out of the mask operand), H1's scale
           o[0] += aW2[mt][nt][0] * wa;
           o[1] += aW2[mt][nt][1] * wa;
           o[8 * kHid] += aW2[mt][nt][2] * wb;
@@ -452,7 +458,7 @@ __global__ void __launch_bounds__(256) bias_bwd_kernel(const float* __restrict__
           gsum[kGW1 + nb * 2 + 1] += aw1y[e];
           gsum[kGb1 + nb] += ab1[e];
           gsum[kGb2 + nb] += ab2[e] * c.w3[e];
-          gsum[kGW3 + nb] += aw3[e];
+          gsum[kGW3 + nb] += aw3[e] * (1.f / s_z);
         }
         if (t == 0) gsum[kGb3] += ab3;
       }
@@ -501,7 +507,7 @@ extern "C" {
 int dml_da2_bias_fwd(const float* vs, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
                      int B, int side, int m, float* bias, void* stream) {
   DML_CHECK_ARG(vs && W1 && b1 && W2 && b2 && W3 && b3 && bias && B > 0 && side > 0 && m > 0 && B * 8 <= 65535);
-  const size_t smem = 1024 * 4 + (size_t)2 * m * 4;
+  const size_t smem = 1024 * 4 + 128 + (size_t)2 * m * 4;
   if (smem > 200 * 1024) return DML_EUNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(bias_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int n = side * side;
@@ -515,7 +521,7 @@ int dml_da2_bias_bwd_parts(int B, int side) { return cdiv(side * side, 8 * kBwdQ
 int dml_da2_bias_bwd(const float* vs, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* ds,
                      int B, int side, int m, float* parts, float* grads, float* dvs, void* stream) {
   DML_CHECK_ARG(vs && W1 && b1 && W2 && b2 && W3 && ds && parts && grads && dvs && B > 0 && side > 0 && m > 0 && B * 8 <= 65535);
-  const size_t smem = 3072 * 4 + 1200 * 4 + (size_t)4 * m * 4;
+  const size_t smem = 2048 * 4 + 128 + 1200 * 4 + (size_t)4 * m * 4;
   if (smem > 200 * 1024) return DML_EUNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(bias_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaStream_t st = (cudaStream_t)stream;
