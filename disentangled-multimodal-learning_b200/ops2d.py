@@ -132,13 +132,15 @@ def dpc_knn(x: torch.Tensor, cluster_num: int, noise: torch.Tensor):
     st = stream()
     density = torch.empty(B, N, device=x.device, dtype=F32)
     rowmax2 = torch.empty_like(density)
-    planes = torch.empty(3, B * N, C, device=x.device, dtype=torch.bfloat16)      # three bf16 parts per value (24 bits)
+    planes = torch.empty(2, B * N, C, device=x.device, dtype=torch.float16)       # fp16 hi / lo parts of the scaled tokens (22 bits)
     norms = torch.empty(B * N, device=x.device, dtype=F32)
-    call("dml_dpc_split", ptr(x), B * N, C, ptr(planes), ptr(norms), st)
-    call("dml_dpc_density", ptr(planes), ptr(norms), ptr(noise.contiguous().float()), B, N, C, ptr(density), ptr(rowmax2), st)
+    inv_s2 = torch.empty(1, device=x.device, dtype=F32)
+    amax = x.abs().amax().reshape(1)
+    call("dml_dpc_split", ptr(x), ptr(amax), B * N, C, ptr(planes), ptr(norms), ptr(inv_s2), st)
+    call("dml_dpc_density", ptr(planes), ptr(norms), ptr(inv_s2), ptr(noise.contiguous().float()), B, N, C, ptr(density), ptr(rowmax2), st)
     dist_max = (rowmax2.max(dim=1)[0].sqrt() / (C ** 0.5)).contiguous()
     parent = torch.empty_like(density)
-    call("dml_dpc_parent", ptr(planes), ptr(norms), ptr(density), ptr(dist_max), B, N, C, ptr(parent), st)
+    call("dml_dpc_parent", ptr(planes), ptr(norms), ptr(inv_s2), ptr(density), ptr(dist_max), B, N, C, ptr(parent), st)
     score = parent * density                                                        # :117
     index_down = torch.topk(score, k=cluster_num, dim=-1)[1].contiguous()           # :118
     idx = torch.empty(B, N, device=x.device, dtype=torch.int64)
@@ -157,7 +159,8 @@ class MergeTokensFn(torch.autograd.Function):
         x, w = x.contiguous().float(), w.contiguous().float()
         merged = torch.empty(B, K, C, device=x.device, dtype=F32)
         all_w = torch.empty(B, K, device=x.device, dtype=F32)
-        call("dml_merge_fwd", ptr(x), ptr(w), ptr(idx), B, N, C, K, ptr(merged), ptr(all_w), stream())
+        ws = torch.empty(_lib.load().dml_merge_ws_floats(B, N, K), device=x.device, dtype=F32)
+        call("dml_merge_fwd", ptr(x), ptr(w), ptr(idx), B, N, C, K, ptr(ws), ptr(merged), ptr(all_w), stream())
         ctx.save_for_backward(x, w, idx, merged, all_w)
         ctx.mark_non_differentiable(all_w)
         return merged, all_w

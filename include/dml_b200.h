@@ -376,19 +376,22 @@ int dml_da2_attn_bwd(const float* q, const float* k, const float* v, const float
 /* ---- ClusterMergeNet (csrc/cluster.cu; models/ClusterMergeNet.py:68-207) ----------------------------------------------------
  * DPC-KNN without the N x N distance matrix: x float [B, N, 128] (LayerNorm output), distances = sqrt(sum of squared
  * differences) / sqrt(C), k = 5 neighbours.                                                                                    */
-/* x float [rows, 128] -> planes bf16 [3][rows][128] (three bf16 parts per value: 24 bits) and norms [rows] = |x|^2              */
-int dml_dpc_split(const float* x, long long rows, int C, void* planes, float* norms, void* stream);
-/* Tiled N x N distances on the tensor cores (mma.sync, 6 MMAs per product), nothing of size N x N is written:
+/* x float [rows, 128] -> planes fp16 [2][rows][128] (hi / lo parts of x * s, s = the power of two that puts amax[0] = max |x|
+ * (device scalar) at 2^12: 22 bits), norms [rows] = |x|^2, inv_scale2[0] = 1 / s^2                                               */
+int dml_dpc_split(const float* x, const float* amax, long long rows, int C, void* planes, float* norms, float* inv_scale2, void* stream);
+/* Tiled N x N distances on the tensor cores (mma.sync on fp16 pairs, 3 MMAs per product), nothing of size N x N is written:
  * density [B, N] = exp(-mean of the 5 smallest d^2) + 1e-6 noise (:98-104); rowmax2 [B, N] = max_j (d sqrt(C))^2                */
-int dml_dpc_density(const void* planes, const float* norms, const float* noise, int B, int N, int C, float* density, float* rowmax2,
-                    void* stream);
+int dml_dpc_density(const void* planes, const float* norms, const float* inv_scale2, const float* noise, int B, int N, int C, float* density,
+                    float* rowmax2, void* stream);
 /* parent [B, N] = min(dist_max[b], min over tokens of higher density of d) (:111-114)                                          */
-int dml_dpc_parent(const void* planes, const float* norms, const float* density, const float* dist_max, int B, int N, int C, float* parent,
-                   void* stream);
+int dml_dpc_parent(const void* planes, const float* norms, const float* inv_scale2, const float* density, const float* dist_max, int B, int N,
+                   int C, float* parent, void* stream);
 /* idx [B, N] (int64) = index of the nearest of the K centre tokens centres [B, K] (int64) (:121-123)                            */
 int dml_dpc_assign(const float* x, const long long* centres, int B, int N, int C, int K, long long* idx, void* stream);
-/* merge_tokens (:133-166): merged [B, K, C] = sum_{i in c} x_i w_i / W_c, all_w [B, K] = W_c = sum w_i + 1e-6; and the adjoint   */
-int dml_merge_fwd(const float* x, const float* w, const long long* idx, int B, int N, int C, int K, float* merged, float* all_w,
+/* merge_tokens (:133-166): merged [B, K, C] = sum_{i in c} x_i w_i / W_c, all_w [B, K] = W_c = sum w_i + 1e-6 (per-chunk partials
+ * in ws: float [dml_merge_ws_floats(B, N, K)], summed in a fixed order); and the adjoint                                          */
+long long dml_merge_ws_floats(int B, int N, int K);
+int dml_merge_fwd(const float* x, const float* w, const long long* idx, int B, int N, int C, int K, float* ws, float* merged, float* all_w,
                   void* stream);
 int dml_merge_bwd(const float* dmerged, const float* x, const float* w, const long long* idx, const float* merged, const float* all_w,
                   int B, int N, int C, int K, float* dx, float* dw, void* stream);
