@@ -78,7 +78,7 @@ class DeformCrossAttn2DFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do, dattn, dvgrid):
         (x1f, x2f, Wqf, Wkf, Wvf, wdw, bdw, w2, W1, b1, W2, b2, W3, b3, q, vs, kvf, k, v, attn) = ctx.saved_tensors
-        side, ks, stride, offset_scale, keep_scale, hk = ctx.cfg
+        side_len, ks, stride, offset_scale, keep_scale, hk = ctx.cfg
         keep = ctx.keep
         lib = _lib.load()
         B, n, _ = x1f.shape
@@ -93,23 +93,32 @@ class DeformCrossAttn2DFn(torch.autograd.Function):
         parts = torch.empty(lib.dml_da2_cols_chunks(B, n, m), 2, B, m, 512, device=dev, dtype=F32)
         call("dml_da2_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(attn), ptr(do), ptr(dA) if dA is not None else None,
              ptr(keep) if keep is not None else None, keep_scale, B, n, m, 64 ** -0.5, ptr(ds), ptr(dq), ptr(parts), ptr(dkv), st)
+        # keys / values -> gathered features: small launches that only need dk / dv, on the auxiliary stream next to the
+        # position-bias backward (buffers are allocated on the main stream first)
+        from .ops import side_stream
+        dkvf = torch.empty(B, m, 128, device=dev, dtype=F32)
+        dx2 = torch.zeros(B, n, 128, device=dev, dtype=F32)
+        kparts = [torch.empty(lib.dml_da2_gproj_parts(B * m), 8192, device=dev, dtype=F32) for _ in range(2)]
+        dWk, dWv = torch.empty(512, 16, device=dev, dtype=F32), torch.empty(512, 16, device=dev, dtype=F32)
+        cur, side = torch.cuda.current_stream(), side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            s2 = stream()
+            call("dml_da2_gproj_bwd", ptr(dkv[0]), ptr(kvf), ptr(Wkf), B * m, 0, ptr(dkvf), ptr(kparts[0]), ptr(dWk), s2)
+            call("dml_da2_gproj_bwd", ptr(dkv[1]), ptr(kvf), ptr(Wvf), B * m, 1, ptr(dkvf), ptr(kparts[1]), ptr(dWv), s2)
         # position-bias MLP: parameter gradients and the gradient at the sampling positions
         dvs = torch.zeros(B * 8, m, 2, device=dev, dtype=F32)
-        bparts = torch.empty(lib.dml_da2_bias_bwd_parts(B, side), BIAS_GRAD_FLOATS, device=dev, dtype=F32)
+        bparts = torch.empty(lib.dml_da2_bias_bwd_parts(B, side_len), BIAS_GRAD_FLOATS, device=dev, dtype=F32)
         bg = torch.empty(BIAS_GRAD_FLOATS, device=dev, dtype=F32)
-        call("dml_da2_bias_bwd", ptr(vs), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(W3), ptr(ds), B, side, m, ptr(bparts), ptr(bg), ptr(dvs), st)
-        # keys / values -> gathered features -> x2 and the sampling positions
-        dkvf = torch.empty(B, m, 128, device=dev, dtype=F32)
-        dWk = _gproj_bwd(dkv[0], kvf, Wkf, B * m, dkvf, False)
-        dWv = _gproj_bwd(dkv[1], kvf, Wvf, B * m, dkvf, True)
-        dx2 = torch.zeros(B, n, 128, device=dev, dtype=F32)
-        call("dml_da2_gather_bwd", ptr(dkvf), ptr(x2f), ptr(vs), B, side, m, ptr(dx2), ptr(dvs), st)
+        call("dml_da2_bias_bwd", ptr(vs), ptr(W1), ptr(b1), ptr(W2), ptr(b2), ptr(W3), ptr(ds), B, side_len, m, ptr(bparts), ptr(bg), ptr(dvs), st)
+        cur.wait_stream(side)
+        call("dml_da2_gather_bwd", ptr(dkvf), ptr(x2f), ptr(vs), B, side_len, m, ptr(dx2), ptr(dvs), st)
         # offset net (adds its share to dq), then the query projection
         dconv = torch.empty(B * 8, m, 64, device=dev, dtype=F32)
-        oparts = torch.empty(lib.dml_da2_offsets_parts(B, side, ks, stride), OFF_GRAD_FLOATS, device=dev, dtype=F32)
+        oparts = torch.empty(lib.dml_da2_offsets_parts(B, side_len, ks, stride), OFF_GRAD_FLOATS, device=dev, dtype=F32)
         og = torch.empty(OFF_GRAD_FLOATS, device=dev, dtype=F32)
         dvg = dvgrid.contiguous().float() if dvgrid is not None else None
-        call("dml_da2_offsets_bwd", ptr(q), ptr(wdw), ptr(bdw), ptr(w2), ptr(dvs), ptr(dvg) if dvg is not None else None, B, side, ks,
+        call("dml_da2_offsets_bwd", ptr(q), ptr(wdw), ptr(bdw), ptr(w2), ptr(dvs), ptr(dvg) if dvg is not None else None, B, side_len, ks,
              stride, offset_scale, ptr(dconv), ptr(oparts), ptr(og), ptr(dq), st)
         dx1 = torch.empty(B, n, 128, device=dev, dtype=F32)
         dWq = _gproj_bwd(dq, x1f, Wqf, B * n, dx1, False)
