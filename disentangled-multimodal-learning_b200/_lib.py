@@ -89,9 +89,10 @@ SIGNATURES = {
     "dml_da2_bias_fwd": (_i, [_fp] * 7 + [_i, _i, _i, _fp, _vp]),
     "dml_da2_bias_bwd_parts": (_i, [_i, _i]),
     "dml_da2_bias_bwd": (_i, [_fp] * 7 + [_i, _i, _i, _fp, _fp, _fp, _vp]),
-    "dml_da2_attn_fwd": (_i, [_fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _fp, _vp]),
+    "dml_da2_attn_ws_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "dml_da2_attn_fwd": (_i, [_fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _vp, _fp, _vp]),
     "dml_da2_cols_chunks": (_i, [_i, _i, _i]),
-    "dml_da2_attn_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _fp, _fp, _fp, _fp, _vp]),
+    "dml_da2_attn_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _fp, _vp, _f, _i, _i, _i, _f, _vp, _fp, _fp, _fp, _fp, _vp]),
     "dml_dpc_split": (_i, [_fp, _fp, _ll, _i, _vp, _fp, _fp, _vp]),
     "dml_dpc_density": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _fp, _fp, _vp]),
     "dml_dpc_parent": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _fp, _vp]),
@@ -218,7 +219,7 @@ KERNELS_PER_CALL = {
     "dml_linear3_fwd": 1, "dml_linear3_bwd": 1,
     "dml_ny_pinv_init_fwd": 2, "dml_ny_pinv_init_bwd": 2, "dml_gram_fwd": 1, "dml_rows_mix": 1,
     "dml_coattn_fq_fwd": 2, "dml_coattn_fq_bwd": 1, "dml_coattn_fk_fwd": 1, "dml_coattn_fk_bwd": 1,
-    "dml_da2_gproj_bwd": 3, "dml_da2_offsets_bwd": 3, "dml_da2_bias_bwd": 2, "dml_da2_attn_bwd": 3, "dml_merge_fwd": 2,
+    "dml_da2_gproj_bwd": 3, "dml_da2_offsets_bwd": 3, "dml_da2_bias_bwd": 2, "dml_da2_attn_bwd": 5, "dml_da2_attn_fwd": 3, "dml_merge_fwd": 2,
 }
 launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events

@@ -1,5 +1,5 @@
-// DeformCrossAttention2D (models/DeformableAttention2D.py:162-342): everything around the position-bias MLP
-// (which lives in deform2d_bias.cu).  All tensors token-major fp32:
+// DeformCrossAttention2D (models/DeformableAttention2D.py:162-342): projections, offset net and bilinear gather
+// (the position-bias MLP lives in deform2d_bias.cu, the attention core in deform2d_attn.cu).  All tensors token-major fp32:
 //   x1, x2 [B, n, 128] (n = side^2), q [B, n, 512], kvf [B, m, 128], k / v [B, m, 512] (m = hk^2), attn [B, 8, n, m].
 // The module is built for the one configuration the reference constructs (Modules.py:107-126, DeformCrossTransMIL.py:45-54):
 // dim 128, 8 heads = 8 offset groups, dim_head 64, grouped 1x1 projections (16 -> 64 channels per group).
@@ -399,294 +399,6 @@ __global__ void gather_bwd_kernel(const float* __restrict__ dkvf, const float* _
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// attention rows (:290-321): s = scale q.k + bias -> softmax -> attn, o = dropout(attn) v.   One warp = 4 query rows;
-// keys stream through shared memory in tiles of 32 (lane = key for the dot products, lane = 2 channels for the aggregation)
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kRowsPerWarp = 4, kRowsPerCta = 32, kKT = 32;
-
-struct RowSmem {
-  float kv[kKT * 65];                        // key / value tile, row stride 65
-  float qrow[8][kRowsPerWarp][64];           // per warp: its query rows (forward: q, backward pass 1: dO)
-  float prow[8][kRowsPerWarp][kKT];          // per warp: probabilities / dS of the current tile
-};
-
-__device__ __forceinline__ void load_kv_tile(float* dst, const float* __restrict__ src, int b, int h, int j0, int m) {
-  // src [B, m, 512]; rows j0 .. j0+31 of head h -> dst[row*65 + c]; rows beyond m are zero
-  for (int i = threadIdx.x; i < kKT * 16; i += 256) {
-    const int r = i >> 4, c4 = i & 15;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j0 + r < m) v = *reinterpret_cast<const float4*>(src + ((size_t)b * m + j0 + r) * kC + h * 64 + c4 * 4);
-    float* d = dst + r * 65 + c4 * 4;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-  }
-}
-
-// dots of the warp's 4 staged rows with key `lane` of the tile
-__device__ __forceinline__ void row_dots(const float (*rows)[64], const float* kv, int lane, float (&s)[kRowsPerWarp]) {
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) s[r] = 0.f;
-  const float* kr = kv + lane * 65;
-#pragma unroll 4
-  for (int c = 0; c < 64; c += 4) {
-    const float k0 = kr[c], k1 = kr[c + 1], k2 = kr[c + 2], k3 = kr[c + 3];
-#pragma unroll
-    for (int r = 0; r < kRowsPerWarp; ++r) {
-      const float4 qv = *reinterpret_cast<const float4*>(&rows[r][c]);
-      s[r] += qv.x * k0 + qv.y * k1 + qv.z * k2 + qv.w * k3;
-    }
-  }
-}
-
-// acc[r] (channels 2*lane, 2*lane+1) += sum_j p[r][j] kv[j][channels]
-__device__ __forceinline__ void row_accum(const float (*p)[kKT], const float* kv, int lane, float2 (&acc)[kRowsPerWarp]) {
-#pragma unroll 2
-  for (int j = 0; j < kKT; j += 4) {
-    float2 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = make_float2(kv[(j + u) * 65 + 2 * lane], kv[(j + u) * 65 + 2 * lane + 1]);
-#pragma unroll
-    for (int r = 0; r < kRowsPerWarp; ++r) {
-      const float4 pv = *reinterpret_cast<const float4*>(&p[r][j]);
-      acc[r].x += pv.x * v[0].x + pv.y * v[1].x + pv.z * v[2].x + pv.w * v[3].x;
-      acc[r].y += pv.x * v[0].y + pv.y * v[1].y + pv.z * v[2].y + pv.w * v[3].y;
-    }
-  }
-}
-
-// attn: in = position bias [B, 8, n, m], out = softmax probabilities.  keep (may be NULL): dropout keep-mask bytes.
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                                       float* __restrict__ attn, const unsigned char* __restrict__ keep, float keep_scale,
-                                                       int n, int m, float scale, float* __restrict__ o) {
-  __shared__ __align__(16) RowSmem S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y >> 3, h = blockIdx.y & 7;
-  const int i0 = blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;
-  for (int r = 0; r < kRowsPerWarp; ++r) {
-    const int i = min(i0 + r, n - 1);
-    const float2 qv = *reinterpret_cast<const float2*>(q + ((size_t)b * n + i) * kC + h * 64 + 2 * lane);
-    S.qrow[warp][r][2 * lane] = qv.x * scale;
-    S.qrow[warp][r][2 * lane + 1] = qv.y * scale;
-  }
-  const size_t arow = ((size_t)(b * 8 + h) * n) * m;
-  float mx[kRowsPerWarp];
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) mx[r] = -INFINITY;
-  // pass 1: raw scores into the attn buffer, running maximum
-  for (int j0 = 0; j0 < m; j0 += kKT) {
-    __syncthreads();
-    load_kv_tile(S.kv, k, b, h, j0, m);
-    __syncthreads();
-    float s[kRowsPerWarp];
-    row_dots(S.qrow[warp], S.kv, lane, s);
-    if (j0 + lane < m) {
-#pragma unroll
-      for (int r = 0; r < kRowsPerWarp; ++r) {
-        if (i0 + r < n) {
-          float* a = attn + arow + (size_t)(i0 + r) * m + j0 + lane;
-          const float sv = s[r] + *a;
-          *a = sv;
-          mx[r] = fmaxf(mx[r], sv);
-        }
-      }
-    }
-  }
-  float inv[kRowsPerWarp];
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) {
-    mx[r] = warp_max(mx[r]);
-    float sum = 0.f;
-    if (i0 + r < n)
-      for (int j = lane; j < m; j += 32) sum += __expf(attn[arow + (size_t)(i0 + r) * m + j] - mx[r]);
-    inv[r] = 1.f / warp_sum(sum);
-  }
-  // pass 2: probabilities out, aggregation of the values
-  float2 acc[kRowsPerWarp];
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) acc[r] = make_float2(0.f, 0.f);
-  for (int j0 = 0; j0 < m; j0 += kKT) {
-    __syncthreads();
-    load_kv_tile(S.kv, v, b, h, j0, m);
-#pragma unroll
-    for (int r = 0; r < kRowsPerWarp; ++r) {
-      float p = 0.f;
-      if (i0 + r < n && j0 + lane < m) {
-        const size_t at = arow + (size_t)(i0 + r) * m + j0 + lane;
-        p = __expf(attn[at] - mx[r]) * inv[r];
-        attn[at] = p;
-        if (keep) p = keep[at] ? p * keep_scale : 0.f;
-      }
-      S.prow[warp][r][lane] = p;
-    }
-    __syncthreads();
-    row_accum(S.prow[warp], S.kv, lane, acc);
-  }
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r)
-    if (i0 + r < n) *reinterpret_cast<float2*>(o + ((size_t)b * n + i0 + r) * kC + h * 64 + 2 * lane) = acc[r];
-}
-
-// Backward over the rows: dP = (dO . v) * keep + dA, D = sum P dP, dS = P (dP - D) -> ds [B, 8, n, m]; dq = scale dS k.
-__global__ void __launch_bounds__(256) attn_bwd_rows_kernel(const float* __restrict__ k, const float* __restrict__ v,
-                                                            const float* __restrict__ attn, const float* __restrict__ dO,
-                                                            const float* __restrict__ dA, const unsigned char* __restrict__ keep,
-                                                            float keep_scale, int n, int m, float scale, float* __restrict__ ds,
-                                                            float* __restrict__ dq) {
-  __shared__ __align__(16) RowSmem S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y >> 3, h = blockIdx.y & 7;
-  const int i0 = blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;
-  for (int r = 0; r < kRowsPerWarp; ++r) {
-    const int i = min(i0 + r, n - 1);
-    const float2 g = *reinterpret_cast<const float2*>(dO + ((size_t)b * n + i) * kC + h * 64 + 2 * lane);
-    S.qrow[warp][r][2 * lane] = g.x;
-    S.qrow[warp][r][2 * lane + 1] = g.y;
-  }
-  const size_t arow = ((size_t)(b * 8 + h) * n) * m;
-  float D[kRowsPerWarp];
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) D[r] = 0.f;
-  for (int j0 = 0; j0 < m; j0 += kKT) {
-    __syncthreads();
-    load_kv_tile(S.kv, v, b, h, j0, m);
-    __syncthreads();
-    float s[kRowsPerWarp];
-    row_dots(S.qrow[warp], S.kv, lane, s);
-    if (j0 + lane < m) {
-#pragma unroll
-      for (int r = 0; r < kRowsPerWarp; ++r) {
-        if (i0 + r < n) {
-          const size_t at = arow + (size_t)(i0 + r) * m + j0 + lane;
-          float dp = s[r];
-          if (keep) dp = keep[at] ? dp * keep_scale : 0.f;
-          if (dA) dp += dA[at];
-          ds[at] = dp;
-          D[r] += attn[at] * dp;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) D[r] = warp_sum(D[r]);
-  float2 acc[kRowsPerWarp];
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r) acc[r] = make_float2(0.f, 0.f);
-  for (int j0 = 0; j0 < m; j0 += kKT) {
-    __syncthreads();
-    load_kv_tile(S.kv, k, b, h, j0, m);
-#pragma unroll
-    for (int r = 0; r < kRowsPerWarp; ++r) {
-      float g = 0.f;
-      if (i0 + r < n && j0 + lane < m) {
-        const size_t at = arow + (size_t)(i0 + r) * m + j0 + lane;
-        g = attn[at] * (ds[at] - D[r]);
-        ds[at] = g;
-      }
-      S.prow[warp][r][lane] = g;
-    }
-    __syncthreads();
-    row_accum(S.prow[warp], S.kv, lane, acc);
-  }
-#pragma unroll
-  for (int r = 0; r < kRowsPerWarp; ++r)
-    if (i0 + r < n)
-      *reinterpret_cast<float2*>(dq + ((size_t)b * n + i0 + r) * kC + h * 64 + 2 * lane) = make_float2(acc[r].x * scale, acc[r].y * scale);
-}
-
-// Backward over the columns: dv[j] = sum_i (P keep)_ij dO_i, dk[j] = scale sum_i dS_ij q_i.  CTA = 32 keys x one query chunk, a
-// thread = 4 keys x 4 channels of both products for half of the rows of a 32-query tile (4 LDS.128 per 32 FMAs);
-// parts[chunk][2][B, m, 512] holds dk and dv of the chunk (summed afterwards by reduce_parts).
-__global__ void __launch_bounds__(256) attn_bwd_cols_kernel(const float* __restrict__ q, const float* __restrict__ attn,
-                                                            const float* __restrict__ ds, const float* __restrict__ dO,
-                                                            const unsigned char* __restrict__ keep, float keep_scale, int n, int m,
-                                                            int B, float scale, int chunk_rows, float* __restrict__ parts) {
-  __shared__ __align__(16) float qs[32][68], gs[32][68];
-  __shared__ __align__(16) float ps[32][36], ss[32][36];              // [query][key]
-  const int b = blockIdx.y >> 3, h = blockIdx.y & 7;
-  const int j0 = blockIdx.x * 32;
-  const int half = threadIdx.x >> 7, tl = threadIdx.x & 127;
-  const int kq = (tl >> 4) * 4, cq = (tl & 15) * 4;                     // 4 keys x 4 channels
-  const int i_begin = blockIdx.z * chunk_rows, i_end = min(n, i_begin + chunk_rows);
-  const size_t arow = ((size_t)(b * 8 + h) * n) * m;
-  float ak[4][4], av[4][4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int w = 0; w < 4; ++w) ak[u][w] = av[u][w] = 0.f;
-  for (int it = i_begin; it < i_end; it += 32) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
-      const int r = i >> 4, c4 = i & 15;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
-      if (it + r < i_end) {
-        a = *reinterpret_cast<const float4*>(q + ((size_t)b * n + it + r) * kC + h * 64 + c4 * 4);
-        g = *reinterpret_cast<const float4*>(dO + ((size_t)b * n + it + r) * kC + h * 64 + c4 * 4);
-      }
-      *reinterpret_cast<float4*>(&qs[r][c4 * 4]) = a;
-      *reinterpret_cast<float4*>(&gs[r][c4 * 4]) = g;
-    }
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-      const int r = i >> 5, c = i & 31;
-      float p = 0.f, s = 0.f;
-      if (it + r < i_end && j0 + c < m) {
-        const size_t at = arow + (size_t)(it + r) * m + j0 + c;
-        p = attn[at];
-        if (keep) p = keep[at] ? p * keep_scale : 0.f;
-        s = ds[at];
-      }
-      ps[r][c] = p;
-      ss[r][c] = s;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = half * 16 + rr;
-      const float4 p4 = *reinterpret_cast<const float4*>(&ps[r][kq]), s4 = *reinterpret_cast<const float4*>(&ss[r][kq]);
-      const float4 g4 = *reinterpret_cast<const float4*>(&gs[r][cq]), q4 = *reinterpret_cast<const float4*>(&qs[r][cq]);
-      const float pv[4] = {p4.x, p4.y, p4.z, p4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        av[u][0] += pv[u] * g4.x; av[u][1] += pv[u] * g4.y; av[u][2] += pv[u] * g4.z; av[u][3] += pv[u] * g4.w;
-        ak[u][0] += sv[u] * q4.x; ak[u][1] += sv[u] * q4.y; ak[u][2] += sv[u] * q4.z; ak[u][3] += sv[u] * q4.w;
-      }
-    }
-  }
-  // combine the two row halves through shared memory (fixed order), then write the chunk's partial
-  __syncthreads();
-  float* red = &qs[0][0];                                             // 32 x 68 floats >= 128 threads x 16
-  float* red2 = &gs[0][0];
-  if (half == 1) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        red[(u * 4 + w) * 128 + tl] = ak[u][w];
-        red2[(u * 4 + w) * 128 + tl] = av[u][w];
-      }
-  }
-  __syncthreads();
-  if (half == 0) {
-    const size_t plane = (size_t)B * m * kC;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (j0 + kq + u < m) {
-        float* o = parts + (size_t)blockIdx.z * 2 * plane + ((size_t)b * m + j0 + kq + u) * kC + h * 64 + cq;
-        float4 vk, vv;
-        vk.x = (ak[u][0] + red[(u * 4 + 0) * 128 + tl]) * scale;
-        vk.y = (ak[u][1] + red[(u * 4 + 1) * 128 + tl]) * scale;
-        vk.z = (ak[u][2] + red[(u * 4 + 2) * 128 + tl]) * scale;
-        vk.w = (ak[u][3] + red[(u * 4 + 3) * 128 + tl]) * scale;
-        vv.x = av[u][0] + red2[(u * 4 + 0) * 128 + tl];
-        vv.y = av[u][1] + red2[(u * 4 + 1) * 128 + tl];
-        vv.z = av[u][2] + red2[(u * 4 + 2) * 128 + tl];
-        vv.w = av[u][3] + red2[(u * 4 + 3) * 128 + tl];
-        *reinterpret_cast<float4*>(o) = vk;
-        *reinterpret_cast<float4*>(o + plane) = vv;
-      }
-    }
-  }
-}
-
 inline int grid_for(long long items, int per_cta, int cap) {
   long long g = (items + per_cta - 1) / per_cta;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -780,36 +492,6 @@ int dml_da2_gather_bwd(const float* dkvf, const float* x2, const float* vs, int 
   DML_CHECK_ARG(dkvf && x2 && vs && dx2 && dvs && B > 0 && side > 0 && m > 0);
   const long long total = (long long)B * m * 32;
   gather_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dkvf, x2, vs, B, side, m, dx2, dvs);
-  DML_RETURN_LAUNCH();
-}
-
-int dml_da2_attn_fwd(const float* q, const float* k, const float* v, float* attn, const unsigned char* keep, float keep_scale, int B, int n,
-                     int m, float scale, float* o, void* stream) {
-  DML_CHECK_ARG(q && k && v && attn && o && B > 0 && n > 0 && m > 0 && B * 8 <= 65535);
-  attn_fwd_kernel<<<dim3(cdiv(n, kRowsPerCta), B * 8), 256, 0, (cudaStream_t)stream>>>(q, k, v, attn, keep, keep_scale, n, m, scale, o);
-  DML_RETURN_LAUNCH();
-}
-
-int dml_da2_cols_chunks(int B, int n, int m) {
-  const int base = B * 8 * cdiv(m, 32);
-  int chunks = cdiv(148 * 8, base);
-  const int max_chunks = cdiv(n, 64);
-  if (chunks > max_chunks) chunks = max_chunks;
-  return chunks < 1 ? 1 : chunks;
-}
-
-/* ds: float [B, 8, n, m] (out: dS); dq [B, n, 512]; dkv [2][B, m, 512] = dk, dv; parts: float [chunks][2][B, m, 512] */
-int dml_da2_attn_bwd(const float* q, const float* k, const float* v, const float* attn, const float* dO, const float* dA,
-                     const unsigned char* keep, float keep_scale, int B, int n, int m, float scale, float* ds, float* dq, float* parts,
-                     float* dkv, void* stream) {
-  DML_CHECK_ARG(q && k && v && attn && dO && ds && dq && parts && dkv && B > 0 && n > 0 && m > 0 && B * 8 <= 65535);
-  cudaStream_t st = (cudaStream_t)stream;
-  attn_bwd_rows_kernel<<<dim3(cdiv(n, kRowsPerCta), B * 8), 256, 0, st>>>(k, v, attn, dO, dA, keep, keep_scale, n, m, scale, ds, dq);
-  const int chunks = dml_da2_cols_chunks(B, n, m);
-  const int chunk_rows = cdiv(cdiv(n, chunks), 32) * 32;
-  attn_bwd_cols_kernel<<<dim3(cdiv(m, 32), B * 8, chunks), 256, 0, st>>>(q, attn, ds, dO, keep, keep_scale, n, m, B, scale, chunk_rows, parts);
-  const long long len = (long long)B * m * 1024;
-  reduce_parts_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(parts, chunks, len, dkv, 0);
   DML_RETURN_LAUNCH();
 }
 

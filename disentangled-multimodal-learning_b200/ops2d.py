@@ -67,8 +67,9 @@ class DeformCrossAttn2DFn(torch.autograd.Function):
             keep = (torch.rand(B, 8, n, m, device=dev) >= drop_p).to(torch.uint8)
             keep_scale = 1.0 / (1.0 - drop_p)
         o = torch.empty(B, n, 512, device=dev, dtype=F32)
+        ws = torch.empty(_lib.load().dml_da2_attn_ws_bytes(B, n, m, 0), device=dev, dtype=torch.uint8)
         call("dml_da2_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(attn), ptr(keep) if keep is not None else None, keep_scale, B, n, m,
-             64 ** -0.5, ptr(o), st)
+             64 ** -0.5, ptr(ws), ptr(o), st)
         ctx.set_materialize_grads(False)
         ctx.cfg = (side, ks, stride, float(offset_scale), keep_scale, hk)
         ctx.keep = keep
@@ -91,8 +92,9 @@ class DeformCrossAttn2DFn(torch.autograd.Function):
         dq = torch.empty(B, n, 512, device=dev, dtype=F32)
         dkv = torch.empty(2, B, m, 512, device=dev, dtype=F32)
         parts = torch.empty(lib.dml_da2_cols_chunks(B, n, m), 2, B, m, 512, device=dev, dtype=F32)
+        ws = torch.empty(lib.dml_da2_attn_ws_bytes(B, n, m, 1), device=dev, dtype=torch.uint8)
         call("dml_da2_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(attn), ptr(do), ptr(dA) if dA is not None else None,
-             ptr(keep) if keep is not None else None, keep_scale, B, n, m, 64 ** -0.5, ptr(ds), ptr(dq), ptr(parts), ptr(dkv), st)
+             ptr(keep) if keep is not None else None, keep_scale, B, n, m, 64 ** -0.5, ptr(ws), ptr(ds), ptr(dq), ptr(parts), ptr(dkv), st)
         # keys / values -> gathered features: small launches that only need dk / dv, on the auxiliary stream next to the
         # position-bias backward (buffers are allocated on the main stream first)
         from .ops import side_stream

@@ -362,16 +362,18 @@ int dml_da2_bias_bwd_parts(int B, int side);                   /* parts: float [
 /* ds = gradient at the bias (= dS); dvs [(B 8), m, 2] (zeroed by the caller) += (atomics)                                        */
 int dml_da2_bias_bwd(const float* vs, const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* ds,
                      int B, int side, int m, float* parts, float* grads, float* dvs, void* stream);
-/* attention rows (:290-321).  attn: in = the position bias, out = softmax(scale q k^T + bias).  keep (may be NULL): dropout
- * keep-mask bytes [B, 8, n, m] applied (x keep_scale) to the aggregation only (:316).  o [B, n, 512].                            */
+/* attention core on the tensor cores (:290-321; csrc/deform2d_attn.cu: mma.sync on three bf16 parts per operand).  attn: in = the
+ * position bias, out = softmax(scale q k^T + bias).  keep (may be NULL): dropout keep-mask bytes [B, 8, n, m] applied (x keep_scale)
+ * to the aggregation only (:316).  o [B, n, 512].  ws: dml_da2_attn_ws_bytes(B, n, m, backward) bytes of scratch (bf16 planes).   */
+size_t dml_da2_attn_ws_bytes(int B, int n, int m, int backward);
 int dml_da2_attn_fwd(const float* q, const float* k, const float* v, float* attn, const unsigned char* keep, float keep_scale, int B, int n,
-                     int m, float scale, float* o, void* stream);
+                     int m, float scale, void* ws, float* o, void* stream);
 int dml_da2_cols_chunks(int B, int n, int m);                  /* parts: float [dml_da2_cols_chunks()][2][B, m, 512]             */
 /* dO [B, n, 512], dA (may be NULL) = gradient that reached the returned attention map.  ds [B, 8, n, m] out = dS (also the
  * gradient of the bias); dq [B, n, 512] out; dkv [2][B, m, 512] out = dk, dv.                                                   */
 int dml_da2_attn_bwd(const float* q, const float* k, const float* v, const float* attn, const float* dO, const float* dA,
-                     const unsigned char* keep, float keep_scale, int B, int n, int m, float scale, float* ds, float* dq, float* parts,
-                     float* dkv, void* stream);
+                     const unsigned char* keep, float keep_scale, int B, int n, int m, float scale, void* ws, float* ds, float* dq,
+                     float* parts, float* dkv, void* stream);
 
 /* ---- ClusterMergeNet (csrc/cluster.cu; models/ClusterMergeNet.py:68-207) ----------------------------------------------------
  * DPC-KNN without the N x N distance matrix: x float [B, N, 128] (LayerNorm output), distances = sqrt(sum of squared

@@ -177,7 +177,8 @@ def test_attention_rows_and_columns(B, n, m, drop):
     attn = bias.clone()
     o = torch.empty(B, n, 512, device=DEV)
     scale = 64 ** -0.5
-    call("dml_da2_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(attn), ptr(keep) if drop else None, ks, B, n, m, scale, ptr(o), st())
+    ws = torch.empty(_lib.load().dml_da2_attn_ws_bytes(B, n, m, 1), device=DEV, dtype=torch.uint8)
+    call("dml_da2_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(attn), ptr(keep) if drop else None, ks, B, n, m, scale, ptr(ws), ptr(o), st())
     qr, kr, vr, br = (t.clone().requires_grad_() for t in (q, k, v, bias))
     hd = lambda t: t.reshape(B, -1, 8, 64).transpose(1, 2)
     sim = hd(qr) @ hd(kr).transpose(2, 3) * scale + br
@@ -194,7 +195,7 @@ def test_attention_rows_and_columns(B, n, m, drop):
     dkv = torch.empty(2, B, m, 512, device=DEV)
     parts = torch.empty(_lib.load().dml_da2_cols_chunks(B, n, m), 2, B, m, 512, device=DEV)
     call("dml_da2_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(attn), ptr(do), ptr(dA), ptr(keep) if drop else None, ks, B, n, m, scale,
-         ptr(ds), ptr(dq), ptr(parts), ptr(dkv), st())
+         ptr(ws), ptr(ds), ptr(dq), ptr(parts), ptr(dkv), st())
     H.assert_close(ds, gb, 1e-4, "dS")
     H.assert_close(dq, gq, 1e-4, "dq")
     H.assert_close(dkv[0], gk, 1e-4, "dk")
