@@ -65,7 +65,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
             and open(stamp).read().strip() == dig):
         return LIB
     prod = [(s_, [], "") for s_ in sources()]
-    test = [(s_, [], "") for s_ in test_sources()] + [(s_, ["-DDML_TEST_KNOBS"], "_knobs") for s_ in TEST_KNOB_SOURCES]
+    knobs = ["-DDML_TEST_KNOBS"] + (["-DDML_TRACE"] if os.environ.get("DML_B200_TRACE") else [])   # clock64() stamps for scripts/trace_dkv.py
+    test = [(s_, [], "") for s_ in test_sources()] + [(s_, knobs, "_knobs") for s_ in TEST_KNOB_SOURCES]
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs_all = list(ex.map(_compile, prod + test))
     objs, test_objs = objs_all[:len(prod)], objs_all[len(prod):]

@@ -51,31 +51,7 @@ def _mm_tokens(A, Bm, out, *, M, N, K, batch, reduce_into_2d=False, **kw):
     return out
 
 
-def pinv_forward(x_pair: Pair, x_f32: torch.Tensor, iters: int, B: int, H: int, m: int, save: bool):
-    """moore_penrose_iter_pinv (NystromAttention.py:20-35).  Returns (z pair, saved iterates)."""
-    bt = (B, H)
-    lib = _lib.load(check_device=True)
-    x_f32 = x_f32.contiguous()
-    sums = torch.empty(lib.dml_ny_pinv_init_sums_floats(B * H, m), device=x_f32.device, dtype=F32)
-    z = Pair.empty((B, H, m, m), x_f32.device)
-    # z0 = x^T / (max row abs-sum * max column abs-sum), both maxima GLOBAL over batch and heads (quirk T3): two launches
-    call("dml_ny_pinv_init_fwd", ptr(x_f32), B * H, m, ptr(sums), ptr(z.planes), z.planes.stride(0), stream())
-    saved = [sums]
-    with chain():        # the 4 x iters dependent products leave as chained cooperative launches (grid barrier between products)
-        for _ in range(iters):
-            xz_f, xz = pgemm(x_pair, z, M=m, N=m, K=m, b_trans=True, batch=bt, want_pair=True)
-            # t3 = 15 I - xz (7 I - xz) = 15 I - (7 xz - xz xz)
-            _, t3 = pgemm(xz, xz, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=-1.0, resid=xz_f, resid_scale=7.0, diag=15.0,
-                          want_f32=False, want_pair=True)
-            _, t5 = pgemm(xz, t3, M=m, N=m, K=m, b_trans=True, batch=bt, diag=13.0, want_f32=False, want_pair=True)
-            _, z_new = pgemm(z, t5, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=0.25, want_f32=False, want_pair=True)
-            if save:
-                saved.append((z, xz, t3, t5))
-            z = z_new
-    return z, saved
-
-
-PINV_BWD_TWO_STREAMS = os.environ.get("DML_B200_PINV_TWO_STREAMS", "1") != "0"
+PINV_TWO_STREAMS = os.environ.get("DML_B200_PINV_TWO_STREAMS", "1") != "0"
 
 
 def _tls_chain():
@@ -88,59 +64,139 @@ def CHAIN_DEFAULT_ON():
     return pairs.CHAIN_DEFAULT
 
 
+def _pinv_side(dev):
+    """The auxiliary stream for the independent products of a pseudo-inverse step (None: everything on the current stream -
+    the chained cooperative launches are one stream by construction)."""
+    from .ops import side_stream
+    if not PINV_TWO_STREAMS or getattr(_tls_chain(), "chain", None) is not None or CHAIN_DEFAULT_ON():
+        return None
+    return side_stream(dev)
+
+
+NY_BRANCH = os.environ.get("DML_B200_NY_BRANCH", "1") != "0"
+
+
+def _branch(dev):
+    from .ops import branch_stream
+    return branch_stream(dev) if NY_BRANCH else None
+
+
+class _on:
+    """Run the block on `s` (a no-op for None); ordering is the caller's business (events / wait_stream)."""
+
+    def __init__(self, s):
+        self.s = s
+
+    def __enter__(self):
+        if self.s is not None:
+            self.ctx = torch.cuda.stream(self.s)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.s is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+
+def pinv_forward(x_pair: Pair, x_f32: torch.Tensor, iters: int, B: int, H: int, m: int, save: bool):
+    """moore_penrose_iter_pinv (NystromAttention.py:20-35).  Returns (z pair, saved iterates).
+
+    One step z' = 1/4 z (13 I - P (15 I - P (7 I - P))), P = x z, is evaluated as
+        P = x z;   t3 = 15 I - (7 P - P P)  ||  Bz = z P;   z' = 13/4 z - 1/4 Bz t3
+    (z (13 I - P t3) = 13 z - (z P) t3): the same four products, but three deep instead of four - the two middle ones are
+    independent and run side by side on two streams (each occupies 64 of the 148 SMs).  Each product costs ~10 us of launch /
+    load / epilogue latency whatever its size, so the depth of the chain is what the pseudo-inverse costs."""
+    bt = (B, H)
+    lib = _lib.load(check_device=True)
+    x_f32 = x_f32.contiguous()
+    dev = x_f32.device
+    shape = (B, H, m, m)
+    sums = torch.empty(lib.dml_ny_pinv_init_sums_floats(B * H, m), device=dev, dtype=F32)
+    z = Pair.empty(shape, dev)
+    # z0 = x^T / (max row abs-sum * max column abs-sum), both maxima GLOBAL over batch and heads (quirk T3): two launches
+    call("dml_ny_pinv_init_fwd", ptr(x_f32), B * H, m, ptr(sums), ptr(z.planes), z.planes.stride(0), stream())
+    z_f = z.float()                                          # the 13/4 z term enters the last product's epilogue in fp32
+    saved = [sums]
+    with chain():        # DML_B200_PGEMM_CHAIN=1: the dependent products leave as chained cooperative launches instead
+        side = _pinv_side(dev)
+        cur = torch.cuda.current_stream()
+        for _ in range(iters):
+            xz_f, xz = pgemm(x_pair, z, M=m, N=m, K=m, b_trans=True, batch=bt, want_pair=True)
+            t3, zp = Pair.empty(shape, dev), Pair.empty(shape, dev)          # both allocated on the calling stream
+            if side is not None:
+                side.wait_stream(cur)
+            with _on(side):
+                pgemm(z, xz, M=m, N=m, K=m, b_trans=True, batch=bt, want_f32=False, pair_out=zp)                  # z P
+            # t3 = 15 I - xz (7 I - xz) = 15 I - (7 xz - xz xz)
+            pgemm(xz, xz, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=-1.0, resid=xz_f, resid_scale=7.0, diag=15.0,
+                  want_f32=False, pair_out=t3)
+            if side is not None:
+                cur.wait_stream(side)
+            z_f_new, z_new = pgemm(zp, t3, M=m, N=m, K=m, b_trans=True, batch=bt, alpha=-0.25, resid=z_f, resid_scale=3.25,
+                                   want_pair=True)
+            if save:
+                saved.append((z, xz, t3, zp))
+            z, z_f = z_new, z_f_new
+    return z, saved
+
+
 def pinv_backward(x_pair: Pair, x_f32: torch.Tensor, saved, G_f: torch.Tensor, G: Pair, B: int, H: int, m: int):
-    """Adjoint of pinv_forward: G = d z_final (fp32 + pair) -> d x (fp32 [B, H, m, m])."""
+    """Adjoint of pinv_forward: G = d z_final (fp32 + pair) -> d x (fp32 [B, H, m, m]).
+
+    Per step (z' = 13/4 z - 1/4 Bz t3, Bz = z P, t3 = 15 I - 7 P + P P, P = x z), eight products four deep on two streams:
+        main   a  dB  = -1/4 G t3^T        d  dP  = z^T dB              f  dP += P^T dt3 + dPe      h  G' = dz + x^T dP
+        side   b  dt3 = -1/4 Bz^T G        e  dPe = dt3 P^T - 7 dt3     c  dz  = 13/4 G + dB P^T    g  dx += dP z^T
+    (c waits for a, f for e, g for f, h for c).  Every buffer is allocated on the calling stream."""
     bt = (B, H)
     dx = None
     sums, saved = saved[0], saved[1:]
-    # Each step is 8 products of dependency depth 5: {dz, du4} | {dP, du2} | dP += | dP += , dPp | {dx, G}.  The second member of
-    # every independent pair goes to the auxiliary stream (each product occupies 64 of the 148 SMs), so the latency-bound chain is
-    # 5 launches deep per step instead of 8.  Outputs of the auxiliary-stream products are allocated on the main stream first.
-    from .ops import side_stream
     dev = x_f32.device
-    two_streams = PINV_BWD_TWO_STREAMS and getattr(_tls_chain(), "chain", None) is None and not CHAIN_DEFAULT_ON()
-    cur = torch.cuda.current_stream()
-    side = side_stream(dev) if two_streams else None
-
-    class _on_side:
-        def __enter__(self):
-            if side is not None:
-                side.wait_stream(cur)
-                self.ctx = torch.cuda.stream(side)
-                self.ctx.__enter__()
-            return self
-
-        def __exit__(self, *a):
-            if side is not None:
-                self.ctx.__exit__(*a)
-            return False
-
     shape = (B, H, m, m)
     with chain():
-        for (z, P, t3, t5) in reversed(saved):
-            # z' = 1/4 z t5
-            dz_f = torch.empty(shape, device=dev, dtype=F32)
-            with _on_side():
-                pgemm(G, t5, M=m, N=m, K=m, batch=bt, alpha=0.25, out=dz_f)                                # 1/4 G t5^T
-            _, du4 = pgemm(z, G, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-0.25, want_f32=False, want_pair=True)
-            # t5 = 13 I - P t3
-            dP = torch.empty(shape, device=dev, dtype=F32)
-            with _on_side():
-                pgemm(du4, t3, M=m, N=m, K=m, batch=bt, out=dP)                                            # du4 t3^T
-            du2_f, du2 = pgemm(P, du4, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, want_pair=True)   # -P^T du4
-            if side is not None:
-                cur.wait_stream(side)
-            # t3 = 15 I - (7 P - P P)  =>  dP += 7 du2 - du2 P^T - P^T du2
-            pgemm(du2, P, M=m, N=m, K=m, batch=bt, alpha=-1.0, resid=du2_f, resid_scale=7.0, out=dP, accumulate=True)
-            _, dPp = pgemm(P, du2, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-1.0, out=dP, accumulate=True,
-                           want_pair=True)
-            # P = x z
+        side = _pinv_side(dev)
+        cur = torch.cuda.current_stream()
+
+        def mark(s):
+            if side is None:
+                return None
+            ev = torch.cuda.Event()
+            ev.record(s)
+            return ev
+
+        def after(s, ev):
+            if ev is not None:
+                s.wait_event(ev)
+
+        for (z, P, t3, zp) in reversed(saved):
             first = dx is None
+            dB, dt3, dPp = Pair.empty(shape, dev), Pair.empty(shape, dev), Pair.empty(shape, dev)
+            dt3_f, dPe, dz_f, dP = (torch.empty(shape, device=dev, dtype=F32) for _ in range(4))
             if first:
                 dx = torch.empty(shape, device=dev, dtype=F32)
-            with _on_side():
-                pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=not first)                       # dP z^T
-            G_f, G = pgemm(x_pair, dPp, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dz_f, accumulate=True, want_pair=True)
+            if side is not None:
+                side.wait_stream(cur)
+            with _on(side):
+                pgemm(zp, G, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, alpha=-0.25, out=dt3_f, pair_out=dt3)      # b
+                pgemm(dt3, P, M=m, N=m, K=m, batch=bt, resid=dt3_f, resid_scale=-7.0, out=dPe)                              # e
+            ev_e = mark(side)
+            pgemm(G, t3, M=m, N=m, K=m, batch=bt, alpha=-0.25, want_f32=False, pair_out=dB)                                 # a
+            ev_a = mark(cur)
+            pgemm(z, dB, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dP)                                       # d
+            with _on(side):
+                after(side, ev_a)
+                pgemm(dB, P, M=m, N=m, K=m, batch=bt, resid=G_f, resid_scale=3.25, out=dz_f)                                # c
+            ev_c = mark(side)
+            after(cur, ev_e)
+            pgemm(P, dt3, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, resid=dPe, out=dP, accumulate=True,
+                  pair_out=dPp)                                                                                             # f
+            ev_f = mark(cur)
+            with _on(side):
+                after(side, ev_f)
+                pgemm(dPp, z, M=m, N=m, K=m, batch=bt, out=dx, accumulate=not first)                                        # g
+            after(cur, ev_c)
+            G_f, G = pgemm(x_pair, dPp, M=m, N=m, K=m, a_trans=True, b_trans=True, batch=bt, out=dz_f, accumulate=True,
+                           want_pair=True)                                                                                  # h
             if side is not None:
                 cur.wait_stream(side)          # the step's operands may be released / overwritten from here on
     # z0 = x^T / (max row-sum * max column-sum): the scalar couples all bags and heads; two launches, the chain's dx added in
@@ -196,15 +252,27 @@ class NystromAttnFn(torch.autograd.Function):
              ptr(lm.planes), lm.planes.stride(0), st)
         q_l, k_l = Pair(lm.planes[:, 0]), Pair(lm.planes[:, 1])
         bt = (B, H)
-        _, attn1 = pgemm(q_h, k_l, M=n_pad, N=m, K=d, batch=bt, softmax=1, want_f32=False, want_pair=True)      # :123,137
         attn2_f, attn2 = pgemm(q_l, k_l, M=m, N=m, K=d, batch=bt, softmax=1, want_pair=True)                    # :124,137
-        sim3, _ = pgemm(q_l, k_h, M=m, N=n_pad, K=d, batch=bt)                                                  # :125
-        attn3 = Pair.empty((B, H, m, n_pad), dev)
-        call("dml_ny_softmax_rows_fwd", ptr(sim3), B * H * m, n_pad, ptr(attn3.planes), attn3.planes.stride(0), st)
-        del sim3
-        z, saved = pinv_forward(attn2, attn2_f, iters, B, H, m, save=True)                                      # :138
+        # Two independent branches from here: the pseudo-inverse of attn2 - a chain of 18 small dependent products, ~10 us of
+        # latency each, on 64-128 SMs - and the token-sized kernels (attn1, sim3 -> attn3, attn3 @ v).  The second branch runs
+        # on an auxiliary stream next to the chain; its buffers are allocated here, on the calling stream, and live until the
+        # streams have joined.
+        attn1, attn3 = Pair.empty((B, H, n_pad, m), dev), Pair.empty((B, H, m, n_pad), dev)
+        sim3 = torch.empty(B, H, m, n_pad, device=dev, dtype=F32)
         T_f = torch.empty(B, H, m, d, device=dev, dtype=F32)
-        _mm_tokens(attn3, v_h, T_f, M=m, N=d, K=n_pad, batch=bt, b_trans=True)                                  # attn3 @ v
+        cur = torch.cuda.current_stream()
+        br = _branch(dev)
+        if br is not None:
+            br.wait_stream(cur)
+        with _on(br):
+            pgemm(q_h, k_l, M=n_pad, N=m, K=d, batch=bt, softmax=1, want_f32=False, pair_out=attn1)             # :123,137
+            pgemm(q_l, k_h, M=m, N=n_pad, K=d, batch=bt, out=sim3)                                              # :125
+            call("dml_ny_softmax_rows_fwd", ptr(sim3), B * H * m, n_pad, ptr(attn3.planes), attn3.planes.stride(0), stream())
+            _mm_tokens(attn3, v_h, T_f, M=m, N=d, K=n_pad, batch=bt, b_trans=True)                              # attn3 @ v
+        z, saved = pinv_forward(attn2, attn2_f, iters, B, H, m, save=True)                                      # :138
+        if br is not None:
+            cur.wait_stream(br)
+        del sim3
         T = Pair.from_f32(T_f)
         _, Wm = pgemm(z, T, M=m, N=d, K=m, b_trans=True, batch=bt, want_f32=False, want_pair=True)              # attn2_inv @ (.)
         agg = torch.empty(B, n_pad, W, device=dev, dtype=F32)
@@ -269,17 +337,26 @@ class NystromAttnFn(torch.autograd.Function):
         dZ_f, dZ = pgemm(dWm, T, M=m, N=m, K=d, batch=bt, want_pair=True)
         _, dT = pgemm(z, dWm, M=m, N=d, K=m, a_trans=True, b_trans=True, batch=bt, want_f32=False, want_pair=True)
         # T = attn3 v ; attn3 = softmax(q_l k^T)
-        dA3, _ = pgemm(dT, v_h, M=m, N=n_pad, K=d, batch=bt)
+        # the token-sized kernels below do not need the pseudo-inverse adjoint (a chain of 24 small dependent products): they run
+        # on the auxiliary stream next to it; buffers allocated here, on the calling stream, and released after the join
+        dA3 = torch.empty(B, H, m, n_pad, device=dev, dtype=F32)
         dS3 = Pair.empty((B, H, m, n_pad), dev)
-        call("dml_ny_softmax_rows_bwd", ptr(attn3.planes), attn3.planes.stride(0), ptr(dA3), B * H * m, n_pad, ptr(dS3.planes),
-             dS3.planes.stride(0), st)
-        del dA3
-        pgemm(attn3, dT, M=n_pad, N=d, K=m, a_trans=True, b_trans=True, batch=bt, out=acc_h[2], accumulate=True)
-        _mm_tokens(dS3, k_h, dl[0], M=m, N=d, K=n_pad, batch=bt, b_trans=True)
-        pgemm(dS3, q_l, M=n_pad, N=d, K=m, a_trans=True, b_trans=True, batch=bt, out=acc_h[1])
-        del dS3
+        cur = torch.cuda.current_stream()
+        br = _branch(dev)
+        if br is not None:
+            br.wait_stream(cur)
+        with _on(br):
+            pgemm(dT, v_h, M=m, N=n_pad, K=d, batch=bt, out=dA3)
+            call("dml_ny_softmax_rows_bwd", ptr(attn3.planes), attn3.planes.stride(0), ptr(dA3), B * H * m, n_pad, ptr(dS3.planes),
+                 dS3.planes.stride(0), stream())
+            pgemm(attn3, dT, M=n_pad, N=d, K=m, a_trans=True, b_trans=True, batch=bt, out=acc_h[2], accumulate=True)
+            _mm_tokens(dS3, k_h, dl[0], M=m, N=d, K=n_pad, batch=bt, b_trans=True)
+            pgemm(dS3, q_l, M=n_pad, N=d, K=m, a_trans=True, b_trans=True, batch=bt, out=acc_h[1])
         # pinv and sim2 = softmax(q_l k_l^T)
         dA2 = pinv_backward(attn2, attn2_f, saved, dZ_f, dZ, B, H, m)
+        if br is not None:
+            cur.wait_stream(br)
+        del dA3, dS3
         dS2_f = attn2_f * (dA2 - (dA2 * attn2_f).sum(-1, keepdim=True))
         dS2 = Pair.from_f32(dS2_f)
         pgemm(dS2, k_l, M=m, N=d, K=m, b_trans=True, batch=bt, out=dl[0], accumulate=True)

@@ -48,6 +48,16 @@ def side_stream(dev) -> torch.cuda.Stream:
     return _SIDE_STREAMS[key]
 
 
+def branch_stream(dev) -> torch.cuda.Stream:
+    """A second auxiliary stream of the CURRENT stream, distinct from side_stream(): NystromAttention runs its token-sized
+    kernels on it next to the latency-bound pseudo-inverse chain (which itself forks onto side_stream)."""
+    idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream, "branch")
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx)
+    return _SIDE_STREAMS[key]
+
+
 # largest dS^T scratch the backward may allocate per call (bytes); DML_B200_DS_WS_MAX_GB overrides, 0 disables it
 DS_WS_MAX_BYTES = int(float(os.environ.get("DML_B200_DS_WS_MAX_GB", "6")) * (1 << 30))
 
