@@ -13,7 +13,18 @@
 namespace dml {
 namespace hd {
 
-constexpr int kThreads = 128, kMaxD = 512;
+constexpr int kThreads = 512, kMaxD = 512;
+// The tower-head kernels are ONE CTA per bag on the critical path between the forward and the backward of the step: both
+// weight matrices ([nc + De, D]) are requested into (dynamic) shared memory by all threads at the top - one global-memory
+// latency instead of one per output unit - when they fit; otherwise they are read through the read-only cache as before.
+constexpr int kStageFloats = 48 * 1024;
+
+__device__ __forceinline__ bool stage_rows(float* stage, const float* __restrict__ W2, int nc, const float* __restrict__ Wp, int De, int D) {
+  if ((nc + De) * D > kStageFloats) return false;
+  for (int i = threadIdx.x; i < nc * D; i += kThreads) stage[i] = __ldg(W2 + i);
+  for (int i = threadIdx.x; i < De * D; i += kThreads) stage[nc * D + i] = __ldg(Wp + i);
+  return true;
+}
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -32,8 +43,10 @@ tower_head_fwd_kernel(const float* __restrict__ x, long long bag_stride, int D, 
                       float eps, const float* __restrict__ W2, const float* __restrict__ b2, int nc, const float* __restrict__ Wp,
                       const float* __restrict__ bp, int De, float* __restrict__ hn, float* __restrict__ stats,
                       float* __restrict__ logits, float* __restrict__ enc) {
+  extern __shared__ float stage[];
   __shared__ float h[kMaxD], red[kThreads / 32];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kThreads / 32;
+  const bool staged = stage_rows(stage, W2, nc, Wp, De, D);
   const float* xr = x + (size_t)b * bag_stride;
   float s = 0.f;
   for (int i = threadIdx.x; i < D; i += kThreads) { h[i] = xr[i]; s += h[i]; }
@@ -49,9 +62,14 @@ tower_head_fwd_kernel(const float* __restrict__ x, long long bag_stride, int D, 
   if (threadIdx.x == 0) { stats[2 * b] = mu; stats[2 * b + 1] = rs; }
   __syncthreads();
   for (int o = warp; o < nc + De; o += nw) {
-    const float* w = o < nc ? W2 + (size_t)o * D : Wp + (size_t)(o - nc) * D;
     float acc = 0.f;
-    for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(w + k), h[k], acc);
+    if (staged) {
+      const float* w = stage + o * D;
+      for (int k = lane; k < D; k += 32) acc = fmaf(w[k], h[k], acc);
+    } else {
+      const float* w = o < nc ? W2 + (size_t)o * D : Wp + (size_t)(o - nc) * D;
+      for (int k = lane; k < D; k += 32) acc = fmaf(__ldg(w + k), h[k], acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0) {
       if (o < nc) logits[(size_t)b * nc + o] = acc + __ldg(b2 + o);
@@ -67,8 +85,10 @@ tower_head_bwd_kernel(const float* __restrict__ x, long long bag_stride, int D, 
                       int nc, const float* __restrict__ Wp, int De, const float* __restrict__ hn, const float* __restrict__ stats,
                       const float* __restrict__ dlogits, const float* __restrict__ denc, float* __restrict__ dparams,
                       float* __restrict__ dx, long long dx_bag_stride) {
+  extern __shared__ float stage[];
   __shared__ float g[kMaxD], go[kMaxD + 16], red[kThreads / 32];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kThreads / 32;
+  const bool staged = stage_rows(stage, W2, nc, Wp, De, D);
   float* dlw = dparams;
   float* dlb = dlw + D;
   float* dW2 = dlb + D;
@@ -92,8 +112,12 @@ tower_head_bwd_kernel(const float* __restrict__ x, long long bag_stride, int D, 
     const int k = k0 + lane;
     if (k < D) {
       float s = 0.f;
-      for (int o = 0; o < nc; ++o) s = fmaf(__ldg(W2 + (size_t)o * D + k), go[o], s);
-      for (int o = 0; o < De; ++o) s = fmaf(__ldg(Wp + (size_t)o * D + k), go[nc + o], s);
+      if (staged) {
+        for (int o = 0; o < nc + De; ++o) s = fmaf(stage[o * D + k], go[o], s);
+      } else {
+        for (int o = 0; o < nc; ++o) s = fmaf(__ldg(W2 + (size_t)o * D + k), go[o], s);
+        for (int o = 0; o < De; ++o) s = fmaf(__ldg(Wp + (size_t)o * D + k), go[nc + o], s);
+      }
       g[k] = s;
     }
   }
@@ -199,7 +223,10 @@ int dml_tower_head_fwd(const float* x, long long bag_stride, int B, int D, const
                        float* logits, float* enc, void* stream) {
   DML_CHECK_ARG(x && ln_w && ln_b && W2 && b2 && Wp && bp && hn && stats && logits && enc && B > 0 && nc > 0 && De > 0);
   if (D <= 0 || D > dml::hd::kMaxD) return DML_EUNSUPPORTED;
-  dml::hd::tower_head_fwd_kernel<<<B, dml::hd::kThreads, 0, (cudaStream_t)stream>>>(x, bag_stride, D, ln_w, ln_b, eps, W2, b2, nc, Wp, bp,
+  const int smem = dml::hd::kStageFloats * (int)sizeof(float);
+  cudaError_t ea = cudaFuncSetAttribute(dml::hd::tower_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ea != cudaSuccess) return (int)ea;
+  dml::hd::tower_head_fwd_kernel<<<B, dml::hd::kThreads, smem, (cudaStream_t)stream>>>(x, bag_stride, D, ln_w, ln_b, eps, W2, b2, nc, Wp, bp,
                                                                                   De, hn, stats, logits, enc);
   DML_RETURN_LAUNCH();
 }
@@ -213,7 +240,10 @@ int dml_tower_head_bwd(const float* x, long long bag_stride, int B, int D, const
   const size_t np = (size_t)2 * D + (size_t)nc * D + nc + (size_t)De * D + De;
   cudaError_t e = cudaMemsetAsync(dparams, 0, np * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
-  dml::hd::tower_head_bwd_kernel<<<B, dml::hd::kThreads, 0, st>>>(x, bag_stride, D, ln_w, W2, nc, Wp, De, hn, stats, dlogits, denc, dparams,
+  const int smem = dml::hd::kStageFloats * (int)sizeof(float);
+  e = cudaFuncSetAttribute(dml::hd::tower_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return (int)e;
+  dml::hd::tower_head_bwd_kernel<<<B, dml::hd::kThreads, smem, st>>>(x, bag_stride, D, ln_w, W2, nc, Wp, De, hn, stats, dlogits, denc, dparams,
                                                                  dx, dx_bag_stride);
   DML_RETURN_LAUNCH();
 }
