@@ -225,8 +225,9 @@ launch_count = 0        # kernels of libdml_b200.so launched by this process
 _timing_hook = None     # bench.py installs a (name, phase) callback to bracket calls with CUDA events
 
 
-def call(name: str, *args):
-    """Invoke an int-returning entry point on the current CUDA device/stream; raise on failure."""
+def call(name: str, *args, kernels=None):
+    """Invoke an int-returning entry point on the current CUDA device/stream; raise on failure.  kernels: how many kernels
+    this particular call launches when that differs from KERNELS_PER_CALL (staged calls)."""
     global launch_count
     lib = load(check_device=True)
     if _timing_hook is not None:
@@ -234,7 +235,7 @@ def call(name: str, *args):
     rc = getattr(lib, name)(*args)
     if _timing_hook is not None:
         _timing_hook(name, 1)
-    launch_count += KERNELS_PER_CALL.get(name, 1)
+    launch_count += KERNELS_PER_CALL.get(name, 1) if kernels is None else kernels
     if rc != 0:
         what = _ERR.get(rc) or (f"CUDA error {rc}" if rc > 0 else f"error {rc}")
         raise DmlError(f"{name} failed: {what}")

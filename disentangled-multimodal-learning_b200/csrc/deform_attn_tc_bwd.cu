@@ -1018,7 +1018,10 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
                            float* segsum, void* ds_ws, void* stream) {
   using namespace dml;
   using namespace dml::tc;
-  DML_CHECK_ARG(q && k && v && g && table && out && d_out && lse && dscale && dsum_ws && dq && dk && dv && dg && segsum);
+  DML_CHECK_ARG(q && k && v && g && table && out && d_out && lse && dscale && dsum_ws && dk && dv && dg && segsum);
+  // dq == NULL with a workspace: stop after the dK / dV / dS^T stage; the caller finishes with dml_deform_attn_dq_from_ds (on
+  // another stream if it likes: everything that only needs dK / dV / dg can then run next to the HBM-bound dQ GEMM)
+  DML_CHECK_ARG(dq || ds_ws);
   if (((uintptr_t)ds_ws) & 15) return DML_EINVAL;
   DML_CHECK_ARG(B > 0 && H > 0 && n > 0 && n_kv > 0 && n_seq >= n);
   if (dim_head != kD || heads_per_group != 2 || (H & 1)) return DML_EUNSUPPORTED;
@@ -1115,9 +1118,9 @@ int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const fl
     }
     deform_attn_dkv_tc_kernel<<<ncta, dkvk::kThreads, dkvk::kSmemBytes, st>>>(mq32, mdo32, mk128, mv128, p, wl);
   }
-  if (ds_ws)
-    deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), G, B), dqg::kThreads, dqg::kSmemBytes, st>>>(mds, mk64, p);
-  else
+  if (ds_ws) {
+    if (dq) deform_attn_dq_gemm_kernel<<<dim3(cdiv(n, dqg::kBM), G, B), dqg::kThreads, dqg::kSmemBytes, st>>>(mds, mk64, p);
+  } else
     deform_attn_dq_tc_kernel<<<dim3(cdiv(n, dqk::kGroups * dqk::kBM), G, B), dqk::kThreads, dqk::kSmemBytes, st>>>(mq128, mdo128, mk32, mv32, p);
   DML_RETURN_LAUNCH();
 }

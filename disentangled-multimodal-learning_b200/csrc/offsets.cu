@@ -336,23 +336,32 @@ int dml_offsets_bwd_pair(const void* q, const float* w0, const float* b0, const 
                          const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
                          float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* dq_pair, long long plane_stride,
                          void* stream) {
-  DML_CHECK_ARG(q && w0 && b0 && w2 && d_off && dq_attn && dy_ws && wgrad && (dq_out || dq_pair) && B > 0 && n > 0 && G > 0);
+  // Two stages, either may be skipped: d_off != NULL runs the offset-network backward (d_off -> dy_ws, wgrad), dq_attn != NULL the
+  // combination dq_out / dq_pair = attn_scale * dq_attn + (transposed convolution of dy_ws).  A caller whose dq_attn is still being
+  // produced on another stream calls stage one first and stage two once it is there.
+  const bool stage1 = d_off != nullptr, stage2 = dq_attn != nullptr;
+  DML_CHECK_ARG(q && w0 && b0 && w2 && dy_ws && wgrad && (stage1 || stage2) && B > 0 && n > 0 && G > 0);
+  DML_CHECK_ARG(!stage2 || dq_out || dq_pair);
   if (dq_pair && ((((uintptr_t)dq_pair) & 7) || (plane_stride & 3))) return DML_EINVAL;
   if (C != G * 128 || ksize > dml::kMaxTaps || ksize < stride || ((ksize - stride) & 1)) return DML_EUNSUPPORTED;
   const int pad = (ksize - stride) / 2, n_kv = dml_offsets_kv_len(n, ksize, stride);
   const int Cg = C / G;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(wgrad, 0, sizeof(float) * (size_t)(Cg * ksize + 2 * Cg), st);
-  if (e != cudaSuccess) return (int)e;
-  const int warps = B * G * n_kv;
-  const int blocks = min(dml::cdiv(warps, 8), 148 * 2);
-  dml::offsets_bwd_kernel<<<blocks, 256, 0, st>>>((const dml::h16*)q, w0, b0, w2, d_off, B, n, C, G, ksize, stride, pad,
-                                                 n_kv, offset_scale, dy_ws, wgrad);
   if (C % 4 != 0 || 256 % (C / 4) != 0 || ((C / G) % 4) != 0) return DML_EUNSUPPORTED;
-  const size_t total4 = (size_t)B * n * C / 4;
-  const int blocks2 = (int)min((total4 + 255) / 256, (size_t)148 * 16);
-  dml::offsets_dq_combine_kernel<<<blocks2, 256, 0, st>>>(dq_attn, dy_ws, w0, B, n, C, G, ksize, stride, pad, n_kv,
-                                                         attn_scale, (float*)dq_out, (dml::bf16*)dq_pair, plane_stride);
+  if (stage1) {
+    cudaError_t e = cudaMemsetAsync(wgrad, 0, sizeof(float) * (size_t)(Cg * ksize + 2 * Cg), st);
+    if (e != cudaSuccess) return (int)e;
+    const int warps = B * G * n_kv;
+    const int blocks = min(dml::cdiv(warps, 8), 148 * 2);
+    dml::offsets_bwd_kernel<<<blocks, 256, 0, st>>>((const dml::h16*)q, w0, b0, w2, d_off, B, n, C, G, ksize, stride, pad,
+                                                   n_kv, offset_scale, dy_ws, wgrad);
+  }
+  if (stage2) {
+    const size_t total4 = (size_t)B * n * C / 4;
+    const int blocks2 = (int)min((total4 + 255) / 256, (size_t)148 * 16);
+    dml::offsets_dq_combine_kernel<<<blocks2, 256, 0, st>>>(dq_attn, dy_ws, w0, B, n, C, G, ksize, stride, pad, n_kv,
+                                                           attn_scale, (float*)dq_out, (dml::bf16*)dq_pair, plane_stride);
+  }
   DML_RETURN_LAUNCH();
 }
 

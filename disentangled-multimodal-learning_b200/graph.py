@@ -17,6 +17,11 @@ import torch
 from .parallel import FlatGradAllReducer
 
 
+def _chain_priority():
+    from .ops import CHAIN_PRIORITY
+    return CHAIN_PRIORITY
+
+
 class GraphedTrainStep:
     """step(inputs) -> loss (a static device tensor): copies `inputs` (dict of tensors, device or pinned host) into
     static device buffers, replays the captured forward + loss + backward, all-reduces the flat gradient buffer when a
@@ -42,7 +47,8 @@ class GraphedTrainStep:
         self.reducer = FlatGradAllReducer(params, static_presence=True)
 
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(device=dev)
+        # kernel nodes keep the priority of the capturing stream (ops.CHAIN_PRIORITY, default 0)
+        side = torch.cuda.Stream(device=dev, priority=_chain_priority())
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             # eager warm-up: one-time library initialisation (kernel attributes, cuBLAS handles/workspaces, driver entry

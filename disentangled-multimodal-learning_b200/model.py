@@ -62,7 +62,8 @@ _TOWER_STREAMS = {}
 def _tower_stream(dev, which=0):
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), which)
     if key not in _TOWER_STREAMS:
-        _TOWER_STREAMS[key] = torch.cuda.Stream(device=key[0])
+        from . import ops
+        _TOWER_STREAMS[key] = torch.cuda.Stream(device=key[0], priority=ops.CHAIN_PRIORITY)      # see ops.branch_stream
     return _TOWER_STREAMS[key]
 
 

@@ -35,6 +35,11 @@ def kv_length(n: int, ksize: int, stride: int) -> int:
 
 
 _SIDE_STREAMS = {}
+# Priority of the streams that carry latency-bound kernel chains (tower, side and graph-capture streams); branch_stream() keeps
+# the default (lowest) one.  Measured on the B200 (same box, A/B): -1 costs the DeformPathomicNet step 0.13 ms (3.70 -> 3.84 ms:
+# the weight-gradient kernels of the side streams then cut into the attention kernels) and changes TransMIL by < 1 %, so the
+# default is 0 = all streams equal; DML_B200_CHAIN_PRIORITY=-1 is kept as a tuning knob.
+CHAIN_PRIORITY = int(os.environ.get("DML_B200_CHAIN_PRIORITY", "0"))
 
 
 def side_stream(dev) -> torch.cuda.Stream:
@@ -44,13 +49,16 @@ def side_stream(dev) -> torch.cuda.Stream:
     idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     key = (idx, torch.cuda.current_stream(idx).cuda_stream)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=idx, priority=CHAIN_PRIORITY)
     return _SIDE_STREAMS[key]
 
 
 def branch_stream(dev) -> torch.cuda.Stream:
-    """A second auxiliary stream of the CURRENT stream, distinct from side_stream(): NystromAttention runs its token-sized
-    kernels on it next to the latency-bound pseudo-inverse chain (which itself forks onto side_stream)."""
+    """A second auxiliary stream of the CURRENT stream, distinct from side_stream(), for BULK kernels that run next to a
+    latency-bound chain: the token-sized kernels of NystromAttention next to the pseudo-inverse chain, the HBM-bound dQ GEMM of
+    the deformable backward next to the dK / dV adjoint chain.  Always default (= lowest) priority; see CHAIN_PRIORITY for
+    what raising the other streams above it does (the block scheduler hands out thread blocks of pending kernels in launch
+    order within a priority, so a 500-CTA bulk kernel waiting for SMs holds back every small kernel launched after it)."""
     idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
     key = (idx, torch.cuda.current_stream(idx).cuda_stream, "branch")
     if key not in _SIDE_STREAMS:
@@ -60,6 +68,7 @@ def branch_stream(dev) -> torch.cuda.Stream:
 
 # largest dS^T scratch the backward may allocate per call (bytes); DML_B200_DS_WS_MAX_GB overrides, 0 disables it
 DS_WS_MAX_BYTES = int(float(os.environ.get("DML_B200_DS_WS_MAX_GB", "6")) * (1 << 30))
+DQ_OVERLAP = os.environ.get("DML_B200_DQ_OVERLAP", "1") != "0"      # dQ GEMM of the backward on its own stream (see backward)
 
 
 def build_bias_table(mlp, hid: int, nout: int, n_kv: int, offset_scale: float, dev):
@@ -235,14 +244,21 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         # time; bags too large for it fall back to the recomputing dQ kernel (same results)
         ws_bytes = _lib.load().dml_deform_attn_bwd_ws_bytes(B, H, n_out, n_kv)
         ds_ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8) if 0 < ws_bytes <= DS_WS_MAX_BYTES else None
+        # With the workspace the HBM-bound dQ GEMM is issued apart, on its own stream: everything that only needs dK / dV / dg
+        # (the key / value projection adjoints, the gather and offset-network backward - a latency-bound chain of ~150 us at
+        # the end of the step) runs next to it and joins before dq is combined with the offset-path gradient.
+        split_dq = ds_ws is not None and DQ_OVERLAP
         call("dml_deform_attn_bwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), ptr(o), ptr(d_o16), ptr(lse), B, H, d,
-             n_out, n_kv, n, C, 2 * C, 2 * C, C, nout, scale, ptr(dscale), ptr(dsum), ptr(dq_attn), ptr(dk), ptr(dv), ptr(dg),
-             ptr(segsum), ptr(ds_ws) if ds_ws is not None else None, st)
-        del ds_ws
-        if n_out != n:                                 # the other query rows only receive the offset-path gradient
-            full = torch.zeros(B, n, C, device=dev, dtype=F32)
-            full[:, :n_out] = dq_attn
-            dq_attn = full
+             n_out, n_kv, n, C, 2 * C, 2 * C, C, nout, scale, ptr(dscale), ptr(dsum), None if split_dq else ptr(dq_attn), ptr(dk),
+             ptr(dv), ptr(dg), ptr(segsum), ptr(ds_ws) if ds_ws is not None else None, st, kernels=2 if split_dq else 3)
+        dqs = None
+        if split_dq:
+            dqs = branch_stream(dev)
+            dqs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(dqs):
+                call("dml_deform_attn_dq_from_ds", ptr(ds_ws), ptr(k), ptr(dscale), B, H, d, n_out, n_kv, 2 * C, ptr(dq_attn), stream())
+        else:
+            del ds_ws
         dk_p, dv_p = Pair.from_f32(dk), Pair.from_f32(dv)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
@@ -281,8 +297,18 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dy_ws = torch.empty(B * G, n_kv, Cg, device=dev, dtype=F32)
         wgrad = torch.empty(Cg * ks + 2 * Cg, device=dev, dtype=F32)
         dq_p = Pair.empty((B, n, C), dev)                                  # total query gradient, as the GEMM operand only
-        call("dml_offsets_bwd_pair", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), ptr(dq_attn), scale, B, n, C, G, ks,
-             stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), None, ptr(dq_p.planes), dq_p.planes.stride(0), st)
+        if dqs is not None:                            # offset-network backward first, the combination once dq has arrived
+            call("dml_offsets_bwd_pair", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), ptr(d_off), None, scale, B, n, C, G, ks,
+                 stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), None, None, 0, st, kernels=1)
+            cur.wait_stream(dqs)
+            del ds_ws                                  # allocated on this stream, last read on the other one: released after the join
+        if n_out != n:                                 # the other query rows only receive the offset-path gradient
+            full = torch.zeros(B, n, C, device=dev, dtype=F32)
+            full[:, :n_out] = dq_attn
+            dq_attn = full
+        call("dml_offsets_bwd_pair", ptr(q), ptr(w0f), ptr(b0f), ptr(w2f), None if dqs is not None else ptr(d_off), ptr(dq_attn),
+             scale, B, n, C, G, ks, stride, float(offset_scale), ptr(dy_ws), ptr(wgrad), None, ptr(dq_p.planes),
+             dq_p.planes.stride(0), st, kernels=1 if dqs is not None else 2)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             dWq = torch.empty(C, dim, device=dev, dtype=F32)

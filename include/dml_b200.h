@@ -67,7 +67,9 @@ int dml_offsets_bwd(const void* q, const float* w0, const float* b0, const float
                     float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* stream);
 
 /* The same with the total query gradient ALSO (or only: dq_out may be NULL) written as a bf16 pair [B, n, C], the operand of
- * the dW_q / dx1 GEMMs (csrc/pgemm.cu).                                                                               */
+ * the dW_q / dx1 GEMMs (csrc/pgemm.cu).  The two stages can be called apart: d_off != NULL runs the offset-network backward
+ * (d_off -> dy_ws, wgrad), dq_attn != NULL the combination of dq_attn with dy_ws into dq_out / dq_pair; either of the two
+ * pointers may be NULL to skip its stage (not both).                                                                    */
 int dml_offsets_bwd_pair(const void* q, const float* w0, const float* b0, const float* w2, const float* d_off,
                          const float* dq_attn, float attn_scale, int B, int n, int C, int G, int ksize, int stride,
                          float offset_scale, float* dy_ws, float* wgrad, void* dq_out, void* dq_pair, long long plane_stride,
@@ -103,7 +105,9 @@ int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const fl
  * heads_per_group must be 2; n_seq as in dml_deform_attn_fwd_tc; every tensor pointer 16-byte aligned).
  * ds_ws: NULL, or a caller-owned scratch buffer of dml_deform_attn_bwd_ws_bytes(B, H, n, n_kv) bytes (contents
  * undefined afterwards).  With it the dK/dV kernel also stores dS^T in fp16 and dQ = dS.K runs as a streaming GEMM
- * over that buffer; without it dQ recomputes P and dS from q, k, lse (no n x n_kv memory).  Same results either way. */
+ * over that buffer; without it dQ recomputes P and dS from q, k, lse (no n x n_kv memory).  Same results either way.
+ * dq may be NULL when ds_ws is given: the call then stops after dk, dv, dg, segsum and dS^T, and the caller obtains dq with
+ * dml_deform_attn_dq_from_ds - on another stream if it likes, next to whatever only needs dk / dv / dg.                */
 size_t dml_deform_attn_bwd_ws_bytes(int B, int H, int n, int n_kv);
 int dml_deform_attn_bwd_tc(const void* q, const void* k, const void* v, const float* gnorm, const void* table,
                            const void* out, const void* d_out, const float* lse, int B, int H, int dim_head, int n,

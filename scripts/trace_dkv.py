@@ -19,10 +19,10 @@ x2 = synth.normal((1, 128, n), 1, "x2").to(dev).requires_grad_()
 ntiles = (n + 31) // 32
 trace = torch.zeros(8 * ntiles, dtype=torch.int64, device=dev)
 orig = _lib.call
-def routed(name, *args):
+def routed(name, *args, **kw):
     if name == "dml_deform_attn_bwd_tc":
         return _lib.call_test(name, *args)
-    return orig(name, *args)
+    return orig(name, *args, **kw)
 import dml_b200.ops as ops
 for m in (ops, _lib):
     if getattr(m, "call", None) is orig:
