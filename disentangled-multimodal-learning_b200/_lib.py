@@ -44,6 +44,7 @@ SIGNATURES = {
     "dml_pair_from_f32": (_i, [_fp, _ll, _i, _i, _f, _vp, _i, _ll, _vp]),
     "dml_colsum": (_i, [_fp, _ll, _i, _i, _fp, _vp]),
     "dml_scale_to_half": (_i, [_fp, _fp, _ll, _vp, _vp]),
+    "dml_loss_scale_from_amax": (_i, [_vp, _fp, _vp]),
     "dml_relu_mask_pair": (_i, [_fp, _fp, _fp, _ll, _i, _i, _i, _vp, _i, _ll, _vp]),
     "dml_layernorm_fwd_pair": (_i, [_fp, _fp, _fp, _ll, _i, _f, _fp, _vp, _ll, _fp, _fp, _vp]),
     "dml_ny_landmark_pool": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _ll, _vp]),

@@ -619,6 +619,24 @@ relu_mask_pair_kernel(const float* __restrict__ g, float* __restrict__ gm, const
   }
 }
 
+// (s, 1 / s) with s the power of two that puts max|t| into (4, 8] (s = 1 for an all-zero tensor, |log2 s| <= 60), from the bit
+// pattern of max|t| that the GEMM epilogue left (`absmax`): one thread, exponent arithmetic only
+__global__ void loss_scale_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ out) {
+  const unsigned bits = *amax_bits & 0x7fffffffu;
+  const float a = __uint_as_float(bits);
+  float s = 1.0f;
+  if (a > 0.f) {
+    // a = m 2^e, 1 <= m < 2 (denormals: frexp-style through the float multiply below):  floor(log2(8 / a)) = 3 - e - (m > 1)
+    int e, ex;
+    const float m = frexpf(fmaxf(a, 1e-30f), &e);      // a = m 2^e with 0.5 <= m < 1
+    ex = 3 - (e - 1) - (m > 0.5f ? 1 : 0);
+    ex = max(-60, min(60, ex));
+    s = ldexpf(1.0f, ex);
+  }
+  out[0] = s;
+  out[1] = 1.0f / s;
+}
+
 // x * (*scale) -> fp16, 8 elements per thread (the loss-scaled dO operand of the attention backward)
 __global__ void __launch_bounds__(256)
 scale_to_half_kernel(const float* __restrict__ x, const float* __restrict__ scale, long long n8, h16* __restrict__ out) {
@@ -855,6 +873,12 @@ int dml_relu_mask_pair(const float* g, float* gm, const float* act, long long ro
   const long long total = rows * (cols / 4);
   const int blocks = (int)min((total + 255) / 256, (long long)148 * 16);
   tc::pg::relu_mask_pair_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, gm, act, rows, cols, ldg, lda, (bf16*)pair, ldp, plane_stride);
+  DML_RETURN_LAUNCH();
+}
+
+int dml_loss_scale_from_amax(const void* amax_bits, float* scale2, void* stream) {
+  DML_CHECK_ARG(amax_bits && scale2);
+  dml::tc::pg::loss_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned*)amax_bits, scale2);
   DML_RETURN_LAUNCH();
 }
 

@@ -86,7 +86,12 @@ def build_bias_table(mlp, hid: int, nout: int, n_kv: int, offset_scale: float, d
 
 def loss_scale_from_amax(amax_bits: torch.Tensor) -> torch.Tensor:
     """Device-side power-of-two loss scale from the bit pattern of max|t| (the `absmax` output of dml_pgemm): float[2] =
-    (s, 1/s) with 4 < s * max|t| <= 8 (s = 1 for an all-zero tensor); no host synchronisation."""
+    (s, 1/s) with 4 < s * max|t| <= 8 (s = 1 for an all-zero tensor); no host synchronisation.  One launch on the GPU (it sits
+    on the chain between the forward and the backward of the step); the torch expression below is the CPU form of the same."""
+    if amax_bits.is_cuda:
+        out = torch.empty(2, device=amax_bits.device, dtype=F32)
+        call("dml_loss_scale_from_amax", ptr(amax_bits), ptr(out), stream())
+        return out
     amax = amax_bits.view(F32).reshape(())
     s = torch.exp2(torch.floor(torch.log2(8.0 / amax.clamp_min(1e-30))).clamp(-60.0, 60.0))
     s = torch.where(amax > 0, s, torch.ones_like(s))
@@ -274,22 +279,25 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         dcentre = torch.empty(B, dim, device=dev, dtype=F32)
         call("dml_kv_gather_bwd", ptr(x2c), ptr(g), ptr(dkv), B, gn, dim, G, n_kv, gi0, gi1, wy0, wy1, ptr(dcentre),
              ptr(dg), st)
-        dx2t = torch.zeros(ctx.x2_shape, device=dev, dtype=F32)
-        dlw = dlb = None
-        if fused:
-            kc = crow[1] - crow[0]
-            dxc = torch.stack([wy0 * dcentre] + ([wy1 * dcentre] if kc == 2 else []), 1).contiguous()      # [B, k, dim]
-            dxc_in = torch.empty_like(dxc)
-            dlw2 = torch.empty(dim, device=dev, dtype=F32)
-            dlb2 = torch.empty_like(dlw2)
-            call("dml_layernorm_bwd", ptr(dxc), ptr(xc_in), ptr(lnw), ptr(mean2), ptr(rstd2), B * kc, dim, ptr(dxc_in), ptr(dlw2),
-                 ptr(dlb2), st)
-            dx2t[:, crow[0]:crow[1]] = dxc_in
-        else:
-            dx2t[:, i0] += wy0 * dcentre
-            if wy1 != 0.0:
-                dx2t[:, i1] += wy1 * dcentre
-
+        # the gradient of x2 (only its centre rows are non-zero) is a leaf of this backward: a handful of microsecond-sized kernels
+        # that leave the critical chain (gather backward -> offset-network backward -> dq) for the auxiliary stream
+        dlw = dlb = dlw2 = dlb2 = None
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            dx2t = torch.zeros(ctx.x2_shape, device=dev, dtype=F32)
+            if fused:
+                kc = crow[1] - crow[0]
+                dxc = torch.stack([wy0 * dcentre] + ([wy1 * dcentre] if kc == 2 else []), 1).contiguous()      # [B, k, dim]
+                dxc_in = torch.empty_like(dxc)
+                dlw2 = torch.empty(dim, device=dev, dtype=F32)
+                dlb2 = torch.empty_like(dlw2)
+                call("dml_layernorm_bwd", ptr(dxc), ptr(xc_in), ptr(lnw), ptr(mean2), ptr(rstd2), B * kc, dim, ptr(dxc_in), ptr(dlw2),
+                     ptr(dlb2), stream())
+                dx2t[:, crow[0]:crow[1]] = dxc_in
+            else:
+                dx2t[:, i0] += wy0 * dcentre
+                if wy1 != 0.0:
+                    dx2t[:, i1] += wy1 * dcentre
         d_off = dg * (2.0 / max(n_kv - 1, 1))                              # g = 2 vgrid / max(n_kv-1,1) - 1
         if dvgrid is not None:
             d_off = d_off + dvgrid
@@ -321,11 +329,13 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
             call("dml_layernorm_bwd", ptr(dx1t), ptr(x1f), ptr(lnw), ptr(mean1), ptr(rstd1), B * n, dim, ptr(dh), ptr(dlw), ptr(dlb), st)
             dh[:, :n_out] += dout                                          # the layer's residual
             dx1t = dh
-            dlw, dlb = dlw + dlw2, dlb + dlb2
         cur.wait_stream(side)
-        for t in (dWo, dbo, mlp_g, dWk, dWv, dWq):                         # allocated on the auxiliary stream, consumed on this one
-            t.record_stream(cur)
-        for t in (dout, segsum, dout_p.planes, dk_p.planes, dv_p.planes, dq_p.planes):      # allocated here, read there
+        if fused:
+            dlw, dlb = dlw + dlw2, dlb + dlb2
+        for t in (dWo, dbo, mlp_g, dWk, dWv, dWq, dx2t, dlw2, dlb2):       # allocated on the auxiliary stream, consumed on this one
+            if t is not None:
+                t.record_stream(cur)
+        for t in (dout, segsum, dout_p.planes, dk_p.planes, dv_p.planes, dq_p.planes, dcentre):      # allocated here, read there
             t.record_stream(side)
 
         dw0 = wgrad[: Cg * ks].reshape(Cg, 1, ks)

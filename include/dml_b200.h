@@ -199,6 +199,9 @@ int dml_pair_from_f32(const float* x, long long rows, int cols, int ld, float mu
  * g[r, c] : 0 as fp32 (row stride ldg for g and gm; gm may alias g) and as a bf16 pair [rows, ldp]; act row stride lda.  */
 int dml_relu_mask_pair(const float* g, float* gm, const float* act, long long rows, int cols, int ldg, int lda, void* pair,
                        int ldp, long long plane_stride, void* stream);
+/* scale2 (device float[2]) = (s, 1 / s): the power-of-two loss scale with 4 < s * max|t| <= 8 (s = 1 for an all-zero tensor,
+ * |log2 s| <= 60) from the bit pattern of max|t| that dml_pgemm's `absmax` epilogue wrote; no host synchronisation.         */
+int dml_loss_scale_from_amax(const void* amax_bits, float* scale2, void* stream);
 /* out (fp16) = x * (*scale_dev) over n contiguous floats (n a multiple of 8): the loss-scaled dO operand of the attention
  * backward, scale from the device-side loss scale (no host synchronisation).                                            */
 int dml_scale_to_half(const float* x, const float* scale_dev, long long n, void* out, void* stream);

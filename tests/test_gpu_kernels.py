@@ -399,3 +399,17 @@ def test_three_classifier_head_matches_torch(sigmoid):
     # only the fused head's output drives the loss in training (train_test.py:833-853): the other two gradients are None
     (ga,) = torch.autograd.grad(ys[0].sum(), [a], allow_unused=True)
     assert ga is not None
+
+
+@pytest.mark.gpu
+def test_loss_scale_kernel_matches_the_host_expression():
+    """dml_loss_scale_from_amax (one thread, exponent arithmetic) against the torch expression it replaces on the step's chain."""
+    vals = [0.0, 1e-42, 3e-39, 1e-30, 3e-7, 0.02, 0.5, 1.0, 1.0000001, 2.0, 3.999, 4.0, 7.9, 8.0, 8.5, 900.0, 2.0 ** 40, 3e30, 3e38]
+    for a in vals:
+        bits = torch.tensor([a], dtype=torch.float32).view(torch.int32)
+        ref = ops.loss_scale_from_amax(bits)                       # CPU: the torch form
+        got = ops.loss_scale_from_amax(bits.to(DEV)).cpu()         # GPU: the kernel
+        assert torch.equal(ref, got), (a, ref.tolist(), got.tolist())
+        av = float(torch.tensor(a, dtype=torch.float32))
+        if 1e-17 < av < 1e17:
+            assert 4.0 < float(got[0]) * av <= 8.0
