@@ -33,6 +33,7 @@ SIGNATURES = {
     "dml_kv_gather_fwd": (_i, [_fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp, _vp]),
     "dml_kv_gather_bwd": (_i, [_fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _fp, _fp, _vp]),
     "dml_deform_attn_fwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 11 + [_f, _vp, _fp, _vp]),
+    "dml_deform_attn_fwd_tc_split": (_i, [_vp, _vp, _vp, _fp, _vp] + [_i] * 11 + [_f, _vp, _fp, _i, _vp]),
     "dml_deform_attn_bwd_tc": (_i, [_vp, _vp, _vp, _fp, _vp, _vp, _vp, _fp] + [_i] * 11 + [_f] + [_fp] * 7 + [_vp, _vp]),
     "dml_deform_attn_bwd_ws_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "dml_deform_attn_dq_from_ds": (_i, [_vp, _vp, _fp] + [_i] * 6 + [_fp, _vp]),
@@ -212,7 +213,7 @@ _ERR = {-1: "invalid argument", -2: "unsupported shape/config", -3: "workspace t
 # kernels launched per entry point (memsets not counted) - bench.py reports the total as gpu_launches
 KERNELS_PER_CALL = {
     "dml_cpb_table_build": 1, "dml_cpb_eval": 1, "dml_cpb_param_grad": 1, "dml_offsets_fwd": 1, "dml_offsets_bwd": 2, "dml_offsets_bwd_pair": 2,
-    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
+    "dml_kv_gather_fwd": 1, "dml_kv_gather_bwd": 1, "dml_deform_attn_fwd_tc": 1, "dml_deform_attn_fwd_tc_split": 1, "dml_deform_attn_bwd_tc": 3, "dml_deform_attn_dq_from_ds": 1,
     "dml_layernorm_fwd": 1, "dml_layernorm_bwd": 1,
     "dml_pgemm": 1, "dml_pgemm_chain": 1, "dml_pair_from_f32": 1, "dml_colsum": 1, "dml_layernorm_fwd_pair": 1, "dml_ny_landmark_pool": 1,
     "dml_ny_softmax_rows_fwd": 1, "dml_ny_softmax_rows_bwd": 1, "dml_ny_res_conv_fwd": 1, "dml_ny_res_conv_bwd": 1,

@@ -76,6 +76,7 @@ struct Params {
   float* lse;            // [B, H, n] (log2 domain)
   int B, H, n, n_kv, ldo, n_seq;
   float scale;
+  int n_full, n_half;    // per (bag, offset group): 256-query CTAs, then 128-query CTAs (launched after every 256-query one)
 };
 
 constexpr uint32_t kIdescS = idesc_f16(128, kBN, false, false);   // S = Q K^T: A, B K-major
@@ -128,8 +129,20 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
-  const int i0 = blockIdx.x * (kGroups * kBM), grp = blockIdx.y, b = blockIdx.z;
+  // blockIdx.x enumerates the 256-query CTAs of every (bag, group) first, then the 128-query ones (one softmax group active):
+  // the hardware hands CTAs out in index order, so the short ones fill the last, partial wave
   const int G = p.H / 2;
+  int i0, grp, b, ngroups;
+  {
+    const int nf = p.n_full * G * p.B;
+    int x = blockIdx.x, per = p.n_full;
+    ngroups = kGroups;
+    if (x >= nf) { x -= nf; per = p.n_half; ngroups = 1; }
+    const int blk = x % per, gb = x / per;
+    i0 = ngroups == kGroups ? blk * (kGroups * kBM) : p.n_full * (kGroups * kBM) + blk * kBM;
+    grp = gb % G;
+    b = gb / G;
+  }
   const int ntiles = cdiv(p.n_kv, kBN);
   auto bar = [&](int i) { return sbase + kOffBar + 8u * i; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffTmemPtr);
@@ -137,7 +150,7 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   // ---- one-time setup ----
   if (tid == 0) {
     mbar_init(bar(kBarQ), 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), kGroups); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarKvFull + s), 32); mbar_init(bar(kBarKvEmpty + s), ngroups); }
     for (int g = 0; g < 2 * kGroups; ++g) { mbar_init(bar(kBarSFull + g), 1); mbar_init(bar(kBarPFull + g), 2 * kBM); }
     for (int g = 0; g < kGroups; ++g) { mbar_init(bar(kBarPvDone + g), 1); mbar_init(bar(kBarOFinal + g), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,8 +170,8 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
   if (warp == kSoftWarps) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      mbar_expect_tx(bar(kBarQ), kGroups * 2 * kTileQ);
-      for (int g = 0; g < kGroups; ++g)
+      mbar_expect_tx(bar(kBarQ), ngroups * 2 * kTileQ);
+      for (int g = 0; g < ngroups; ++g)
         for (int h = 0; h < 2; ++h)
           tma_load_3d(sbase + kOffQ + (g * 2 + h) * kTileQ, &mq, bar(kBarQ), (grp * 2 + h) * kD, i0 + g * kBM, b);
     }
@@ -183,6 +196,8 @@ deform_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mq, const __grid_c
       if (lane == 0) { gs[32] = gmn; gs[33] = gmx; }
       mbar_arrive(bar(kBarKvFull + st));                     // 32 arrivals (release) + the TMA bytes complete the phase
     }
+  } else if (warp > kSoftWarps + ngroups || (warp < kSoftWarps && (warp >> 3) >= ngroups)) {
+    // the second query group of a 128-query CTA: its MMA warp and its eight softmax warps have nothing to do
   } else if (warp > kSoftWarps) {
     // =========================== MMA issuers: one warp per query group ===========================
     // All 32 lanes run the loop (uniform operands); one elected lane executes each tcgen05 instruction.
@@ -393,9 +408,16 @@ extern "C" {
 int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const float* g, const void* table, int B,
                            int H, int dim_head, int n, int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo,
                            int heads_per_group, float scale, void* out, float* lse, void* stream) {
+  return dml_deform_attn_fwd_tc_split(q, k, v, g, table, B, H, dim_head, n, n_kv, n_seq, ldq, ldk, ldv, ldo, heads_per_group, scale,
+                                      out, lse, 0, stream);
+}
+
+int dml_deform_attn_fwd_tc_split(const void* q, const void* k, const void* v, const float* g, const void* table, int B,
+                                 int H, int dim_head, int n, int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo,
+                                 int heads_per_group, float scale, void* out, float* lse, int half_blocks, void* stream) {
   using namespace dml;
   using namespace dml::tc;
-  DML_CHECK_ARG(q && k && v && g && table && out && lse && B > 0 && H > 0 && n > 0 && n_kv > 0 && n_seq >= n);
+  DML_CHECK_ARG(q && k && v && g && table && out && lse && B > 0 && H > 0 && n > 0 && n_kv > 0 && n_seq >= n && half_blocks >= 0);
   if (dim_head != kD || heads_per_group != 2 || (H & 1)) return DML_EUNSUPPORTED;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 4)) return DML_EINVAL;
   if (ldq < H * kD || ldk < H * kD || ldv < H * kD || ldo < H * kD) return DML_EINVAL;
@@ -414,8 +436,15 @@ int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const fl
   Params p{};
   p.g = g; p.table = (const uint32_t*)table; p.o = (float*)out; p.lse = lse;
   p.B = B; p.H = H; p.n = n; p.n_kv = n_kv; p.ldo = ldo; p.n_seq = n_seq; p.scale = scale;
-  dim3 grid(cdiv(n, kGroups * kBM), H / 2, B);
-  deform_attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  // 129 row groups of 128 queries at n = 16 385: 64 CTAs of two groups + one of one group per (bag, offset group); the last
+  // half_blocks two-group blocks of every (bag, group) run as twice as many one-group CTAs, launched after all two-group ones
+  const int rg = cdiv(n, kBM);
+  const int tail = half_blocks;
+  p.n_full = max(rg / kGroups - tail, 0);
+  p.n_half = rg - kGroups * p.n_full;
+  const long long ncta = (long long)(p.n_full + p.n_half) * (H / 2) * B;
+  if (ncta > 0x7fffffffLL) return DML_EUNSUPPORTED;
+  deform_attn_fwd_tc_kernel<<<(unsigned)ncta, kThreads, kSmemBytes, (cudaStream_t)stream>>>(mq, mk, mv, p);
   DML_RETURN_LAUNCH();
 }
 

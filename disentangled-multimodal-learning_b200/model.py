@@ -112,6 +112,11 @@ class DeformPathomicNet(nn.Module):
         # versa; autograd replays each backward node on the stream of its forward, so the backward overlaps the same way.
         x_path = kwargs['x_path']
         two_streams = x_path.is_cuda and getattr(self.args, "overlap_towers", True)
+        from . import ops
+        with ops.concurrent_attention_launches(2 if two_streams else 1):      # the two towers' attention kernels share the SMs
+            return self._forward_towers(kwargs, x_path, two_streams)
+
+    def _forward_towers(self, kwargs, x_path, two_streams):
         if two_streams:
             cur = torch.cuda.current_stream()
             side = _tower_stream(x_path.device)

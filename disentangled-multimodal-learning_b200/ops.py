@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 
 import torch
 
@@ -82,6 +83,62 @@ def build_bias_table(mlp, hid: int, nout: int, n_kv: int, offset_scale: float, d
         call("dml_cpb_table_build", *[ptr(t) for t in mlp], hid, nout, t_max, ptr(table), stream())
         ev = side.record_event()
     return table, ev
+
+
+# How many attention-forward launches of the same shape share the GPU (set by the caller that knows: DeformPathomicNet runs its two
+# towers on two streams).  Host-side planning state only; the C entry point takes the resulting block count explicitly.
+_CONCURRENT_ATTN = threading.local()
+
+
+class concurrent_attention_launches:
+    """with concurrent_attention_launches(2): ... - the deformable-attention forwards issued inside are planned as `count`
+    same-shaped launches sharing the SMs (see fwd_half_blocks)."""
+
+    def __init__(self, count: int):
+        self.count = max(1, int(count))
+
+    def __enter__(self):
+        self.prev = getattr(_CONCURRENT_ATTN, "count", 1)
+        _CONCURRENT_ATTN.count = self.count
+        return self
+
+    def __exit__(self, *a):
+        _CONCURRENT_ATTN.count = self.prev
+        return False
+
+
+def plan_half_blocks(n: int, B: int, G: int, concurrent: int, nsm: int) -> int:
+    """`half_blocks` of dml_deform_attn_fwd_tc_split.  The forward kernel's CTAs take 256 queries (two 128-row softmax groups) of
+    one (bag, offset group) and cost the same; `concurrent` launches of U such CTAs each fill floor(c U / nsm) whole waves and
+    spill the rest into one more.  When the spill, cut into 128-query CTAs (measured at ~0.8 of a 256-query CTA's time, not 0.5:
+    one group alone cannot alternate with another on the tensor pipe), fits into ONE wave together with the trailing one-group
+    CTAs, the step ends that much earlier; otherwise nothing is split.  n = 16 385, G = 4, two towers, 148 SMs: 512 CTAs = 3 waves +
+    68 -> 9 blocks per (bag, group) become 18 short CTAs (measured A/B on one box: 3.680 -> 3.631 ms per step; 8 or 10 blocks are
+    worse than none)."""
+    rg = -(-n // 128)
+    nf = rg // 2
+    per = G * B
+    tot = concurrent * nf * per
+    waves = tot // nsm
+    spill = tot - waves * nsm
+    if waves == 0 or spill == 0 or nf == 0:
+        return 0
+    t = min(-(-spill // (concurrent * per)), nf)
+    halves = concurrent * (2 * t + (rg - 2 * nf)) * per
+    slack = waves * nsm - concurrent * (nf - t) * per
+    return t if slack >= 0 and halves <= nsm + slack else 0
+
+
+_FWD_HALF_ENV = os.environ.get("DML_B200_FWD_HALF_BLOCKS")      # tuning aid: a fixed count instead of the plan ("0" = never split)
+
+
+def fwd_half_blocks(n: int, B: int, G: int, dev) -> int:
+    if _FWD_HALF_ENV is not None:
+        return max(0, int(_FWD_HALF_ENV))
+    c = getattr(_CONCURRENT_ATTN, "count", 1)
+    if c <= 1:
+        return 0
+    return plan_half_blocks(n, B, G, c, torch.cuda.get_device_properties(dev).multi_processor_count)
 
 
 def loss_scale_from_amax(amax_bits: torch.Tensor) -> torch.Tensor:
@@ -188,8 +245,8 @@ class DeformCrossAttn1DFn(torch.autograd.Function):
         q_att = q if n_out == n else q[:, :n_out].contiguous()
         o = torch.empty(B, n_out, C, device=dev, dtype=F32)
         lse = torch.empty(B, H, n_out, device=dev, dtype=F32)
-        call("dml_deform_attn_fwd_tc", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n_out, n_kv, n, C, 2 * C, 2 * C, C,
-             nout, scale, ptr(o), ptr(lse), st)
+        call("dml_deform_attn_fwd_tc_split", ptr(q_att), ptr(k), ptr(v), ptr(g), ptr(table), B, H, d, n_out, n_kv, n, C, 2 * C, 2 * C, C,
+             nout, scale, ptr(o), ptr(lse), fwd_half_blocks(n_out, B, G, dev), st)
         o_p = Pair.from_f32(o)
         out, _ = pgemm(o_p, Wo_p.b1(), M=n_out, N=dim, K=C, batch=(B,), bias=bo.contiguous().float(),
                        resid=x1f[:, :n_out] if fused else None)          # to_out (:233) [+ the layer's residual]

@@ -96,6 +96,14 @@ int dml_kv_gather_bwd(const float* x2, const float* gnorm, const float* dkv, int
 int dml_deform_attn_fwd_tc(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
                            int H, int dim_head, int n, int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo,
                            int heads_per_group, float scale, void* out, float* lse, void* stream);
+/* The same with the CTA decomposition made explicit.  A CTA normally takes 256 queries of one (bag, offset group) - two softmax
+ * groups of 128 rows alternating on the tensor pipe; a trailing group of <= 128 rows gets a CTA with one group.  half_blocks > 0
+ * runs the LAST half_blocks 256-query blocks of every (bag, group) as 2 * half_blocks one-group CTAs, placed after every two-group
+ * CTA in launch order: when the two-group CTAs of the launches that share the GPU (e.g. the two towers of DeformPathomicNet) do
+ * not fill a whole number of waves, the short CTAs fill the partial one (planner: ops.fwd_half_blocks).  Results are identical. */
+int dml_deform_attn_fwd_tc_split(const void* q, const void* k, const void* v, const float* gnorm, const void* table, int B,
+                                 int H, int dim_head, int n, int n_kv, int n_seq, int ldq, int ldk, int ldv, int ldo,
+                                 int heads_per_group, float scale, void* out, float* lse, int half_blocks, void* stream);
 /* out float [B,n,ldo] as written by the forward; d_out fp16 [B,n,ldo] (ldo == H*dim_head) = s * dL/dout with the
  * power-of-two loss scale s the caller chose so that s*max|dL/dout| is O(10) (fp16 range); dscale: device float[2]
  * = (s, 1/s), read by the kernels (no host sync) to un-scale every output.  dsum_ws float [B,H,n] workspace.  Outputs (fp32, dense

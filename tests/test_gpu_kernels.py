@@ -106,6 +106,13 @@ def test_deform_attn_fwd_tcgen05_matches_torch(B, n, n_kv):
     call_test("dml_deform_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, C, C, C, C, nout, scale,
          ptr(o2), ptr(lse2), stream())
     H.assert_close(lse, lse2, 1e-5, "log-sum-exp (tcgen05 vs mma.sync)")
+    # the same launch with trailing 256-query blocks cut into 128-query CTAs (dml_deform_attn_fwd_tc_split): identical results
+    for hb in (1, 3, 1000):
+        o3 = torch.full_like(o, float("nan"))
+        lse3 = torch.full_like(lse, float("nan"))
+        call("dml_deform_attn_fwd_tc_split", ptr(q), ptr(k), ptr(v), ptr(g), ptr(table), B, Hh, d, n, n_kv, n, C, C, C, C, nout,
+             scale, ptr(o3), ptr(lse3), hb, stream())
+        assert torch.equal(o3, o) and torch.equal(lse3, lse), f"half_blocks = {hb}"
 
 
 @pytest.mark.parametrize("B,n,n_kv", [(1, 300, 70), (2, 1000, 257)])

@@ -41,3 +41,16 @@ def test_length_bucketed_sampler_partitions_like_a_distributed_sampler():
     s0 = LengthBucketedSampler(lengths, world, 0, seed=11)
     a = list(s0); s0.set_epoch(1); b = list(s0)
     assert a != b and sorted(a) != [] 
+
+
+def test_forward_cta_plan_only_splits_when_the_spill_fits_one_wave():
+    """ops.plan_half_blocks: the north-star shape on two towers and 148 SMs cuts 9 blocks per (bag, group); a single launch, a
+    shape without a partial wave or a spill too large for one wave of short CTAs is left alone."""
+    assert ops.plan_half_blocks(16385, 1, 4, 2, 148) == 9
+    assert ops.plan_half_blocks(16385, 1, 4, 1, 148) == 0          # 256 CTAs = 1 wave + 108: 216 short CTAs do not fit one wave
+    assert ops.plan_half_blocks(300, 1, 4, 2, 148) == 0            # less than one wave in all
+    for n in (1, 127, 128, 129, 4097, 6001, 16385, 100001):
+        for c in (1, 2, 3):
+            for nsm in (132, 148):
+                t = ops.plan_half_blocks(n, 1, 4, c, nsm)
+                assert 0 <= t <= (-(-n // 128)) // 2
