@@ -789,8 +789,13 @@ def main():
             cur.wait_event(ready[slot])
             loss = step(staged[slot])
             consumed[slot].record(cur)
-            losses_host[s].copy_(loss.detach(), non_blocking=True)
+            # the 4-byte loss goes to the host from the copy stream, behind this step: a device-to-host copy queued on the
+            # compute stream would hold the next step's first kernel back by the copy's latency
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                losses_host[s].copy_(loss.detach(), non_blocking=True)
         cur.synchronize()
+        copy_stream.synchronize()
 
     e2e(args.warmup)
     ms_e2e = timed(e2e, args.steps)
