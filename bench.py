@@ -791,9 +791,12 @@ def main():
             consumed[slot].record(cur)
             # the 4-byte loss goes to the host from the copy stream, behind this step: a device-to-host copy queued on the
             # compute stream would hold the next step's first kernel back by the copy's latency
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[slot])
+            if os.environ.get("DML_BENCH_LOSS_ON_COMPUTE_STREAM"):
                 losses_host[s].copy_(loss.detach(), non_blocking=True)
+            else:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[slot])
+                    losses_host[s].copy_(loss.detach(), non_blocking=True)
         cur.synchronize()
         copy_stream.synchronize()
 
