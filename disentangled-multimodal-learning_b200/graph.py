@@ -124,10 +124,13 @@ class GraphedTrainStep:
         views, grads = [], []
         for p, v, has in zip(r.params, r._views(r.flat), r._present):
             if has:
-                assert p.grad is not None, "GraphedTrainStep: a parameter lost its gradient (static presence violated)"
-                views.append(v.view_as(p))
-                grads.append(p.grad)
-        torch._foreach_copy_(views, grads)
+                if p.grad is None:            # used by another captured step (e.g. another bag length) but not by this one
+                    v.zero_()
+                else:
+                    views.append(v.view_as(p))
+                    grads.append(p.grad)
+        if views:
+            torch._foreach_copy_(views, grads)
         return loss
 
     def __call__(self, inputs: Dict[str, torch.Tensor]) -> torch.Tensor:
